@@ -1,0 +1,557 @@
+// cells.cu -- link-cell binning, stable cell sort and Verlet neighbour-list kernels.
+//
+// Follows neighbours.F90::link_cell_pairs (:356-1306).  Every floating-point expression that decides an integer
+// (cell index, list membership) is evaluated with the reference's operation order and WITHOUT fused multiply-add:
+// this translation unit is compiled with -fmad=false (see __graft_entry__.build), so `a*b + c*d` rounds each product.
+//
+// Device layout produced by a build ("sorted" = link-cell order, the reference's at_list/xxt/yyt/zzt, :803-823):
+//   which_cell[i]  cell id of local index i (0 = residual halo)         lct_start[c]  first sorted slot of cell c (0-based)
+//   at_list[s]     local index held by sorted slot s                    cell_s[s]     cell id of slot s
+//   posq_s[s]      {x,y,z,chge} of slot s (refreshed every force call)  loc_slot[t]   slot of the t-th LOCAL atom
+//   nbr[t][k]      full neighbour row of local atom t: slot | flags     xnbr[t][k]    excluded partners (ewald_excl_forces)
+//   ref_list       optional reference-format half list (-3:max_list,1:natms), bit-exact incl. row order
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- host geometry (neighbours.F90:401-601)
+void h_dcell(const double* aaa0, double* b /*1..10*/) {   // numerics.F90:1344-1446
+  const double* aaa = aaa0 - 1;
+  b[1] = std::sqrt(aaa[1] * aaa[1] + aaa[2] * aaa[2] + aaa[3] * aaa[3]);
+  b[2] = std::sqrt(aaa[4] * aaa[4] + aaa[5] * aaa[5] + aaa[6] * aaa[6]);
+  b[3] = std::sqrt(aaa[7] * aaa[7] + aaa[8] * aaa[8] + aaa[9] * aaa[9]);
+  double axb1 = aaa[2] * aaa[6] - aaa[3] * aaa[5], axb2 = aaa[3] * aaa[4] - aaa[1] * aaa[6], axb3 = aaa[1] * aaa[5] - aaa[2] * aaa[4];
+  double bxc1 = aaa[5] * aaa[9] - aaa[6] * aaa[8], bxc2 = aaa[6] * aaa[7] - aaa[4] * aaa[9], bxc3 = aaa[4] * aaa[8] - aaa[5] * aaa[7];
+  double cxa1 = aaa[8] * aaa[3] - aaa[9] * aaa[2], cxa2 = aaa[9] * aaa[1] - aaa[7] * aaa[3], cxa3 = aaa[7] * aaa[2] - aaa[8] * aaa[1];
+  b[10] = std::fabs(aaa[1] * bxc1 + aaa[2] * bxc2 + aaa[3] * bxc3);
+  double d[4], x[4], y[4];
+  d[1] = b[10] / std::sqrt(bxc1 * bxc1 + bxc2 * bxc2 + bxc3 * bxc3);
+  d[2] = b[10] / std::sqrt(cxa1 * cxa1 + cxa2 * cxa2 + cxa3 * cxa3);
+  d[3] = b[10] / std::sqrt(axb1 * axb1 + axb2 * axb2 + axb3 * axb3);
+  x[1] = std::fabs(aaa[1]) / b[1]; y[1] = std::fabs(aaa[2]) / b[1];
+  x[2] = std::fabs(aaa[4]) / b[2]; y[2] = std::fabs(aaa[5]) / b[2];
+  x[3] = std::fabs(aaa[7]) / b[3]; y[3] = std::fabs(aaa[8]) / b[3];
+  if (x[1] >= x[2] && x[1] >= x[3]) { b[7] = d[1]; if (y[2] >= y[3]) { b[8] = d[2]; b[9] = d[3]; } else { b[8] = d[3]; b[9] = d[2]; } }
+  else if (x[2] >= x[1] && x[2] >= x[3]) { b[7] = d[2]; if (y[1] >= y[3]) { b[8] = d[1]; b[9] = d[3]; } else { b[8] = d[3]; b[9] = d[1]; } }
+  else { b[7] = d[3]; if (y[1] >= y[2]) { b[8] = d[1]; b[9] = d[2]; } else { b[8] = d[2]; b[9] = d[1]; } }
+}
+void h_invert(const double* a0, double* b0) {   // numerics.F90:1448-1509
+  const double* a = a0 - 1;
+  double* b = b0 - 1;
+  b[1] = a[5] * a[9] - a[6] * a[8]; b[2] = a[3] * a[8] - a[2] * a[9]; b[3] = a[2] * a[6] - a[3] * a[5];
+  b[4] = a[6] * a[7] - a[4] * a[9]; b[5] = a[1] * a[9] - a[3] * a[7]; b[6] = a[3] * a[4] - a[1] * a[6];
+  b[7] = a[4] * a[8] - a[5] * a[7]; b[8] = a[2] * a[7] - a[1] * a[8]; b[9] = a[1] * a[5] - a[2] * a[4];
+  double d = a[1] * b[1] + a[4] * b[2] + a[7] * b[3];
+  double r = 0.0;
+  if (std::fabs(d) > 0.0) r = 1.0 / d;
+  for (int i = 1; i <= 9; ++i) b[i] = r * b[i];
+}
+
+int h_geometry(dlpgpu_ctx* ctx) {
+  LCGeom& g = ctx->g;
+  double celprp[11];
+  h_dcell(ctx->cell, celprp);
+  double det = std::min(celprp[7], std::min(celprp[8], celprp[9]));
+  if (ctx->rx >= det / 2.0)   // :409-412
+    return dlp_fail(ctx, DLPGPU_ERR_CUTOFF_HALF_CELL, "error 95: cutoff_extended %.6f >= half the minimum cell width %.6f", ctx->rx, det / 2.0);
+  double cut = ctx->rx + 1.0e-6;   // smalldr, :416
+  g.rcsq = ctx->rx * ctx->rx;      // :417
+  double nx_recip = 1.0 / (double)ctx->nx, ny_recip = 1.0 / (double)ctx->ny, nz_recip = 1.0 / (double)ctx->nz;
+  double dispx = nx_recip * celprp[7] / cut, dispy = ny_recip * celprp[8] / cut, dispz = nz_recip * celprp[9] / cut;
+  int nlx = (int)dispx, nly = (int)dispy, nlz = (int)dispz;
+  if (nlx * nly * nlz == 0) return dlp_fail(ctx, DLPGPU_ERR_LINK_CELLS, "error 307: link cell algorithm violation (domain narrower than cutoff_extended)");
+  int nlp = 1;   // :441-454
+  double nlr2 = (double)ctx->natms;
+  det = nlr2 / (double)(nlx * nly * nlz);
+  while (det > ctx->pdplnc) {
+    nlp = nlp + 1;
+    double rsq = (double)nlp;
+    nlx = (int)(dispx * rsq); nly = (int)(dispy * rsq); nlz = (int)(dispz * rsq);
+    det = nlr2 / (double)(nlx * nly * nlz);
+  }
+  g.nlx = nlx; g.nly = nly; g.nlz = nlz; g.nlp = nlp;
+  g.sx = nlx + 2 * nlp; g.sy = nly + 2 * nlp; g.sz = nlz + 2 * nlp;
+  long long nc = (long long)g.sx * g.sy * g.sz;
+  if (nc > 0x3fffffffLL) return dlp_fail(ctx, DLPGPU_ERR_ARG, "too many link cells");
+  g.ncells = (int)nc;
+  g.idx = ctx->idx; g.idy = ctx->idy; g.idz = ctx->idz;
+  g.xdc = (double)(nlx * ctx->nx); g.ydc = (double)(nly * ctx->ny); g.zdc = (double)(nlz * ctx->nz);   // :545-547
+  g.jx = nlp - nlx * ctx->idx; g.jy = nlp - nly * ctx->idy; g.jz = nlp - nlz * ctx->idz;               // :554-556
+  h_invert(ctx->cell, g.rcell);
+  g.nir_r2 = (nlp - 1) * (nlp - 1);
+  // semi-ball stencil :490-540 in reference order
+  ctx->h_nix.clear(); ctx->h_niy.clear(); ctx->h_niz.clear(); ctx->h_nir.clear();
+  int nlp2 = nlp * nlp, nlp3 = (nlp - 1) * (nlp - 1);
+  int W = 2 * nlp + 1;
+  ctx->h_xb.assign((size_t)W * W, -1);
+  for (int iz = 0; iz <= nlp; ++iz) {
+    int iz1 = (iz > 0) ? (iz - 1) * (iz - 1) : 0;
+    int jz = iz * iz;
+    for (int iy = -nlp; iy <= nlp; ++iy) {
+      if (iz == 0 && iy < 0) continue;
+      int a = std::abs(iy);
+      int iy1 = (a > 0) ? (a - 1) * (a - 1) : 0;
+      int ll = iz1 + iy1;
+      if (ll > nlp2) continue;
+      int jy = jz + iy * iy;
+      for (int ix = -nlp; ix <= nlp; ++ix) {
+        if (iz == 0 && iy == 0 && ix < 0) continue;
+        int b = std::abs(ix);
+        int ix1 = (b > 0) ? (b - 1) * (b - 1) : 0;
+        if (ll + ix1 > nlp2) continue;
+        int jxx = jy + ix * ix;
+        ctx->h_nix.push_back(ix); ctx->h_niy.push_back(iy); ctx->h_niz.push_back(iz);
+        ctx->h_nir.push_back(jxx < nlp3 ? 1 : 0);
+        // symmetric half extent of row (iy,iz) and of its mirror (-iy,-iz)
+        int& e1 = ctx->h_xb[(size_t)(iz + nlp) * W + (iy + nlp)];
+        int& e2 = ctx->h_xb[(size_t)(-iz + nlp) * W + (-iy + nlp)];
+        e1 = std::max(e1, b);
+        e2 = std::max(e2, b);
+      }
+    }
+  }
+  g.nsbcll = (int)ctx->h_nix.size();
+  return 0;
+}
+
+// ---------------------------------------------------------------- binning (neighbours.F90:612-799)
+__device__ __forceinline__ bool f_equal(double a, double b) { return fabs(a - b) < DBL_EPSILON; }   // numerics.F90:3888-3893
+
+__global__ void k_cell_index(LCGeom g, int natms, int nlast, const double4* __restrict__ posq, int* __restrict__ which_cell,
+                             int* __restrict__ lct_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlast) return;
+  const double half_plus = 0.50000000000000011102230246251565404236316680908203125;   // Nearest(0.5,+1)
+  double4 p = posq[i];
+  double x = g.rcell[0] * p.x + g.rcell[3] * p.y + g.rcell[6] * p.z;
+  double y = g.rcell[1] * p.x + g.rcell[4] * p.y + g.rcell[7] * p.z;
+  double z = g.rcell[2] * p.x + g.rcell[5] * p.y + g.rcell[8] * p.z;
+  const int nlp = g.nlp, nlx = g.nlx, nly = g.nly, nlz = g.nlz;
+  const int nlx0e = nlp - 1, nly0e = nlp - 1, nlz0e = nlp - 1;
+  const int nlx1s = nlx + nlp, nly1s = nly + nlp, nlz1s = nlz + nlp;
+  const int nlx1e = nlx + 2 * nlp - 1, nly1e = nly + 2 * nlp - 1, nlz1e = nlz + 2 * nlp - 1;
+  int ix, iy, iz, icell;
+  if (i < natms) {
+    ix = __double2int_rz(g.xdc * (x + 0.5)) + g.jx;
+    iy = __double2int_rz(g.ydc * (y + 0.5)) + g.jy;
+    iz = __double2int_rz(g.zdc * (z + 0.5)) + g.jz;
+    ix = max(min(ix, nlx1s - 1), nlx0e + 1);
+    iy = max(min(iy, nly1s - 1), nly0e + 1);
+    iz = max(min(iz, nlz1s - 1), nlz0e + 1);
+    icell = 1 + ix + g.sx * (iy + g.sy * iz);
+  } else {
+    double dpx, dpy, dpz;
+    if (x > -half_plus) { dpx = g.xdc * (x + 0.5); ix = __double2int_rz(dpx) + g.jx; }
+    else { dpx = g.xdc * fabs(x + 0.5); ix = -__double2int_rz(dpx) + g.jx - 1; }
+    if (y > -half_plus) { dpy = g.ydc * (y + 0.5); iy = __double2int_rz(dpy) + g.jy; }
+    else { dpy = g.ydc * fabs(y + 0.5); iy = -__double2int_rz(dpy) + g.jy - 1; }
+    if (z > -half_plus) { dpz = g.zdc * (z + 0.5); iz = __double2int_rz(dpz) + g.jz; }
+    else { dpz = g.zdc * fabs(z + 0.5); iz = -__double2int_rz(dpz) + g.jz - 1; }
+    if (ix >= 0 && iy >= 0 && iz >= 0) {
+      bool lx0 = (ix > nlx0e), lx1 = (ix < nlx1s), ly0 = (iy > nly0e), ly1 = (iy < nly1s), lz0 = (iz > nlz0e), lz1 = (iz < nlz1s);
+      if ((lx0 && lx1) && (ly0 && ly1) && (lz0 && lz1)) {   // halo atom kicked into the domain: put on the border (:699-756)
+        double xa = fabs(dpx - (double)(nlx * g.idx)), x1 = fabs(dpx - (double)(nlx * (g.idx + 1)));
+        dpx = fmin(xa, x1);
+        double ya = fabs(dpy - (double)(nly * g.idy)), y1 = fabs(dpy - (double)(nly * (g.idy + 1)));
+        dpy = fmin(ya, y1);
+        double za = fabs(dpz - (double)(nlz * g.idz)), z1 = fabs(dpz - (double)(nlz * (g.idz + 1)));
+        dpz = fmin(za, z1);
+        if (dpx <= dpy && dpx <= dpz) {
+          ix = (xa < x1) ? nlx0e : nlx1s;
+          if (f_equal(dpx, dpy)) iy = (ya < y1) ? nly0e : nly1s;
+          if (f_equal(dpx, dpz)) iz = (za < z1) ? nlz0e : nlz1s;
+        } else if (dpy <= dpx && dpy <= dpz) {
+          iy = (ya < y1) ? nly0e : nly1s;
+          if (f_equal(dpy, dpz)) iz = (za < z1) ? nlz0e : nlz1s;
+        } else {
+          iz = (za < z1) ? nlz0e : nlz1s;
+        }
+      }
+      bool out = (ix < 0) || (ix > nlx1e) || (iy < 0) || (iy > nly1e) || (iz < 0) || (iz > nlz1e);
+      icell = out ? 0 : 1 + ix + g.sx * (iy + g.sy * iz);
+    } else {
+      icell = 0;
+    }
+  }
+  which_cell[i] = icell;
+  atomicAdd(&lct_count[icell], 1);
+}
+
+__global__ void k_cell_scatter(int nlast, const int* __restrict__ which_cell, const int* __restrict__ lct_start,
+                               int* __restrict__ lct_fill, int* __restrict__ at_tmp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlast) return;
+  int c = which_cell[i];
+  int pos = lct_start[c] + atomicAdd(&lct_fill[c], 1);
+  at_tmp[pos] = i;
+}
+
+// Stable order inside each cell = ascending local index, as the reference's sequential counting sort gives (:811-823).
+// One warp per cell, rank by counting.
+__global__ void k_cell_order(int ncells_p1, const int* __restrict__ lct_start, const int* __restrict__ at_tmp,
+                             int* __restrict__ at_list, int* __restrict__ cell_s) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (c >= ncells_p1) return;
+  int s0 = lct_start[c], n = lct_start[c + 1] - s0;
+  for (int a = lane; a < n; a += 32) {
+    int e = at_tmp[s0 + a];
+    int r = 0;
+    for (int b = 0; b < n; ++b) r += (at_tmp[s0 + b] < e);
+    at_list[s0 + r] = e;
+    cell_s[s0 + a] = c;
+  }
+}
+
+__global__ void k_sorted_static(int nlast, int natms, const int* __restrict__ at_list, const int* __restrict__ ltype,
+                                const int* __restrict__ ltg, const int* __restrict__ lfrzn, int* __restrict__ type_s,
+                                int* __restrict__ gid_s, int* __restrict__ frz_s, int* __restrict__ is_local) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nlast) return;
+  if (s == nlast) { is_local[s] = 0; return; }   // zero pad for the scan's total slot
+  int i = at_list[s];
+  type_s[s] = ltype[i]; gid_s[s] = ltg[i]; frz_s[s] = lfrzn[i];
+  is_local[s] = (i < natms) ? 1 : 0;
+}
+__global__ void k_loc_slot(int nlast, const int* __restrict__ is_local, const int* __restrict__ rank, int* __restrict__ loc_slot) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nlast && is_local[s]) loc_slot[rank[s]] = s;
+}
+__global__ void k_gather_posq(int nlast, const int* __restrict__ at_list, const double4* __restrict__ posq, double4* __restrict__ posq_s) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nlast) posq_s[s] = posq[at_list[s]];
+}
+
+// ---------------------------------------------------------------- list kernels
+__device__ __forceinline__ double pair_rsq(const double4& a, double xi, double yi, double zi) {
+  // neighbours.F90:991-992  rsq = (xxt(jj)-x_i)**2 + (yyt(jj)-y_i)**2 + (zzt(jj)-z_i)**2   (left-to-right, no FMA)
+  double dx = a.x - xi, dy = a.y - yi, dz = a.z - zi;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+__device__ __forceinline__ bool nir_of(const LCGeom& g, int cj, int ix, int iy, int iz) {
+  if (g.nir_r2 <= 0) return false;
+  int c = cj - 1;
+  int jx = c % g.sx, jz = c / (g.sx * g.sy), jy = c / g.sx - g.sy * jz;
+  int dx = jx - ix, dy = jy - iy, dz = jz - iz;
+  return dx * dx + dy * dy + dz * dz < g.nir_r2;
+}
+
+// Reference-format half list.  One warp per local atom; candidates are taken 32 at a time in the reference's visiting
+// order (stencil order kk, then ascending sorted slot), accepted ones are appended with ballot/popc prefix compaction,
+// so row contents AND order equal the sequential algorithm's.
+__global__ void k_list_ref(LCGeom g, int natms, int max_list, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
+                           const int* __restrict__ lct_start, const int* __restrict__ cell_s, const double4* __restrict__ posq_s,
+                           const int* __restrict__ nix, const int* __restrict__ niy, const int* __restrict__ niz,
+                           const int* __restrict__ nir, int* __restrict__ list, int* __restrict__ status) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (t >= natms) return;
+  const int ii = loc_slot[t];
+  const int i = at_list[ii];
+  const int ic = cell_s[ii];
+  const int ix = (ic - 1) % g.sx, iz = (ic - 1) / (g.sx * g.sy), iy = (ic - 1) / g.sx - g.sy * iz;
+  const double4 pi = posq_s[ii];
+  int* row = list + (size_t)i * (max_list + 4) + 3;   // row[k] == list(k, i)
+  int cnt = 0;
+  const int nlp = g.nlp;
+  const int lo_x = nlp - 1, hi_x = g.nlx + nlp, lo_y = nlp - 1, hi_y = g.nly + nlp, lo_z = nlp - 1, hi_z = g.nlz + nlp;
+
+  auto scan_range = [&](int s0, int s1, bool nirflag) {
+    for (int b = s0; b < s1; b += 32) {
+      int jj = b + lane;
+      bool ok = false;
+      if (jj < s1) {
+        if (nirflag) ok = true;
+        else ok = pair_rsq(posq_s[jj], pi.x, pi.y, pi.z) <= g.rcsq;
+      }
+      unsigned m = __ballot_sync(DLP_FULL, ok);
+      if (ok) {
+        int ll = cnt + __popc(m & ((1u << lane) - 1)) + 1;
+        if (ll <= max_list) row[ll] = at_list[jj] + 1;
+        else { atomicOr(&status[0], 1); atomicMax(&status[1], ll); }
+      }
+      cnt += __popc(m);
+    }
+  };
+  // pass 1: positive semi-ball (:877-1027)
+  for (int kk = 0; kk < g.nsbcll; ++kk) {
+    int jx = ix + nix[kk], jy = iy + niy[kk], jz = iz + niz[kk];
+    int jc = 1 + jx + g.sx * (jy + g.sy * jz);
+    int s0 = (jc != ic) ? lct_start[jc] : ii + 1;
+    scan_range(s0, lct_start[jc + 1], nir[kk] != 0);
+  }
+  // pass 2: negative semi-ball, halo cells only, border cells only (:1033-1184)
+  bool border = (ix - lo_x <= nlp) || (hi_x - ix <= nlp) || (iy - lo_y <= nlp) || (hi_y - iy <= nlp) || (iz - lo_z <= nlp) || (hi_z - iz <= nlp);
+  if (border) {
+    for (int kk = 1; kk < g.nsbcll; ++kk) {
+      int jx = ix - nix[kk], jy = iy - niy[kk], jz = iz - niz[kk];
+      if ((jx <= lo_x) || (jx >= hi_x) || (jy <= lo_y) || (jy >= hi_y) || (jz <= lo_z) || (jz >= hi_z)) {
+        int jc = 1 + jx + g.sx * (jy + g.sy * jz);
+        scan_range(lct_start[jc], lct_start[jc + 1], nir[kk] != 0);
+      }
+    }
+  }
+  if (lane == 0) { row[0] = cnt; row[-1] = cnt; row[-2] = cnt; row[-3] = cnt; }
+}
+
+__device__ __forceinline__ bool excl_match(int n, int ind_top, const int* __restrict__ list1 /*1-based view*/) {
+  // numerics.F90:1048-1098 match()
+  if (ind_top < 1) return false;
+  int ind_old = 1, ind_now = 1;
+  for (;;) {
+    int v = list1[ind_now];
+    if (n == v) return true;
+    else if (n > v) {
+      if (ind_old == ind_top) return false;
+      ind_old = ind_now;
+      ind_now = (ind_old + ind_top + 1) / 2;
+    } else {
+      ind_now = (ind_old + ind_now) / 2;
+      if (ind_now == ind_old) return false;
+    }
+  }
+}
+
+// Row partition of the reference-format list: frozen-frozen pairs, then excluded pairs, swapped to the row tail with
+// the reference's backwards sweep (:1198-1251) -- one thread per row, sequential like the original, so the order matches.
+__global__ void k_row_partition(int natms, int max_list, int megfrz, int lbook, int max_exclude, int excl_by_gid,
+                                const int* __restrict__ lfrzn, const int* __restrict__ ltg, const int* __restrict__ excl,
+                                int* __restrict__ list) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natms) return;
+  int* row = list + (size_t)i * (max_list + 4) + 3;
+  if (row[0] > max_list) return;   // overflowed row: the build fails with error 106 anyway
+  if (megfrz > 1) {
+    int l_end = row[0], m_end = l_end;
+    if (lfrzn[i] > 0) {
+      for (int kk = l_end; kk >= 1; --kk) {
+        int j = row[kk];
+        if (lfrzn[j - 1] > 0) {
+          if (kk < m_end) { row[kk] = row[m_end]; row[m_end] = j; }
+          m_end = m_end - 1;
+        }
+      }
+    }
+    row[-2] = row[0];
+    row[0] = m_end;
+  } else {
+    row[-2] = row[0];
+  }
+  if (lbook) {
+    int l_end = row[0], m_end = l_end;
+    const int* ex = excl + (size_t)(excl_by_gid ? (ltg[i] - 1) : i) * (max_exclude + 1);
+    int ii = ex[0];
+    if (ii > 0) {
+      for (int kk = l_end; kk >= 1; --kk) {
+        int j = row[kk];
+        int jj = ltg[j - 1];
+        if (excl_match(jj, ii, ex)) {
+          if (kk < m_end) { row[kk] = row[m_end]; row[m_end] = j; }
+          m_end = m_end - 1;
+        }
+      }
+    }
+    row[-1] = row[0];
+    row[0] = m_end;
+    row[-3] = row[0];
+  } else {
+    row[-1] = row[0];
+    row[-3] = row[0];
+  }
+}
+
+// Device-internal lists.  FULL: every partner (local or halo) of local atom t within the Verlet radius -- the
+// symmetrised reference list restricted to local primaries, so no force scatter is needed.  HALF additionally keeps the
+// reference's pair ownership (local-local pairs once) for the Newton's-third-law kernel.
+// Candidate cells are exactly the reference's (semi-ball and its mirror); x-runs of one (dy,dz) row are contiguous in
+// the sorted arrays, which is what makes 32-wide candidate batches dense.
+template <bool HALF>
+__global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid,
+                           const int* __restrict__ loc_slot, const int* __restrict__ at_list, const int* __restrict__ lct_start,
+                           const int* __restrict__ cell_s, const double4* __restrict__ posq_s, const int* __restrict__ gid_s,
+                           const int* __restrict__ frz_s, const int* __restrict__ xb, const int* __restrict__ excl,
+                           unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
+                           int* __restrict__ status) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (t >= natms) return;
+  const int ii = loc_slot[t];
+  const int i = at_list[ii];
+  const int ic = cell_s[ii];
+  const int ix = (ic - 1) % g.sx, iz = (ic - 1) / (g.sx * g.sy), iy = (ic - 1) / g.sx - g.sy * iz;
+  const double4 pi = posq_s[ii];
+  const int gid_i = gid_s[ii];
+  const int frz_i = (megfrz > 1) ? frz_s[ii] : 0;
+  const int* ex = lbook ? excl + (size_t)(excl_by_gid ? (gid_i - 1) : i) * (max_exclude + 1) : nullptr;
+  const int nex = lbook ? ex[0] : 0;
+  unsigned* row = nbr + (size_t)t * pitch;
+  unsigned* xrow = xnbr + (size_t)t * (xpitch > 0 ? xpitch : 1);
+  int cnt = 0, xcnt = 0;
+  const int nlp = g.nlp, W = 2 * nlp + 1;
+  for (int dz = -nlp; dz <= nlp; ++dz) {
+    for (int dy = -nlp; dy <= nlp; ++dy) {
+      int b = xb[(dz + nlp) * W + (dy + nlp)];
+      if (b < 0) continue;
+      int xlo = -b, xhi = b;
+      int jy = iy + dy, jz = iz + dz;
+      int c0 = 1 + (ix + xlo) + g.sx * (jy + g.sy * jz);
+      int c1 = 1 + (ix + xhi) + g.sx * (jy + g.sy * jz);
+      int s0 = lct_start[c0], s1 = lct_start[c1 + 1];
+      for (int bb = s0; bb < s1; bb += 32) {
+        int jj = bb + lane;
+        bool ok = false, isx = false;
+        unsigned entry = 0;
+        if (jj < s1 && jj != ii) {
+          int cj = cell_s[jj];
+          bool acc = nir_of(g, cj, ix, iy, iz) || (pair_rsq(posq_s[jj], pi.x, pi.y, pi.z) <= g.rcsq);
+          if (acc) {
+            int jref = at_list[jj];
+            bool halo = jref >= natms;
+            int gj = gid_s[jj];
+            bool keep = true;
+            if (HALF && !halo) {
+              // pair ownership of the reference: the atom whose cell sees the other in the positive semi-ball; same cell: lower slot
+              int cdx = (cj - 1) % g.sx - ix, cdz = (cj - 1) / (g.sx * g.sy) - iz, cdy = (cj - 1) / g.sx - g.sy * ((cj - 1) / (g.sx * g.sy)) - iy;
+              bool pos = (cdz > 0) || (cdz == 0 && (cdy > 0 || (cdy == 0 && (cdx > 0 || (cdx == 0 && jj > ii)))));
+              keep = pos;
+            }
+            if (keep) {
+              if (frz_i > 0 && frz_s[jj] > 0) keep = false;   // frozen-frozen pairs never reach the force loops (:1198-1225)
+            }
+            if (keep) {
+              entry = (unsigned)jj | (halo ? DLP_F_HALO : 0u) | ((halo && gid_i < gj) ? DLP_F_ECNT : 0u);
+              if (nex > 0 && excl_match(gj, nex, ex)) isx = true; else ok = true;
+            }
+          }
+        }
+        unsigned m = __ballot_sync(DLP_FULL, ok), mx = __ballot_sync(DLP_FULL, isx);
+        if (ok) {
+          int ll = cnt + __popc(m & ((1u << lane) - 1));
+          if (ll < pitch) row[ll] = entry; else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
+        }
+        if (isx) {
+          int ll = xcnt + __popc(mx & ((1u << lane) - 1));
+          if (ll < xpitch) xrow[ll] = entry; else { atomicOr(&status[0], 2); }
+        }
+        cnt += __popc(m);
+        xcnt += __popc(mx);
+      }
+    }
+  }
+  if (lane == 0) { nnbr[t] = cnt; nxnbr[t] = xcnt; }
+}
+
+__global__ void k_bg_copy(int n, const double4* __restrict__ posq, double* xbg, double* ybg, double* zbg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { double4 p = posq[i]; xbg[i] = p.x; ybg[i] = p.y; zbg[i] = p.z; }
+}
+
+}  // namespace
+
+int dlp_gather_sorted(dlpgpu_ctx* ctx) {
+  int n = ctx->list_nlast;
+  if (n > 0) LAUNCH(ctx, k_gather_posq, cdiv(n, 256), 256, 0, n, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
+  return 0;
+}
+
+int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
+  cudaStream_t s = ctx->stream;
+  ctx->list_valid = false; ctx->ref_valid = false;
+  if (ibig) *ibig = 0;
+  if (ctx->max_list < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "build: max_list not set");
+  CKRC(h_geometry(ctx));
+  LCGeom& g = ctx->g;
+  const int natms = ctx->natms, nlast = ctx->nlast;
+  cudaEventRecord(ctx->ev[0], s);
+  // stencil upload
+  size_t ns = ctx->h_nix.size();
+  CK(ctx->st_nix.ensure(ns, s)); CK(ctx->st_niy.ensure(ns, s)); CK(ctx->st_niz.ensure(ns, s)); CK(ctx->st_nir.ensure(ns, s));
+  CK(ctx->st_xb.ensure(ctx->h_xb.size(), s));
+  CK(cudaMemcpyAsync(ctx->st_nix.p, ctx->h_nix.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->st_niy.p, ctx->h_niy.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->st_niz.p, ctx->h_niz.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->st_nir.p, ctx->h_nir.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->st_xb.p, ctx->h_xb.data(), ctx->h_xb.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  // buffers
+  size_t nc = (size_t)g.ncells + 3;
+  CK(ctx->which_cell.ensure(nlast + 1, s)); CK(ctx->at_list.ensure(nlast + 1, s)); CK(ctx->at_tmp.ensure(nlast + 1, s));
+  CK(ctx->cell_s.ensure(nlast + 1, s)); CK(ctx->posq_s.ensure(nlast + 1, s));
+  CK(ctx->type_s.ensure(nlast + 1, s)); CK(ctx->gid_s.ensure(nlast + 1, s)); CK(ctx->frz_s.ensure(nlast + 1, s));
+  CK(ctx->lct_count.ensure(nc, s)); CK(ctx->lct_start.ensure(nc, s)); CK(ctx->lct_fill.ensure(nc, s));
+  CK(ctx->loc_slot.ensure(natms + 1, s));
+  CK(ctx->flag.ensure((size_t)nlast + 2, s)); CK(ctx->scan_out.ensure((size_t)nlast + 2, s));
+  CK(cudaMemsetAsync(ctx->lct_count.p, 0, nc * sizeof(int), s));
+  CK(cudaMemsetAsync(ctx->lct_fill.p, 0, nc * sizeof(int), s));
+  CK(cudaMemsetAsync(ctx->status.p, 0, 8 * sizeof(int), s));
+  if (nlast > 0) LAUNCH(ctx, k_cell_index, cdiv(nlast, 256), 256, 0, g, natms, nlast, ctx->posq.p, ctx->which_cell.p, ctx->lct_count.p);
+  // lct_start[c] for c = 0..ncells+1 (0-based slots): exclusive scan over counts of cells 0..ncells (+ zero pad)
+  CKRC(dlp_exclusive_scan(ctx, ctx->lct_count.p, ctx->lct_start.p, g.ncells + 1, nullptr));
+  if (nlast > 0) {
+    LAUNCH(ctx, k_cell_scatter, cdiv(nlast, 256), 256, 0, nlast, ctx->which_cell.p, ctx->lct_start.p, ctx->lct_fill.p, ctx->at_tmp.p);
+    LAUNCH(ctx, k_cell_order, cdiv((long long)(g.ncells + 1) * 32, 256), 256, 0, g.ncells + 1, ctx->lct_start.p, ctx->at_tmp.p,
+           ctx->at_list.p, ctx->cell_s.p);
+  }
+  LAUNCH(ctx, k_sorted_static, cdiv(nlast + 1, 256), 256, 0, nlast, natms, ctx->at_list.p, ctx->ltype.p, ctx->ltg.p, ctx->lfrzn.p,
+         ctx->type_s.p, ctx->gid_s.p, ctx->frz_s.p, ctx->flag.p);
+  CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nlast, nullptr));
+  if (nlast > 0) {
+    LAUNCH(ctx, k_loc_slot, cdiv(nlast, 256), 256, 0, nlast, ctx->flag.p, ctx->scan_out.p, ctx->loc_slot.p);
+    LAUNCH(ctx, k_gather_posq, cdiv(nlast, 256), 256, 0, nlast, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
+  }
+  ctx->list_natms = natms; ctx->list_nlast = nlast;
+  // device-internal lists
+  ctx->pitch = ((ctx->max_list + 31) / 32) * 32;
+  ctx->xpitch = ctx->lbook ? ((ctx->max_exclude + 31) / 32) * 32 : 0;
+  const int wpb = 8;   // warps per block
+  if (natms > 0) {
+    CK(ctx->nnbr.ensure(natms + 1, s)); CK(ctx->nxnbr.ensure(natms + 1, s));
+    CK(ctx->xnbr.ensure((size_t)natms * std::max(ctx->xpitch, 1) + 1, s));
+    cudaEventRecord(ctx->ev[2], s);
+    if (ctx->force_mode == 0) {
+      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
+      LAUNCH(ctx, k_list_dev<false>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
+             ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
+             ctx->gid_s.p, ctx->frz_s.p, ctx->st_xb.p, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+    } else {
+      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
+      LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
+             ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
+             ctx->gid_s.p, ctx->frz_s.p, ctx->st_xb.p, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+    }
+    cudaEventRecord(ctx->ev[3], s);
+    if (want_ref_list) {
+      CK(ctx->ref_list.ensure((size_t)natms * (ctx->max_list + 4) + 1, s));
+      LAUNCH(ctx, k_list_ref, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->max_list, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p,
+             ctx->cell_s.p, ctx->posq_s.p, ctx->st_nix.p, ctx->st_niy.p, ctx->st_niz.p, ctx->st_nir.p, ctx->ref_list.p, ctx->status.p);
+      LAUNCH(ctx, k_row_partition, cdiv(natms, 128), 128, 0, natms, ctx->max_list, ctx->megfrz, ctx->lbook, ctx->max_exclude,
+             ctx->excl_by_gid, ctx->lfrzn.p, ctx->ltg.p, ctx->excl.p, ctx->ref_list.p);
+    }
+  }
+  cudaEventRecord(ctx->ev[1], s);
+  int st[8];
+  CK(cudaMemcpyAsync(st, ctx->status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->t_list = ms;
+  if (natms > 0) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->t_full = ms; }
+  if (st[0]) {
+    if (ibig) *ibig = st[1];
+    return dlp_fail(ctx, DLPGPU_ERR_LIST_OVERFLOW, "error 106: neighbour list array exceeded (row length %d > max_list %d)", st[1], ctx->max_list);
+  }
+  ctx->list_valid = true;
+  ctx->ref_valid = want_ref_list != 0 && natms > 0;
+  return 0;
+}
+
+int dlp_vnl_set_check(dlpgpu_ctx* ctx) {
+  int n = ctx->nlast;
+  if (n > 0) LAUNCH(ctx, k_bg_copy, cdiv(n, 256), 256, 0, n, ctx->posq.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p);
+  ctx->have_bg = true;
+  return 0;
+}
+
+extern "C" int dlpgpu_dev_link_cell_pairs(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return dlp_build_lists(ctx, want_ref_list, ibig);
+}

@@ -1,0 +1,196 @@
+// common.cuh -- context, device buffers and launch helpers shared by the libdlpgpu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dlpgpu.h"
+
+#define DLP_WARP 32
+#define DLP_FULL 0xffffffffu
+
+// list entry flags of the device-internal full list (sorted slot index in the low 30 bits)
+#define DLP_J_MASK 0x3fffffffu
+#define DLP_F_HALO 0x40000000u   // partner is a halo atom (one-sided pair)
+#define DLP_F_ECNT 0x80000000u   // halo partner whose pair energy is counted here (idi < ltg(jatm))
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  // grow to at least n elements; keep=true preserves the first `keep_n` elements
+  cudaError_t ensure(size_t n, cudaStream_t s = 0, bool keep = false, size_t keep_n = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = n + n / 8 + 64;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && keep_n) {
+      e = cudaMemcpyAsync(q, p, std::min(keep_n, cap) * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// link-cell geometry of one build (neighbours.F90:401-601), filled on the host with the reference's arithmetic
+struct LCGeom {
+  double rcell[9];
+  double xdc, ydc, zdc;
+  double rcsq;
+  int jx, jy, jz;
+  int nlx, nly, nlz, nlp;
+  int sx, sy, sz;     // cells per direction incl. halo layers: nlx + 2 nlp ...
+  int ncells;         // sx*sy*sz ; cell ids 1..ncells, 0 = residual halo
+  int idx, idy, idz;
+  int nsbcll;
+  int nir_r2;         // (nlp-1)^2: offsets with ix^2+iy^2+iz^2 < nir_r2 skip the distance test (neighbours.F90:537)
+};
+
+struct HaloStage {    // one export_atomic_data direction as recorded at halo build, replayed by the refresh
+  int count = 0;      // atoms sent (== received from the opposite neighbour in a serial run)
+  int recv_off = 0;   // first local index (0-based) the received atoms were appended at
+  int recv_count = 0;
+  double shift[3] = {0, 0, 0};
+  bool lwrap = false;
+  DBuf<int> idx;      // source indices (0-based), ascending
+};
+
+struct dlpgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  int sm_count = 148;
+
+  // ---- setup
+  int nx = 1, ny = 1, nz = 1, idx = 0, idy = 0, idz = 0;
+  double cell[9] = {0};
+  int imcon = 1;
+  double rcut = 0, padding = 0, rx = 0, pdplnc = 50.0;
+  double ecw[3] = {0, 0, 0};
+  int force_mode = 0;
+
+  // vdw
+  bool vdw_on = false, vdw_fshift = false, vdw_direct = false;
+  int ntypes = 0, n_vdw = 0, max_vdw = 0, max_grid = 0;
+  double rvdw = 0, vdw_rdr = 0, thr_vdw = 0;   // thr_vdw: rsq < thr_vdw  <=>  Sqrt(rsq) < rvdw
+  DBuf<int> pair_k;        // [ntypes*ntypes] -> potential index k (0-based) or -1 (no interaction)
+  DBuf<int> ltp;           // [max_vdw]
+  DBuf<double2> vdw_tab;   // [max_vdw][max_grid+1] {tab_force, tab_potential}
+  DBuf<double> vdw_par;    // [max_vdw][10] param(1:7), afs, bfs, pad
+  // ewald
+  bool ew_on = false;
+  double alpha = 0, scaling = 0, ew_rdr = 0, thr_coul = 0;
+  int ew_n = 0;
+  DBuf<double2> ew_tab;    // [ew_n+1] {erfc_deriv, erfc}
+
+  // sites (native mode)
+  int nsites = 0;
+  DBuf<int> type_site, freeze_site;
+  DBuf<double> charge_site, weight_site;
+  // exclusions
+  int lbook = 0, megfrz = 0, max_exclude = 0;
+  int excl_by_gid = 0;     // rows indexed by global id (native) or by local index (drop-in)
+  DBuf<int> excl;          // [(max_exclude+1) * rows]
+
+  // ---- atoms in DL_POLY local order (0-based here)
+  int natms = 0, nlast = 0, capacity = 0;
+  DBuf<double4> posq;      // x,y,z,chge
+  DBuf<double> fx, fy, fz;
+  DBuf<double> fsx, fsy, fsz;   // sorted-slot accumulators (force_mode 1)
+  DBuf<double> vx, vy, vz;
+  DBuf<int> ltg, lsite, ltype, lfrzn, ixyz;
+  DBuf<double> xbg, ybg, zbg;
+  bool have_bg = false;
+
+  // ---- link cells / lists of the last build
+  LCGeom g{};
+  bool list_valid = false;
+  int list_natms = 0, list_nlast = 0;
+  int max_list = 0;
+  DBuf<int> which_cell, at_list, at_tmp, lct_count, lct_start, lct_fill;
+  DBuf<int> cell_s;        // cell id per sorted slot
+  DBuf<int> loc_slot;      // [natms] sorted slot of the t-th local atom in sorted order
+  DBuf<int> flag, scan_out, scan_tmp;
+  DBuf<double4> posq_s;    // sorted copy, refreshed every force call
+  DBuf<int> type_s, gid_s, frz_s;
+  DBuf<int> st_nix, st_niy, st_niz, st_nir;   // semi-ball stencil in reference order
+  DBuf<int> st_xb;         // [(2nlp+1)^2] half x-extent per (dy,dz) row of the full ball, -1 = row absent
+  std::vector<int> h_nix, h_niy, h_niz, h_nir, h_xb;
+  // reference-format half list (optional)
+  DBuf<int> ref_list;      // (-3:max_list, 1:natms)
+  bool ref_valid = false;
+  // device-internal lists, row t = t-th local atom in sorted order
+  int pitch = 0, xpitch = 0;
+  DBuf<unsigned> nbr;      // [natms][pitch]
+  DBuf<int> nnbr;          // [natms]
+  DBuf<unsigned> xnbr;     // [natms][xpitch] excluded partners
+  DBuf<int> nxnbr;
+  DBuf<unsigned> hnbr;     // half list (force_mode 1): [natms][pitch]
+  DBuf<int> nhnbr;
+  DBuf<double> xfer;       // internal exchange buffer of the serial halo / refresh
+  DBuf<int> hole_pos;
+  DBuf<int> status;        // [4] device status words: 0 overflow flag, 1 ibig, 2 lost atoms, 3 spare
+  // halo replay
+  HaloStage stage[6];
+  bool halo_valid = false;
+  // reductions
+  DBuf<double> partial;    // [blocks][16]
+  DBuf<double> out_dev;    // [16]
+  DBuf<unsigned long long> tol_bits;
+  // staging for the host-buffer entry points
+  DBuf<dlpgpu_corepart> parts_dev;
+  std::vector<double> h_f;
+  // timings
+  cudaEvent_t ev[8] = {nullptr};
+  double t_list = 0, t_force = 0, t_pair = 0, t_full = 0;
+};
+
+int dlp_fail(dlpgpu_ctx* ctx, int code, const char* fmt, ...);
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return dlp_fail(ctx, DLPGPU_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define CKRC(expr)          \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc != 0) return _rc; \
+  } while (0)
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                    \
+  do {                                                               \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \
+    (ctx)->launches++;                                               \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// util.cu
+int dlp_exclusive_scan(dlpgpu_ctx* ctx, const int* in_dev, int* out_dev, int n, int* total_host /*nullable*/);
+int dlp_ensure_atoms(dlpgpu_ctx* ctx, int n);
+// cells.cu
+int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig);
+int dlp_gather_sorted(dlpgpu_ctx* ctx);
+// forces.cu
+int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]);
+// halo.cu
+int dlp_vnl_set_check(dlpgpu_ctx* ctx);
+int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol);

@@ -1,0 +1,557 @@
+// halo.cu -- padding-driven rebuild test, halo build / refresh and particle migration kernels.
+//
+//   neighbours.F90:123-296  vnl_check (max displacement, minimum image via numerics.F90:1511-1600 images)
+//   halo.F90:153-355        set_halo_particles        deport_data.F90:1673-1951  export_atomic_data
+//   halo.F90:47-113         refresh_halo_positions    deport_data.F90:2301-2553  export_atomic_positions
+//   deport_data.F90:2870-3202 relocate_particles      deport_data.F90:81-960     deport_atomic_data
+//   numerics.F90:1851-1950  pbcshift_parts
+//
+// The wire format is the reference's (6 doubles per halo atom on a build, 3 on a refresh, the sender applies the
+// periodic shift); selection, ordering (ascending local index, appended in stage order -x,+x,-y,+y,-z,+z) and the
+// restack of staying atoms after migration reproduce the reference so local indices agree with a DL_POLY run.
+// Compiled with -fmad=false: thresholds and shifts decide set membership.
+#include "common.cuh"
+
+namespace {
+
+struct Dir { int kx, ky, kz, jxyz, kxyz; double xadd, yadd, zadd; int lwrap; };
+
+Dir dir_settings(const dlpgpu_ctx* c, int mdir) {   // deport_data.F90:1728-1796
+  Dir s{0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool lsx = false, lex = false, lsy = false, ley = false, lsz = false, lez = false;
+  switch (mdir) {
+    case -1: s.kx = 1; s.jxyz = 1; s.kxyz = 3; lsx = (c->idx == 0); break;
+    case 1: s.kx = 1; s.jxyz = 2; s.kxyz = 3; lex = (c->idx == c->nx - 1); break;
+    case -2: s.ky = 1; s.jxyz = 10; s.kxyz = 30; lsy = (c->idy == 0); break;
+    case 2: s.ky = 1; s.jxyz = 20; s.kxyz = 30; ley = (c->idy == c->ny - 1); break;
+    case -3: s.kz = 1; s.jxyz = 100; s.kxyz = 300; lsz = (c->idz == 0); break;
+    case 3: s.kz = 1; s.jxyz = 200; s.kxyz = 300; lez = (c->idz == c->nz - 1); break;
+  }
+  double uuu = 0.0; if (lsx) uuu = +1.0; if (lex) uuu = -1.0;
+  double vvv = 0.0; if (lsy) vvv = +1.0; if (ley) vvv = -1.0;
+  double www = 0.0; if (lsz) www = +1.0; if (lez) www = -1.0;
+  s.lwrap = (std::fabs(uuu) + std::fabs(vvv) + std::fabs(www) > 0.5) ? 1 : 0;
+  if (s.lwrap) {
+    const double* cell = c->cell - 1;
+    s.xadd = cell[1] * uuu + cell[4] * vvv + cell[7] * www;
+    s.yadd = cell[2] * uuu + cell[5] * vvv + cell[8] * www;
+    s.zadd = cell[3] * uuu + cell[6] * vvv + cell[9] * www;
+  }
+  return s;
+}
+int stage_of(int mdir) { return mdir == -1 ? 0 : mdir == 1 ? 1 : mdir == -2 ? 2 : mdir == 2 ? 3 : mdir == -3 ? 4 : mdir == 3 ? 5 : -1; }
+
+void h_invert(const double* a0, double* b0) {
+  const double* a = a0 - 1;
+  double* b = b0 - 1;
+  b[1] = a[5] * a[9] - a[6] * a[8]; b[2] = a[3] * a[8] - a[2] * a[9]; b[3] = a[2] * a[6] - a[3] * a[5];
+  b[4] = a[6] * a[7] - a[4] * a[9]; b[5] = a[1] * a[9] - a[3] * a[7]; b[6] = a[3] * a[4] - a[1] * a[6];
+  b[7] = a[4] * a[8] - a[5] * a[7]; b[8] = a[2] * a[7] - a[1] * a[8]; b[9] = a[1] * a[5] - a[2] * a[4];
+  double d = a[1] * b[1] + a[4] * b[2] + a[7] * b[3];
+  double r = 0.0;
+  if (std::fabs(d) > 0.0) r = 1.0 / d;
+  for (int i = 1; i <= 9; ++i) b[i] = r * b[i];
+}
+void h_widths(const double* aaa0, double* w3) {   // dcell bbb(7:9), numerics.F90:1344-1446
+  const double* aaa = aaa0 - 1;
+  double b1 = std::sqrt(aaa[1] * aaa[1] + aaa[2] * aaa[2] + aaa[3] * aaa[3]);
+  double b2 = std::sqrt(aaa[4] * aaa[4] + aaa[5] * aaa[5] + aaa[6] * aaa[6]);
+  double b3 = std::sqrt(aaa[7] * aaa[7] + aaa[8] * aaa[8] + aaa[9] * aaa[9]);
+  double axb1 = aaa[2] * aaa[6] - aaa[3] * aaa[5], axb2 = aaa[3] * aaa[4] - aaa[1] * aaa[6], axb3 = aaa[1] * aaa[5] - aaa[2] * aaa[4];
+  double bxc1 = aaa[5] * aaa[9] - aaa[6] * aaa[8], bxc2 = aaa[6] * aaa[7] - aaa[4] * aaa[9], bxc3 = aaa[4] * aaa[8] - aaa[5] * aaa[7];
+  double cxa1 = aaa[8] * aaa[3] - aaa[9] * aaa[2], cxa2 = aaa[9] * aaa[1] - aaa[7] * aaa[3], cxa3 = aaa[7] * aaa[2] - aaa[8] * aaa[1];
+  double vol = std::fabs(aaa[1] * bxc1 + aaa[2] * bxc2 + aaa[3] * bxc3);
+  double d[4], x[4], y[4];
+  d[1] = vol / std::sqrt(bxc1 * bxc1 + bxc2 * bxc2 + bxc3 * bxc3);
+  d[2] = vol / std::sqrt(cxa1 * cxa1 + cxa2 * cxa2 + cxa3 * cxa3);
+  d[3] = vol / std::sqrt(axb1 * axb1 + axb2 * axb2 + axb3 * axb3);
+  x[1] = std::fabs(aaa[1]) / b1; y[1] = std::fabs(aaa[2]) / b1;
+  x[2] = std::fabs(aaa[4]) / b2; y[2] = std::fabs(aaa[5]) / b2;
+  x[3] = std::fabs(aaa[7]) / b3; y[3] = std::fabs(aaa[8]) / b3;
+  if (x[1] >= x[2] && x[1] >= x[3]) { w3[0] = d[1]; if (y[2] >= y[3]) { w3[1] = d[2]; w3[2] = d[3]; } else { w3[1] = d[3]; w3[2] = d[2]; } }
+  else if (x[2] >= x[1] && x[2] >= x[3]) { w3[0] = d[2]; if (y[1] >= y[3]) { w3[1] = d[1]; w3[2] = d[3]; } else { w3[1] = d[3]; w3[2] = d[1]; } }
+  else { w3[0] = d[3]; if (y[1] >= y[2]) { w3[1] = d[1]; w3[2] = d[2]; } else { w3[1] = d[2]; w3[2] = d[1]; } }
+}
+
+struct Mat9 { double m[9]; };
+
+// ---------------------------------------------------------------- vnl_check
+__global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const double4* __restrict__ posq, const double* __restrict__ xbg,
+                          const double* __restrict__ ybg, const double* __restrict__ zbg, unsigned long long* __restrict__ tol_bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0;
+  if (i < natms) {
+    double4 p = posq[i];
+    double x = p.x - xbg[i], y = p.y - ybg[i], z = p.z - zbg[i];   // neighbours.F90:157-161
+    if (imcon == 1) {                                              // numerics.F90:1553-1563
+      double aaa = 1.0 / cell.m[0];
+      x = x - cell.m[0] * round(aaa * x) ; y = y - cell.m[0] * round(aaa * y); z = z - cell.m[0] * round(aaa * z);
+    } else if (imcon == 2 || imcon == 0) {
+      double aaa = 1.0 / cell.m[0], bbb = 1.0 / cell.m[4], ccc = 1.0 / cell.m[8];
+      x = x - cell.m[0] * round(aaa * x); y = y - cell.m[4] * round(bbb * y); z = z - cell.m[8] * round(ccc * z);
+    } else if (imcon == 3) {
+      double xss = rcell.m[0] * x + rcell.m[3] * y + rcell.m[6] * z;
+      double yss = rcell.m[1] * x + rcell.m[4] * y + rcell.m[7] * z;
+      double zss = rcell.m[2] * x + rcell.m[5] * y + rcell.m[8] * z;
+      xss = xss - round(xss); yss = yss - round(yss); zss = zss - round(zss);
+      x = cell.m[0] * xss + cell.m[3] * yss + cell.m[6] * zss;
+      y = cell.m[1] * xss + cell.m[4] * yss + cell.m[7] * zss;
+      z = cell.m[2] * xss + cell.m[5] * yss + cell.m[8] * zss;
+    }
+    r = sqrt(x * x + y * y + z * z);                               // :166
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
+  if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));   // r >= 0: bits are order-preserving
+}
+
+// ---------------------------------------------------------------- halo build
+struct HaloThr { double ecwx, ecwy, ecwz, cwx, cwy, cwz; };
+
+__global__ void k_halo_tag(int natms, Mat9 rcell, HaloThr t, const double4* __restrict__ posq, int* __restrict__ ixyz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natms) return;
+  double4 p = posq[i];
+  double x = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;   // halo.F90:265-267
+  double y = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
+  double z = rcell.m[2] * p.x + rcell.m[5] * p.y + rcell.m[8] * p.z;
+  int v = 0;
+  if (x <= t.ecwx) v += 1;
+  if (x >= t.cwx) v += 2;
+  if (y <= t.ecwy) v += 10;
+  if (y >= t.cwy) v += 20;
+  if (z <= t.ecwz) v += 100;
+  if (z >= t.cwz) v += 200;
+  ixyz[i] = v;
+}
+
+__device__ __forceinline__ int halo_sel(int v, Dir d) {   // deport_data.F90:1814-1828 -> 0: not selected, 1: j==jxyz, 2: both sides
+  if (v <= 0) return 0;
+  int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
+  int j = ix * d.kx + iy * d.ky + iz * d.kz;
+  if (j == d.jxyz) return 1;
+  if (j > d.jxyz && j % 3 == 0) return 2;
+  return 0;
+}
+__global__ void k_halo_flag(int n, Dir d, const int* __restrict__ ixyz, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  flag[i] = (i < n && halo_sel(ixyz[i], d) != 0) ? 1 : 0;   // flag[n] = 0 pads the scan
+}
+__global__ void k_halo_pack(int n, Dir d, int cap, const int* __restrict__ flag, const int* __restrict__ pos, const double4* __restrict__ posq,
+                            const int* __restrict__ ltg, const int* __restrict__ lsite, const int* __restrict__ ixyz,
+                            double* __restrict__ buf, int* __restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  int k = pos[i];
+  idx[k] = i;
+  if (k >= cap) return;
+  double4 p = posq[i];
+  double* b = buf + (size_t)k * 6;
+  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // :1836-1844
+  b[3] = (double)ltg[i];
+  b[4] = (double)lsite[i];
+  int v = ixyz[i];
+  b[5] = (double)(v - (halo_sel(v, d) == 1 ? d.jxyz : d.kxyz));            // :1853
+}
+__global__ void k_halo_unpack(int count, int off, const double* __restrict__ buf, double4* __restrict__ posq, int* __restrict__ ltg,
+                              int* __restrict__ lsite, int* __restrict__ ixyz, double* fx, double* fy, double* fz) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* b = buf + (size_t)k * 6;
+  int i = off + k;
+  posq[i] = make_double4(b[0], b[1], b[2], 0.0);
+  ltg[i] = __double2int_rn(b[3]); lsite[i] = __double2int_rn(b[4]); ixyz[i] = __double2int_rn(b[5]);   // Nint, :1935-1940
+  fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0;
+}
+__global__ void k_assign_sites(int from, int to, const int* __restrict__ lsite, const int* __restrict__ type_site,
+                               const double* __restrict__ charge_site, const int* __restrict__ freeze_site, double4* __restrict__ posq,
+                               int* __restrict__ ltype, int* __restrict__ lfrzn) {
+  int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= to) return;
+  int s = lsite[i] - 1;
+  ltype[i] = type_site[s];                      // halo.F90:296-302 / deport_data.F90:3062-3069
+  posq[i].w = charge_site[s];
+  lfrzn[i] = freeze_site[s];
+}
+
+// ---------------------------------------------------------------- halo refresh
+__global__ void k_refresh_pack(int count, Dir d, const int* __restrict__ idx, const double4* __restrict__ posq, double* __restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double4 p = posq[idx[k]];
+  double* b = buf + (size_t)k * 3;
+  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:2460-2468
+}
+__global__ void k_refresh_unpack(int count, int off, const double* __restrict__ buf, double4* __restrict__ posq) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* b = buf + (size_t)k * 3;
+  double4 p = posq[off + k];
+  p.x = b[0]; p.y = b[1]; p.z = b[2];
+  posq[off + k] = p;
+}
+
+// ---------------------------------------------------------------- relocation
+__global__ void k_pbcshift(int natms, int imcon, Mat9 cell, Mat9 rcell, double4* __restrict__ posq) {   // numerics.F90:1889-1950
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natms) return;
+  const double half_minus = 0.499999999999999944488848768742172978818416595458984375;
+  double4 p = posq[i];
+  double xss, yss, zss;
+  // Anint: round half away from zero
+  if (imcon == 1) {
+    double aaa = 1.0 / cell.m[0];
+    xss = aaa * p.x; yss = aaa * p.y; zss = aaa * p.z;
+  } else if (imcon == 2 || imcon == 0) {
+    xss = (1.0 / cell.m[0]) * p.x; yss = (1.0 / cell.m[4]) * p.y; zss = (1.0 / cell.m[8]) * p.z;
+  } else {
+    xss = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;
+    yss = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
+    zss = rcell.m[2] * p.x + rcell.m[5] * p.y + rcell.m[8] * p.z;
+  }
+  xss = xss - round(xss); if (xss >= half_minus) xss = -xss;
+  yss = yss - round(yss); if (yss >= half_minus) yss = -yss;
+  zss = zss - round(zss); if (zss >= half_minus) zss = -zss;
+  if (imcon == 1) { p.x = cell.m[0] * xss; p.y = cell.m[0] * yss; p.z = cell.m[0] * zss; }
+  else if (imcon == 2 || imcon == 0) { p.x = cell.m[0] * xss; p.y = cell.m[4] * yss; p.z = cell.m[8] * zss; }
+  else {
+    p.x = cell.m[0] * xss + cell.m[3] * yss + cell.m[6] * zss;
+    p.y = cell.m[1] * xss + cell.m[4] * yss + cell.m[7] * zss;
+    p.z = cell.m[2] * xss + cell.m[5] * yss + cell.m[8] * zss;
+  }
+  posq[i] = p;
+}
+
+struct DomI { int nx, ny, nz, idx, idy, idz; };
+__global__ void k_reloc_tag(int natms, Mat9 rcell, DomI D, const double4* __restrict__ posq, int* __restrict__ ixyz) {   // deport_data.F90:2981-3025
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natms) return;
+  const double half_plus = 0.50000000000000011102230246251565404236316680908203125;
+  const double half_minus = 0.499999999999999944488848768742172978818416595458984375;
+  double4 p = posq[i];
+  double x = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;
+  double y = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
+  double z = rcell.m[2] * p.x + rcell.m[5] * p.y + rcell.m[8] * p.z;
+  int ipx = __double2int_rz((x + 0.5) * (double)D.nx), ipy = __double2int_rz((y + 0.5) * (double)D.ny), ipz = __double2int_rz((z + 0.5) * (double)D.nz);
+  int v = 0;
+  if (D.idx == 0) { if (x < -half_plus) v += 1; } else { if (ipx < D.idx) v += 1; }
+  if (D.idx == D.nx - 1) { if (x >= half_minus) v += 2; } else { if (ipx > D.idx) v += 2; }
+  if (D.idy == 0) { if (y < -half_plus) v += 10; } else { if (ipy < D.idy) v += 10; }
+  if (D.idy == D.ny - 1) { if (y >= half_minus) v += 20; } else { if (ipy > D.idy) v += 20; }
+  if (D.idz == 0) { if (z < -half_plus) v += 100; } else { if (ipz < D.idz) v += 100; }
+  if (D.idz == D.nz - 1) { if (z >= half_minus) v += 200; } else { if (ipz > D.idz) v += 200; }
+  ixyz[i] = v;
+}
+__global__ void k_reloc_flag(int n, Dir d, int* __restrict__ ixyz, int* __restrict__ leave) {   // deport_data.F90:254-274
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int f = 0;
+  if (i < n) {
+    int v = ixyz[i];
+    if (v != 0) {
+      int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
+      int j = ix * d.kx + iy * d.ky + iz * d.kz;
+      if (j == d.jxyz) { ixyz[i] = v - d.jxyz; f = 1; }
+    }
+  }
+  leave[i] = f;
+}
+__global__ void k_reloc_pack(int n, int k_stay, Dir d, int cap, const int* __restrict__ leave, const int* __restrict__ lpos,
+                             const double4* __restrict__ posq, const double* __restrict__ vx, const double* __restrict__ vy,
+                             const double* __restrict__ vz, const double* __restrict__ fx, const double* __restrict__ fy,
+                             const double* __restrict__ fz, const int* __restrict__ ltg, const int* __restrict__ lsite,
+                             const int* __restrict__ ixyz, double* __restrict__ buf, int* __restrict__ hole_pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !leave[i]) return;
+  int k = lpos[i];                       // rank among leavers, ascending index == the reference's buffer order
+  if (i < k_stay) hole_pos[k] = i;       // holes below the new natms are the first ones (ascending)
+  if (k >= cap) return;
+  double4 p = posq[i];
+  double* b = buf + (size_t)k * 12;
+  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
+  b[3] = vx[i]; b[4] = vy[i]; b[5] = vz[i];
+  b[6] = fx[i]; b[7] = fy[i]; b[8] = fz[i];
+  b[9] = (double)ltg[i]; b[10] = (double)lsite[i]; b[11] = (double)ixyz[i];
+}
+// restack (deport_data.F90:822-925): the r-th hole (ascending) below the new natms takes the r-th staying atom counted
+// from the end.  stay_prefix[j] = j - lpos[j] staying atoms precede j.
+__global__ void k_reloc_restack(int n, int k_stay, const int* __restrict__ leave, const int* __restrict__ lpos, const int* __restrict__ hole_pos,
+                                double4* __restrict__ posq, double* vx, double* vy, double* vz, double* fx, double* fy, double* fz,
+                                int* ltg, int* lsite, int* ixyz) {
+  int j = k_stay + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || leave[j]) return;
+  int stay_prefix = j - lpos[j];
+  int r = k_stay - 1 - stay_prefix;
+  int dst = hole_pos[r];
+  posq[dst] = posq[j];
+  vx[dst] = vx[j]; vy[dst] = vy[j]; vz[dst] = vz[j];
+  fx[dst] = fx[j]; fy[dst] = fy[j]; fz[dst] = fz[j];
+  ltg[dst] = ltg[j]; lsite[dst] = lsite[j]; ixyz[dst] = ixyz[j];
+}
+__global__ void k_reloc_unpack(int count, int off, const double* __restrict__ buf, double4* __restrict__ posq, double* vx, double* vy,
+                               double* vz, double* fx, double* fy, double* fz, int* ltg, int* lsite, int* ixyz) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* b = buf + (size_t)k * 12;
+  int i = off + k;
+  posq[i] = make_double4(b[0], b[1], b[2], 0.0);
+  vx[i] = b[3]; vy[i] = b[4]; vz[i] = b[5];
+  fx[i] = b[6]; fy[i] = b[7]; fz[i] = b[8];
+  ltg[i] = __double2int_rn(b[9]); lsite[i] = __double2int_rn(b[10]); ixyz[i] = __double2int_rn(b[11]);
+}
+__global__ void k_count_nonzero(int n, const int* __restrict__ ixyz, int* __restrict__ status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ixyz[i] != 0) atomicAdd(&status[2], 1);
+}
+
+Mat9 mat(const double* a) { Mat9 m; for (int i = 0; i < 9; ++i) m.m[i] = a[i]; return m; }
+
+}  // namespace
+
+int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol) {
+  cudaStream_t s = ctx->stream;
+  if (!ctx->have_bg) return dlp_fail(ctx, DLPGPU_ERR_STATE, "vnl_check: no checkpoint");
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
+           ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  unsigned long long bits = 0;
+  CK(cudaMemcpyAsync(&bits, ctx->tol_bits.p, sizeof bits, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double r;
+  std::memcpy(&r, &bits, sizeof r);
+  *tol = r;
+  return 0;
+}
+
+extern "C" {
+
+int dlpgpu_dev_vnl_check(dlpgpu_ctx* ctx, double* tol) {
+  if (!ctx || !tol) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return dlp_vnl_check(ctx, tol);
+}
+
+int dlpgpu_dev_halo_begin(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  // thresholds, halo.F90:190-249
+  double cut = ctx->rx + 1.0e-6;
+  double w3[3];
+  h_widths(ctx->cell, w3);
+  double nxr = (double)ctx->nx, nyr = (double)ctx->ny, nzr = (double)ctx->nz;
+  int nlx = (int)(w3[0] / (cut * nxr)), nly = (int)(w3[1] / (cut * nyr)), nlz = (int)(w3[2] / (cut * nzr));
+  if (nlx * nly * nlz == 0) return dlp_fail(ctx, DLPGPU_ERR_LINK_CELLS, "error 307: domain narrower than cutoff_extended");
+  double xdc = (double)(nlx * ctx->nx), ydc = (double)(nly * ctx->ny), zdc = (double)(nlz * ctx->nz);
+  double cwx = 1.0 / xdc, cwy = 1.0 / ydc, cwz = 1.0 / zdc;
+  double ecwx = std::max(cwx, ctx->ecw[0]), ecwy = std::max(cwy, ctx->ecw[1]), ecwz = std::max(cwz, ctx->ecw[2]);
+  double nx_recip = 1.0 / nxr, ny_recip = 1.0 / nyr, nz_recip = 1.0 / nzr;
+  const double zero_plus = DBL_MIN;
+  HaloThr t;
+  t.ecwx = std::nextafter((-0.5 + ecwx) + (double)ctx->idx * nx_recip, DBL_MAX) + zero_plus;
+  t.ecwy = std::nextafter((-0.5 + ecwy) + (double)ctx->idy * ny_recip, DBL_MAX) + zero_plus;
+  t.ecwz = std::nextafter((-0.5 + ecwz) + (double)ctx->idz * nz_recip, DBL_MAX) + zero_plus;
+  t.cwx = std::nextafter((-0.5 - cwx) + (double)(ctx->idx + 1) * nx_recip, -DBL_MAX) - zero_plus - (nlx == 1 ? cwx * 1.0e-10 : 0.0);
+  t.cwy = std::nextafter((-0.5 - cwy) + (double)(ctx->idy + 1) * ny_recip, -DBL_MAX) - zero_plus - (nly == 1 ? cwy * 1.0e-10 : 0.0);
+  t.cwz = std::nextafter((-0.5 - cwz) + (double)(ctx->idz + 1) * nz_recip, -DBL_MAX) - zero_plus - (nlz == 1 ? cwz * 1.0e-10 : 0.0);
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  ctx->nlast = ctx->natms;   // halo.F90:259
+  if (ctx->natms > 0) LAUNCH(ctx, k_halo_tag, cdiv(ctx->natms, 256), 256, 0, ctx->natms, mat(rc), t, ctx->posq.p, ctx->ixyz.p);
+  ctx->halo_valid = false; ctx->list_valid = false;
+  for (int q = 0; q < 6; ++q) { ctx->stage[q].count = 0; ctx->stage[q].recv_count = 0; ctx->stage[q].recv_off = ctx->natms; }
+  return 0;
+}
+
+int dlpgpu_dev_halo_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int capacity_atoms, int* count) {
+  if (!ctx || !count || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  Dir d = dir_settings(ctx, mdir);
+  HaloStage& st = ctx->stage[stage_of(mdir)];
+  int n = ctx->nlast;
+  CK(ctx->flag.ensure((size_t)n + 2, s)); CK(ctx->scan_out.ensure((size_t)n + 2, s));
+  LAUNCH(ctx, k_halo_flag, cdiv(n + 1, 256), 256, 0, n, d, ctx->ixyz.p, ctx->flag.p);
+  int total = 0;
+  CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, n, &total));
+  st.count = total; st.lwrap = d.lwrap != 0; st.shift[0] = d.xadd; st.shift[1] = d.yadd; st.shift[2] = d.zadd;
+  *count = total;
+  if (total > capacity_atoms || (total > 0 && !sendbuf_dev))
+    return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 54: outgoing halo buffer too small (%d atoms > capacity %d)", total, capacity_atoms);
+  CK(st.idx.ensure((size_t)total + 1, s));
+  if (total > 0)
+    LAUNCH(ctx, k_halo_pack, cdiv(n, 256), 256, 0, n, d, capacity_atoms, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->ltg.p, ctx->lsite.p,
+           ctx->ixyz.p, sendbuf_dev, st.idx.p);
+  return 0;
+}
+
+int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count) {
+  if (!ctx || count < 0 || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  HaloStage& st = ctx->stage[stage_of(mdir)];
+  CKRC(dlp_ensure_atoms(ctx, ctx->nlast + count + 16));
+  st.recv_off = ctx->nlast; st.recv_count = count;
+  if (count > 0)
+    LAUNCH(ctx, k_halo_unpack, cdiv(count, 256), 256, 0, count, ctx->nlast, recvbuf_dev, ctx->posq.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p,
+           ctx->fx.p, ctx->fy.p, ctx->fz.p);
+  ctx->nlast += count;
+  return 0;
+}
+
+int dlpgpu_dev_halo_end(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "halo_end: sites not set");
+  int nh = ctx->nlast - ctx->natms;
+  if (nh > 0)
+    LAUNCH(ctx, k_assign_sites, cdiv(nh, 256), 256, 0, ctx->natms, ctx->nlast, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p,
+           ctx->freeze_site.p, ctx->posq.p, ctx->ltype.p, ctx->lfrzn.p);
+  CKRC(dlp_vnl_set_check(ctx));   // halo.F90:315
+  ctx->halo_valid = true;
+  return 0;
+}
+
+int dlpgpu_dev_halo_serial(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  if (ctx->nx * ctx->ny * ctx->nz != 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "halo_serial: domain decomposition is not 1x1x1");
+  CKRC(dlpgpu_dev_halo_begin(ctx));
+  const int mdirs[6] = {-1, 1, -2, 2, -3, 3};
+  for (int q = 0; q < 6; ++q) {
+    // jmove = imove (deport_data.F90:1884-1886): the rank is its own neighbour.  Size the buffer from the flag count.
+    int cnt = 0;
+    int cap = (int)(ctx->xfer.cap / 6);
+    int rc = dlpgpu_dev_halo_pack(ctx, mdirs[q], ctx->xfer.p, cap, &cnt);
+    if (rc == DLPGPU_ERR_BUFFER) {
+      CK(ctx->xfer.ensure((size_t)cnt * 6 + 64, ctx->stream));
+      rc = dlpgpu_dev_halo_pack(ctx, mdirs[q], ctx->xfer.p, (int)(ctx->xfer.cap / 6), &cnt);
+    }
+    if (rc) return rc;
+    CKRC(dlpgpu_dev_halo_unpack(ctx, mdirs[q], ctx->xfer.p, cnt));
+  }
+  return dlpgpu_dev_halo_end(ctx);
+}
+
+int dlpgpu_dev_refresh_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int* count) {
+  if (!ctx || !count || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->halo_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "refresh: no halo has been built");
+  HaloStage& st = ctx->stage[stage_of(mdir)];
+  Dir d = dir_settings(ctx, mdir);
+  *count = st.count;
+  if (st.count > 0) {
+    if (!sendbuf_dev) return DLPGPU_ERR_ARG;
+    LAUNCH(ctx, k_refresh_pack, cdiv(st.count, 256), 256, 0, st.count, d, st.idx.p, ctx->posq.p, sendbuf_dev);
+  }
+  return 0;
+}
+
+int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count) {
+  if (!ctx || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  HaloStage& st = ctx->stage[stage_of(mdir)];
+  if (count != st.recv_count)   // halo.F90:104-106
+    return dlp_fail(ctx, DLPGPU_ERR_HALO_COUNT, "error 138: refreshed halo size %d differs from the built one %d", count, st.recv_count);
+  if (count > 0) LAUNCH(ctx, k_refresh_unpack, cdiv(count, 256), 256, 0, count, st.recv_off, recvbuf_dev, ctx->posq.p);
+  return 0;
+}
+
+int dlpgpu_dev_refresh_serial(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  const int mdirs[6] = {-1, 1, -2, 2, -3, 3};
+  for (int q = 0; q < 6; ++q) {
+    int cnt = 0;
+    CK(ctx->xfer.ensure((size_t)ctx->stage[q].count * 3 + 64, ctx->stream));
+    CKRC(dlpgpu_dev_refresh_pack(ctx, mdirs[q], ctx->xfer.p, &cnt));
+    CKRC(dlpgpu_dev_refresh_unpack(ctx, mdirs[q], ctx->xfer.p, cnt));
+  }
+  return 0;
+}
+
+int dlpgpu_dev_relocate_serial(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  if (ctx->natms > 0 && ctx->imcon != 0)
+    LAUNCH(ctx, k_pbcshift, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p);
+  ctx->nlast = ctx->natms;
+  ctx->halo_valid = false; ctx->list_valid = false;
+  return 0;
+}
+
+int dlpgpu_dev_relocate_begin(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  DomI D{ctx->nx, ctx->ny, ctx->nz, ctx->idx, ctx->idy, ctx->idz};
+  ctx->nlast = ctx->natms;
+  if (ctx->natms > 0) LAUNCH(ctx, k_reloc_tag, cdiv(ctx->natms, 256), 256, 0, ctx->natms, mat(rc), D, ctx->posq.p, ctx->ixyz.p);
+  ctx->halo_valid = false; ctx->list_valid = false;
+  return 0;
+}
+
+int dlpgpu_dev_relocate_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int capacity_atoms, int* count) {
+  if (!ctx || !count || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  Dir d = dir_settings(ctx, mdir);
+  int n = ctx->natms;
+  CK(ctx->flag.ensure((size_t)n + 2, s)); CK(ctx->scan_out.ensure((size_t)n + 2, s));
+  LAUNCH(ctx, k_reloc_flag, cdiv(n + 1, 256), 256, 0, n, d, ctx->ixyz.p, ctx->flag.p);
+  int total = 0;
+  CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, n, &total));
+  *count = total;
+  if (total == 0) return 0;
+  if (total > capacity_atoms || !sendbuf_dev)
+    return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 43: outgoing migration buffer too small (%d atoms > capacity %d)", total, capacity_atoms);
+  int k_stay = n - total;
+  CK(ctx->hole_pos.ensure((size_t)total + 1, s));
+  LAUNCH(ctx, k_reloc_pack, cdiv(n, 256), 256, 0, n, k_stay, d, capacity_atoms, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->vx.p, ctx->vy.p,
+         ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p, sendbuf_dev, ctx->hole_pos.p);
+  if (n - k_stay > 0 && k_stay > 0)
+    LAUNCH(ctx, k_reloc_restack, cdiv(n - k_stay, 256), 256, 0, n, k_stay, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, ctx->posq.p,
+           ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
+  ctx->natms = k_stay; ctx->nlast = k_stay;
+  return 0;
+}
+
+int dlpgpu_dev_relocate_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count) {
+  if (!ctx || count < 0 || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (count == 0) return 0;
+  CKRC(dlp_ensure_atoms(ctx, ctx->natms + count + 16));
+  LAUNCH(ctx, k_reloc_unpack, cdiv(count, 256), 256, 0, count, ctx->natms, recvbuf_dev, ctx->posq.p, ctx->vx.p, ctx->vy.p, ctx->vz.p,
+         ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
+  ctx->natms += count; ctx->nlast = ctx->natms;
+  return 0;
+}
+
+int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "relocate_end: sites not set");
+  int n = ctx->natms;
+  CK(cudaMemsetAsync(ctx->status.p, 0, 8 * sizeof(int), s));
+  if (n > 0) {
+    LAUNCH(ctx, k_count_nonzero, cdiv(n, 256), 256, 0, n, ctx->ixyz.p, ctx->status.p);
+    LAUNCH(ctx, k_assign_sites, cdiv(n, 256), 256, 0, 0, n, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p, ctx->freeze_site.p,
+           ctx->posq.p, ctx->ltype.p, ctx->lfrzn.p);
+  }
+  int st[8];
+  CK(cudaMemcpyAsync(st, ctx->status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (natms_now) *natms_now = n;
+  if (st[2] != 0)   // deport_data.F90:3056-3058: an atom still wants to leave after the six stages
+    return dlp_fail(ctx, DLPGPU_ERR_LOST_ATOMS, "error 58: %d atoms moved further than one domain in a single relocation", st[2]);
+  return 0;
+}
+
+}  // extern "C"

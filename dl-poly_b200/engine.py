@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference call sites of the short-range path, on top of the libdlpgpu C ABI.
+
+:class:`ShortRange` carries the state the reference keeps in ``neighbours_type`` / ``vdw_type`` /
+``electrostatic_type`` for this path and exposes
+
+* ``link_cell_pairs``   -- neighbours.F90:356   (call site drivers.F90:675-679)
+* ``two_body_forces``   -- two_body.F90:339-606 (the two pair loops; SPME / gsum / LRC stay with the caller)
+* ``vnl_check``         -- neighbours.F90:123   (max displacement; the caller does gmax and the comparison)
+
+with host (numpy) buffers, i.e. exactly what the ISO_C_BINDING module passes, plus the device-resident ``dev_*`` calls
+the native multi-GPU engine (:mod:`.dd`) drives.  Errors surface as :class:`lib.DlpError` carrying DL_POLY's error number.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import COREPART, DlpError, ptr
+
+HALF_MINUS = np.nextafter(0.5, 0.0)          # constants.F90:198
+
+
+class ShortRange:
+    def __init__(self, device=0, dd=(1, 1, 1, 0, 0, 0)):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.dlpgpu_create(C.byref(h), int(device))
+        if rc != 0:
+            raise DlpError(rc, "dlpgpu_create failed on device %d (is a CUDA GPU visible?)" % device)
+        self.h = h
+        self.device = device
+        self.set_domain(dd)
+        self.max_list = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dlpgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DlpError(rc, self.L.dlpgpu_last_error(self.h).decode(errors="replace"))
+
+    # ---- setup -------------------------------------------------------------------------------------------------
+    def set_domain(self, dd):
+        a = np.ascontiguousarray(dd, dtype=np.int32)
+        self.dd = tuple(int(v) for v in a)
+        self._ck(self.L.dlpgpu_set_domain(self.h, ptr(a)))
+
+    def set_cell(self, cell, imcon=1):
+        c = np.ascontiguousarray(cell, dtype=np.float64).reshape(9)
+        self.cell = c.copy()
+        self.imcon = imcon
+        self._ck(self.L.dlpgpu_set_cell(self.h, ptr(c), int(imcon)))
+
+    def set_cutoffs(self, rcut, padding, pdplnc=50.0):
+        self.rcut, self.padding = float(rcut), float(padding)
+        self._ck(self.L.dlpgpu_set_cutoffs(self.h, float(rcut), float(padding), float(pdplnc)))
+
+    def set_forcefield(self, ff):
+        """ff: tables.ForceField (or anything with the same arrays -- what read_field leaves in vdw_type/electrostatic)."""
+        lst = np.ascontiguousarray(ff.vdw_list_c, dtype=np.int32)
+        ltp = np.ascontiguousarray(ff.ltp, dtype=np.int32)
+        tp = np.ascontiguousarray(ff.tab_potential, dtype=np.float64)
+        tf = np.ascontiguousarray(ff.tab_force, dtype=np.float64)
+        par = np.ascontiguousarray(ff.param, dtype=np.float64)
+        afs = np.ascontiguousarray(ff.afs, dtype=np.float64)
+        bfs = np.ascontiguousarray(ff.bfs, dtype=np.float64)
+        self._ck(self.L.dlpgpu_set_vdw(self.h, ff.ntypes, ptr(lst), ff.max_vdw, ff.n_vdw, ptr(ltp), ff.mxgrid, ptr(tp), ptr(tf),
+                                       float(ff.rvdw), int(ff.force_shift), int(ff.direct), ptr(par), ptr(afs), ptr(bfs)))
+        if ff.ew_active:
+            e = np.ascontiguousarray(ff.erfc, dtype=np.float64)
+            d = np.ascontiguousarray(ff.erfc_deriv, dtype=np.float64)
+            self._ck(self.L.dlpgpu_set_ewald(self.h, 1, float(ff.alpha), float(ff.scaling), int(ff.ew_n), ptr(e), ptr(d),
+                                             float(ff.ew_recip)))
+        else:
+            self._ck(self.L.dlpgpu_set_ewald(self.h, 0, 0.0, 0.0, 0, None, None, 0.0))
+
+    def set_force_mode(self, mode):
+        self._ck(self.L.dlpgpu_set_force_mode(self.h, int(mode)))
+
+    # ---- drop-in entry points (host buffers, Fortran index conventions) ------------------------------------------
+    def link_cell_pairs(self, natms, nlast, parts, ltype, ltg, lfrzn=None, lbook=False, megfrz=0, list_excl=None,
+                        max_list=None, want_list=True):
+        """Returns the reference-format list as an int32 array (natms, max_list+4): column k+3 == list(k, i)."""
+        assert parts.dtype == COREPART and parts.flags.c_contiguous
+        ltype = np.ascontiguousarray(ltype, dtype=np.int32)
+        ltg = np.ascontiguousarray(ltg, dtype=np.int32)
+        lf = None if lfrzn is None else np.ascontiguousarray(lfrzn, dtype=np.int32)
+        mxex = 0
+        le = None
+        if lbook and list_excl is not None:
+            le = np.ascontiguousarray(list_excl, dtype=np.int32)
+            mxex = le.shape[1] - 1
+        self.max_list = int(max_list)
+        out = np.zeros((natms, self.max_list + 4), dtype=np.int32) if want_list else None
+        ibig = C.c_int(0)
+        rc = self.L.dlpgpu_link_cell_pairs(self.h, int(natms), int(nlast), ptr(parts), ptr(ltype), ptr(ltg), ptr(lf), int(bool(lbook)),
+                                           int(megfrz), int(mxex), ptr(le), self.max_list, ptr(out), C.byref(ibig))
+        self.ibig = ibig.value
+        self._ck(rc)
+        return out
+
+    def two_body_forces(self, natms, nlast, parts):
+        """Adds the pair forces into parts['fxx','fyy','fzz'][:natms]; returns the 16 partial sums of the C ABI."""
+        assert parts.dtype == COREPART and parts.flags.c_contiguous
+        out = np.zeros(16)
+        self._ck(self.L.dlpgpu_two_body_forces(self.h, int(natms), int(nlast), ptr(parts), ptr(out)))
+        return out
+
+    def vnl_check(self, natms, parts):
+        tol = C.c_double(0.0)
+        self._ck(self.L.dlpgpu_vnl_check(self.h, int(natms), ptr(parts), C.byref(tol)))
+        return tol.value
+
+    def vnl_set_check(self, nlast, parts):
+        self._ck(self.L.dlpgpu_vnl_set_check(self.h, int(nlast), ptr(parts)))
+
+    def vnl_update(self, tol_global):
+        """neighbours.F90:182."""
+        return tol_global >= HALF_MINUS * self.padding
+
+    # ---- native device-resident mode -------------------------------------------------------------------------------
+    def dev_setup_system(self, sysm, capacity=None):
+        """Everything read_field / set_bounds would hand over for ``sysm`` (a systems.System)."""
+        self.set_cell(sysm.cell, sysm.imcon)
+        self.set_cutoffs(sysm.rcut, sysm.padding, sysm.pdplnc)
+        self.set_forcefield(sysm.ff)
+        t = np.ascontiguousarray(sysm.type_site, dtype=np.int32)
+        q = np.ascontiguousarray(sysm.charge_site, dtype=np.float64)
+        f = np.ascontiguousarray(sysm.freeze_site, dtype=np.int32)
+        w = np.ascontiguousarray(sysm.weight_site, dtype=np.float64)
+        self._ck(self.L.dlpgpu_dev_set_sites(self.h, len(t), ptr(t), ptr(q), ptr(f), ptr(w)))
+        if sysm.excl is not None:
+            e = np.ascontiguousarray(sysm.excl, dtype=np.int32)
+            self._ck(self.L.dlpgpu_dev_set_excl(self.h, e.shape[0], e.shape[1] - 1, ptr(e)))
+        self.max_list = int(sysm.max_list)
+        self._ck(self.L.dlpgpu_dev_set_list_capacity(self.h, self.max_list, int(sysm.megfrz)))
+
+    def dev_load_atoms(self, xyz, vel, ltg, lsite, capacity=0):
+        x = np.ascontiguousarray(xyz, dtype=np.float64)
+        v = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
+        g = np.ascontiguousarray(ltg, dtype=np.int32)
+        s = np.ascontiguousarray(lsite, dtype=np.int32)
+        self._ck(self.L.dlpgpu_dev_load_atoms(self.h, x.shape[0], ptr(x), ptr(v), ptr(g), ptr(s), int(capacity)))
+
+    def dev_set_halo_width(self, ecw):
+        e = np.ascontiguousarray(ecw, dtype=np.float64)
+        self._ck(self.L.dlpgpu_dev_set_halo_width(self.h, ptr(e)))
+
+    def dev_counts(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.dlpgpu_dev_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def dev_zero_forces(self):
+        self._ck(self.L.dlpgpu_dev_zero_forces(self.h))
+
+    def dev_vv(self, stage, dt):
+        self._ck(self.L.dlpgpu_dev_vv(self.h, int(stage), float(dt)))
+
+    def dev_vnl_check(self):
+        tol = C.c_double(0.0)
+        self._ck(self.L.dlpgpu_dev_vnl_check(self.h, C.byref(tol)))
+        return tol.value
+
+    def dev_halo_serial(self):
+        self._ck(self.L.dlpgpu_dev_halo_serial(self.h))
+
+    def dev_refresh_serial(self):
+        self._ck(self.L.dlpgpu_dev_refresh_serial(self.h))
+
+    def dev_relocate_serial(self):
+        self._ck(self.L.dlpgpu_dev_relocate_serial(self.h))
+
+    def dev_halo_begin(self):
+        self._ck(self.L.dlpgpu_dev_halo_begin(self.h))
+
+    def dev_halo_pack(self, mdir, sendbuf_ptr, capacity_atoms):
+        n = C.c_int(0)
+        rc = self.L.dlpgpu_dev_halo_pack(self.h, int(mdir), C.c_void_p(sendbuf_ptr), int(capacity_atoms), C.byref(n))
+        if rc != 0 and rc != 54:
+            self._ck(rc)
+        return rc, n.value
+
+    def dev_halo_unpack(self, mdir, recvbuf_ptr, count):
+        self._ck(self.L.dlpgpu_dev_halo_unpack(self.h, int(mdir), C.c_void_p(recvbuf_ptr), int(count)))
+
+    def dev_halo_end(self):
+        self._ck(self.L.dlpgpu_dev_halo_end(self.h))
+
+    def dev_refresh_pack(self, mdir, sendbuf_ptr):
+        n = C.c_int(0)
+        self._ck(self.L.dlpgpu_dev_refresh_pack(self.h, int(mdir), C.c_void_p(sendbuf_ptr), C.byref(n)))
+        return n.value
+
+    def dev_refresh_unpack(self, mdir, recvbuf_ptr, count):
+        self._ck(self.L.dlpgpu_dev_refresh_unpack(self.h, int(mdir), C.c_void_p(recvbuf_ptr), int(count)))
+
+    def dev_relocate_begin(self):
+        self._ck(self.L.dlpgpu_dev_relocate_begin(self.h))
+
+    def dev_relocate_pack(self, mdir, sendbuf_ptr, capacity_atoms):
+        n = C.c_int(0)
+        rc = self.L.dlpgpu_dev_relocate_pack(self.h, int(mdir), C.c_void_p(sendbuf_ptr), int(capacity_atoms), C.byref(n))
+        if rc != 0 and rc != 54:
+            self._ck(rc)
+        return rc, n.value
+
+    def dev_relocate_unpack(self, mdir, recvbuf_ptr, count):
+        self._ck(self.L.dlpgpu_dev_relocate_unpack(self.h, int(mdir), C.c_void_p(recvbuf_ptr), int(count)))
+
+    def dev_relocate_end(self):
+        n = C.c_int(0)
+        self._ck(self.L.dlpgpu_dev_relocate_end(self.h, C.byref(n)))
+        return n.value
+
+    def dev_link_cell_pairs(self, want_ref_list=False):
+        ibig = C.c_int(0)
+        rc = self.L.dlpgpu_dev_link_cell_pairs(self.h, int(bool(want_ref_list)), C.byref(ibig))
+        self.ibig = ibig.value
+        self._ck(rc)
+
+    def dev_two_body_forces(self, zero_forces=True):
+        out = np.zeros(16)
+        self._ck(self.L.dlpgpu_dev_two_body_forces(self.h, int(bool(zero_forces)), ptr(out)))
+        return out
+
+    # ---- read-back -------------------------------------------------------------------------------------------------
+    def dev_get_parts(self, n=None):
+        if n is None:
+            n = self.dev_counts()[1]
+        p = np.zeros(n, dtype=COREPART)
+        self._ck(self.L.dlpgpu_dev_get_parts(self.h, ptr(p), int(n)))
+        return p
+
+    def dev_get_ints(self, n=None):
+        if n is None:
+            n = self.dev_counts()[1]
+        arrs = [np.zeros(n, dtype=np.int32) for _ in range(5)]
+        self._ck(self.L.dlpgpu_dev_get_ints(self.h, int(n), *[ptr(a) for a in arrs]))
+        return dict(zip(["ltg", "lsite", "ltype", "lfrzn", "ixyz"], arrs))
+
+    def dev_get_vel(self, n=None):
+        if n is None:
+            n = self.dev_counts()[0]
+        v = np.zeros((n, 3))
+        self._ck(self.L.dlpgpu_dev_get_vel(self.h, int(n), ptr(v)))
+        return v
+
+    def dev_get_list(self):
+        natms = self.dev_counts()[0]
+        out = np.zeros((natms, self.max_list + 4), dtype=np.int32)
+        self._ck(self.L.dlpgpu_dev_get_list(self.h, natms, self.max_list, ptr(out)))
+        return out
+
+    def dev_get_cells(self, arrays=True):
+        info = np.zeros(6, dtype=np.int32)
+        self._ck(self.L.dlpgpu_dev_get_cells(self.h, ptr(info), None, None, None))
+        keys = ["nlx", "nly", "nlz", "nlp", "ncells", "nsbcll"]
+        d = dict(zip(keys, (int(v) for v in info)))
+        if arrays:
+            nlast = self.dev_counts()[1]
+            wc = np.zeros(nlast, dtype=np.int32)
+            al = np.zeros(nlast, dtype=np.int32)
+            ls = np.zeros(d["ncells"] + 2, dtype=np.int32)
+            self._ck(self.L.dlpgpu_dev_get_cells(self.h, ptr(info), ptr(wc), ptr(al), ptr(ls)))
+            d.update(which_cell=wc, at_list=al, lct_start=ls)
+        return d
+
+    def dev_get_full_row(self, i):
+        cap = self.max_list + 64
+        m = np.zeros(cap, dtype=np.int32)
+        x = np.zeros(cap, dtype=np.int32)
+        nm, nx = C.c_int(), C.c_int()
+        self._ck(self.L.dlpgpu_dev_get_full_row(self.h, int(i), C.byref(nm), ptr(m), C.byref(nx), ptr(x), cap))
+        return m[:nm.value].copy(), x[:nx.value].copy()
+
+    # ---- measurement -----------------------------------------------------------------------------------------------
+    def fp64_peak(self, seconds=0.2):
+        t = C.c_double(0.0)
+        self._ck(self.L.dlpgpu_fp64_peak(self.h, float(seconds), C.byref(t)))
+        return t.value
+
+    def last_timings(self):
+        t = np.zeros(4)
+        self._ck(self.L.dlpgpu_last_timings(self.h, ptr(t)))
+        return dict(list_ms=t[0], force_ms=t[1], pair_kernel_ms=t[2], full_list_kernel_ms=t[3])
+
+    def launch_count(self):
+        return int(self.L.dlpgpu_launch_count(self.h))
+
+    def stream(self):
+        return self.L.dlpgpu_stream(self.h)

@@ -1,0 +1,166 @@
+/* =============================================================================
+ * dlpgpu.h -- C ABI of libdlpgpu.so: DL_POLY 5.1.0's short-range two-body path on one NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference has no plugin registry; force providers are direct Fortran calls
+ * (precedent: the OpenKIM coupling, source/kim.F90:880-999, called from source/two_body.F90:269-279).  The entry
+ * points below are what an ISO_C_BINDING module (fortran/dlp_gpu_binding.F90) binds to replace
+ *
+ *   source/drivers.F90:675-679     Call link_cell_pairs(...)            -> dlpgpu_link_cell_pairs
+ *   source/two_body.F90:339-525    Do i = 1, natms (vdw + ewald real)   \
+ *   source/two_body.F90:552-606    Do i = 1, natms (excluded pairs)     -> dlpgpu_two_body_forces
+ *   source/neighbours.F90:157-171  max displacement in vnl_check        -> dlpgpu_vnl_check
+ *   source/neighbours.F90:337-341  vnl_set_check snapshot               -> dlpgpu_vnl_set_check
+ *
+ * Conventions
+ *   - every function returns 0 on success or a non-zero code; where DL_POLY has a numbered error for the condition
+ *     the same number is returned (errors_warnings.F90), so the Fortran wrapper can `Call error(code)`.
+ *     dlpgpu_last_error(ctx) gives a message.  No exceptions cross the boundary.
+ *   - all pointers are plain host pointers owned by the caller unless the name ends in `_dev`.
+ *   - index values inside arrays keep the Fortran convention (1-based local indices, global ids from 1).
+ *   - arrays are passed in Fortran memory order; shapes are written in Fortran notation in the comments.
+ *   - one context per MPI rank / GPU; not thread-safe; calls are synchronous on return.
+ *   - outputs are per-rank partial sums: the caller still performs gsum(buffer) (two_body.F90:729) and
+ *     gsum(stress) (drivers.F90:795), so MPI semantics are unchanged.
+ * ============================================================================= */
+#ifndef DLPGPU_H
+#define DLPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlpgpu_ctx dlpgpu_ctx;
+
+/* source/particle.F90:14-20  Type corePart (Sequence): 64 bytes */
+typedef struct dlpgpu_corepart {
+  double xxx, yyy, zzz;
+  double fxx, fyy, fzz;
+  double chge;
+  int32_t pad1, pad2;
+} dlpgpu_corepart;
+
+/* error codes (DL_POLY error numbers where one exists) */
+#define DLPGPU_OK 0
+#define DLPGPU_ERR_CUTOFF_HALF_CELL 95  /* neighbours.F90:409-412  cutoff_extended >= half min cell width  */
+#define DLPGPU_ERR_LIST_OVERFLOW 106    /* neighbours.F90:1189-1194 neighbour list array exceeded          */
+#define DLPGPU_ERR_HALO_COUNT 138       /* halo.F90:104-106        refreshed halo size mismatch            */
+#define DLPGPU_ERR_LINK_CELLS 307       /* neighbours.F90:431      no link cells fit the domain            */
+#define DLPGPU_ERR_LOST_ATOMS 58        /* deport_data.F90:3056-3058                                       */
+#define DLPGPU_ERR_BUFFER 54            /* deport_data.F90:1871-1876 outgoing transfer buffer too small    */
+#define DLPGPU_ERR_CUDA 9001
+#define DLPGPU_ERR_ARG 9002
+#define DLPGPU_ERR_STATE 9003
+
+/* ---------------------------------------------------------------- lifecycle */
+int dlpgpu_create(dlpgpu_ctx** ctx, int device);
+int dlpgpu_destroy(dlpgpu_ctx* ctx);
+const char* dlpgpu_last_error(const dlpgpu_ctx* ctx);
+int dlpgpu_version(void);
+/* number of CUDA kernels this context has launched since creation (bench.py's gpu_launches) */
+long long dlpgpu_launch_count(const dlpgpu_ctx* ctx);
+/* CUDA stream every kernel of the context is launched on (cudaStream_t as void*) */
+void* dlpgpu_stream(dlpgpu_ctx* ctx);
+
+/* ---------------------------------------------------------------- setup (once, or when the quantity changes) */
+/* domains.F90:35-57  dd = {nx, ny, nz, idx, idy, idz} of this rank (map_domains stays on the host) */
+int dlpgpu_set_domain(dlpgpu_ctx* ctx, const int dd[6]);
+/* configuration.F90: cell(1:9) row-major lattice vectors, imcon (0,1,2,3 supported: numerics.F90:1511-1600) */
+int dlpgpu_set_cell(dlpgpu_ctx* ctx, const double cell[9], int imcon);
+/* neighbours.F90:62-84  neigh%cutoff, neigh%padding (cutoff_extended = sum), neigh%pdplnc */
+int dlpgpu_set_cutoffs(dlpgpu_ctx* ctx, double rcut, double padding, double pdplnc);
+/* vdw.F90 vdw_type:  list(1:ntypes(ntypes+1)/2), ltp(1:max_vdw), tab_potential/tab_force(0:max_grid,1:max_vdw),
+ * cutoff, l_force_shift, l_direct, param(1:7,1:max_vdw), afs/bfs(1:max_vdw).  n_vdw<=0 switches vdW off. */
+int dlpgpu_set_vdw(dlpgpu_ctx* ctx, int ntypes, const int* vdw_list, int max_vdw, int n_vdw, const int* ltp, int max_grid,
+                   const double* tab_potential, const double* tab_force, double rvdw, int force_shift, int direct,
+                   const double* param, const double* afs, const double* bfs);
+/* ewald_type%alpha, spme_data(0)%scaling = r4pie0/eps (two_body.F90:188), electro%erfc / erfc_deriv interp_tables:
+ * arrays hold nsamples+1 doubles with element i == Fortran table(i); element 0 is never read for r >= spacing
+ * (numerics.F90:235).  active=0 switches electrostatics off (coul_method off). */
+int dlpgpu_set_ewald(dlpgpu_ctx* ctx, int active, double alpha, double scaling, int nsamples, const double* erfc_tab,
+                     const double* erfc_deriv_tab, double recip_spacing);
+
+/* ---------------------------------------------------------------- drop-in entry points (host buffers) */
+/* neighbours.F90:356-1306.  parts(1:nlast), ltype/ltg/lfrzn(1:nlast), list_excl(0:max_exclude,1:natms) (may be NULL
+ * when lbook==0).  list_out(-3:max_list,1:natms) receives the reference-format half list (may be NULL: the list
+ * then stays device-resident only).  *ibig = largest row length seen when the list overflows (error 106).
+ * Also takes the vnl_set_check snapshot of parts(1:nlast) (halo.F90:315 runs at the same positions). */
+int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_corepart* parts, const int* ltype,
+                           const int* ltg, const int* lfrzn, int lbook, int megfrz, int max_exclude,
+                           const int* list_excl, int max_list, int* list_out, int* ibig);
+/* two_body.F90:339-525 and :552-606 for the device-resident list.  parts(1:nlast): xyz and chge are read, fxx/fyy/fzz
+ * of parts(1:natms) are incremented.  out[0..5] = engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex;
+ * out[6..14] = this rank's contribution to stats%stress(1:9); out[15] = 0. */
+int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepart* parts, double out[16]);
+/* neighbours.F90:157-171: tol = max_i |r_i - r_bg,i| (minimum image) over parts(1:natms); caller does gmax + test */
+int dlpgpu_vnl_check(dlpgpu_ctx* ctx, int natms, const dlpgpu_corepart* parts, double* tol);
+int dlpgpu_vnl_set_check(dlpgpu_ctx* ctx, int nlast, const dlpgpu_corepart* parts);
+
+/* ---------------------------------------------------------------- native device-resident mode
+ * The same kernels, driven without a Fortran host (bench.py, multi-GPU engine): atoms live on the device in
+ * DL_POLY's local order 1..natms | natms+1..nlast; halo build / refresh / migration run as pack / unpack kernels
+ * around a transport the caller owns (torch.distributed NCCL send/recv on `*_dev` buffers). */
+int dlpgpu_dev_set_sites(dlpgpu_ctx* ctx, int nsites, const int* type_site, const double* charge_site,
+                         const int* freeze_site, const double* weight_site);
+/* exclusion rows by GLOBAL id: excl(0:max_exclude, 1:megatm), row 0 = count, ids ascending (build_excl.F90:1181-1184) */
+int dlpgpu_dev_set_excl(dlpgpu_ctx* ctx, int megatm, int max_exclude, const int* excl_by_gid);
+/* halo.F90:219-233 reduced-space width of the negative-direction halo requested by SPME (0 = link-cell width) */
+int dlpgpu_dev_set_halo_width(dlpgpu_ctx* ctx, const double ecw[3]);
+int dlpgpu_dev_set_list_capacity(dlpgpu_ctx* ctx, int max_list, int megfrz);
+int dlpgpu_dev_load_atoms(dlpgpu_ctx* ctx, int natms, const double* xyz, const double* vel, const int* ltg,
+                          const int* lsite, int capacity_atoms);
+int dlpgpu_dev_counts(dlpgpu_ctx* ctx, int* natms, int* nlast);
+int dlpgpu_dev_zero_forces(dlpgpu_ctx* ctx);
+/* nve.F90:163-173 (stage 1) and :198-217 (stage 2) velocity-Verlet half steps -- the trajectory driver of bench.py */
+int dlpgpu_dev_vv(dlpgpu_ctx* ctx, int stage, double dt);
+int dlpgpu_dev_vnl_check(dlpgpu_ctx* ctx, double* tol);
+/* set_halo_particles (halo.F90:153-355) split around the transport: begin (tag ixyz) -> for mdir in -1,1,-2,2,-3,3:
+ * pack (export_atomic_data select + pack, 6 doubles per atom, deport_data.F90:1810-1866), [exchange], unpack
+ * (:1921-1943) -> end (types/charges from lsite, vnl_set_check).  *count = atoms packed. */
+int dlpgpu_dev_halo_begin(dlpgpu_ctx* ctx);
+int dlpgpu_dev_halo_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int capacity_atoms, int* count);
+int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
+int dlpgpu_dev_halo_end(dlpgpu_ctx* ctx);
+/* refresh_halo_positions (halo.F90:47-113): same atoms in the same order, 3 doubles per atom */
+int dlpgpu_dev_refresh_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int* count);
+int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
+/* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */
+int dlpgpu_dev_halo_serial(dlpgpu_ctx* ctx);
+int dlpgpu_dev_refresh_serial(dlpgpu_ctx* ctx);
+/* relocate_particles (deport_data.F90:2870-3202): serial = pbcshift; DD = tag, then per direction pack (12 doubles per
+ * atom: x,v,f,ltg,lsite,ixyz) / unpack, then end (lost-atom check is the caller's gsum) */
+int dlpgpu_dev_relocate_serial(dlpgpu_ctx* ctx);
+int dlpgpu_dev_relocate_begin(dlpgpu_ctx* ctx);
+int dlpgpu_dev_relocate_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int capacity_atoms, int* count);
+int dlpgpu_dev_relocate_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
+int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now);
+/* link_cell_pairs / two_body_forces on the resident atoms.  want_ref_list!=0 additionally materialises the
+ * reference-format half list on the device (for dlpgpu_dev_get_list). */
+int dlpgpu_dev_link_cell_pairs(dlpgpu_ctx* ctx, int want_ref_list, int* ibig);
+int dlpgpu_dev_two_body_forces(dlpgpu_ctx* ctx, int zero_forces, double out[16]);
+/* read-back (tests, diagnostics) */
+int dlpgpu_dev_get_parts(dlpgpu_ctx* ctx, dlpgpu_corepart* parts_out, int n);
+int dlpgpu_dev_get_ints(dlpgpu_ctx* ctx, int n, int* ltg, int* lsite, int* ltype, int* lfrzn, int* ixyz);
+int dlpgpu_dev_get_vel(dlpgpu_ctx* ctx, int n, double* vel3);
+int dlpgpu_dev_get_list(dlpgpu_ctx* ctx, int natms, int max_list, int* list_out);
+/* link-cell diagnostics of the last build: info = {nlx,nly,nlz,nlp,ncells,nsbcll}; arrays may be NULL */
+int dlpgpu_dev_get_cells(dlpgpu_ctx* ctx, int info[6], int* which_cell, int* at_list, int* lct_start);
+/* the device-internal full neighbour rows of local atom i (1-based local index): partners as 1-based local
+ * indices; n_main/n_excl counts.  Test hook for "full list == symmetrised reference list". */
+int dlpgpu_dev_get_full_row(dlpgpu_ctx* ctx, int i, int* n_main, int* main_out, int* n_excl, int* excl_out, int cap);
+
+/* ---------------------------------------------------------------- measurement helpers */
+/* DFMA micro-benchmark: sustained fp64 FMA throughput of this GPU in TFLOP/s (2 flop per FMA) */
+int dlpgpu_fp64_peak(dlpgpu_ctx* ctx, double seconds, double* tflops);
+/* device time (ms, CUDA events on the context's stream) of the last list build and the last force evaluation,
+ * and of their dominant kernels: t[0]=list total, t[1]=force total, t[2]=pair-force kernel, t[3]=full-list kernel */
+int dlpgpu_last_timings(dlpgpu_ctx* ctx, double t[4]);
+/* 0: full list, no atomics (default).  1: half list + fp64 RED atomics (Newton's third law). */
+int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLPGPU_H */

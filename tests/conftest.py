@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import _pkg  # noqa: E402
+
+_pkg.load()
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as ora
+    ora.build()
+    return ora

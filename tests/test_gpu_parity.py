@@ -1,0 +1,284 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): neighbour list bit-exact (we check the whole reference-format array, i.e. set, row
+partition AND order); per-atom forces within 1e-9 relative; engsrp/engcpe/virial terms within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+from dl_poly_b200 import engine, systems
+from dl_poly_b200.lib import COREPART
+from util import domain_inputs, force_errors, parts_forces, rel_err, world_for
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1.0e-9      # north star: per-atom forces, relative (to the largest force; the per-atom ratio is asserted looser below)
+ENERGY_TOL = 1.0e-10    # north star: energies / virials, relative
+
+
+def make_sr(s, dd=(1, 1, 1, 0, 0, 0)):
+    sr = engine.ShortRange(0, dd)
+    sr.set_cell(s.cell, s.imcon)
+    sr.set_cutoffs(s.rcut, s.padding, s.pdplnc)
+    sr.set_forcefield(s.ff)
+    return sr
+
+
+def check_dropin(s, P, ranks=None, mode=0):
+    """Feeds each oracle domain through dlpgpu_link_cell_pairs / dlpgpu_two_body_forces exactly like the Fortran shim."""
+    w = world_for(s, P=P)
+    w.two_body()
+    worst = dict(frel=0.0, fatom=0.0, erel=0.0)
+    for r in (ranks if ranks is not None else range(P)):
+        d = domain_inputs(w, r)
+        sr = make_sr(s, d["dd"])
+        sr.set_force_mode(mode)
+        parts = d["parts"].copy()
+        for k in ("fxx", "fyy", "fzz"):
+            parts[k] = 0.0
+        lst = sr.link_cell_pairs(d["natms"], d["nlast"], parts, d["ltype"], d["ltg"], d["lfrzn"], lbook=s.lbook, megfrz=s.megfrz,
+                                 list_excl=d["list_excl"], max_list=d["max_list"])
+        ref = w.list(r)
+        assert lst.shape == ref.shape
+        # bit-exact: counters (-3..0), members and order of the used part of every row
+        assert np.array_equal(lst[:, :4], ref[:, :4])
+        used = np.arange(ref.shape[1] - 4)[None, :] < ref[:, 1:2]
+        assert np.array_equal(np.where(used, lst[:, 4:], 0), np.where(used, ref[:, 4:], 0))
+        cells = sr.dev_get_cells()
+        c = w.counts(r)
+        assert (cells["nlx"], cells["nly"], cells["nlz"], cells["nlp"], cells["ncells"], cells["nsbcll"]) == \
+            (c["nlx"], c["nly"], c["nlz"], c["nlp"], c["ncells"], c["nsbcll"])
+        wc, al, ls = w.cells(r)
+        assert np.array_equal(cells["which_cell"], wc)
+        assert np.array_equal(cells["lct_start"] + 1, ls)                # 0-based slots vs Fortran 1-based
+        assert np.array_equal(cells["at_list"] + 1, al)
+        out = sr.two_body_forces(d["natms"], d["nlast"], parts)
+        fo = parts_forces(d["parts"], d["natms"])
+        fg = parts_forces(parts, d["natms"])
+        a, b = force_errors(fg, fo)
+        worst["frel"] = max(worst["frel"], a); worst["fatom"] = max(worst["fatom"], b)
+        oo = w.results(r)
+        scale = max(abs(oo[:6]).max(), 1.0)
+        for k in range(6):
+            e = abs(out[k] - oo[k]) / max(abs(oo[k]), 1e-6 * scale)
+            worst["erel"] = max(worst["erel"], e)
+            assert e <= ENERGY_TOL, ("energy/virial term", k, out[k], oo[k])
+        sscale = abs(oo[6:15]).max()
+        assert np.abs(out[6:15] - oo[6:15]).max() <= ENERGY_TOL * sscale
+        assert a <= FORCE_TOL
+        assert b <= 1.0e-7      # per-atom ratio: atoms whose net force nearly cancels lose digits to summation order
+        sr.close()
+    return worst
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_argon_small_serial(mode):
+    check_dropin(systems.argon(6), 1, mode=mode)
+
+
+def test_argon_lj_direct_and_shifted():
+    check_dropin(systems.argon(6, form="lj", direct=True, force_shift=True), 1)
+    check_dropin(systems.argon(6, form="lj", force_shift=True), 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_nacl_small_serial_and_domains(mode):
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2), 1, mode=mode)
+    check_dropin(systems.nacl(8, rcut=8.0, padding=0.2), 8, mode=mode)
+
+
+def test_nacl_table_file_force_shift():
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, tabfile=True, force_shift=True), 1)
+
+
+def test_nacl_bhm_direct():
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, direct=True), 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_water_exclusions_subcells(mode):
+    w = check_dropin(systems.spce_water(512, rcut=8.0, padding=0.2), 1, mode=mode)
+    check_dropin(systems.spce_water(4096, rcut=8.0, padding=0.2), 8, ranks=[0, 7], mode=mode)
+
+
+def test_frozen_pairs_partition():
+    s = systems.nacl(4, rcut=8.0, padding=0.2)
+    s.freeze_site[:] = [1, 0]          # all Na+ frozen: Na-Na pairs go to the frozen tail
+    s.megfrz = int((s.freeze_site[s.lsite - 1] > 0).sum())
+    check_dropin(s, 1)
+
+
+def test_full_list_is_symmetrised_reference_list():
+    s = systems.spce_water(512, rcut=8.0, padding=0.2)
+    w = world_for(s, P=1)
+    d = domain_inputs(w, 0)
+    sr = make_sr(s)
+    lst = sr.link_cell_pairs(d["natms"], d["nlast"], d["parts"], d["ltype"], d["ltg"], d["lfrzn"], lbook=True, megfrz=0,
+                             list_excl=d["list_excl"], max_list=d["max_list"])
+    nat = d["natms"]
+    main = [set() for _ in range(nat)]
+    excl = [set() for _ in range(nat)]
+    for i in range(nat):
+        n0, n1 = lst[i, 3], lst[i, 2]
+        for k in range(1, n1 + 1):
+            j = lst[i, 3 + k]
+            tgt = main if k <= n0 else excl
+            tgt[i].add(j)
+            if j <= nat:
+                tgt[j - 1].add(i + 1)
+    for i in list(range(0, nat, 37)) + [nat - 1]:
+        m, x = sr.dev_get_full_row(i + 1)
+        assert set(m.tolist()) == main[i] and len(m) == len(main[i])
+        assert set(x.tolist()) == excl[i] and len(x) == len(excl[i])
+    sr.close()
+
+
+def test_list_overflow_is_error_106():
+    s = systems.argon(6)
+    w = world_for(s, P=1)
+    d = domain_inputs(w, 0)
+    sr = make_sr(s)
+    with pytest.raises(engine.DlpError) as ei:
+        sr.link_cell_pairs(d["natms"], d["nlast"], d["parts"], d["ltype"], d["ltg"], d["lfrzn"], max_list=20)
+    assert ei.value.code == 106 and sr.ibig > 20
+    sr.close()
+
+
+def test_cutoff_too_large_is_error_95():
+    s = systems.argon(4)                 # L = 22.9 A < 2 * 8.8
+    sr = make_sr(s)
+    parts = np.zeros(s.megatm, dtype=COREPART)
+    parts["xxx"], parts["yyy"], parts["zzz"] = s.xyz.T
+    with pytest.raises(engine.DlpError) as ei:
+        sr.link_cell_pairs(s.megatm, s.megatm, parts, np.ones(s.megatm, np.int32), np.arange(1, s.megatm + 1, dtype=np.int32),
+                           max_list=s.max_list)
+    assert ei.value.code == 95
+    sr.close()
+
+
+def test_two_body_without_list_is_an_error():
+    s = systems.argon(6)
+    sr = make_sr(s)
+    parts = np.zeros(10, dtype=COREPART)
+    with pytest.raises(engine.DlpError):
+        sr.two_body_forces(10, 10, parts)
+    sr.close()
+
+
+def test_empty_domain():
+    s = systems.argon(6)
+    sr = make_sr(s)
+    parts = np.zeros(0, dtype=COREPART)
+    lst = sr.link_cell_pairs(0, 0, parts, np.zeros(0, np.int32), np.zeros(0, np.int32), max_list=s.max_list)
+    assert lst.shape[0] == 0
+    out = sr.two_body_forces(0, 0, parts)
+    assert np.all(out == 0.0)
+    sr.close()
+
+
+# ---- native device-resident path ------------------------------------------------------------------------------------
+def native_serial(s):
+    sr = engine.ShortRange(0)
+    sr.dev_setup_system(s)
+    sr.dev_load_atoms(s.xyz, s.vel, np.arange(1, s.megatm + 1, dtype=np.int32), s.lsite)
+    return sr
+
+
+@pytest.mark.parametrize("name", ["argon", "nacl", "water"])
+def test_native_serial_halo_list_forces(name):
+    s = {"argon": lambda: systems.argon(6), "nacl": lambda: systems.nacl(4, rcut=8.0, padding=0.2),
+         "water": lambda: systems.spce_water(512, rcut=8.0, padding=0.2)}[name]()
+    w = world_for(s, P=1, with_halo=False, with_list=False)
+    w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
+    oo = w.two_body()
+    sr = native_serial(s)
+    sr.dev_relocate_serial()
+    sr.dev_halo_serial()
+    natms, nlast = sr.dev_counts()
+    c = w.counts(0)
+    assert (natms, nlast) == (c["natms"], c["nlast"])
+    po, pg = w.parts(0), sr.dev_get_parts()
+    for k in ("xxx", "yyy", "zzz", "chge"):
+        assert np.array_equal(po[k], pg[k]), k                           # halo images: same atoms, same order, same bits
+    io, ig = w.ints(0), sr.dev_get_ints()
+    for k in ("ltg", "lsite", "ltype", "lfrzn", "ixyz"):
+        assert np.array_equal(io[k], ig[k]), k
+    sr.dev_link_cell_pairs(want_ref_list=True)
+    assert np.array_equal(sr.dev_get_list()[:, :4], w.list(0)[:, :4])
+    ref = w.list(0)
+    used = np.arange(ref.shape[1] - 4)[None, :] < ref[:, 1:2]
+    assert np.array_equal(np.where(used, sr.dev_get_list()[:, 4:], 0), np.where(used, ref[:, 4:], 0))
+    out = sr.dev_two_body_forces()
+    fg = parts_forces(sr.dev_get_parts(), natms)
+    fo = parts_forces(w.parts(0), natms)
+    a, b = force_errors(fg, fo)
+    assert a <= FORCE_TOL
+    for k in range(6):
+        assert abs(out[k] - oo[k]) <= ENERGY_TOL * max(abs(oo[k]), 1e-6 * abs(oo[:6]).max())
+    sr.close()
+
+
+def test_native_trajectory_vnl_refresh_rebuild():
+    """A short NVE trajectory: vnl_check decisions, refreshed halo positions and rebuilt lists track the oracle."""
+    s = systems.argon(6, temperature=300.0)
+    dt = 0.004
+    w = world_for(s, P=1, with_halo=False, with_list=False)
+    sr = native_serial(s)
+    w.relocate(); w.set_halo(); w.link_cell_pairs(); w.two_body()
+    sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs(); sr.dev_two_body_forces()
+    rebuilds = 0
+    for step in range(30):
+        w.vv(1, dt, s.weight_by_type); sr.dev_vv(1, dt)
+        upd_o, tol_o = w.vnl_check()
+        tol_g = sr.dev_vnl_check()
+        assert abs(tol_g - tol_o) <= 1e-12 * max(tol_o, 1e-30)
+        upd_g = sr.vnl_update(tol_g)
+        assert upd_g == upd_o
+        if upd_o:
+            rebuilds += 1
+            w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
+            sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs()
+        else:
+            assert w.refresh_halo() == 0
+            sr.dev_refresh_serial()
+        oo = w.two_body()
+        og = sr.dev_two_body_forces()
+        w.vv(2, dt, s.weight_by_type); sr.dev_vv(2, dt)
+        natms, nlast = sr.dev_counts()
+        assert nlast == w.counts(0)["nlast"]
+        po, pg = w.parts(0), sr.dev_get_parts()
+        # positions follow the same arithmetic; forces differ by summation order, so trajectories drift at ~1e-13
+        assert np.abs(po["xxx"] - pg["xxx"]).max() < 1e-9
+        assert abs(og[0] - oo[0]) <= 1e-9 * abs(oo[0])
+    assert rebuilds >= 2
+    sr.close()
+
+
+# ---- BASELINE sizes: oracle comparison where it finishes in seconds + size-independent properties --------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c3"])
+def test_baseline_configs_full_size(name):
+    s = systems.by_name(name)
+    w = world_for(s, P=1, with_halo=False, with_list=False)
+    w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
+    oo = w.two_body()
+    sr = native_serial(s)
+    sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs(want_ref_list=True)
+    natms, nlast = sr.dev_counts()
+    ref, got = w.list(0), sr.dev_get_list()
+    assert np.array_equal(got[:, :4], ref[:, :4])
+    used = np.arange(ref.shape[1] - 4)[None, :] < ref[:, 1:2]
+    assert np.array_equal(np.where(used, got[:, 4:], 0), np.where(used, ref[:, 4:], 0))
+    out = sr.dev_two_body_forces()
+    fg = parts_forces(sr.dev_get_parts(), natms)
+    fo = parts_forces(w.parts(0), natms)
+    a, b = force_errors(fg, fo)
+    assert a <= FORCE_TOL
+    for k in range(6):
+        assert abs(out[k] - oo[k]) <= ENERGY_TOL * max(abs(oo[k]), 1e-6 * abs(oo[:6]).max())
+    # properties that hold at any size: Newton's third law over the periodic system, virial == -trace(stress),
+    # symmetric stress
+    assert np.abs(fg.sum(0)).max() <= 1e-9 * np.abs(fg).sum()
+    vir = out[1] + out[3] + out[5]
+    assert abs((out[6] + out[10] + out[14]) + vir) <= 1e-10 * abs(vir)
+    assert out[7] == out[9] and out[8] == out[12] and out[11] == out[13]
+    sr.close()
