@@ -188,9 +188,22 @@ __global__ void k_cell_scatter(int nlast, const int* __restrict__ which_cell, co
 
 // Stable order inside each cell = ascending local index, as the reference's sequential counting sort gives (:811-823).
 // One warp per cell, rank by counting.
+// Cell 0 (the residual halo, :775-789) can hold a large share of the halo, so its stable order comes from a scan instead.
+__global__ void k_cell0_flag(int nlast, const int* __restrict__ which_cell, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nlast) return;
+  flag[i] = (i < nlast && which_cell[i] == 0) ? 1 : 0;
+}
+__global__ void k_cell0_place(int nlast, const int* __restrict__ which_cell, const int* __restrict__ rank, int* __restrict__ at_list,
+                              int* __restrict__ cell_s) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlast || which_cell[i] != 0) return;
+  at_list[rank[i]] = i;      // lct_start[0] == 0
+  cell_s[rank[i]] = 0;
+}
 __global__ void k_cell_order(int ncells_p1, const int* __restrict__ lct_start, const int* __restrict__ at_tmp,
                              int* __restrict__ at_list, int* __restrict__ cell_s) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int c = 1 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
   if (c >= ncells_p1) return;
   int s0 = lct_start[c], n = lct_start[c + 1] - s0;
@@ -488,7 +501,10 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   CKRC(dlp_exclusive_scan(ctx, ctx->lct_count.p, ctx->lct_start.p, g.ncells + 1, nullptr));
   if (nlast > 0) {
     LAUNCH(ctx, k_cell_scatter, cdiv(nlast, 256), 256, 0, nlast, ctx->which_cell.p, ctx->lct_start.p, ctx->lct_fill.p, ctx->at_tmp.p);
-    LAUNCH(ctx, k_cell_order, cdiv((long long)(g.ncells + 1) * 32, 256), 256, 0, g.ncells + 1, ctx->lct_start.p, ctx->at_tmp.p,
+    LAUNCH(ctx, k_cell0_flag, cdiv(nlast + 1, 256), 256, 0, nlast, ctx->which_cell.p, ctx->flag.p);
+    CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nlast, nullptr));
+    LAUNCH(ctx, k_cell0_place, cdiv(nlast, 256), 256, 0, nlast, ctx->which_cell.p, ctx->scan_out.p, ctx->at_list.p, ctx->cell_s.p);
+    LAUNCH(ctx, k_cell_order, cdiv((long long)g.ncells * 32, 256), 256, 0, g.ncells + 1, ctx->lct_start.p, ctx->at_tmp.p,
            ctx->at_list.p, ctx->cell_s.p);
   }
   LAUNCH(ctx, k_sorted_static, cdiv(nlast + 1, 256), 256, 0, nlast, natms, ctx->at_list.p, ctx->ltype.p, ctx->ltg.p, ctx->lfrzn.p,

@@ -461,6 +461,13 @@ int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_d
   return 0;
 }
 
+int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]) {
+  if (!ctx || !sent || !received) return DLPGPU_ERR_ARG;
+  if (!ctx->halo_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "halo_stage_counts: no halo has been built");
+  for (int q = 0; q < 6; ++q) { sent[q] = ctx->stage[q].count; received[q] = ctx->stage[q].recv_count; }
+  return 0;
+}
+
 int dlpgpu_dev_refresh_serial(dlpgpu_ctx* ctx) {
   if (!ctx) return DLPGPU_ERR_ARG;
   const int mdirs[6] = {-1, 1, -2, 2, -3, 3};

@@ -1,0 +1,336 @@
+"""Native multi-GPU driver of the short-range path: DL_POLY's domain decomposition, one domain per GPU.
+
+Mirrors, on top of :class:`engine.ShortRange` and ``torch.distributed``:
+
+* ``map_domains``            -- domains.F90:63-258 (factor search minimising the domain surface, rank -> (idx,idy,idz),
+                                the six face neighbours ``map(1:6)``)
+* ``relocate_particles``     -- deport_data.F90:2870-3202 (six staged moves -x,+x,-y,+y,-z,+z)
+* ``set_halo_particles``     -- halo.F90:153-355 + export_atomic_data (six staged exports, 6 doubles per atom)
+* ``refresh_halo_positions`` -- halo.F90:47-113 (same atoms, same order, 3 doubles per atom)
+* the per-step control flow of ``md_vv`` around the path (drivers.F90:1910-2290): VV stage 1, ``vnl_check`` + ``gmax``,
+  rebuild or refresh, ``two_body_forces``, VV stage 2; the 16-double ``gsum`` is :meth:`Domain.gsum`.
+
+The wire format is the reference's; the transport is NCCL send/recv (``batch_isend_irecv``) on device buffers -- or, for
+a direction in which the decomposition has a single domain, the rank is its own neighbour (deport_data.F90:1884-1886)
+and the buffer never leaves the GPU.  All device work is enqueued on the context's own CUDA stream (torch sees it as an
+``ExternalStream``), so pack -> send/recv -> unpack are ordered without host synchronisation; the only host syncs are the
+ones the reference has too (counts on rebuild steps, the ``gmax`` result).
+
+The transport is duck-typed (anything with ``exchange(sendbuf, n_send_items, recvbuf, dst, src)`` and
+``exchange_counts``), so the staging logic is exercised on CPU with the gloo backend in tests/test_dd_gloo.py.
+"""
+import numpy as np
+
+MDIRS = (-1, 1, -2, 2, -3, 3)          # stage order of halo.F90:277-292 / deport_data.F90:3031-3052
+HALF_MINUS = np.nextafter(0.5, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------- map_domains
+def _divisors(p):
+    return [d for d in range(1, p + 1) if p % d == 0]
+
+
+def map_domains(mxnode, widths, imcon=1):
+    """domains.F90:103-182: (nx, ny, nz) minimising S = 2(dx dy + dy dz + dz dx) with the reference's tie rules.
+    ``widths`` = celprp(7:9), the perpendicular cell widths."""
+    if mxnode == 1:
+        return 1, 1, 1
+    wx, wy, wz = (float(w) for w in widths)
+    tol = 1.0e-6
+    big = 1 << 30
+    limx = big if imcon != 0 else 2
+    limy = big if imcon != 0 else 2
+    limz = big if (imcon != 0 and imcon != 6) else 2
+    best, min_s = (-1, -1, -1), float("inf")
+    for nx in _divisors(mxnode):
+        if nx > limx:
+            continue
+        dx = wx / nx
+        pyz = mxnode // nx
+        for ny in _divisors(pyz):
+            if ny > limy:
+                continue
+            nz = pyz // ny
+            if nz > limz:
+                continue
+            dy, dz = wy / ny, wz / nz
+            s = 2.0 * (dx * dy + dy * dz + dz * dx)
+            if min_s - s > tol:
+                min_s, best = s, (nx, ny, nz)
+            elif abs(min_s - s) < tol:
+                if max(nx, ny, nz) < max(best):
+                    min_s, best = s, (nx, ny, nz)
+                elif max(nx, ny, nz) == max(best):
+                    if nx < best[0] or (nx == best[0] and ny < best[1]):
+                        min_s, best = s, (nx, ny, nz)
+    if -1 in best:
+        raise RuntimeError("error 520: no domain decomposition found")
+    return best
+
+
+def domain_of_rank(rank, nx, ny, nz):
+    """domains.F90:198-200."""
+    idz = rank // (nx * ny)
+    idy = rank // nx - idz * ny
+    idx = rank % nx
+    return idx, idy, idz
+
+
+def idcube(i, j, k, nx, ny):
+    return i + nx * (j + ny * k)
+
+
+def face_neighbours(rank, nx, ny, nz):
+    """domains.F90:206-211: map(1:6) = ranks in -x,+x,-y,+y,-z,+z."""
+    idx, idy, idz = domain_of_rank(rank, nx, ny, nz)
+    return [idcube((idx - 1) % nx, idy, idz, nx, ny), idcube((idx + 1) % nx, idy, idz, nx, ny),
+            idcube(idx, (idy - 1) % ny, idz, nx, ny), idcube(idx, (idy + 1) % ny, idz, nx, ny),
+            idcube(idx, idy, (idz - 1) % nz, nx, ny), idcube(idx, idy, (idz + 1) % nz, nx, ny)]
+
+
+def cell_widths(cell):
+    """celprp(7:9) of numerics.F90::dcell for the lattice vectors in ``cell`` (rows)."""
+    a = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    vol = abs(np.linalg.det(a))
+    bxc, cxa, axb = np.cross(a[1], a[2]), np.cross(a[2], a[0]), np.cross(a[0], a[1])
+    return vol / np.linalg.norm(bxc), vol / np.linalg.norm(cxa), vol / np.linalg.norm(axb)
+
+
+def assign_domains(xyz, cell, nx, ny, nz):
+    """configuration.F90:1183-1205: reduced coordinates folded into [-0.5,0.5), ip = Int((s+0.5)*n) -> owning rank."""
+    rc = np.linalg.inv(np.asarray(cell, dtype=np.float64).reshape(3, 3))
+    s = np.asarray(xyz) @ rc
+    s = s - np.rint(s)
+    s = np.where(s >= HALF_MINUS, -s, s)
+    ipx = np.minimum((( s[:, 0] + 0.5) * nx).astype(np.int64), nx - 1)
+    ipy = np.minimum(((s[:, 1] + 0.5) * ny).astype(np.int64), ny - 1)
+    ipz = np.minimum(((s[:, 2] + 0.5) * nz).astype(np.int64), nz - 1)
+    return (ipx + nx * (ipy + ny * ipz)).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------- transports
+class SelfTransport:
+    """mxnode == 1 in every direction: never called with a remote peer."""
+    rank, world = 0, 1
+
+    def exchange_counts(self, n_send, dst, src):
+        raise RuntimeError("SelfTransport cannot reach another rank")
+
+    def allreduce_max(self, v):
+        return v
+
+    def allreduce_sum(self, arr):
+        return arr
+
+    def barrier(self):
+        pass
+
+
+class TorchTransport:
+    """NCCL (GPU) or gloo (CPU tests) point-to-point through torch.distributed."""
+
+    def __init__(self, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.device = device
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._cnt_s = torch.zeros(1, dtype=torch.int64, device=device)
+        self._cnt_r = torch.zeros(1, dtype=torch.int64, device=device)
+        self._red = torch.zeros(1, dtype=torch.float64, device=device)
+
+    def _p2p(self, ops):
+        for r in self.dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def exchange_counts(self, n_send, dst, src):
+        """Send my count to ``dst`` and receive the count ``src`` sends me (deport_data.F90:1888-1893)."""
+        d = self.dist
+        self._cnt_s.fill_(int(n_send))
+        self._p2p([d.P2POp(d.isend, self._cnt_s, dst, self.group), d.P2POp(d.irecv, self._cnt_r, src, self.group)])
+        return int(self._cnt_r.item())
+
+    def exchange(self, sendbuf, n_send, recvbuf, n_recv, dst, src):
+        """sendbuf[:n_send] -> dst ; recvbuf[:n_recv] <- src (flat float64 tensors on the transport's device)."""
+        d = self.dist
+        ops = []
+        if n_send > 0:
+            ops.append(d.P2POp(d.isend, sendbuf[:n_send], dst, self.group))
+        if n_recv > 0:
+            ops.append(d.P2POp(d.irecv, recvbuf[:n_recv], src, self.group))
+        if ops:
+            self._p2p(ops)
+
+    def allreduce_max(self, v):
+        self._red.fill_(float(v))
+        self.dist.all_reduce(self._red, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float(self._red.item())
+
+    def allreduce_sum(self, arr):
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+# ---------------------------------------------------------------------------------------------- staging logic
+def staged_exchange(transport, neighbours, dims, pack, unpack, alloc, width, self_copy=None):
+    """The six-stage exchange pattern shared by halo build and migration.
+
+    For mdir in (-1,+1,-2,+2,-3,+3): ``pack(mdir, buf, cap)`` -> (rc, n_atoms) fills ``buf`` with ``width`` doubles per
+    atom (rc == 54: buffer too small, n_atoms = needed); the buffer goes to the neighbour in direction mdir and the
+    one arriving from the opposite neighbour is handed to ``unpack(mdir, buf, n_atoms)``.
+    ``alloc(n_doubles)`` returns a (buffer, raw pointer) pair on the right device.
+    """
+    bufs = {}
+
+    def get(kind, n_atoms):
+        need = max(n_atoms, 1) * width
+        b = bufs.get(kind)
+        if b is None or b[2] < need:
+            cap = need + need // 4 + 64 * width
+            t, p = alloc(cap)
+            b = (t, p, cap)
+            bufs[kind] = b
+        return b
+
+    for q, mdir in enumerate(MDIRS):
+        axis = abs(mdir) - 1
+        dst = neighbours[q]                       # map(1..6)[q]: the neighbour the data travels to
+        src = neighbours[q ^ 1]                   # and the opposite one it arrives from
+        st, sp, scap = get("s", 0)
+        rc, n = pack(mdir, sp, scap // width)
+        if rc == 54:
+            st, sp, scap = get("s", n)
+            rc, n2 = pack(mdir, sp, scap // width)
+            assert rc == 0 and n2 == n
+        if dims[axis] == 1:                       # the rank is its own neighbour: no transport
+            unpack(mdir, sp, n)
+            continue
+        n_in = transport.exchange_counts(n, dst, src)
+        rt, rp, rcap = get("r", n_in)
+        transport.exchange(st, n * width, rt, n_in * width, dst, src)
+        unpack(mdir, rp, n_in)
+    return bufs
+
+
+class Domain:
+    """One DL_POLY domain resident on one GPU."""
+
+    def __init__(self, sysm, device=0, transport=None, capacity_factor=1.6):
+        import torch
+        from . import engine
+        self.torch = torch
+        self.sys = sysm
+        self.t = transport if transport is not None else SelfTransport()
+        self.rank, self.world = self.t.rank, self.t.world
+        self.dims = map_domains(self.world, cell_widths(sysm.cell), sysm.imcon)
+        nx, ny, nz = self.dims
+        self.idx = domain_of_rank(self.rank, nx, ny, nz)
+        self.neigh = face_neighbours(self.rank, nx, ny, nz)
+        self.device = torch.device("cuda", device)
+        self.sr = engine.ShortRange(device, (nx, ny, nz) + tuple(self.idx))
+        self.sr.dev_setup_system(sysm)
+        self.stream = torch.cuda.ExternalStream(self.sr.stream(), device=self.device)
+        owner = assign_domains(sysm.xyz, sysm.cell, nx, ny, nz)
+        mine = np.nonzero(owner == self.rank)[0]
+        self.natms0 = len(mine)
+        cap = int(capacity_factor * max(sysm.megatm / self.world, 1.0) * 1.0) + 4096
+        # halo thickness grows the resident count: capacity covers local + halo with head-room (bounds.F90 mxatms)
+        ltg = (mine + 1).astype(np.int32)
+        vel = None if sysm.vel is None else sysm.vel[mine]
+        self.sr.dev_load_atoms(sysm.xyz[mine], vel, ltg, sysm.lsite[mine], capacity=cap * 2)
+        self._refresh_bufs = None
+        self.rebuilds = 0
+        self.steps = 0
+
+    # ---- buffers on the context's device
+    def _alloc(self, n_doubles):
+        t = self.torch.empty(int(n_doubles), dtype=self.torch.float64, device=self.device)
+        return t, t.data_ptr()
+
+    # ---- the reference's three exchange routines
+    def relocate(self):
+        sr = self.sr
+        with self.torch.cuda.stream(self.stream):
+            if self.world == 1:
+                sr.dev_relocate_serial()
+                return
+            sr.dev_relocate_begin()
+            staged_exchange(self.t, self.neigh, self.dims, sr.dev_relocate_pack, sr.dev_relocate_unpack, self._alloc, 12)
+            sr.dev_relocate_end()
+
+    def set_halo(self):
+        sr = self.sr
+        with self.torch.cuda.stream(self.stream):
+            if self.world == 1:
+                sr.dev_halo_serial()
+                return
+            sr.dev_halo_begin()
+            staged_exchange(self.t, self.neigh, self.dims, sr.dev_halo_pack, sr.dev_halo_unpack, self._alloc, 6)
+            sr.dev_halo_end()
+            self._refresh_bufs = None
+
+    def refresh_halo(self):
+        sr = self.sr
+        with self.torch.cuda.stream(self.stream):
+            if self.world == 1:
+                sr.dev_refresh_serial()
+                return
+            if self._refresh_bufs is None:
+                cs, cr = sr.dev_halo_stage_counts()
+                ns, nr = max(max(cs), 1) * 3, max(max(cr), 1) * 3
+                self._refresh_bufs = (self._alloc(ns), self._alloc(nr), cs, cr)
+            (st, sp), (rt, rp), cs, cr = self._refresh_bufs
+            for q, mdir in enumerate(MDIRS):
+                axis = abs(mdir) - 1
+                n = sr.dev_refresh_pack(mdir, sp)
+                if self.dims[axis] == 1:
+                    sr.dev_refresh_unpack(mdir, sp, n)
+                    continue
+                self.t.exchange(st, n * 3, rt, cr[q] * 3, self.neigh[q], self.neigh[q ^ 1])
+                sr.dev_refresh_unpack(mdir, rp, cr[q])
+
+    # ---- md_vv around the path
+    def rebuild(self):
+        self.relocate()
+        self.set_halo()
+        with self.torch.cuda.stream(self.stream):
+            self.sr.dev_link_cell_pairs()
+        self.rebuilds += 1
+
+    def vnl_update(self):
+        with self.torch.cuda.stream(self.stream):
+            tol = self.sr.dev_vnl_check()
+            tol = self.t.allreduce_max(tol)                 # gmax, neighbours.F90:176
+        return self.sr.vnl_update(tol)
+
+    def forces(self):
+        with self.torch.cuda.stream(self.stream):
+            return self.sr.dev_two_body_forces(zero_forces=True)
+
+    def step(self, dt):
+        """One velocity-Verlet step with the short-range path as the only force provider."""
+        sr = self.sr
+        with self.torch.cuda.stream(self.stream):
+            sr.dev_vv(1, dt)
+        if self.vnl_update():
+            self.rebuild()
+        else:
+            self.refresh_halo()
+        out = self.forces()
+        with self.torch.cuda.stream(self.stream):
+            sr.dev_vv(2, dt)
+        self.steps += 1
+        return out
+
+    def gsum(self, out):
+        """two_body.F90:729 / drivers.F90:795."""
+        return self.t.allreduce_sum(out)
+
+    def close(self):
+        self.sr.close()

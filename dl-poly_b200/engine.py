@@ -195,6 +195,11 @@ class ShortRange:
     def dev_halo_end(self):
         self._ck(self.L.dlpgpu_dev_halo_end(self.h))
 
+    def dev_halo_stage_counts(self):
+        a, b = np.zeros(6, dtype=np.int32), np.zeros(6, dtype=np.int32)
+        self._ck(self.L.dlpgpu_dev_halo_stage_counts(self.h, ptr(a), ptr(b)))
+        return [int(v) for v in a], [int(v) for v in b]
+
     def dev_refresh_pack(self, mdir, sendbuf_ptr):
         n = C.c_int(0)
         self._ck(self.L.dlpgpu_dev_refresh_pack(self.h, int(mdir), C.c_void_p(sendbuf_ptr), C.byref(n)))

@@ -52,9 +52,17 @@ class System:
         return self.excl is not None
 
 
+def _n3(ncell):
+    """ncell may be an int (cubic box) or a 3-tuple of lattice repeats (orthorhombic box, used for weak scaling)."""
+    if np.isscalar(ncell):
+        return (int(ncell),) * 3
+    return tuple(int(v) for v in ncell)
+
+
 def _fcc(ncell, a):
     base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
-    g = np.stack(np.meshgrid(np.arange(ncell), np.arange(ncell), np.arange(ncell), indexing="ij"), -1).reshape(-1, 3)
+    nx, ny, nz = _n3(ncell)
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3)
     return ((g[:, None, :] + base[None, :, :]).reshape(-1, 3)) * a
 
 
@@ -68,9 +76,10 @@ def _wrap(xyz, L):
 def argon(ncell=20, seed=1001, rcut=8.5, padding=0.3, form="12-6", direct=False, force_shift=False, jitter=0.25,
           temperature=85.0):
     """C1: Ar 12-6 fluid, 4*ncell^3 atoms (32,000 at ncell=20), rho=0.02138 A^-3."""
-    n = 4 * ncell ** 3
-    L = (n / 0.02138) ** (1.0 / 3.0)
-    a = L / ncell
+    nc = np.array(_n3(ncell), dtype=np.float64)
+    n = int(4 * nc.prod())
+    a = (4.0 / 0.02138) ** (1.0 / 3.0)
+    L = nc * a
     rng = np.random.default_rng(seed)
     xyz = _fcc(ncell, a) - 0.5 * L + 0.25 * a
     xyz = _wrap(xyz + rng.uniform(-jitter, jitter, xyz.shape), L)
@@ -81,7 +90,7 @@ def argon(ncell=20, seed=1001, rcut=8.5, padding=0.3, form="12-6", direct=False,
     else:
         ff.add(1, 1, "lj", [eps, sig])
     ff.finalize()
-    cell = np.diag([L, L, L])
+    cell = np.diag(L)
     return System("C1-argon-%d" % n, cell, xyz, np.ones(n, dtype=np.int32), [1], [0.0], [39.948], ff, rcut, padding,
                   temperature=temperature, seed=seed)
 
@@ -92,9 +101,10 @@ _BHM = {(1, 1): [2544.35, 3.1545, 2.3400, 1.0117e4, 4.8177e3],
         (2, 2): [1526.61, 3.1545, 3.1700, 6.9857e5, 1.4032e6]}
 
 
-def _rocksalt(ncell, L, seed, jitter):
-    a = L / ncell
-    g = np.stack(np.meshgrid(np.arange(2 * ncell), np.arange(2 * ncell), np.arange(2 * ncell), indexing="ij"),
+def _rocksalt(ncell, a, seed, jitter):
+    nx, ny, nz = _n3(ncell)
+    L = np.array([nx, ny, nz], dtype=np.float64) * a
+    g = np.stack(np.meshgrid(np.arange(2 * nx), np.arange(2 * ny), np.arange(2 * nz), indexing="ij"),
                  -1).reshape(-1, 3)
     species = (g.sum(1) % 2).astype(np.int32) + 1             # 1 = Na+, 2 = Cl-
     rng = np.random.default_rng(seed)
@@ -107,9 +117,11 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
          jitter=0.3, temperature=1200.0, spme_precision=1.0e-6):
     """C2/C4/C5-ionic: molten NaCl, 8*ncell^3 ions at the TEST01 density (V=963,882.2 A^3 for 27,000 ions).
     tabfile=True builds the three pair tables through a TABLE-format round trip (C4)."""
-    n = 8 * ncell ** 3
-    L = (963882.2 * n / 27000.0) ** (1.0 / 3.0)
-    xyz, species = _rocksalt(ncell, L, seed, jitter)
+    nc = np.array(_n3(ncell), dtype=np.float64)
+    n = int(8 * nc.prod())
+    a = (963882.2 * 8.0 / 27000.0) ** (1.0 / 3.0)             # rock-salt cell edge at the TEST01 density
+    L = nc * a
+    xyz, species = _rocksalt(ncell, a, seed, jitter)
     ff = tables.ForceField(2, rcut, rcut, force_shift=force_shift, direct=direct)
     if tabfile:
         g = ff.mxgrid
@@ -127,7 +139,7 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
     if ewald:
         ff.set_ewald(precision=spme_precision)
     ff.finalize()
-    cell = np.diag([L, L, L])
+    cell = np.diag(L)
     return System("NaCl-%d%s" % (n, "-TABLE" if tabfile else ""), cell, xyz, species, [1, 2], [1.0, -1.0],
                   [22.9898, 35.453], ff, rcut, padding, temperature=temperature, seed=seed)
 

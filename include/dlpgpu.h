@@ -126,6 +126,8 @@ int dlpgpu_dev_halo_end(dlpgpu_ctx* ctx);
 /* refresh_halo_positions (halo.F90:47-113): same atoms in the same order, 3 doubles per atom */
 int dlpgpu_dev_refresh_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int* count);
 int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
+/* atoms sent / received in each of the six stages of the last halo build (order -x,+x,-y,+y,-z,+z) */
+int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]);
 /* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */
 int dlpgpu_dev_halo_serial(dlpgpu_ctx* ctx);
 int dlpgpu_dev_refresh_serial(dlpgpu_ctx* ctx);

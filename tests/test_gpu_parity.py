@@ -145,7 +145,7 @@ def test_list_overflow_is_error_106():
 
 
 def test_cutoff_too_large_is_error_95():
-    s = systems.argon(4)                 # L = 22.9 A < 2 * 8.8
+    s = systems.argon(3)                 # L = 17.2 A < 2 * 8.8
     sr = make_sr(s)
     parts = np.zeros(s.megatm, dtype=COREPART)
     parts["xxx"], parts["yyy"], parts["zzz"] = s.xyz.T
