@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- pair-force atom-steps/s (list + forces) of the DL_POLY short-range path on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W     (CPU restatement of the reference on the host cores)
+
+A "step" is one MD step of the hot path on the device-resident engine: velocity-Verlet stage 1,
+vnl_check + gmax, then EITHER the rebuild path (relocate_particles, set_halo_particles, link_cell_pairs) OR
+refresh_halo_positions, then two_body_forces (vdW + real-space Ewald + exclusion correction, energies / virial / stress
+reduced), then velocity-Verlet stage 2.  Rebuilds happen at their natural, padding-driven frequency.  Prints ONE JSON
+line on rank 0.
+
+Workloads (weak scaling: the per-GPU domain is fixed, the box grows with N as (1,1,1),(2,1,1),(2,2,1),(2,2,2) domains):
+  ionic  -- BASELINE configs[4] "8M-atom ionic ... weak scaling": molten NaCl, Born-Huggins-Mayer (tabulated, the
+            reference default) + real-space Ewald, rc 12 A, padding 0.24 A, 1,000,000 ions per GPU (8M at N=8)
+  table  -- configs[3]: the same melt with the three pair tables read through a TABLE-file round trip
+  lj     -- configs[4] LJ: argon 12-6, rc 8.5 A, padding 0.3 A, 1,000,188 atoms per GPU
+  c1/c2/c3 -- the small BASELINE configs as they are (single GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIMS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+METRIC = "pair-force atom-steps/s (list+forces)"
+UNIT = "atom-steps/s"
+
+# Algorithmic flop per pair, counted from the reference source (div and sqrt = 1 flop each; every
+# unique pair once -- the reference's half list / Newton's third law count):
+FLOP_GATHER = 9      # two_body.F90:346-352, every listed pair
+FLOP_VDW = 55        # vdw.F90:1896-1982, in-cutoff pair with a defined potential
+FLOP_EWALD = 56      # ewald_spole.F90:133-197, in-cutoff charged pair
+FLOP_EXCL = 50       # ewald_spole.F90:570-649, excluded pair
+
+
+def make_system(workload, dims, per_gpu_cells=None):
+    import _pkg
+    _pkg.load()
+    from dl_poly_b200 import systems
+    dx, dy, dz = dims
+    if workload in ("ionic", "table"):
+        c = per_gpu_cells or 50
+        return systems.nacl((c * dx, c * dy, c * dz), seed=1005, tabfile=(workload == "table"))
+    if workload == "lj":
+        c = per_gpu_cells or 63
+        return systems.argon((c * dx, c * dy, c * dz), seed=1005)
+    if workload in ("c1", "c2", "c3"):
+        if dims != (1, 1, 1):
+            raise SystemExit("workload %s is a single-GPU configuration" % workload)
+        return systems.by_name(workload, temperature={"c1": 85.0, "c2": 1200.0, "c3": 300.0}[workload])
+    raise SystemExit("unknown workload " + workload)
+
+
+def workload_name(workload, sysm, n):
+    d = {"ionic": "C5-ionic weak scaling: molten NaCl BHM(tabulated)+Ewald real space, rc 12 A, padding 0.24 A",
+         "table": "C4 TABLE vdW + Ewald real space ionic melt, rc 12 A, padding 0.24 A",
+         "lj": "C5-LJ weak scaling: argon 12-6 (tabulated), rc 8.5 A, padding 0.3 A",
+         "c1": "C1 argon 32,000", "c2": "C2 NaCl 27,000", "c3": "C3 SPC/E 216,000"}[workload]
+    return "%s; %d atoms on %d GPU(s)" % (d, sysm.megatm, n)
+
+
+def flop_per_atom_step(sysm, listed_pairs_per_atom):
+    """9 n_l + (55 [+56]) n_c (+ exclusions); n_c = n_l (rc/rx)^3."""
+    n_l = listed_pairs_per_atom
+    n_c = n_l * (sysm.rcut / sysm.rx) ** 3
+    per_pair = 0.0
+    ff = sysm.ff
+    if ff.n_vdw > 0:
+        # fraction of pairs with a defined vdW potential (SPC/E: O-O only)
+        types = np.asarray(sysm.type_site)[np.asarray(sysm.lsite) - 1]
+        frac = 0.0
+        cnt = np.bincount(types, minlength=ff.ntypes + 1)[1:].astype(np.float64) / len(types)
+        for a in range(ff.ntypes):
+            for b in range(ff.ntypes):
+                hi, lo = max(a, b) + 1, min(a, b) + 1
+                if ff.vdw_list_c[hi * (hi - 1) // 2 + lo - 1] > 0:
+                    frac += cnt[a] * cnt[b]
+        per_pair += FLOP_VDW * frac
+    if ff.ew_active:
+        per_pair += FLOP_EWALD
+    excl = 0.0
+    if sysm.excl is not None:
+        excl = FLOP_EXCL * 0.5 * float(np.asarray(sysm.excl)[:, 0].mean())
+    return FLOP_GATHER * n_l + per_pair * n_c + excl
+
+
+def bytes_per_atom_step(sysm, listed_pairs_per_atom):
+    """read x,y,z 24 + type 4 [+ q 8] + write f 24 + list 4 n_l."""
+    return 24 + 4 + (8 if sysm.ff.ew_active else 0) + 24 + 4.0 * listed_pairs_per_atom
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.path = "/tmp/dlp_clocks_%d.csv" % os.getpid()
+        self.p = None
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- CPU restatement arm
+def cpu_trajectory(sample, nthreads_hint, steps, warmup, dt, budget_s=None):
+    """Runs the oracle (oracle/: CPU restatement of the reference algorithm, test infrastructure) as the reference's CPU
+    path: P domains on P host threads (the reference's MPI decomposition), natural trajectory with vnl_check-driven
+    rebuilds.  Returns (atom_steps_per_s, info)."""
+    from oracle import oracle as ora
+    ora.build(perf=True)
+    cores = os.cpu_count() or 1
+    P = 1
+    while P * 2 <= min(cores, nthreads_hint or cores, 64):
+        P *= 2
+    w = ora.World.from_system(sample, P=P, perf=True)
+    w.relocate(); w.set_halo()
+    rc = w.link_cell_pairs(P)
+    assert rc == 0, "oracle link_cell_pairs rc=%d" % rc
+    w.two_body(P)
+    wt = sample.weight_by_type
+    rebuilds = 0
+
+    def one_step():
+        nonlocal rebuilds
+        w.vv(1, dt, wt)
+        upd, _ = w.vnl_check()
+        if upd:
+            w.relocate(); w.set_halo()
+            assert w.link_cell_pairs(P) == 0
+            rebuilds += 1
+        else:
+            assert w.refresh_halo() == 0
+        w.two_body(P)
+        w.vv(2, dt, wt)
+
+    for _ in range(warmup):
+        one_step()
+    rebuilds = 0
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one_step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    t = time.perf_counter() - t0
+    return sample.megatm * done / t, dict(cores=P, steps=done, seconds=t, rebuilds=rebuilds, atoms=sample.megatm)
+
+
+def sample_system(workload):
+    import _pkg
+    _pkg.load()
+    from dl_poly_b200 import systems
+    if workload in ("ionic", "table"):
+        return systems.nacl(25, seed=1005, tabfile=(workload == "table")), "125,000-ion box of the same melt (same density, potentials, cutoffs)"
+    if workload == "lj":
+        return systems.argon(40, seed=1005), "256,000-atom box of the same fluid"
+    return systems.by_name(workload, temperature={"c1": 85.0, "c2": 1200.0, "c3": 300.0}[workload]), "the full configuration"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample, what = sample_system(args.workload)
+    v, info = cpu_trajectory(sample, None, args.steps, min(args.warmup, 3), args.dt, budget_s=150.0)
+    dims = DIMS[args.gpus]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps"],
+        "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * info["seconds"] / info["steps"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CPU path of " + args.workload + " (bounded sample)", "sample": what,
+                   "domains_per_gpu_run": list(dims)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                         "sample": "%s; %d MD steps on %d host threads (one reference domain per thread), %d rebuilds; "
+                                   "oracle/dlp_oracle.cpp is a restatement of the reference algorithm, not the reference "
+                                   "binary (the reference is Fortran; no Fortran compiler in this image)"
+                                   % (what, info["steps"], info["cores"], info["rebuilds"])},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import _pkg
+    _pkg.load()
+    from dl_poly_b200 import dd, lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torch.distributed.run with --nproc-per-node %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU: the short-range path has no CPU fallback")
+    torch.cuda.set_device(local)
+    transport = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        transport = dd.TorchTransport(torch.device("cuda", local))
+    dims = DIMS[world]
+    sysm = make_system(args.workload, dims, args.cells_per_gpu)
+    dom = dd.Domain(sysm, device=local, transport=transport)
+    sr = dom.sr
+    if args.force_mode is not None:
+        sr.set_force_mode(args.force_mode)
+    dt = args.dt
+    fp64_peak = sr.fp64_peak(0.3)               # DFMA micro-benchmark on this GPU, TFLOP/s
+    # first build + forces (untimed)
+    dom.rebuild()
+    dom.forces()
+    for _ in range(args.warmup):
+        dom.step(dt)
+    dom.rebuilds = 0
+    stream = dom.stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if transport is not None:
+        transport.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = sr.launch_count()
+    pair_ms, list_ms, force_ms, nlist = 0.0, 0.0, 0.0, 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        r0 = dom.rebuilds
+        out = dom.step(dt)
+        t = sr.last_timings()
+        pair_ms += t["pair_kernel_ms"]; force_ms += t["force_ms"]
+        if dom.rebuilds != r0:
+            list_ms += t["list_ms"]; nlist += 1
+    ev1.record(stream)
+    if transport is not None:
+        transport.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1)
+    launches = sr.launch_count() - l0
+    natms, nlast = sr.dev_counts()
+    pairs = sr.dev_list_pairs()
+    if transport is not None:
+        ms = transport.allreduce_max(ms)
+        tot = transport.allreduce_sum([natms, launches, pairs, pair_ms, dom.rebuilds, list_ms, force_ms])
+        natoms_total, launches, pairs = int(round(tot[0])), int(round(tot[1])), tot[2]
+        pair_ms_avg = tot[3] / world / args.steps
+        list_ms_tot, force_ms_tot = tot[5] / world, tot[6] / world
+    else:
+        natoms_total = natms
+        pair_ms_avg = pair_ms / args.steps
+        list_ms_tot, force_ms_tot = list_ms, force_ms
+    value = natoms_total * args.steps / (ms * 1e-3)
+    n_l = pairs / natoms_total                              # listed half pairs per atom, measured from the list
+    flop_as = flop_per_atom_step(sysm, n_l)
+    byte_as = bytes_per_atom_step(sysm, n_l)
+    atoms_per_launch = natoms_total / world
+    ach_tf = flop_as * atoms_per_launch / (pair_ms_avg * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach_gbs = byte_as * atoms_per_launch / (pair_ms_avg * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                "traffic": traffic, "kernel": "k_pair_forces (two_body_forces pair loop)",
+                "kernel_ms_avg": pair_ms_avg, "flop_per_atom_step": flop_as, "listed_pairs_per_atom": n_l,
+                "peak_source": "DFMA micro-benchmark run in this process (dlpgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                "whole_step": {"achieved": flop_as * value / world / 1e12, "frac": flop_as * value / world / 1e12 / fp64_peak},
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "bytes_per_atom_step": byte_as,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}
+
+    # ---- end-to-end through the drop-in C ABI with HOST buffers (what the ISO_C_BINDING shim calls)
+    e2e = run_e2e(args, torch, dom, transport, world, natoms_total, max(1, args.steps // max(dom.rebuilds, 1)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample, what = sample_system(args.workload)
+        v, info = cpu_trajectory(sample, None, 40, 2, dt, budget_s=25.0)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
+               "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread; restatement "
+                         "of the reference algorithm (oracle/), not the reference binary" % (what, info["steps"], info["rebuilds"], info["cores"])}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, sysm, world), "domains": list(dims), "atoms": natoms_total,
+                       "rcut": sysm.rcut, "padding": sysm.padding, "timestep_ps": dt,
+                       "rebuilds_in_timed_region": dom.rebuilds if transport is None else int(round(tot[4] / world)),
+                       "list_build_ms_total": list_ms_tot, "force_call_ms_total": force_ms_tot,
+                       "l2": "inputs larger than L2: positions+list of one step are %.0f MB per GPU" % (byte_as * atoms_per_launch / 1e6),
+                       "force_mode": "half list + fp64 RED (Newton 3)" if sr.force_mode == 1 else "full list, no atomics"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    dom.close()
+    if transport is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
+    """The same metric through dlpgpu_link_cell_pairs / dlpgpu_two_body_forces with host (pinned) corePart buffers:
+    every step uploads parts(1:nlast) (64 B per atom) and reads the forces of parts(1:natms) back; every `interval`-th
+    step (the rebuild frequency observed in the device-resident run) also rebuilds the list from host arrays."""
+    from dl_poly_b200 import engine
+    from dl_poly_b200.lib import COREPART
+    sr = dom.sr
+    natms, nlast = sr.dev_counts()
+    ints = sr.dev_get_ints(nlast)
+    parts_now = sr.dev_get_parts(nlast)
+    pin = torch.empty(nlast * 64, dtype=torch.uint8).pin_memory()
+    parts = pin.numpy().view(COREPART)
+    parts[:] = parts_now
+    sysm = dom.sys
+    sr2 = engine.ShortRange(dom.device.index, sr.dd)
+    sr2.set_cell(sysm.cell, sysm.imcon)
+    sr2.set_cutoffs(sysm.rcut, sysm.padding, sysm.pdplnc)
+    sr2.set_forcefield(sysm.ff)
+    if args.force_mode is not None:
+        sr2.set_force_mode(args.force_mode)
+    excl = None
+    if sysm.excl is not None:
+        excl = np.ascontiguousarray(np.asarray(sysm.excl)[ints["ltg"][:natms] - 1])
+    kw = dict(lbook=sysm.lbook, megfrz=sysm.megfrz, list_excl=excl, max_list=sysm.max_list, want_list=False)
+    sr2.link_cell_pairs(natms, nlast, parts, ints["ltype"], ints["ltg"], ints["lfrzn"], **kw)
+    sr2.two_body_forces(natms, nlast, parts)
+    steps = max(10, min(args.steps, 50))
+    if transport is not None:
+        transport.barrier()
+    torch.cuda.synchronize()
+    nb = 0
+    t0 = time.perf_counter()
+    for s in range(steps):
+        if s % interval == 0:
+            sr2.link_cell_pairs(natms, nlast, parts, ints["ltype"], ints["ltg"], ints["lfrzn"], **kw)
+            nb += 1
+        sr2.two_body_forces(natms, nlast, parts)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    if transport is not None:
+        t = transport.allreduce_max(t)
+    h2d = nlast * 64 + (nb / steps) * (nlast * 64 + 3 * 4 * nlast)
+    d2h = natms * 24 + 16 * 8
+    sr2.close()
+    return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+            "steps": steps, "rebuild_every": interval, "ms_per_step": 1e3 * t / steps,
+            "api": "dlpgpu_link_cell_pairs + dlpgpu_two_body_forces (include/dlpgpu.h) on host corePart arrays"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ionic", choices=["ionic", "table", "lj", "c1", "c2", "c3"])
+    ap.add_argument("--cells-per-gpu", type=int, default=None, help="lattice repeats per domain edge (ionic: 50 -> 1,000,000 ions)")
+    ap.add_argument("--dt", type=float, default=0.001, help="timestep in ps")
+    ap.add_argument("--force-mode", type=int, default=None, choices=[0, 1])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.gpus not in DIMS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

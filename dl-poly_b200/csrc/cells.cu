@@ -566,6 +566,33 @@ int dlp_vnl_set_check(dlpgpu_ctx* ctx) {
   return 0;
 }
 
+namespace {
+__global__ void k_count_pairs(int natms, int pitch, const unsigned* __restrict__ nbr, const int* __restrict__ nnbr,
+                              unsigned long long* __restrict__ out /*[2]: local partners, halo partners*/) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= natms) return;
+  int n = nnbr[t], nl = 0, nh = 0;
+  for (int k = lane; k < n; k += 32) { if (nbr[(size_t)t * pitch + k] & DLP_F_HALO) ++nh; else ++nl; }
+  for (int d = 16; d > 0; d >>= 1) { nl += __shfl_xor_sync(DLP_FULL, nl, d); nh += __shfl_xor_sync(DLP_FULL, nh, d); }
+  if (lane == 0) { atomicAdd(&out[0], (unsigned long long)nl); atomicAdd(&out[1], (unsigned long long)nh); }
+}
+}  // namespace
+
+// number of pairs the reference's half list holds for this domain (local-local once + local-halo), from the device list
+extern "C" int dlpgpu_dev_list_pairs(dlpgpu_ctx* ctx, long long* pairs) {
+  if (!ctx || !pairs) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->list_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "list_pairs: no list");
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemsetAsync(ctx->tol_bits.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (ctx->list_natms > 0)
+    LAUNCH(ctx, k_count_pairs, cdiv(ctx->list_natms, 8), 256, 0, ctx->list_natms, ctx->pitch, ctx->nbr.p, ctx->nnbr.p, ctx->tol_bits.p);
+  CK(cudaMemcpyAsync(h, ctx->tol_bits.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *pairs = (long long)(ctx->force_mode == 1 ? h[0] : h[0] / 2) + (long long)h[1];
+  return 0;
+}
+
 extern "C" int dlpgpu_dev_link_cell_pairs(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));

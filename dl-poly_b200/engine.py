@@ -31,6 +31,7 @@ class ShortRange:
         self.device = device
         self.set_domain(dd)
         self.max_list = 0
+        self.force_mode = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -84,6 +85,7 @@ class ShortRange:
 
     def set_force_mode(self, mode):
         self._ck(self.L.dlpgpu_set_force_mode(self.h, int(mode)))
+        self.force_mode = int(mode)
 
     # ---- drop-in entry points (host buffers, Fortran index conventions) ------------------------------------------
     def link_cell_pairs(self, natms, nlast, parts, ltype, ltg, lfrzn=None, lbook=False, megfrz=0, list_excl=None,
@@ -236,6 +238,11 @@ class ShortRange:
         out = np.zeros(16)
         self._ck(self.L.dlpgpu_dev_two_body_forces(self.h, int(bool(zero_forces)), ptr(out)))
         return out
+
+    def dev_list_pairs(self):
+        n = C.c_longlong(0)
+        self._ck(self.L.dlpgpu_dev_list_pairs(self.h, C.byref(n)))
+        return int(n.value)
 
     # ---- read-back -------------------------------------------------------------------------------------------------
     def dev_get_parts(self, n=None):
