@@ -218,12 +218,13 @@ __global__ void k_cell_order(int ncells_p1, const int* __restrict__ lct_start, c
 
 __global__ void k_sorted_static(int nlast, int natms, const int* __restrict__ at_list, const int* __restrict__ ltype,
                                 const int* __restrict__ ltg, const int* __restrict__ lfrzn, int* __restrict__ type_s,
-                                int* __restrict__ gid_s, int* __restrict__ frz_s, int* __restrict__ is_local) {
+                                int* __restrict__ gid_s, int* __restrict__ frz_s, int2* __restrict__ info_s, int* __restrict__ is_local) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nlast) return;
   if (s == nlast) { is_local[s] = 0; return; }   // zero pad for the scan's total slot
   int i = at_list[s];
   type_s[s] = ltype[i]; gid_s[s] = ltg[i]; frz_s[s] = lfrzn[i];
+  info_s[s] = make_int2(ltg[i], (ltype[i] & 0xffff) | (lfrzn[i] > 0 ? (1 << 16) : 0) | (i >= natms ? (1 << 17) : 0));
   is_local[s] = (i < natms) ? 1 : 0;
 }
 __global__ void k_loc_slot(int nlast, const int* __restrict__ is_local, const int* __restrict__ rank, int* __restrict__ loc_slot) {
@@ -382,7 +383,8 @@ template <bool HALF>
 __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid,
                            const int* __restrict__ loc_slot, const int* __restrict__ at_list, const int* __restrict__ lct_start,
                            const int* __restrict__ cell_s, const double4* __restrict__ posq_s, const int* __restrict__ gid_s,
-                           const int* __restrict__ frz_s, const int* __restrict__ xb, const int* __restrict__ excl,
+                           const int* __restrict__ frz_s, const int* __restrict__ type_s, const int* __restrict__ pair_k, int ntypes,
+                           const int* __restrict__ xb, const int* __restrict__ excl,
                            unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
                            int* __restrict__ status) {
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -395,6 +397,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
   const double4 pi = posq_s[ii];
   const int gid_i = gid_s[ii];
   const int frz_i = (megfrz > 1) ? frz_s[ii] : 0;
+  const int type_i = type_s[ii];
   const int* ex = lbook ? excl + (size_t)(excl_by_gid ? (gid_i - 1) : i) * (max_exclude + 1) : nullptr;
   const int nex = lbook ? ex[0] : 0;
   unsigned* row = nbr + (size_t)t * pitch;
@@ -432,7 +435,8 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
               if (frz_i > 0 && frz_s[jj] > 0) keep = false;   // frozen-frozen pairs never reach the force loops (:1198-1225)
             }
             if (keep) {
-              entry = (unsigned)jj | (halo ? DLP_F_HALO : 0u) | ((halo && gid_i < gj) ? DLP_F_ECNT : 0u);
+              const int kc = pair_k ? pair_k[(type_i - 1) * ntypes + (type_s[jj] - 1)] + 1 : 0;
+              entry = (unsigned)jj | ((unsigned)kc << DLP_K_SHIFT) | (halo ? DLP_F_HALO : 0u) | ((halo && gid_i < gj) ? DLP_F_ECNT : 0u);
               if (nex > 0 && excl_match(gj, nex, ex)) isx = true; else ok = true;
             }
           }
@@ -452,6 +456,154 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
     }
   }
   if (lane == 0) { nnbr[t] = cnt; nxnbr[t] = xcnt; }
+}
+
+
+// ---------------------------------------------------------------- half list, one warp per link cell
+// The reference visits, for every local atom, the positive semi-ball of cells (:877-1027) and -- for border cells -- the
+// halo cells of the negative semi-ball (:1033-1184).  All atoms of one link cell share those candidate cells, so one warp
+// takes a cell: the candidate slots (contiguous x-runs of the cell-sorted arrays, flattened through a small per-warp run
+// table) are loaded ONCE per cell, 32 at a time, and tested against each atom of the cell, whose coordinates sit in shared
+// memory and are read as broadcasts.  Accepted partners are appended with ballot/popc prefix compaction.  Entry format:
+// see DLP_J_MASK.  Row order is irrelevant to the force kernel (sums are order-tolerant); membership is exact.
+#define LC_WARPS 8
+#define LC_MAXRUN 96
+struct LCRow { int dy, dz, b; };
+
+__global__ void __launch_bounds__(LC_WARPS * 32)
+k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid, int nrows,
+            const LCRow* __restrict__ rows, const int* __restrict__ at_list, const int* __restrict__ lct_start,
+            const int* __restrict__ cell_s, const int* __restrict__ slot_rank, const double4* __restrict__ posq_s,
+            const int2* __restrict__ info_s, const int* __restrict__ pair_k, int ntypes, const int* __restrict__ excl,
+            unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
+            int* __restrict__ status, unsigned long long* __restrict__ cnt64) {
+  __shared__ double4 s_pi[LC_WARPS][32];
+  __shared__ int2 s_info[LC_WARPS][32];
+  __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
+  __shared__ int s_pre[LC_WARPS][LC_MAXRUN + 1];   // candidates before run r
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncell_dom = g.nlx * g.nly * g.nlz;
+  const int cd = blockIdx.x * LC_WARPS + wid;
+  if (cd >= ncell_dom) return;
+  const int nlp = g.nlp;
+  const int cx = cd % g.nlx + nlp, cy = (cd / g.nlx) % g.nly + nlp, cz = cd / (g.nlx * g.nly) + nlp;
+  const int ic = 1 + cx + g.sx * (cy + g.sy * cz);
+  const int s_own0 = lct_start[ic], s_own1 = lct_start[ic + 1];
+  if (s_own1 == s_own0) return;
+  const int lo_x = nlp - 1, hi_x = g.nlx + nlp, lo_y = nlp - 1, hi_y = g.nly + nlp, lo_z = nlp - 1, hi_z = g.nlz + nlp;
+  const bool border = (cx - lo_x <= nlp) || (hi_x - cx <= nlp) || (cy - lo_y <= nlp) || (hi_y - cy <= nlp) || (cz - lo_z <= nlp) || (hi_z - cz <= nlp);
+  // ---- run table: potential run p < nrows: positive row p; p >= nrows: negative row (p-nrows)/2, low / high x part
+  const int npot = border ? 3 * nrows : nrows;
+  for (int p0 = 0; p0 < LC_MAXRUN; p0 += 32) {
+    const int p = p0 + lane;
+    int start = 0, len = 0;
+    if (p < npot) {
+      int xa, xbb, jy, jz;
+      if (p < nrows) {
+        const LCRow r = rows[p];
+        jy = cy + r.dy; jz = cz + r.dz;
+        xa = (r.dy == 0 && r.dz == 0) ? cx : cx - r.b;
+        xbb = cx + r.b;
+      } else {
+        const LCRow r = rows[(p - nrows) >> 1];
+        const int side = (p - nrows) & 1;
+        jy = cy - r.dy; jz = cz - r.dz;
+        xa = cx - r.b;
+        xbb = (r.dy == 0 && r.dz == 0) ? cx - 1 : cx + r.b;
+        const bool row_halo = (jy <= lo_y) || (jy >= hi_y) || (jz <= lo_z) || (jz >= hi_z);
+        if (row_halo) { if (side == 1) xbb = xa - 1; }            // whole range is halo: side 0 takes it
+        else if (side == 0) xbb = min(xbb, lo_x);                // low-x halo cells
+        else xa = max(xa, hi_x);                                 // high-x halo cells
+      }
+      if (xa <= xbb) {
+        const int c0 = 1 + xa + g.sx * (jy + g.sy * jz), c1 = 1 + xbb + g.sx * (jy + g.sy * jz);
+        start = lct_start[c0];
+        len = lct_start[c1 + 1] - start;
+      }
+    }
+    int inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(DLP_FULL, inc, d); if (lane >= d) inc += v; }
+    const int carry = (p0 == 0) ? 0 : s_pre[wid][p0];
+    s_run0[wid][p] = start;
+    s_pre[wid][p + 1] = carry + inc;
+    if (p0 == 0 && lane == 0) s_pre[wid][0] = 0;
+    __syncwarp();
+  }
+  const int total = s_pre[wid][LC_MAXRUN];
+  long long written = 0;
+  for (int a0 = s_own0; a0 < s_own1; a0 += 32) {   // atoms of the cell, 32 at a time (one pass unless the cell is crowded)
+    const int na = min(32, s_own1 - a0);
+    int cnt = 0, xcnt = 0;
+    int nex_l = 0;
+    const int* ex_l = nullptr;
+    __syncwarp();
+    if (lane < na) {
+      s_pi[wid][lane] = posq_s[a0 + lane];
+      const int2 inf = info_s[a0 + lane];
+      s_info[wid][lane] = inf;
+      if (lbook) {
+        ex_l = excl + (size_t)(excl_by_gid ? (inf.x - 1) : at_list[a0 + lane]) * (max_exclude + 1);
+        nex_l = ex_l[0];
+      }
+    }
+    __syncwarp();
+    const int t0 = slot_rank[a0];
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      const bool valid = c < total;
+      int jj = 0;
+      if (valid) {   // largest run r with pre[r] <= c
+        int lo = 0, hi = LC_MAXRUN - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[wid][mid] <= c) lo = mid; else hi = mid - 1; }
+        jj = s_run0[wid][lo] + (c - s_pre[wid][lo]);
+      }
+      double4 pj = make_double4(0, 0, 0, 0);
+      int2 infj = make_int2(0, 0);
+      int cj = 0;
+      if (valid) { pj = posq_s[jj]; infj = info_s[jj]; if (g.nir_r2 > 0) cj = cell_s[jj]; }
+      const bool halo_j = (infj.y >> 17) & 1;
+      const bool nir = valid && g.nir_r2 > 0 && nir_of(g, cj, cx, cy, cz);
+      for (int a = 0; a < na; ++a) {
+        const double4 pi = s_pi[wid][a];
+        const int2 infi = s_info[wid][a];
+        const int ii = a0 + a;
+        bool acc = valid && (jj > ii || jj < s_own0) && (nir || pair_rsq(pj, pi.x, pi.y, pi.z) <= g.rcsq);
+        if (acc && megfrz > 1 && ((infi.y >> 16) & 1) && ((infj.y >> 16) & 1)) acc = false;   // frozen-frozen (:1198-1225)
+        bool isx = false;
+        if (lbook) {
+          const int nex = __shfl_sync(DLP_FULL, nex_l, a);
+          const unsigned long long exq = __shfl_sync(DLP_FULL, (unsigned long long)(size_t)ex_l, a);
+          if (acc && nex > 0 && excl_match(infj.x, nex, reinterpret_cast<const int*>((size_t)exq))) { isx = true; acc = false; }
+        }
+        const unsigned m = __ballot_sync(DLP_FULL, acc);
+        const int ca = __shfl_sync(DLP_FULL, cnt, a);
+        if (acc) {
+          const int kc = pair_k ? pair_k[((infi.y & 0xffff) - 1) * ntypes + ((infj.y & 0xffff) - 1)] + 1 : 0;
+          const unsigned entry = (unsigned)jj | ((unsigned)kc << DLP_K_SHIFT) | (halo_j ? DLP_F_HALO : 0u) |
+                                 ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
+          const int ll = ca + __popc(m & ((1u << lane) - 1));
+          if (ll < pitch) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
+          else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
+        }
+        if (lane == a) cnt += __popc(m);
+        if (lbook) {
+          const unsigned mx = __ballot_sync(DLP_FULL, isx);
+          const int cxa = __shfl_sync(DLP_FULL, xcnt, a);
+          if (isx) {
+            const unsigned entry = (unsigned)jj | (halo_j ? DLP_F_HALO : 0u) | ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
+            const int ll = cxa + __popc(mx & ((1u << lane) - 1));
+            if (ll < xpitch) xnbr[(size_t)(t0 + a) * xpitch + ll] = entry; else atomicOr(&status[0], 2);
+          }
+          if (lane == a) xcnt += __popc(mx);
+        }
+      }
+    }
+    if (lane < na) { nnbr[t0 + lane] = cnt; nxnbr[t0 + lane] = xcnt; written += cnt; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) written += __shfl_xor_sync(DLP_FULL, written, d);
+  if (lane == 0) atomicAdd(&cnt64[0], (unsigned long long)written);
 }
 
 __global__ void k_bg_copy(int n, const double4* __restrict__ posq, double* xbg, double* ybg, double* zbg) {
@@ -490,6 +642,8 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   CK(ctx->which_cell.ensure(nlast + 1, s)); CK(ctx->at_list.ensure(nlast + 1, s)); CK(ctx->at_tmp.ensure(nlast + 1, s));
   CK(ctx->cell_s.ensure(nlast + 1, s)); CK(ctx->posq_s.ensure(nlast + 1, s));
   CK(ctx->type_s.ensure(nlast + 1, s)); CK(ctx->gid_s.ensure(nlast + 1, s)); CK(ctx->frz_s.ensure(nlast + 1, s));
+  CK(ctx->info_s.ensure(nlast + 1, s));
+  if (nlast >= DLP_MAX_SLOTS) return dlp_fail(ctx, DLPGPU_ERR_ARG, "more than %d resident atoms (local + halo) per GPU are not supported", DLP_MAX_SLOTS);
   CK(ctx->lct_count.ensure(nc, s)); CK(ctx->lct_start.ensure(nc, s)); CK(ctx->lct_fill.ensure(nc, s));
   CK(ctx->loc_slot.ensure(natms + 1, s));
   CK(ctx->flag.ensure((size_t)nlast + 2, s)); CK(ctx->scan_out.ensure((size_t)nlast + 2, s));
@@ -508,7 +662,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
            ctx->at_list.p, ctx->cell_s.p);
   }
   LAUNCH(ctx, k_sorted_static, cdiv(nlast + 1, 256), 256, 0, nlast, natms, ctx->at_list.p, ctx->ltype.p, ctx->ltg.p, ctx->lfrzn.p,
-         ctx->type_s.p, ctx->gid_s.p, ctx->frz_s.p, ctx->flag.p);
+         ctx->type_s.p, ctx->gid_s.p, ctx->frz_s.p, ctx->info_s.p, ctx->flag.p);
   CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nlast, nullptr));
   if (nlast > 0) {
     LAUNCH(ctx, k_loc_slot, cdiv(nlast, 256), 256, 0, nlast, ctx->flag.p, ctx->scan_out.p, ctx->loc_slot.p);
@@ -527,12 +681,34 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
       CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
       LAUNCH(ctx, k_list_dev<false>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
              ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
-             ctx->gid_s.p, ctx->frz_s.p, ctx->st_xb.p, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+             ctx->gid_s.p, ctx->frz_s.p, ctx->type_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->st_xb.p, ctx->excl.p,
+             ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
     } else {
       CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
-      LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
-             ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
-             ctx->gid_s.p, ctx->frz_s.p, ctx->st_xb.p, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+      // semi-ball rows (dy,dz) with their half x-extent, for the warp-per-cell kernel
+      std::vector<LCRow> hrows;
+      const int nlp = g.nlp, W = 2 * nlp + 1;
+      for (int dz = 0; dz <= nlp; ++dz)
+        for (int dy = -nlp; dy <= nlp; ++dy) {
+          if (dz == 0 && dy < 0) continue;
+          int b = ctx->h_xb[(size_t)(dz + nlp) * W + (dy + nlp)];
+          if (b >= 0) hrows.push_back(LCRow{dy, dz, b});
+        }
+      CK(cudaMemsetAsync(ctx->cnt64.p, 0, 4 * sizeof(unsigned long long), s));
+      if (3 * hrows.size() <= LC_MAXRUN) {
+        CK(ctx->st_rows.ensure(hrows.size() * 3 + 3, s));
+        CK(cudaMemcpyAsync(ctx->st_rows.p, hrows.data(), hrows.size() * sizeof(LCRow), cudaMemcpyHostToDevice, s));
+        const int ncd = g.nlx * g.nly * g.nlz;
+        LAUNCH(ctx, k_list_cell, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook,
+               ctx->max_exclude, ctx->excl_by_gid, (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p,
+               ctx->lct_start.p, ctx->cell_s.p, ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr,
+               ctx->ntypes, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p);
+      } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
+        LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
+               ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
+               ctx->gid_s.p, ctx->frz_s.p, ctx->type_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->st_xb.p, ctx->excl.p,
+               ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+      }
     }
     cudaEventRecord(ctx->ev[3], s);
     if (want_ref_list) {
@@ -545,8 +721,11 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   }
   cudaEventRecord(ctx->ev[1], s);
   int st[8];
+  unsigned long long c64[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(st, ctx->status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c64, ctx->cnt64.p, sizeof c64, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  ctx->list_entries = c64[0] ? (long long)c64[0] : (long long)natms * (ctx->max_list / 4);   // row-length hint for the force kernel
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->t_list = ms;
   if (natms > 0) { cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->t_full = ms; }

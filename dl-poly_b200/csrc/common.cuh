@@ -15,8 +15,13 @@
 #define DLP_WARP 32
 #define DLP_FULL 0xffffffffu
 
-// list entry flags of the device-internal full list (sorted slot index in the low 30 bits)
-#define DLP_J_MASK 0x3fffffffu
+// entries of the device-internal lists: sorted slot of the partner in the low 24 bits, then 6 bits "vdW potential of this
+// type pair + 1" (0: no vdW interaction, vdw.F90:1875-1892 resolved at build time), then two flags
+#define DLP_J_MASK 0x00ffffffu
+#define DLP_K_SHIFT 24
+#define DLP_K_MASK 0x3fu
+#define DLP_MAX_SLOTS (1 << 24)
+#define DLP_MAX_KCODE 62
 #define DLP_F_HALO 0x40000000u   // partner is a halo atom (one-sided pair)
 #define DLP_F_ECNT 0x80000000u   // halo partner whose pair energy is counted here (idi < ltg(jatm))
 
@@ -84,7 +89,7 @@ struct dlpgpu_ctx {
   int imcon = 1;
   double rcut = 0, padding = 0, rx = 0, pdplnc = 50.0;
   double ecw[3] = {0, 0, 0};
-  int force_mode = 0;
+  int force_mode = 1;     // 1: half list + fp64 RED (Newton 3), 0: full list without atomics
 
   // vdw
   bool vdw_on = false, vdw_fshift = false, vdw_direct = false;
@@ -99,6 +104,13 @@ struct dlpgpu_ctx {
   double alpha = 0, scaling = 0, ew_rdr = 0, thr_coul = 0;
   int ew_n = 0;
   DBuf<double2> ew_tab;    // [ew_n+1] {erfc_deriv, erfc}
+  // quadratic-form tables of the pair kernel: [max_vdw][max_grid+1] then [ew_n+1] entries {g_f, g_e, h_f, h_e}
+  DBuf<double> tab4;
+  size_t tab4_entries = 0;
+  int ew_off = 0;
+  bool tab4_valid = false;
+  std::vector<double> h_vdw_f, h_vdw_e, h_ew_d, h_ew_e;   // host copies the tab4 build reads
+  int tpr_override = 0;
 
   // sites (native mode)
   int nsites = 0;
@@ -130,6 +142,8 @@ struct dlpgpu_ctx {
   DBuf<int> flag, scan_out, scan_tmp;
   DBuf<double4> posq_s;    // sorted copy, refreshed every force call
   DBuf<int> type_s, gid_s, frz_s;
+  DBuf<int2> info_s;       // per sorted slot {global id, type | frozen<<16 | halo<<17}
+  DBuf<int> st_rows;       // semi-ball rows {dy,dz,half x-extent} of the warp-per-cell list kernel
   DBuf<int> st_nix, st_niy, st_niz, st_nir;   // semi-ball stencil in reference order
   DBuf<int> st_xb;         // [(2nlp+1)^2] half x-extent per (dy,dz) row of the full ball, -1 = row absent
   std::vector<int> h_nix, h_niy, h_niz, h_nir, h_xb;
@@ -146,7 +160,9 @@ struct dlpgpu_ctx {
   DBuf<int> nhnbr;
   DBuf<double> xfer;       // internal exchange buffer of the serial halo / refresh
   DBuf<int> hole_pos;
-  DBuf<int> status;        // [4] device status words: 0 overflow flag, 1 ibig, 2 lost atoms, 3 spare
+  DBuf<int> status;        // [8] device status words: 0 overflow flag, 1 ibig, 2 lost atoms, 3 spare
+  DBuf<unsigned long long> cnt64;   // [4] 0: entries of the device list
+  long long list_entries = 0;
   // halo replay
   HaloStage stage[6];
   bool halo_valid = false;
@@ -191,6 +207,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig);
 int dlp_gather_sorted(dlpgpu_ctx* ctx);
 // forces.cu
 int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]);
+int dlp_build_tab4(dlpgpu_ctx* ctx);
 // halo.cu
 int dlp_vnl_set_check(dlpgpu_ctx* ctx);
 int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol);

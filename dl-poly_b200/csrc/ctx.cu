@@ -141,7 +141,7 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
-      ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
+      ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
   *out = ctx;
   return 0;
 }
@@ -162,6 +162,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   for (auto* b : db) b->release();
   ctx->vdw_tab.release(); ctx->ew_tab.release(); ctx->posq.release(); ctx->posq_s.release();
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
+  ctx->tab4.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
@@ -206,7 +207,9 @@ int dlpgpu_set_vdw(dlpgpu_ctx* ctx, int ntypes, const int* vdw_list, int max_vdw
                    const double* param, const double* afs, const double* bfs) {
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  ctx->tab4_valid = false; ctx->list_valid = false;   // list entries carry the potential index of their type pair
   if (n_vdw <= 0) { ctx->vdw_on = false; ctx->ntypes = ntypes; return 0; }
+  if (max_vdw > DLP_MAX_KCODE) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: more than %d vdW potentials are not supported", DLP_MAX_KCODE);
   if (ntypes < 1 || !vdw_list || !ltp || max_vdw < n_vdw) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: bad arguments");
   if (!direct && (!tab_potential || !tab_force || max_grid < 8)) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: tables missing");
   if (direct && !param) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: direct evaluation needs param");
@@ -246,6 +249,8 @@ int dlpgpu_set_vdw(dlpgpu_ctx* ctx, int ntypes, const int* vdw_list, int max_vdw
     size_t n = (size_t)max_vdw * (max_grid + 1);
     std::vector<double2> t(n);
     for (size_t i = 0; i < n; ++i) t[i] = make_double2(tab_force[i], tab_potential[i]);
+    ctx->h_vdw_f.assign(tab_force, tab_force + n);
+    ctx->h_vdw_e.assign(tab_potential, tab_potential + n);
     CK(ctx->vdw_tab.ensure(n, ctx->stream));
     CK(cudaMemcpyAsync(ctx->vdw_tab.p, t.data(), n * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -259,11 +264,14 @@ int dlpgpu_set_ewald(dlpgpu_ctx* ctx, int active, double alpha, double scaling, 
                      const double* erfc_deriv_tab, double recip_spacing) {
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  ctx->tab4_valid = false;
   if (!active) { ctx->ew_on = false; return 0; }
   if (!erfc_tab || !erfc_deriv_tab || nsamples < 10) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_ewald: tables missing");
   ctx->alpha = alpha; ctx->scaling = scaling; ctx->ew_n = nsamples; ctx->ew_rdr = recip_spacing;
   std::vector<double2> t((size_t)nsamples + 1);
   for (int i = 0; i <= nsamples; ++i) t[i] = make_double2(erfc_deriv_tab[i], erfc_tab[i]);
+  ctx->h_ew_d.assign(erfc_deriv_tab, erfc_deriv_tab + nsamples + 1);
+  ctx->h_ew_e.assign(erfc_tab, erfc_tab + nsamples + 1);
   CK(ctx->ew_tab.ensure(t.size(), ctx->stream));
   CK(cudaMemcpyAsync(ctx->ew_tab.p, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -374,6 +382,7 @@ __global__ void k_zero3(int n, double* a, double* b, double* c) {
 }  // namespace
 
 static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
+  if (n <= 0) return 0;
   CK(ctx->parts_dev.ensure(n, ctx->stream));
   CK(cudaMemcpyAsync(ctx->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, ctx->parts_dev.p, n, ctx->posq.p);

@@ -15,9 +15,9 @@
 namespace {
 
 struct FParams {
-  int natms, pitch, xpitch, ntypes, max_grid, max_vdw, ew_n;
-  int vdw_on, vdw_direct, vdw_fshift, ew_on, half, zero_forces, lbook;
-  double rvdw, r_rvdw, vdw_rdr, rcut, ew_rdr, alpha, scaling;
+  int natms, pitch, xpitch, max_grid, max_vdw, ew_n, tstride, ew_off;
+  int vdw_on, vdw_direct, vdw_fshift, ew_on, half, zero_forces, lbook, same_grid;
+  double rvdw, r_rvdw, vdw_rdr, rcut, ew_rdr, alpha, scaling, thr_vdw, thr_coul;
 };
 
 constexpr double ZERO_PLUS = 2.2250738585072014e-308;   // Tiny(1.0_wp), constants.F90:189
@@ -67,143 +67,162 @@ __device__ __forceinline__ void pot_direct(int key, const double* __restrict__ p
   }
 }
 
+// numerics.F90:280-282 / vdw.F90:1918-1921 as written (used for the l == 0 corner where g(0) is scaled by r)
 __device__ __forceinline__ double interp3(double g0, double g1, double g2, double ppp) {
-  // numerics.F90:280-282 / vdw.F90:1918-1921
   double t1 = g0 + (g1 - g0) * ppp;
   double t2 = g1 + (g2 - g1) * (ppp - 1.0);
   return t1 + (t2 - t1) * ppp * 0.5;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(256) k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
-                                                     const double4* __restrict__ posq_s, const int* __restrict__ type_s,
-                                                     const unsigned* __restrict__ nbr, const int* __restrict__ nnbr,
-                                                     const unsigned* __restrict__ xnbr, const int* __restrict__ nxnbr,
-                                                     const int* __restrict__ pair_k_g, const int* __restrict__ ltp,
-                                                     const double2* __restrict__ vdw_tab_g, const double* __restrict__ vdw_par,
-                                                     const double2* __restrict__ ew_tab_g, double* __restrict__ fx,
-                                                     double* __restrict__ fy, double* __restrict__ fz, double* __restrict__ fsx,
-                                                     double* __restrict__ fsy, double* __restrict__ fsz, double* __restrict__ partial) {
+__device__ __forceinline__ double4 ld_posq(const double4* p) {   // one 256-bit read-only load (LDG.E.ENL2.256)
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+// The reference's 3-point interpolation t1 + (t2 - t1) p/2 (vdw.F90:1914-1921, numerics.F90:280-282) is the quadratic
+// g0 + p (d0 - h + p h) with d0 = g1 - g0 and h = (g2 - 2 g1 + g0)/2.  Table entries hold {g_force, g_energy, h_force,
+// h_energy} (32 B), so one pair reads 48 bytes per table: entry l whole and the g-half of entry l+1.
+struct Tab4 { double2 lo, hi; };   // lo = {g_force, g_energy}, hi = {h_force, h_energy}
+
+template <int TPR, bool SMEM>
+__global__ void __launch_bounds__(512, 1)
+k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict__ at_list, const double4* __restrict__ posq_s,
+              const unsigned* __restrict__ nbr, const int* __restrict__ nnbr, const unsigned* __restrict__ xnbr,
+              const int* __restrict__ nxnbr, const int* __restrict__ ltp, const Tab4* __restrict__ tab4_g,
+              const double2* __restrict__ vdw_raw, const double* __restrict__ vdw_par, const double2* __restrict__ ew_raw,
+              double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz, double* __restrict__ fsx,
+              double* __restrict__ fsy, double* __restrict__ fsz, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const double2* vdw_tab = vdw_tab_g;
-  const double2* ew_tab = ew_tab_g;
-  const int* pair_k = pair_k_g;
+  const Tab4* tab4 = tab4_g;
   if (SMEM) {
     double2* sv = reinterpret_cast<double2*>(smem_raw);
-    size_t nv = P.vdw_on && !P.vdw_direct ? (size_t)P.max_vdw * (P.max_grid + 1) : 0;
-    size_t ne = P.ew_on ? (size_t)P.ew_n + 1 : 0;
-    double2* se = sv + nv;
-    int* sp = reinterpret_cast<int*>(se + ne);
-    for (size_t k = threadIdx.x; k < nv; k += blockDim.x) sv[k] = vdw_tab_g[k];
-    for (size_t k = threadIdx.x; k < ne; k += blockDim.x) se[k] = ew_tab_g[k];
-    for (int k = threadIdx.x; k < P.ntypes * P.ntypes; k += blockDim.x) sp[k] = P.vdw_on ? pair_k_g[k] : -1;
+    const double2* gv = reinterpret_cast<const double2*>(tab4_g);
+    const int n2 = 2 * (P.ew_off + (P.ew_on ? P.ew_n + 1 : 0));
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) sv[k] = gv[k];
     __syncthreads();
-    vdw_tab = sv; ew_tab = se; pair_k = sp;
+    tab4 = reinterpret_cast<const Tab4*>(smem_raw);
   }
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int tstride = P.max_grid + 1;
+  constexpr int RPB = 512 / TPR;              // rows per block pass
+  const int lg = threadIdx.x % TPR;           // lane within the row group
+  const int grp = threadIdx.x / TPR;
   double acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.0;
 
-  for (int t = gw; t < P.natms; t += nwarps) {
-    const int ii = loc_slot[t];
-    const double4 pi = posq_s[ii];
-    const int ai = type_s[ii] - 1;
+  for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
+    const int t = base + grp;
+    const bool live = t < P.natms;
+    int ii = 0, n = 0;
+    double4 pi = make_double4(0, 0, 0, 0);
+    if (live) { ii = loc_slot[t]; pi = posq_s[ii]; n = nnbr[t]; }
     const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
     const bool coul_i = P.ew_on && !(fabs(qi_s) < ZERO_PLUS);                 // :117
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
     const unsigned* row = nbr + (size_t)t * P.pitch;
-    const int n = nnbr[t];
-    for (int k = lane; k < n; k += 32) {
-      const unsigned e = row[k];
+    int k = lg;
+    unsigned e_nx = 0;
+    double4 pj_nx = pi;
+    if (k < n) { e_nx = row[k]; pj_nx = ld_posq(posq_s + (e_nx & DLP_J_MASK)); }
+    for (; k < n; k += TPR) {
+      const unsigned e = e_nx;
+      const double4 pj = pj_nx;
+      if (k + TPR < n) { e_nx = row[k + TPR]; pj_nx = ld_posq(posq_s + (e_nx & DLP_J_MASK)); }   // software prefetch
       const int j = (int)(e & DLP_J_MASK);
+      const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
       const bool halo = (e & DLP_F_HALO) != 0;
-      const double w = P.half ? (halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0) : (halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : 0.5);
-      const double4 pj = posq_s[j];
+      const double w = halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : (P.half ? 1.0 : 0.5);
       const double xxt = pi.x - pj.x, yyt = pi.y - pj.y, zzt = pi.z - pj.z;   // two_body.F90:348-350
-      const double rrr = sqrt(xxt * xxt + yyt * yyt + zzt * zzt);            // :351
-      double gtx = 0.0, gty = 0.0, gtz = 0.0;   // pair force on i (sum of providers), for the HALF-mode scatter
-      if (P.vdw_on) {
-        const int kp = pair_k[ai * P.ntypes + (type_s[j] - 1)];
-        if (kp >= 0 && rrr < P.rvdw) {                                        // vdw.F90:1892 / :1680
-          const double r_rrr = 1.0 / rrr;
-          const double rsq = rrr * rrr;
-          const double r_rsq = r_rrr * r_rrr;
-          double gamma, eng;
-          if (!P.vdw_direct) {
-            const double2* tb = vdw_tab + (size_t)kp * tstride;
-            const int l = __double2int_rz(rrr * P.vdw_rdr);                   // :1909-1910
-            const double ppp = rrr * P.vdw_rdr - (double)l;
-            double2 a0 = tb[l], a1 = tb[l + 1], a2 = tb[l + 2];
-            double gk = a0.x; if (l == 0) gk = gk * rrr;
-            gamma = interp3(gk, a1.x, a2.x, ppp) * r_rsq;                     // :1914-1921
-            eng = interp3(a0.y, a1.y, a2.y, ppp);                             // :1953-1960
-            if (P.vdw_fshift) {                                               // :1922, :1962-1965
-              const double2 c = tb[P.max_grid - 4];
-              gamma = gamma - c.x * (r_rrr * P.r_rvdw);
-              eng = eng + c.x * (rrr * P.r_rvdw - 1.0) - c.y;
-            }
-          } else {
-            const double* pp = vdw_par + (size_t)kp * 10;
-            double e0, g0;
-            pot_direct(ltp[kp], pp, rrr, e0, g0);
-            eng = e0 + pp[7] * rrr + pp[8];                                   // :1698-1699
-            gamma = g0 * r_rsq - pp[7] * r_rrr;
+      const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(xxt, xxt), __dmul_rn(yyt, yyt)), __dmul_rn(zzt, zzt));
+      // Sqrt(rsq) < rvdw  <=>  rsq < thr_vdw (thr = smallest double whose IEEE sqrt reaches the cutoff)
+      const bool in_v = kc != 0 && rsq < P.thr_vdw;                           // vdw.F90:1892 / :1680
+      const bool in_c = coul_i && fabs(pj.w) > ZERO_PLUS && rsq < P.thr_coul; // ewald_spole.F90:133
+      if (!(in_v || in_c)) continue;
+      const double r_rrr = rsqrt(rsq);
+      const double rrr = rsq * r_rrr;                                         // two_body.F90:351 to ~1 ulp
+      const double r_rsq = r_rrr * r_rrr;
+      double gamma = 0.0;
+      int l = 0;
+      double ppp = 0.0;
+      if (in_v) {
+        const int kp = kc - 1;
+        double gam, eng;
+        if (!P.vdw_direct) {
+          const double tt = rrr * P.vdw_rdr;                                  // vdw.F90:1909-1910
+          l = __double2int_rz(tt);
+          ppp = tt - (double)l;
+          const Tab4* tb = tab4 + (size_t)kp * P.tstride + l;
+          if (l > 0) {
+            const double2 a = tb[0].lo, h = tb[0].hi, b = tb[1].lo;
+            gam = (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x)) * r_rsq;    // :1914-1921
+            eng = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);              // :1953-1960
+          } else {                                                            // g(0) is scaled by r when l == 0
+            const double2* rt = vdw_raw + (size_t)kp * P.tstride;
+            gam = interp3(rt[0].x * rrr, rt[1].x, rt[2].x, ppp) * r_rsq;
+            eng = interp3(rt[0].y, rt[1].y, rt[2].y, ppp);
           }
-          const double f1 = gamma * xxt, f2 = gamma * yyt, f3 = gamma * zzt;
-          fix = fix + f1; fiy = fiy + f2; fiz = fiz + f3;
-          gtx += f1; gty += f2; gtz += f3;
-          if (w != 0.0) {
-            acc[0] += w * eng;
-            acc[1] -= w * (gamma * rsq);
-            acc[6] += w * (xxt * f1); acc[7] += w * (xxt * f2); acc[8] += w * (xxt * f3);
-            acc[9] += w * (yyt * f2); acc[10] += w * (yyt * f3); acc[11] += w * (zzt * f3);
+          if (P.vdw_fshift) {                                                 // :1922, :1962-1965
+            const double2 c = vdw_raw[(size_t)kp * P.tstride + P.max_grid - 4];
+            gam = gam - c.x * (r_rrr * P.r_rvdw);
+            eng = eng + c.x * (rrr * P.r_rvdw - 1.0) - c.y;
           }
+        } else {
+          const double* pp = vdw_par + (size_t)kp * 10;
+          double e0, g0;
+          pot_direct(ltp[kp], pp, rrr, e0, g0);
+          eng = e0 + pp[7] * rrr + pp[8];                                     // vdw.F90:1698-1699
+          gam = g0 * r_rsq - pp[7] * r_rrr;
         }
+        gamma = gam;
+        acc[0] += w * eng;
+        acc[1] -= w * (gam * rsq);
       }
-      if (coul_i) {
-        if (fabs(pj.w) > ZERO_PLUS && rrr < P.rcut) {                         // ewald_spole.F90:133
-          const double prefac = qi_s * pj.w;
-          const int l = __double2int_rz(rrr * P.ew_rdr);                      // :140-146
-          const double diff = rrr * P.ew_rdr - (double)l;
-          double2 a0 = ew_tab[l], a1 = ew_tab[l + 1], a2 = ew_tab[l + 2];
-          double p1 = a0.x, q1 = a0.y;
-          if (l == 0) { p1 = p1 * rrr; q1 = q1 * rrr; }
-          const double erf_gamma = prefac * interp3(p1, a1.x, a2.x, diff);
-          const double f1 = erf_gamma * xxt, f2 = erf_gamma * yyt, f3 = erf_gamma * zzt;
-          fix = fix + f1; fiy = fiy + f2; fiz = fiz + f3;
-          gtx += f1; gty += f2; gtz += f3;
-          if (w != 0.0) {
-            const double e_comp = prefac * interp3(q1, a1.y, a2.y, diff);     // :168-174
-            acc[2] += w * e_comp;
-            acc[3] -= w * (erf_gamma * (rrr * rrr));                          // :189
-            acc[6] += w * (xxt * f1); acc[7] += w * (xxt * f2); acc[8] += w * (xxt * f3);
-            acc[9] += w * (yyt * f2); acc[10] += w * (yyt * f3); acc[11] += w * (zzt * f3);
-          }
+      if (in_c) {
+        const double prefac = qi_s * pj.w;
+        if (!(P.same_grid && in_v && !P.vdw_direct)) {
+          const double tt = rrr * P.ew_rdr;                                   // ewald_spole.F90:140-146
+          l = __double2int_rz(tt);
+          ppp = tt - (double)l;
         }
+        const Tab4* tb = tab4 + P.ew_off + l;
+        double gd, ge;
+        if (l > 0) {
+          const double2 a = tb[0].lo, h = tb[0].hi, b = tb[1].lo;
+          gd = a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x);
+          ge = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);
+        } else {
+          gd = interp3(ew_raw[0].x * rrr, ew_raw[1].x, ew_raw[2].x, ppp);
+          ge = interp3(ew_raw[0].y * rrr, ew_raw[1].y, ew_raw[2].y, ppp);
+        }
+        const double erf_gamma = prefac * gd;
+        gamma += erf_gamma;
+        acc[2] += w * (prefac * ge);                                          // :168-174
+        acc[3] -= w * (erf_gamma * rsq);                                      // :189
       }
+      const double f1 = gamma * xxt, f2 = gamma * yyt, f3 = gamma * zzt;
+      fix += f1; fiy += f2; fiz += f3;
+      const double wx = w * xxt, wy = w * yyt, wz = w * zzt;
+      acc[6] += wx * f1; acc[7] += wx * f2; acc[8] += wx * f3;
+      acc[9] += wy * f2; acc[10] += wy * f3; acc[11] += wz * f3;
       if (P.half && !halo) {   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161)
-        atomicAdd(&fsx[j], -gtx); atomicAdd(&fsy[j], -gty); atomicAdd(&fsz[j], -gtz);
+        atomicAdd(&fsx[j], -f1); atomicAdd(&fsy[j], -f2); atomicAdd(&fsz[j], -f3);
       }
     }
     // excluded pairs (two_body.F90:555-606 -> ewald_excl_forces)
-    if (P.lbook && P.ew_on) {
+    if (P.lbook && P.ew_on && live) {
       const int nx = nxnbr[t];
       if (nx > 0 && fabs(pi.w) > ZERO_PLUS) {                                 // ewald_spole.F90:541
         const double chgea = pi.w * P.scaling;
         const unsigned* xrow = xnbr + (size_t)t * P.xpitch;
-        for (int k = lane; k < nx; k += 32) {
-          const unsigned e = xrow[k];
+        for (int kx = lg; kx < nx; kx += TPR) {
+          const unsigned e = xrow[kx];
           const int j = (int)(e & DLP_J_MASK);
           const bool halo = (e & DLP_F_HALO) != 0;
-          const double w = P.half ? (halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0) : (halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : 0.5);
+          const double w = halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : (P.half ? 1.0 : 0.5);
           const double4 pj = posq_s[j];
           const double xxt = pi.x - pj.x, yyt = pi.y - pj.y, zzt = pi.z - pj.z;
-          const double rrr = sqrt(xxt * xxt + yyt * yyt + zzt * zzt);          // two_body.F90:576
+          const double rsq0 = __dadd_rn(__dadd_rn(__dmul_rn(xxt, xxt), __dmul_rn(yyt, yyt)), __dmul_rn(zzt, zzt));
+          const double rrr = sqrt(rsq0);                                      // two_body.F90:576
           double chgprd = pj.w;
           if (fabs(chgprd) > ZERO_PLUS && rrr < P.rcut) {                     // :570
             const double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429,
@@ -226,26 +245,25 @@ __global__ void __launch_bounds__(256) k_pair_forces(FParams P, const int* __res
               egamma = -(erfr - 2.0 * chgprd * (P.alpha / sqrpi) * exp1) / rsq;
             }
             const double f1 = egamma * xxt, f2 = egamma * yyt, f3 = egamma * zzt;
-            fix = fix + f1; fiy = fiy + f2; fiz = fiz + f3;
+            fix += f1; fiy += f2; fiz += f3;
             if (P.half && !halo) { atomicAdd(&fsx[j], -f1); atomicAdd(&fsy[j], -f2); atomicAdd(&fsz[j], -f3); }
-            if (w != 0.0) {
-              acc[4] -= w * erfr;
-              acc[5] -= w * (egamma * rsq);
-              acc[6] += w * (xxt * f1); acc[7] += w * (xxt * f2); acc[8] += w * (xxt * f3);
-              acc[9] += w * (yyt * f2); acc[10] += w * (yyt * f3); acc[11] += w * (zzt * f3);
-            }
+            acc[4] -= w * erfr;
+            acc[5] -= w * (egamma * rsq);
+            const double wx = w * xxt, wy = w * yyt, wz = w * zzt;
+            acc[6] += wx * f1; acc[7] += wx * f2; acc[8] += wx * f3;
+            acc[9] += wy * f2; acc[10] += wy * f3; acc[11] += wz * f3;
           }
         }
       }
     }
-    // force on atom i: warp shuffle reduction, lane 0 commits
+    // force on atom i: shuffle reduction inside the row group, its first lane commits
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
+    for (int d = TPR / 2; d > 0; d >>= 1) {
       fix += __shfl_xor_sync(DLP_FULL, fix, d);
       fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
       fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
     }
-    if (lane == 0) {
+    if (lg == 0 && live) {
       if (P.half) {
         atomicAdd(&fsx[ii], fix); atomicAdd(&fsy[ii], fiy); atomicAdd(&fsz[ii], fiz);
       } else {
@@ -256,7 +274,8 @@ __global__ void __launch_bounds__(256) k_pair_forces(FParams P, const int* __res
     }
   }
   // energies / virials / stress: warp shuffle, then per-block in a fixed order
-  __shared__ double red[8][12];
+  __shared__ double red[16][12];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 12; ++k) {
     double v = acc[k];
@@ -330,29 +349,77 @@ __global__ void k_dfma(int iters, double* out) {
 
 }  // namespace
 
+template <int TPR>
+static int launch_pair(dlpgpu_ctx* ctx, const FParams& P, bool use_smem, size_t smem, int blocks, double* fsx, double* fsy, double* fsz) {
+  const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
+  if (use_smem) {
+    CK(cudaFuncSetAttribute(k_pair_forces<TPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, (k_pair_forces<TPR, true>), blocks, 512, smem, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx,
+           fsy, fsz, ctx->partial.p);
+  } else {
+    LAUNCH(ctx, (k_pair_forces<TPR, false>), blocks, 512, 0, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx,
+           fsy, fsz, ctx->partial.p);
+  }
+  return 0;
+}
+
+// {g_force, g_energy, h_force, h_energy} entries for every vdW table and the Ewald table (see Tab4)
+int dlp_build_tab4(dlpgpu_ctx* ctx) {
+  const int ts = ctx->max_grid + 1;
+  const bool vt = ctx->vdw_on && !ctx->vdw_direct && !ctx->h_vdw_f.empty();
+  const size_t nv = vt ? (size_t)ctx->max_vdw * ts : 0;
+  const size_t ne = ctx->ew_on ? (size_t)ctx->ew_n + 1 : 0;
+  ctx->ew_off = (int)nv;
+  std::vector<double> t((nv + ne) * 4 + 4, 0.0);
+  auto fill = [&](double* dst, const double* f, const double* e, int n) {   // n+1 entries 0..n
+    for (int l = 0; l <= n; ++l) {
+      dst[4 * l + 0] = f[l]; dst[4 * l + 1] = e[l];
+      if (l + 2 <= n) {
+        dst[4 * l + 2] = ((f[l + 2] - f[l + 1]) - (f[l + 1] - f[l])) * 0.5;
+        dst[4 * l + 3] = ((e[l + 2] - e[l + 1]) - (e[l + 1] - e[l])) * 0.5;
+      }
+    }
+  };
+  for (int k = 0; vt && k < ctx->max_vdw; ++k)
+    fill(t.data() + (size_t)k * ts * 4, ctx->h_vdw_f.data() + (size_t)k * ts, ctx->h_vdw_e.data() + (size_t)k * ts, ctx->max_grid);
+  if (ne) fill(t.data() + nv * 4, ctx->h_ew_d.data(), ctx->h_ew_e.data(), ctx->ew_n);
+  CK(ctx->tab4.ensure(t.size(), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tab4.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->tab4_entries = nv + ne;
+  ctx->tab4_valid = true;
+  return 0;
+}
+
 int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   cudaStream_t s = ctx->stream;
   if (!ctx->list_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "two_body: no valid neighbour list");
   if (ctx->natms != ctx->list_natms || ctx->nlast != ctx->list_nlast)
     return dlp_fail(ctx, DLPGPU_ERR_HALO_COUNT, "two_body: atom counts changed since the list build");
+  if (!ctx->tab4_valid) CKRC(dlp_build_tab4(ctx));
   const int natms = ctx->natms;
   cudaEventRecord(ctx->ev[4], s);
   CKRC(dlp_gather_sorted(ctx));
   FParams P{};
-  P.natms = natms; P.pitch = ctx->pitch; P.xpitch = ctx->xpitch > 0 ? ctx->xpitch : 1; P.ntypes = std::max(ctx->ntypes, 1);
-  P.max_grid = ctx->max_grid; P.max_vdw = ctx->max_vdw; P.ew_n = ctx->ew_n;
+  P.natms = natms; P.pitch = ctx->pitch; P.xpitch = ctx->xpitch > 0 ? ctx->xpitch : 1;
+  P.max_grid = ctx->max_grid; P.max_vdw = ctx->max_vdw; P.ew_n = ctx->ew_n; P.tstride = ctx->max_grid + 1; P.ew_off = ctx->ew_off;
   P.vdw_on = ctx->vdw_on; P.vdw_direct = ctx->vdw_direct; P.vdw_fshift = ctx->vdw_fshift; P.ew_on = ctx->ew_on;
   P.half = ctx->force_mode == 1; P.zero_forces = zero_forces; P.lbook = ctx->lbook;
+  P.same_grid = ctx->vdw_on && ctx->ew_on && ctx->vdw_rdr == ctx->ew_rdr;
   P.rvdw = ctx->rvdw; P.r_rvdw = ctx->rvdw > 0 ? 1.0 / ctx->rvdw : 0.0; P.vdw_rdr = ctx->vdw_rdr; P.rcut = ctx->rcut;
-  P.ew_rdr = ctx->ew_rdr; P.alpha = ctx->alpha; P.scaling = ctx->scaling;
+  P.ew_rdr = ctx->ew_rdr; P.alpha = ctx->alpha; P.scaling = ctx->scaling; P.thr_vdw = ctx->thr_vdw; P.thr_coul = ctx->thr_coul;
   // shared-memory tables when they fit
-  size_t nv = (ctx->vdw_on && !ctx->vdw_direct) ? (size_t)ctx->max_vdw * (ctx->max_grid + 1) : 0;
-  size_t ne = ctx->ew_on ? (size_t)ctx->ew_n + 1 : 0;
-  size_t smem = (nv + ne) * sizeof(double2) + (size_t)P.ntypes * P.ntypes * sizeof(int);
-  bool use_smem = smem <= 200 * 1024;
-  const int threads = 256;
-  int bps = use_smem ? std::max(1, std::min(4, (int)((220 * 1024) / std::max(smem, (size_t)1)))) : 4;
-  int blocks = std::max(1, std::min(cdiv(natms, threads / 32), ctx->sm_count * bps));
+  size_t smem = ctx->tab4_entries * 4 * sizeof(double);
+  bool use_smem = smem > 0 && smem <= 210 * 1024;
+  const int bps = (use_smem && smem > 100 * 1024) ? 1 : 2;
+  // threads per row from the mean row length: the group width that wastes the fewest lanes on the last pass
+  long long pairs_hint = ctx->list_entries;
+  double mean = natms > 0 ? (double)pairs_hint / natms : 0.0;
+  int tpr = mean > 80.0 ? 16 : 8;
+  if (ctx->tpr_override) tpr = ctx->tpr_override;
+  int blocks = std::max(1, std::min(cdiv(natms, 512 / tpr), ctx->sm_count * bps));
   CK(ctx->partial.ensure((size_t)blocks * 12 + 16, s));
   double *fsx = nullptr, *fsy = nullptr, *fsz = nullptr;
   if (P.half) {   // sorted-slot force accumulators of the atomics path
@@ -364,16 +431,9 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   }
   cudaEventRecord(ctx->ev[6], s);
   if (natms > 0) {
-    if (use_smem) {
-      CK(cudaFuncSetAttribute(k_pair_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(ctx, k_pair_forces<true>, blocks, threads, smem, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->type_s.p,
-             ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->pair_k.p, ctx->ltp.p, ctx->vdw_tab.p, ctx->vdw_par.p,
-             ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx, fsy, fsz, ctx->partial.p);
-    } else {
-      LAUNCH(ctx, k_pair_forces<false>, blocks, threads, 0, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->type_s.p,
-             ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->pair_k.p, ctx->ltp.p, ctx->vdw_tab.p, ctx->vdw_par.p,
-             ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx, fsy, fsz, ctx->partial.p);
-    }
+    if (tpr == 32) CKRC(launch_pair<32>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
+    else if (tpr == 16) CKRC(launch_pair<16>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
+    else CKRC(launch_pair<8>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
   }
   cudaEventRecord(ctx->ev[7], s);
   if (natms > 0 && P.half)

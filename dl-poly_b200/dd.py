@@ -96,16 +96,55 @@ def cell_widths(cell):
     return vol / np.linalg.norm(bxc), vol / np.linalg.norm(cxa), vol / np.linalg.norm(axb)
 
 
+def invert(cell):
+    """numerics.F90:1448-1509 with its operation order (adjugate scaled by 1/det)."""
+    a = [0.0] + [float(v) for v in np.asarray(cell, dtype=np.float64).reshape(9)]
+    b = [0.0] * 10
+    b[1] = a[5] * a[9] - a[6] * a[8]; b[2] = a[3] * a[8] - a[2] * a[9]; b[3] = a[2] * a[6] - a[3] * a[5]
+    b[4] = a[6] * a[7] - a[4] * a[9]; b[5] = a[1] * a[9] - a[3] * a[7]; b[6] = a[3] * a[4] - a[1] * a[6]
+    b[7] = a[4] * a[8] - a[5] * a[7]; b[8] = a[2] * a[7] - a[1] * a[8]; b[9] = a[1] * a[5] - a[2] * a[4]
+    d = a[1] * b[1] + a[4] * b[2] + a[7] * b[3]
+    r = 1.0 / d if abs(d) > 0.0 else 0.0
+    return np.array([r * v for v in b[1:]])
+
+
+def _anint(x):
+    """Fortran Anint: round half away from zero."""
+    r = np.rint(x)
+    t = np.trunc(x)
+    half = np.abs(x - t) == 0.5
+    return np.where(half, t + np.sign(x), r)
+
+
+def read_config_fold(xyz, cell, dims=(1, 1, 1)):
+    """configuration.F90:1183-1205: fold every atom into the reduced cell [-0.5,0.5), RECOMPUTE its Cartesian position
+    from cell.s, and assign it to domain idm = ipx + nx (ipy + ny ipz), ip = Int((s+0.5) n).  Returns (xyz_folded, owner).
+    Same operation order as the reference, so the positions carry the bits a DL_POLY run starts from."""
+    x = np.asarray(xyz, dtype=np.float64)
+    c = np.asarray(cell, dtype=np.float64).reshape(9)
+    rc = invert(c)
+    ax, ay, az = x[:, 0], x[:, 1], x[:, 2]
+    sx = rc[0] * ax + rc[3] * ay + rc[6] * az
+    sy = rc[1] * ax + rc[4] * ay + rc[7] * az
+    sz = rc[2] * ax + rc[5] * ay + rc[8] * az
+    out = []
+    for s in (sx, sy, sz):
+        s = s - _anint(s)
+        out.append(np.where(s >= HALF_MINUS, -s, s))
+    sx, sy, sz = out
+    f = np.empty_like(x)
+    f[:, 0] = c[0] * sx + c[3] * sy + c[6] * sz
+    f[:, 1] = c[1] * sx + c[4] * sy + c[7] * sz
+    f[:, 2] = c[2] * sx + c[5] * sy + c[8] * sz
+    nx, ny, nz = dims
+    ipx = np.clip(((sx + 0.5) * float(nx)).astype(np.int64), 0, nx - 1)
+    ipy = np.clip(((sy + 0.5) * float(ny)).astype(np.int64), 0, ny - 1)
+    ipz = np.clip(((sz + 0.5) * float(nz)).astype(np.int64), 0, nz - 1)
+    return f, (ipx + nx * (ipy + ny * ipz)).astype(np.int32)
+
+
 def assign_domains(xyz, cell, nx, ny, nz):
-    """configuration.F90:1183-1205: reduced coordinates folded into [-0.5,0.5), ip = Int((s+0.5)*n) -> owning rank."""
-    rc = np.linalg.inv(np.asarray(cell, dtype=np.float64).reshape(3, 3))
-    s = np.asarray(xyz) @ rc
-    s = s - np.rint(s)
-    s = np.where(s >= HALF_MINUS, -s, s)
-    ipx = np.minimum((( s[:, 0] + 0.5) * nx).astype(np.int64), nx - 1)
-    ipy = np.minimum(((s[:, 1] + 0.5) * ny).astype(np.int64), ny - 1)
-    ipz = np.minimum(((s[:, 2] + 0.5) * nz).astype(np.int64), nz - 1)
-    return (ipx + nx * (ipy + ny * ipz)).astype(np.int32)
+    return read_config_fold(xyz, cell, (nx, ny, nz))[1]
 
 
 # ---------------------------------------------------------------------------------------------- transports
@@ -236,14 +275,14 @@ class Domain:
         self.sr = engine.ShortRange(device, (nx, ny, nz) + tuple(self.idx))
         self.sr.dev_setup_system(sysm)
         self.stream = torch.cuda.ExternalStream(self.sr.stream(), device=self.device)
-        owner = assign_domains(sysm.xyz, sysm.cell, nx, ny, nz)
+        xyz_f, owner = read_config_fold(sysm.xyz, sysm.cell, (nx, ny, nz))
         mine = np.nonzero(owner == self.rank)[0]
         self.natms0 = len(mine)
         cap = int(capacity_factor * max(sysm.megatm / self.world, 1.0) * 1.0) + 4096
         # halo thickness grows the resident count: capacity covers local + halo with head-room (bounds.F90 mxatms)
         ltg = (mine + 1).astype(np.int32)
         vel = None if sysm.vel is None else sysm.vel[mine]
-        self.sr.dev_load_atoms(sysm.xyz[mine], vel, ltg, sysm.lsite[mine], capacity=cap * 2)
+        self.sr.dev_load_atoms(xyz_f[mine], vel, ltg, sysm.lsite[mine], capacity=cap * 2)
         self._refresh_bufs = None
         self.rebuilds = 0
         self.steps = 0

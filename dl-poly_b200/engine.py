@@ -31,7 +31,7 @@ class ShortRange:
         self.device = device
         self.set_domain(dd)
         self.max_list = 0
-        self.force_mode = 0
+        self.force_mode = 1
 
     def close(self):
         if getattr(self, "h", None):

@@ -6,7 +6,7 @@ partition AND order); per-atom forces within 1e-9 relative; engsrp/engcpe/virial
 import numpy as np
 import pytest
 
-from dl_poly_b200 import engine, systems
+from dl_poly_b200 import dd, engine, systems
 from dl_poly_b200.lib import COREPART
 from util import domain_inputs, force_errors, parts_forces, rel_err, world_for
 
@@ -108,11 +108,14 @@ def test_frozen_pairs_partition():
     check_dropin(s, 1)
 
 
-def test_full_list_is_symmetrised_reference_list():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_device_list_is_the_reference_list(mode):
+    """mode 0: the device rows are the symmetrised reference list; mode 1: the reference's own half rows (as sets)."""
     s = systems.spce_water(512, rcut=8.0, padding=0.2)
     w = world_for(s, P=1)
     d = domain_inputs(w, 0)
     sr = make_sr(s)
+    sr.set_force_mode(mode)
     lst = sr.link_cell_pairs(d["natms"], d["nlast"], d["parts"], d["ltype"], d["ltg"], d["lfrzn"], lbook=True, megfrz=0,
                              list_excl=d["list_excl"], max_list=d["max_list"])
     nat = d["natms"]
@@ -124,7 +127,7 @@ def test_full_list_is_symmetrised_reference_list():
             j = lst[i, 3 + k]
             tgt = main if k <= n0 else excl
             tgt[i].add(j)
-            if j <= nat:
+            if j <= nat and mode == 0:
                 tgt[j - 1].add(i + 1)
     for i in list(range(0, nat, 37)) + [nat - 1]:
         m, x = sr.dev_get_full_row(i + 1)
@@ -180,7 +183,8 @@ def test_empty_domain():
 def native_serial(s):
     sr = engine.ShortRange(0)
     sr.dev_setup_system(s)
-    sr.dev_load_atoms(s.xyz, s.vel, np.arange(1, s.megatm + 1, dtype=np.int32), s.lsite)
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]          # what read_config leaves in parts (the oracle's load does the same)
+    sr.dev_load_atoms(xyz, s.vel, np.arange(1, s.megatm + 1, dtype=np.int32), s.lsite)
     return sr
 
 

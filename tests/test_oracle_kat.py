@@ -178,3 +178,18 @@ def test_golden_fixture_matches_oracle(oracle):
             assert abs(out[k] - v) <= 1e-13 * max(abs(v), 1.0), (fn, k)
         f = w.gather_forces()
         assert abs(float(np.abs(f).sum()) - g["force_l1"]) <= 1e-12 * g["force_l1"]
+
+
+def test_read_config_fold_matches_oracle_load_bits(oracle):
+    """dd.read_config_fold (numpy) reproduces the oracle's read_config restatement bit for bit, incl. domain assignment."""
+    from dl_poly_b200 import dd
+    for s, P in ((systems.argon(6), 1), (systems.nacl((4, 2, 2), rcut=5.0, padding=0.2), 4), (systems.spce_water(512, rcut=8.0, padding=0.2), 8)):
+        w = oracle.World.from_system(s, P=P)
+        dims = dd.map_domains(P, dd.cell_widths(s.cell), s.imcon)
+        assert tuple(w.dd(0)[0][:3]) == dims
+        xyz, owner = dd.read_config_fold(s.xyz, s.cell, dims)
+        got = w.gather_positions()
+        assert np.array_equal(got, xyz)
+        for r in range(P):
+            assert np.array_equal(np.sort(w.ints(r)["ltg"][:w.counts(r)["natms"]]), np.nonzero(owner == r)[0] + 1)
+            assert list(w.dd(r)[1][:6]) == dd.face_neighbours(r, *dims)
