@@ -111,6 +111,7 @@ struct dlpgpu_ctx {
   bool tab4_valid = false;
   std::vector<double> h_vdw_f, h_vdw_e, h_ew_d, h_ew_e;   // host copies the tab4 build reads
   int tpr_override = 0;
+  bool no_fast = false;    // DLPGPU_NO_FAST=1: always use the general pair kernel
 
   // sites (native mode)
   int nsites = 0;
@@ -125,7 +126,7 @@ struct dlpgpu_ctx {
   int natms = 0, nlast = 0, capacity = 0;
   DBuf<double4> posq;      // x,y,z,chge
   DBuf<double> fx, fy, fz;
-  DBuf<double> fsx, fsy, fsz;   // sorted-slot accumulators (force_mode 1)
+  DBuf<double> fsx, fsy, fsz;   // force_mode 1: fsx = row sums [3][natms], fsy = blocked j-side accumulators, fsz unused
   DBuf<double> vx, vy, vz;
   DBuf<int> ltg, lsite, ltype, lfrzn, ixyz;
   DBuf<double> xbg, ybg, zbg;

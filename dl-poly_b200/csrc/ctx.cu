@@ -1,5 +1,6 @@
 // ctx.cu -- context lifecycle, setup entry points, host-buffer (drop-in) wrappers and read-back of libdlpgpu.
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -140,6 +141,8 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  if (const char* e = getenv("DLPGPU_TPR")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) ctx->tpr_override = v; }   // tuning knob
+  if (const char* e = getenv("DLPGPU_NO_FAST")) ctx->no_fast = atoi(e) != 0;
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
   *out = ctx;

@@ -15,7 +15,7 @@
 namespace {
 
 struct FParams {
-  int natms, pitch, xpitch, max_grid, max_vdw, ew_n, tstride, ew_off;
+  int natms, pitch, xpitch, max_grid, max_vdw, ew_n, tstride, ew_off, tab_ne;
   int vdw_on, vdw_direct, vdw_fshift, ew_on, half, zero_forces, lbook, same_grid;
   double rvdw, r_rvdw, vdw_rdr, rcut, ew_rdr, alpha, scaling, thr_vdw, thr_coul;
 };
@@ -85,25 +85,27 @@ __device__ __forceinline__ double4 ld_posq(const double4* p) {   // one 256-bit 
 // h_energy} (32 B), so one pair reads 48 bytes per table: entry l whole and the g-half of entry l+1.
 struct Tab4 { double2 lo, hi; };   // lo = {g_force, g_energy}, hi = {h_force, h_energy}
 
-template <int TPR, bool SMEM>
-__global__ void __launch_bounds__(512, 1)
+// j-side (Newton's third law) accumulators: blocks of 4 sorted slots {x0..x3, y0..y3, z0..z3} (96 B), so the three REDs
+// of a pair share one address computation and partners that are neighbours in the sorted order share 32-byte sectors.
+__device__ __forceinline__ double* fneg_ptr(double* base, int j) { return base + (size_t)(j >> 2) * 12 + (j & 3); }
+
+template <int TPR, bool SMEM, int NT>
+__global__ void __launch_bounds__(NT, 1)
 k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict__ at_list, const double4* __restrict__ posq_s,
               const unsigned* __restrict__ nbr, const int* __restrict__ nnbr, const unsigned* __restrict__ xnbr,
               const int* __restrict__ nxnbr, const int* __restrict__ ltp, const Tab4* __restrict__ tab4_g,
               const double2* __restrict__ vdw_raw, const double* __restrict__ vdw_par, const double2* __restrict__ ew_raw,
-              double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz, double* __restrict__ fsx,
-              double* __restrict__ fsy, double* __restrict__ fsz, double* __restrict__ partial) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Tab4* tab4 = tab4_g;
+              double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz, double* __restrict__ fpos,
+              double* __restrict__ fneg, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double2 s_tab[];   // Tab4 entries as pairs of double2: [2e] = lo, [2e+1] = hi
   if (SMEM) {
-    double2* sv = reinterpret_cast<double2*>(smem_raw);
     const double2* gv = reinterpret_cast<const double2*>(tab4_g);
     const int n2 = 2 * (P.ew_off + (P.ew_on ? P.ew_n + 1 : 0));
-    for (int k = threadIdx.x; k < n2; k += blockDim.x) sv[k] = gv[k];
+    for (int k = threadIdx.x; k < n2; k += NT) s_tab[k] = gv[k];
     __syncthreads();
-    tab4 = reinterpret_cast<const Tab4*>(smem_raw);
   }
-  constexpr int RPB = 512 / TPR;              // rows per block pass
+  const double2* gtab = reinterpret_cast<const double2*>(tab4_g);
+  constexpr int RPB = NT / TPR;               // rows per block pass
   const int lg = threadIdx.x % TPR;           // lane within the row group
   const int grp = threadIdx.x / TPR;
   double acc[12];
@@ -120,15 +122,18 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
     const bool coul_i = P.ew_on && !(fabs(qi_s) < ZERO_PLUS);                 // :117
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
     const unsigned* row = nbr + (size_t)t * P.pitch;
+    // software pipeline: list entries are fetched two passes ahead, partner coordinates one pass ahead
     int k = lg;
-    unsigned e_nx = 0;
-    double4 pj_nx = pi;
-    if (k < n) { e_nx = row[k]; pj_nx = ld_posq(posq_s + (e_nx & DLP_J_MASK)); }
+    unsigned e_cur = (k < n) ? row[k] : 0u;
+    unsigned e_nx = (k + TPR < n) ? row[k + TPR] : 0u;
+    double4 pj_cur = pi;
+    if (k < n) pj_cur = ld_posq(posq_s + (e_cur & DLP_J_MASK));
     for (; k < n; k += TPR) {
-      const unsigned e = e_nx;
-      const double4 pj = pj_nx;
-      if (k + TPR < n) { e_nx = row[k + TPR]; pj_nx = ld_posq(posq_s + (e_nx & DLP_J_MASK)); }   // software prefetch
-      const int j = (int)(e & DLP_J_MASK);
+      const unsigned e = e_cur;
+      const double4 pj = pj_cur;
+      const unsigned e_nx2 = (k + 2 * TPR < n) ? row[k + 2 * TPR] : 0u;
+      if (k + TPR < n) pj_cur = ld_posq(posq_s + (e_nx & DLP_J_MASK));
+      e_cur = e_nx; e_nx = e_nx2;
       const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
       const bool halo = (e & DLP_F_HALO) != 0;
       const double w = halo ? ((e & DLP_F_ECNT) ? 1.0 : 0.0) : (P.half ? 1.0 : 0.5);
@@ -151,9 +156,11 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
           const double tt = rrr * P.vdw_rdr;                                  // vdw.F90:1909-1910
           l = __double2int_rz(tt);
           ppp = tt - (double)l;
-          const Tab4* tb = tab4 + (size_t)kp * P.tstride + l;
           if (l > 0) {
-            const double2 a = tb[0].lo, h = tb[0].hi, b = tb[1].lo;
+            const int u = 2 * (kp * P.tstride + l);
+            double2 a, h, b;
+            if (SMEM) { a = s_tab[u]; h = s_tab[u + 1]; b = s_tab[u + 2]; }
+            else { a = gtab[u]; h = gtab[u + 1]; b = gtab[u + 2]; }
             gam = (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x)) * r_rsq;    // :1914-1921
             eng = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);              // :1953-1960
           } else {                                                            // g(0) is scaled by r when l == 0
@@ -184,10 +191,12 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
           l = __double2int_rz(tt);
           ppp = tt - (double)l;
         }
-        const Tab4* tb = tab4 + P.ew_off + l;
         double gd, ge;
         if (l > 0) {
-          const double2 a = tb[0].lo, h = tb[0].hi, b = tb[1].lo;
+          const int u = 2 * (P.ew_off + l);
+          double2 a, h, b;
+          if (SMEM) { a = s_tab[u]; h = s_tab[u + 1]; b = s_tab[u + 2]; }
+          else { a = gtab[u]; h = gtab[u + 1]; b = gtab[u + 2]; }
           gd = a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x);
           ge = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);
         } else {
@@ -205,7 +214,8 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
       acc[6] += wx * f1; acc[7] += wx * f2; acc[8] += wx * f3;
       acc[9] += wy * f2; acc[10] += wy * f3; acc[11] += wz * f3;
       if (P.half && !halo) {   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161)
-        atomicAdd(&fsx[j], -f1); atomicAdd(&fsy[j], -f2); atomicAdd(&fsz[j], -f3);
+        double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
+        atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3);
       }
     }
     // excluded pairs (two_body.F90:555-606 -> ewald_excl_forces)
@@ -246,7 +256,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
             }
             const double f1 = egamma * xxt, f2 = egamma * yyt, f3 = egamma * zzt;
             fix += f1; fiy += f2; fiz += f3;
-            if (P.half && !halo) { atomicAdd(&fsx[j], -f1); atomicAdd(&fsy[j], -f2); atomicAdd(&fsz[j], -f3); }
+            if (P.half && !halo) { double* q = fneg_ptr(fneg, j); atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3); }
             acc[4] -= w * erfr;
             acc[5] -= w * (egamma * rsq);
             const double wx = w * xxt, wy = w * yyt, wz = w * zzt;
@@ -256,7 +266,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
         }
       }
     }
-    // force on atom i: shuffle reduction inside the row group, its first lane commits
+    // force on atom i: shuffle reduction inside the row group, its first lane commits (each row has one owner: plain stores)
 #pragma unroll
     for (int d = TPR / 2; d > 0; d >>= 1) {
       fix += __shfl_xor_sync(DLP_FULL, fix, d);
@@ -265,7 +275,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
     }
     if (lg == 0 && live) {
       if (P.half) {
-        atomicAdd(&fsx[ii], fix); atomicAdd(&fsy[ii], fiy); atomicAdd(&fsz[ii], fiz);
+        fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz;
       } else {
         const int i = at_list[ii];
         if (P.zero_forces) { fx[i] = fix; fy[i] = fiy; fz[i] = fiz; }
@@ -274,7 +284,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
     }
   }
   // energies / virials / stress: warp shuffle, then per-block in a fixed order
-  __shared__ double red[16][12];
+  __shared__ double red[NT / 32][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 12; ++k) {
@@ -286,7 +296,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
   __syncthreads();
   if (threadIdx.x < 12) {
     double v = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < NT / 32; ++w) v += red[w][threadIdx.x];
     partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
   }
 }
@@ -307,14 +317,171 @@ __global__ void k_final_reduce(int nblocks, const double* __restrict__ partial, 
   if (k == 0) out[15] = 0.0;
 }
 
-__global__ void k_scatter_half(int nlast, int natms, int zero_forces, const int* __restrict__ at_list, const double* __restrict__ fsx,
-                               const double* __restrict__ fsy, const double* __restrict__ fsz, double* fx, double* fy, double* fz) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nlast) return;
-  int i = at_list[s];
-  if (i >= natms) return;
-  if (zero_forces) { fx[i] = fsx[s]; fy[i] = fsy[s]; fz[i] = fsz[s]; }
-  else { fx[i] += fsx[s]; fy[i] += fsy[s]; fz[i] += fsz[s]; }
+// ---------------------------------------------------------------- fast path
+// Tabulated vdW (VT = 1) and / or tabulated real-space Ewald (EW = 1), half list, tables in shared memory, no force
+// shift, no exclusion rows: the configurations the BASELINE sizes run.  Same arithmetic as k_pair_forces; the body is
+// straight-line (out-of-range pairs are masked, not branched around) and every lane works on two pairs at a time, so
+// the two independent dependency chains hide the fp64 / LDS / MUFU latencies at 16 warps per SM.
+struct PairOut { double gamma, ev, vv, ec, vc; };
+
+template <int VT, int EW>
+__device__ __forceinline__ PairOut pair_terms(const FParams& P, const double2* s_tab, unsigned e, bool live, double qi_s, bool coul_i,
+                                              double qj, double rsq_in) {
+  const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
+  const bool in_v = VT && live && kc != 0 && rsq_in < P.thr_vdw;                       // vdw.F90:1892
+  const bool in_c = EW && live && coul_i && fabs(qj) > ZERO_PLUS && rsq_in < P.thr_coul;   // ewald_spole.F90:133
+  const double rsq = (in_v || in_c) ? rsq_in : 1.0;                                    // masked pairs compute on a harmless value
+  const double r_rrr = rsqrt(rsq);
+  const double rrr = rsq * r_rrr;
+  const double r_rsq = r_rrr * r_rrr;
+  PairOut o;
+  o.gamma = 0.0; o.ev = 0.0; o.vv = 0.0; o.ec = 0.0; o.vc = 0.0;
+  int l = 1;
+  double ppp = 0.0;
+  if (VT) {
+    const double tt = rrr * P.vdw_rdr;                                                 // vdw.F90:1909-1910
+    l = max(__double2int_rz(tt), 1);                                                   // r < one grid step does not occur
+    ppp = tt - (double)l;
+    const int u = max(kc - 1, 0) * P.tstride + l;
+    const double2 a = s_tab[u], h = s_tab[P.tab_ne + u], b = s_tab[u + 1];
+    const double gam = (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x)) * r_rsq;        // :1914-1921
+    const double eng = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);                  // :1953-1960
+    o.gamma = in_v ? gam : 0.0;
+    o.ev = in_v ? eng : 0.0;
+    o.vv = o.gamma * rsq;
+  }
+  if (EW) {
+    if (!(VT && P.same_grid)) {
+      const double tt = rrr * P.ew_rdr;                                                // ewald_spole.F90:140-146
+      l = max(__double2int_rz(tt), 1);
+      ppp = tt - (double)l;
+    }
+    const int u = P.ew_off + l;
+    const double2 a = s_tab[u], h = s_tab[P.tab_ne + u], b = s_tab[u + 1];
+    const double prefac = in_c ? qi_s * qj : 0.0;
+    const double gd = prefac * (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x));
+    o.ec = prefac * (a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y));                   // :168-174
+    o.vc = gd * rsq;                                                                   // :189
+    o.gamma += gd;
+  }
+  return o;
+}
+
+template <int TPR, int VT, int EW>
+__global__ void __launch_bounds__(512, 1)
+k_pair_fast(FParams P, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
+            const int* __restrict__ nnbr, const Tab4* __restrict__ tab4_g, double* __restrict__ fpos, double* __restrict__ fneg,
+            double* __restrict__ partial) {
+  extern __shared__ __align__(16) double2 s_tab[];
+  {   // Tab4 entries are split into a g-array and an h-array of 16-byte units, so that consecutive l fall into consecutive
+      // bank groups (an interleaved layout would put every g-unit on an even group and double the conflicts)
+    const double2* gv = reinterpret_cast<const double2*>(tab4_g);
+    for (int k = threadIdx.x; k < P.tab_ne; k += 512) { s_tab[k] = gv[2 * k]; s_tab[P.tab_ne + k] = gv[2 * k + 1]; }
+    __syncthreads();
+  }
+  constexpr int RPB = 512 / TPR;
+  const int lg = threadIdx.x % TPR;
+  const int grp = threadIdx.x / TPR;
+  double acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+
+  for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
+    const int t = base + grp;
+    const bool rowlive = t < P.natms;
+    int n = 0;
+    double4 pi = make_double4(0, 0, 0, 0);
+    if (rowlive) { pi = posq_s[loc_slot[t]]; n = nnbr[t]; }
+    const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
+    const bool coul_i = EW && !(fabs(qi_s) < ZERO_PLUS);                      // :117
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    const unsigned* row = nbr + (size_t)t * P.pitch;
+    int k = lg;
+    unsigned ea = (k < n) ? row[k] : 0u, eb = (k + TPR < n) ? row[k + TPR] : 0u;
+    unsigned ea_nx = (k + 2 * TPR < n) ? row[k + 2 * TPR] : 0u, eb_nx = (k + 3 * TPR < n) ? row[k + 3 * TPR] : 0u;
+    double4 pa = pi, pb = pi;
+    if (k < n) pa = ld_posq(posq_s + (ea & DLP_J_MASK));
+    if (k + TPR < n) pb = ld_posq(posq_s + (eb & DLP_J_MASK));
+    for (; k < n; k += 2 * TPR) {
+      const unsigned e0 = ea, e1 = eb;
+      const double4 p0 = pa, p1 = pb;
+      const bool live0 = true, live1 = (k + TPR) < n;
+      // prefetch: entries two passes ahead, coordinates one pass ahead
+      const unsigned ea_n2 = (k + 4 * TPR < n) ? row[k + 4 * TPR] : 0u, eb_n2 = (k + 5 * TPR < n) ? row[k + 5 * TPR] : 0u;
+      if (k + 2 * TPR < n) pa = ld_posq(posq_s + (ea_nx & DLP_J_MASK));
+      if (k + 3 * TPR < n) pb = ld_posq(posq_s + (eb_nx & DLP_J_MASK));
+      ea = ea_nx; eb = eb_nx; ea_nx = ea_n2; eb_nx = eb_n2;
+
+      const double x0 = pi.x - p0.x, y0 = pi.y - p0.y, z0 = pi.z - p0.z;      // two_body.F90:348-350
+      const double x1 = pi.x - p1.x, y1 = pi.y - p1.y, z1 = pi.z - p1.z;
+      const double rsq0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(y0, y0)), __dmul_rn(z0, z0));
+      const double rsq1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(y1, y1)), __dmul_rn(z1, z1));
+      const PairOut o0 = pair_terms<VT, EW>(P, s_tab, e0, live0, qi_s, coul_i, p0.w, rsq0);
+      const PairOut o1 = pair_terms<VT, EW>(P, s_tab, e1, live1, qi_s, coul_i, p1.w, rsq1);
+      const bool h0 = (e0 & DLP_F_HALO) != 0, h1 = (e1 & DLP_F_HALO) != 0;
+      const double w0 = h0 ? ((e0 & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0;
+      const double w1 = h1 ? ((e1 & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0;
+      const double f0x = o0.gamma * x0, f0y = o0.gamma * y0, f0z = o0.gamma * z0;
+      const double f1x = o1.gamma * x1, f1y = o1.gamma * y1, f1z = o1.gamma * z1;
+      fix += f0x; fiy += f0y; fiz += f0z;
+      fix += f1x; fiy += f1y; fiz += f1z;
+      if (VT) { acc[0] += w0 * o0.ev; acc[1] -= w0 * o0.vv; acc[0] += w1 * o1.ev; acc[1] -= w1 * o1.vv; }
+      if (EW) { acc[2] += w0 * o0.ec; acc[3] -= w0 * o0.vc; acc[2] += w1 * o1.ec; acc[3] -= w1 * o1.vc; }
+      {
+        const double wx = w0 * x0, wy = w0 * y0, wz = w0 * z0;
+        acc[4] += wx * f0x; acc[5] += wx * f0y; acc[6] += wx * f0z; acc[7] += wy * f0y; acc[8] += wy * f0z; acc[9] += wz * f0z;
+      }
+      {
+        const double wx = w1 * x1, wy = w1 * y1, wz = w1 * z1;
+        acc[4] += wx * f1x; acc[5] += wx * f1y; acc[6] += wx * f1z; acc[7] += wy * f1y; acc[8] += wy * f1z; acc[9] += wz * f1z;
+      }
+      if (!h0 && o0.gamma != 0.0) {   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161)
+        double* q = fneg_ptr(fneg, (int)(e0 & DLP_J_MASK));
+        atomicAdd(q, f0x); atomicAdd(q + 4, f0y); atomicAdd(q + 8, f0z);
+      }
+      if (live1 && !h1 && o1.gamma != 0.0) {
+        double* q = fneg_ptr(fneg, (int)(e1 & DLP_J_MASK));
+        atomicAdd(q, f1x); atomicAdd(q + 4, f1y); atomicAdd(q + 8, f1z);
+      }
+    }
+#pragma unroll
+    for (int d = TPR / 2; d > 0; d >>= 1) {
+      fix += __shfl_xor_sync(DLP_FULL, fix, d);
+      fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
+      fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
+    }
+    if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
+  }
+  __shared__ double red[16][10];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    // partial[] keeps the 12-slot layout of k_pair_forces: 0..3 vdw/coul energy+virial, 4..5 exclusion terms (none here), 6..11 stress
+    const int src = threadIdx.x < 4 ? threadIdx.x : (threadIdx.x < 6 ? -1 : threadIdx.x - 2);
+    double v = 0.0;
+    if (src >= 0) for (int w = 0; w < 16; ++w) v += red[w][src];
+    partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
+  }
+}
+
+// half mode epilogue: f(i) (+)= [row sum of atom i] - [what its partners' rows pushed onto it]
+__global__ void k_scatter_half(int natms, int zero_forces, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
+                               const double* __restrict__ fpos, const double* __restrict__ fneg, double* fx, double* fy, double* fz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= natms) return;
+  const int ii = loc_slot[t];
+  const int i = at_list[ii];
+  const double* q = fneg + (size_t)(ii >> 2) * 12 + (ii & 3);
+  const double a = fpos[t] - q[0], b = fpos[(size_t)natms + t] - q[4], c = fpos[2 * (size_t)natms + t] - q[8];
+  if (zero_forces) { fx[i] = a; fy[i] = b; fz[i] = c; }
+  else { fx[i] += a; fy[i] += b; fz[i] += c; }
 }
 
 // nve.F90:163-173, :198-217
@@ -349,18 +516,18 @@ __global__ void k_dfma(int iters, double* out) {
 
 }  // namespace
 
-template <int TPR>
-static int launch_pair(dlpgpu_ctx* ctx, const FParams& P, bool use_smem, size_t smem, int blocks, double* fsx, double* fsy, double* fsz) {
+template <int TPR, int NT>
+static int launch_pair(dlpgpu_ctx* ctx, const FParams& P, bool use_smem, size_t smem, int blocks, double* fpos, double* fneg) {
   const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
   if (use_smem) {
-    CK(cudaFuncSetAttribute(k_pair_forces<TPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(ctx, (k_pair_forces<TPR, true>), blocks, 512, smem, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
-           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx,
-           fsy, fsz, ctx->partial.p);
+    CK(cudaFuncSetAttribute(k_pair_forces<TPR, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, (k_pair_forces<TPR, true, NT>), blocks, NT, smem, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fpos,
+           fneg, ctx->partial.p);
   } else {
-    LAUNCH(ctx, (k_pair_forces<TPR, false>), blocks, 512, 0, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
-           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fsx,
-           fsy, fsz, ctx->partial.p);
+    LAUNCH(ctx, (k_pair_forces<TPR, false, NT>), blocks, NT, 0, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fpos,
+           fneg, ctx->partial.p);
   }
   return 0;
 }
@@ -404,7 +571,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   CKRC(dlp_gather_sorted(ctx));
   FParams P{};
   P.natms = natms; P.pitch = ctx->pitch; P.xpitch = ctx->xpitch > 0 ? ctx->xpitch : 1;
-  P.max_grid = ctx->max_grid; P.max_vdw = ctx->max_vdw; P.ew_n = ctx->ew_n; P.tstride = ctx->max_grid + 1; P.ew_off = ctx->ew_off;
+  P.max_grid = ctx->max_grid; P.max_vdw = ctx->max_vdw; P.ew_n = ctx->ew_n; P.tstride = ctx->max_grid + 1; P.ew_off = ctx->ew_off; P.tab_ne = (int)ctx->tab4_entries;
   P.vdw_on = ctx->vdw_on; P.vdw_direct = ctx->vdw_direct; P.vdw_fshift = ctx->vdw_fshift; P.ew_on = ctx->ew_on;
   P.half = ctx->force_mode == 1; P.zero_forces = zero_forces; P.lbook = ctx->lbook;
   P.same_grid = ctx->vdw_on && ctx->ew_on && ctx->vdw_rdr == ctx->ew_rdr;
@@ -417,27 +584,41 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   // threads per row from the mean row length: the group width that wastes the fewest lanes on the last pass
   long long pairs_hint = ctx->list_entries;
   double mean = natms > 0 ? (double)pairs_hint / natms : 0.0;
-  int tpr = mean > 80.0 ? 16 : 8;
+  int tpr = mean > 64.0 ? 8 : 16;   // measured on B200: long (ionic) rows run best 8 lanes wide, short (LJ) rows 16 wide
   if (ctx->tpr_override) tpr = ctx->tpr_override;
-  int blocks = std::max(1, std::min(cdiv(natms, 512 / tpr), ctx->sm_count * bps));
+  const int NT = 512;
+  int blocks = std::max(1, std::min(cdiv(natms, NT / tpr), ctx->sm_count * bps));
   CK(ctx->partial.ensure((size_t)blocks * 12 + 16, s));
-  double *fsx = nullptr, *fsy = nullptr, *fsz = nullptr;
-  if (P.half) {   // sorted-slot force accumulators of the atomics path
-    CK(ctx->fsx.ensure(ctx->nlast + 1, s)); CK(ctx->fsy.ensure(ctx->nlast + 1, s)); CK(ctx->fsz.ensure(ctx->nlast + 1, s));
-    CK(cudaMemsetAsync(ctx->fsx.p, 0, (size_t)ctx->nlast * sizeof(double), s));
-    CK(cudaMemsetAsync(ctx->fsy.p, 0, (size_t)ctx->nlast * sizeof(double), s));
-    CK(cudaMemsetAsync(ctx->fsz.p, 0, (size_t)ctx->nlast * sizeof(double), s));
-    fsx = ctx->fsx.p; fsy = ctx->fsy.p; fsz = ctx->fsz.p;
+  double *fpos = nullptr, *fneg = nullptr;
+  if (P.half) {   // row sums (per local atom) and the blocked j-side accumulators (per sorted slot) of the Newton-3 path
+    const size_t nneg = ((size_t)ctx->nlast / 4 + 2) * 12;
+    CK(ctx->fsx.ensure(3 * (size_t)natms + 4, s)); CK(ctx->fsy.ensure(nneg, s));
+    CK(cudaMemsetAsync(ctx->fsy.p, 0, nneg * sizeof(double), s));
+    fpos = ctx->fsx.p; fneg = ctx->fsy.p;
   }
   cudaEventRecord(ctx->ev[6], s);
-  if (natms > 0) {
-    if (tpr == 32) CKRC(launch_pair<32>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
-    else if (tpr == 16) CKRC(launch_pair<16>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
-    else CKRC(launch_pair<8>(ctx, P, use_smem, smem, blocks, fsx, fsy, fsz));
+  const bool fast = P.half && use_smem && !ctx->no_fast && !(P.lbook && P.ew_on) && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) &&
+                    (P.vdw_on || P.ew_on) && (tpr == 8 || tpr == 16);
+  if (natms > 0 && fast) {
+    const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
+#define DLP_FAST(T, V, E)                                                                                                      \
+  do {                                                                                                                         \
+    CK(cudaFuncSetAttribute(k_pair_fast<T, V, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+    LAUNCH(ctx, (k_pair_fast<T, V, E>), blocks, 512, smem, P, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, t4, fpos, fneg, \
+           ctx->partial.p);                                                                                                    \
+  } while (0)
+    const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0;
+    if (tpr == 8) { if (v && e) DLP_FAST(8, 1, 1); else if (v) DLP_FAST(8, 1, 0); else DLP_FAST(8, 0, 1); }
+    else { if (v && e) DLP_FAST(16, 1, 1); else if (v) DLP_FAST(16, 1, 0); else DLP_FAST(16, 0, 1); }
+#undef DLP_FAST
+  } else if (natms > 0) {
+    if (tpr == 32) CKRC((launch_pair<32, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
+    else if (tpr == 16) CKRC((launch_pair<16, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
+    else CKRC((launch_pair<8, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
   }
   cudaEventRecord(ctx->ev[7], s);
   if (natms > 0 && P.half)
-    LAUNCH(ctx, k_scatter_half, cdiv(ctx->nlast, 256), 256, 0, ctx->nlast, natms, zero_forces, ctx->at_list.p, fsx, fsy, fsz, ctx->fx.p,
+    LAUNCH(ctx, k_scatter_half, cdiv(natms, 256), 256, 0, natms, zero_forces, ctx->loc_slot.p, ctx->at_list.p, fpos, fneg, ctx->fx.p,
            ctx->fy.p, ctx->fz.p);
   LAUNCH(ctx, k_final_reduce, 1, 32, 0, natms > 0 ? blocks : 0, ctx->partial.p, ctx->out_dev.p);
   cudaEventRecord(ctx->ev[5], s);

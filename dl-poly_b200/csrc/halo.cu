@@ -245,7 +245,7 @@ __global__ void k_reloc_tag(int natms, Mat9 rcell, DomI D, const double4* __rest
   if (D.idz == D.nz - 1) { if (z >= half_minus) v += 200; } else { if (ipz > D.idz) v += 200; }
   ixyz[i] = v;
 }
-__global__ void k_reloc_flag(int n, Dir d, int* __restrict__ ixyz, int* __restrict__ leave) {   // deport_data.F90:254-274
+__global__ void k_reloc_flag(int n, Dir d, const int* __restrict__ ixyz, int* __restrict__ leave) {   // deport_data.F90:254-274
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   int f = 0;
@@ -254,7 +254,7 @@ __global__ void k_reloc_flag(int n, Dir d, int* __restrict__ ixyz, int* __restri
     if (v != 0) {
       int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
       int j = ix * d.kx + iy * d.ky + iz * d.kz;
-      if (j == d.jxyz) { ixyz[i] = v - d.jxyz; f = 1; }
+      if (j == d.jxyz) f = 1;   // the tag is decremented when the atom is packed (a too-small buffer retries the stage)
     }
   }
   leave[i] = f;
@@ -275,7 +275,7 @@ __global__ void k_reloc_pack(int n, int k_stay, Dir d, int cap, const int* __res
   else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
   b[3] = vx[i]; b[4] = vy[i]; b[5] = vz[i];
   b[6] = fx[i]; b[7] = fy[i]; b[8] = fz[i];
-  b[9] = (double)ltg[i]; b[10] = (double)lsite[i]; b[11] = (double)ixyz[i];
+  b[9] = (double)ltg[i]; b[10] = (double)lsite[i]; b[11] = (double)(ixyz[i] - d.jxyz);
 }
 // restack (deport_data.F90:822-925): the r-th hole (ascending) below the new natms takes the r-th staying atom counted
 // from the end.  stay_prefix[j] = j - lpos[j] staying atoms precede j.
