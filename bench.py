@@ -108,7 +108,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(gpu_index),
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -257,6 +257,7 @@ def run_gpu(args):
     # first build + forces (untimed)
     dom.rebuild()
     dom.forces()
+    sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(args.warmup):
         dom.step(dt)
     dom.rebuilds = 0
@@ -265,7 +266,6 @@ def run_gpu(args):
     if transport is not None:
         transport.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = sr.launch_count()
     pair_ms, list_ms, force_ms, nlist = 0.0, 0.0, 0.0, 0
     ev0.record(stream)
@@ -332,6 +332,9 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread; restatement "
                          "of the reference algorithm (oracle/), not the reference binary" % (what, info["steps"], info["rebuilds"], info["cores"])}
+    if rank == 0 and dom.profile is not None:
+        sys.stderr.write("phase profile (ms per step, synchronised phases): %s\n" %
+                         {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()})
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -470,6 +470,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
 #define LC_MAXRUN 96
 struct LCRow { int dy, dz, b; };
 
+template <bool SIMPLE>   // SIMPLE: no exclusion lists, no frozen pairs, nlp < 3 -- the lean inner loop
 __global__ void __launch_bounds__(LC_WARPS * 32)
 k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid, int nrows,
             const LCRow* __restrict__ rows, const int* __restrict__ at_list, const int* __restrict__ lct_start,
@@ -481,7 +482,12 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   __shared__ int2 s_info[LC_WARPS][32];
   __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
   __shared__ int s_pre[LC_WARPS][LC_MAXRUN + 1];   // candidates before run r
+  __shared__ int s_cnt[LC_WARPS][32];
+  __shared__ int s_pk[256];                        // (type_i, type_j) -> vdW potential index + 1, when ntypes <= 16
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool pk_smem = pair_k != nullptr && ntypes <= 16;
+  if (pk_smem) for (int q = threadIdx.x; q < ntypes * ntypes; q += LC_WARPS * 32) s_pk[q] = pair_k[q] + 1;
+  __syncthreads();
   const int ncell_dom = g.nlx * g.nly * g.nlz;
   const int cd = blockIdx.x * LC_WARPS + wid;
   if (cd >= ncell_dom) return;
@@ -549,6 +555,50 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
     }
     __syncwarp();
     const int t0 = slot_rank[a0];
+    if (SIMPLE) {
+      s_cnt[wid][lane] = 0;
+      __syncwarp();
+      const unsigned ltmask = (1u << lane) - 1u;
+      for (int c0 = 0; c0 < total; c0 += 32) {
+        const int c = c0 + lane;
+        const bool valid = c < total;
+        int jj = 0x7fffffff;
+        double4 pj = make_double4(1e300, 1e300, 1e300, 0);
+        int2 infj = make_int2(0, 0);
+        if (valid) {   // largest run r with pre[r] <= c
+          int lo = 0, hi = LC_MAXRUN - 1;
+          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[wid][mid] <= c) lo = mid; else hi = mid - 1; }
+          jj = s_run0[wid][lo] + (c - s_pre[wid][lo]);
+          pj = posq_s[jj]; infj = info_s[jj];
+        }
+        const bool halo_j = (infj.y >> 17) & 1;
+        const unsigned jbits = (unsigned)jj | (halo_j ? DLP_F_HALO : 0u);
+        const int tj = (infj.y & 0xffff) - 1;
+        const bool before = jj < s_own0;
+        // nlp == 2: the only stencil entry with the "no distance check" flag is the cell itself (neighbours.F90:537, :922-943)
+        const bool own_nir = g.nir_r2 > 0 && valid && jj >= s_own0 && jj < s_own1;
+        for (int a = 0; a < na; ++a) {
+          const double4 pi = s_pi[wid][a];
+          const bool acc = (own_nir || pair_rsq(pj, pi.x, pi.y, pi.z) <= g.rcsq) && (jj > a0 + a || before);   // invalid lanes sit at 1e300
+          const unsigned m = __ballot_sync(DLP_FULL, acc);
+          if (m == 0u) continue;
+          const int ca = s_cnt[wid][a];
+          if (acc) {
+            const int2 infi = s_info[wid][a];
+            const int kidx = ((infi.y & 0xffff) - 1) * ntypes + tj;
+            const int kc = pk_smem ? s_pk[kidx] : (pair_k ? pair_k[kidx] + 1 : 0);
+            const unsigned entry = jbits | ((unsigned)kc << DLP_K_SHIFT) | ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
+            const int ll = ca + __popc(m & ltmask);
+            if (ll < pitch) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
+            else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
+          }
+          if (lane == 0) s_cnt[wid][a] = ca + __popc(m);
+        }
+        __syncwarp();
+      }
+      cnt = s_cnt[wid][lane];
+    } else
+    {
     for (int c0 = 0; c0 < total; c0 += 32) {
       const int c = c0 + lane;
       const bool valid = c < total;
@@ -598,6 +648,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
           if (lane == a) xcnt += __popc(mx);
         }
       }
+    }
     }
     if (lane < na) { nnbr[t0 + lane] = cnt; nxnbr[t0 + lane] = xcnt; written += cnt; }
   }
@@ -699,10 +750,14 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
         CK(ctx->st_rows.ensure(hrows.size() * 3 + 3, s));
         CK(cudaMemcpyAsync(ctx->st_rows.p, hrows.data(), hrows.size() * sizeof(LCRow), cudaMemcpyHostToDevice, s));
         const int ncd = g.nlx * g.nly * g.nlz;
-        LAUNCH(ctx, k_list_cell, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook,
-               ctx->max_exclude, ctx->excl_by_gid, (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p,
-               ctx->lct_start.p, ctx->cell_s.p, ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr,
-               ctx->ntypes, ctx->excl.p, ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p);
+        const bool simple = !ctx->lbook && ctx->megfrz <= 1 && g.nir_r2 <= 1;
+#define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
+               (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
+               ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
+               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p
+        if (simple) LAUNCH(ctx, k_list_cell<true>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else LAUNCH(ctx, k_list_cell<false>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+#undef DLP_LC_ARGS
       } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
                ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,

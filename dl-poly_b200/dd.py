@@ -286,6 +286,8 @@ class Domain:
         self._refresh_bufs = None
         self.rebuilds = 0
         self.steps = 0
+        import os
+        self.profile = {} if os.environ.get("DLP_DD_PROFILE") else None
 
     # ---- buffers on the context's device
     def _alloc(self, n_doubles):
@@ -355,6 +357,8 @@ class Domain:
     def step(self, dt):
         """One velocity-Verlet step with the short-range path as the only force provider."""
         sr = self.sr
+        if self.profile is not None:
+            return self._step_profiled(dt)
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(1, dt)
         if self.vnl_update():
@@ -364,6 +368,40 @@ class Domain:
         out = self.forces()
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(2, dt)
+        self.steps += 1
+        return out
+
+    def _step_profiled(self, dt):
+        """step() with a device synchronisation after every phase (DLP_DD_PROFILE=1): wall time per phase in self.profile."""
+        import time
+        sr, prof = self.sr, self.profile
+
+        def lap(name, t0):
+            self.torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            prof[name] = prof.get(name, 0.0) + (t1 - t0)
+            return t1
+
+        self.torch.cuda.synchronize()
+        t = time.perf_counter()
+        with self.torch.cuda.stream(self.stream):
+            sr.dev_vv(1, dt)
+        t = lap("vv1", t)
+        upd = self.vnl_update()
+        t = lap("vnl_check+gmax", t)
+        if upd:
+            self.relocate(); t = lap("relocate", t)
+            self.set_halo(); t = lap("set_halo", t)
+            with self.torch.cuda.stream(self.stream):
+                sr.dev_link_cell_pairs()
+            t = lap("link_cell_pairs", t)
+            self.rebuilds += 1
+        else:
+            self.refresh_halo(); t = lap("refresh_halo", t)
+        out = self.forces(); t = lap("two_body_forces", t)
+        with self.torch.cuda.stream(self.stream):
+            sr.dev_vv(2, dt)
+        t = lap("vv2", t)
         self.steps += 1
         return out
 
