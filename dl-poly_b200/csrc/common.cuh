@@ -67,6 +67,8 @@ struct LCGeom {
   int nir_r2;         // (nlp-1)^2: offsets with ix^2+iy^2+iz^2 < nir_r2 skip the distance test (neighbours.F90:537)
 };
 
+#define DLP_HALO_W 9   // doubles per atom on a halo build: the reference's six (x,y,z,ltg,lsite,ixyz) + origin rank, index, wraps
+
 struct HaloStage {    // one export_atomic_data direction as recorded at halo build, replayed by the refresh
   int count = 0;      // atoms sent (== received from the opposite neighbour in a serial run)
   int recv_off = 0;   // first local index (0-based) the received atoms were appended at
@@ -129,6 +131,16 @@ struct dlpgpu_ctx {
   DBuf<double> fsx, fsy, fsz;   // force_mode 1: fsx = row sums [3][natms], fsy = blocked j-side accumulators, fsz unused
   DBuf<double> vx, vy, vz;
   DBuf<int> ltg, lsite, ltype, lfrzn, ixyz;
+  // origin of every resident atom, carried through the halo build: owning rank, local index there, and the periodic
+  // wraps applied on the way ((u+1) + 3(v+1) + 9(w+1), u,v,w in {-1,0,1}) -- what the one-kernel halo refresh replays
+  DBuf<int> org_rank, org_idx, org_wrap;
+  // peer-visible copies of the local coordinates (double-buffered by step parity), CUDA-IPC mapped on every rank
+  double4* pub[2] = {nullptr, nullptr};
+  int pub_cap = 0, pub_parity = 0;
+  int p2p_rank = 0, p2p_nranks = 0;
+  bool p2p_ready = false, pub_valid = false;
+  std::vector<double4*> peer_pub;   // [2 * nranks]
+  DBuf<unsigned long long> peer_pub_dev;   // the same table on the device
   DBuf<double> xbg, ybg, zbg;
   bool have_bg = false;
 

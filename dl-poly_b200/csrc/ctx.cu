@@ -108,6 +108,9 @@ int dlp_ensure_atoms(dlpgpu_ctx* ctx, int n) {
   CK(ctx->ltype.ensure(n, s, true, keep));
   CK(ctx->lfrzn.ensure(n, s, true, keep));
   CK(ctx->ixyz.ensure(n, s, true, keep));
+  CK(ctx->org_rank.ensure(n, s, true, keep));
+  CK(ctx->org_idx.ensure(n, s, true, keep));
+  CK(ctx->org_wrap.ensure(n, s, true, keep));
   CK(ctx->xbg.ensure(n, s, true, keep));
   CK(ctx->ybg.ensure(n, s, true, keep));
   CK(ctx->zbg.ensure(n, s, true, keep));
@@ -155,7 +158,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   // buffers are released with the context; DBuf has no destructor on purpose (explicit lifetime)
   DBuf<int>* ib[] = {&ctx->pair_k, &ctx->ltp, &ctx->type_site, &ctx->freeze_site, &ctx->excl, &ctx->ltg, &ctx->lsite, &ctx->ltype,
-                     &ctx->lfrzn, &ctx->ixyz, &ctx->which_cell, &ctx->at_list, &ctx->at_tmp, &ctx->lct_count, &ctx->lct_start,
+                     &ctx->lfrzn, &ctx->ixyz, &ctx->org_rank, &ctx->org_idx, &ctx->org_wrap, &ctx->which_cell, &ctx->at_list, &ctx->at_tmp, &ctx->lct_count, &ctx->lct_start,
                      &ctx->lct_fill, &ctx->cell_s, &ctx->loc_slot, &ctx->flag, &ctx->scan_out, &ctx->scan_tmp, &ctx->type_s,
                      &ctx->gid_s, &ctx->frz_s, &ctx->st_nix, &ctx->st_niy, &ctx->st_niz, &ctx->st_nir, &ctx->st_xb, &ctx->ref_list,
                      &ctx->nnbr, &ctx->nxnbr, &ctx->nhnbr, &ctx->status};
@@ -167,6 +170,12 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
   ctx->tab4.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
+  for (int r = 0; r < ctx->p2p_nranks; ++r)
+    if (r != ctx->p2p_rank)
+      for (int b = 0; b < 2; ++b)
+        if (ctx->peer_pub.size() > (size_t)(2 * r + b) && ctx->peer_pub[2 * r + b]) cudaIpcCloseMemHandle(ctx->peer_pub[2 * r + b]);
+  for (int b = 0; b < 2; ++b) if (ctx->pub[b]) cudaFree(ctx->pub[b]);
+  ctx->peer_pub_dev.release();
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

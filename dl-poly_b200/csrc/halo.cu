@@ -6,8 +6,8 @@
 //   deport_data.F90:2870-3202 relocate_particles      deport_data.F90:81-960     deport_atomic_data
 //   numerics.F90:1851-1950  pbcshift_parts
 //
-// The wire format is the reference's (6 doubles per halo atom on a build, 3 on a refresh, the sender applies the
-// periodic shift); selection, ordering (ascending local index, appended in stage order -x,+x,-y,+y,-z,+z) and the
+// The wire format is the reference's (x,y,z,ltg,lsite,ixyz per halo atom on a build -- plus three doubles naming the
+// atom's origin for the one-kernel refresh below --, 3 doubles on a staged refresh, the sender applies the periodic shift); selection, ordering (ascending local index, appended in stage order -x,+x,-y,+y,-z,+z) and the
 // restack of staying atoms after migration reproduce the reference so local indices agree with a DL_POLY run.
 // Compiled with -fmad=false: thresholds and shifts decide set membership.
 #include "common.cuh"
@@ -108,9 +108,11 @@ __global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const dou
 // ---------------------------------------------------------------- halo build
 struct HaloThr { double ecwx, ecwy, ecwz, cwx, cwy, cwz; };
 
-__global__ void k_halo_tag(int natms, Mat9 rcell, HaloThr t, const double4* __restrict__ posq, int* __restrict__ ixyz) {
+__global__ void k_halo_tag(int natms, Mat9 rcell, HaloThr t, const double4* __restrict__ posq, int* __restrict__ ixyz, int my_rank,
+                           int* __restrict__ org_rank, int* __restrict__ org_idx, int* __restrict__ org_wrap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natms) return;
+  org_rank[i] = my_rank; org_idx[i] = i; org_wrap[i] = 13;   // 13 = no wrap on any axis
   double4 p = posq[i];
   double x = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;   // halo.F90:265-267
   double y = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
@@ -140,6 +142,7 @@ __global__ void k_halo_flag(int n, Dir d, const int* __restrict__ ixyz, int* __r
 }
 __global__ void k_halo_pack(int n, Dir d, int cap, const int* __restrict__ flag, const int* __restrict__ pos, const double4* __restrict__ posq,
                             const int* __restrict__ ltg, const int* __restrict__ lsite, const int* __restrict__ ixyz,
+                            const int* __restrict__ org_rank, const int* __restrict__ org_idx, const int* __restrict__ org_wrap, int wrap_add,
                             double* __restrict__ buf, int* __restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !flag[i]) return;
@@ -147,7 +150,8 @@ __global__ void k_halo_pack(int n, Dir d, int cap, const int* __restrict__ flag,
   idx[k] = i;
   if (k >= cap) return;
   double4 p = posq[i];
-  double* b = buf + (size_t)k * 6;
+  double* b = buf + (size_t)k * DLP_HALO_W;
+  b[6] = (double)org_rank[i]; b[7] = (double)org_idx[i]; b[8] = (double)(org_wrap[i] + wrap_add);
   if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
   else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // :1836-1844
   b[3] = (double)ltg[i];
@@ -156,11 +160,13 @@ __global__ void k_halo_pack(int n, Dir d, int cap, const int* __restrict__ flag,
   b[5] = (double)(v - (halo_sel(v, d) == 1 ? d.jxyz : d.kxyz));            // :1853
 }
 __global__ void k_halo_unpack(int count, int off, const double* __restrict__ buf, double4* __restrict__ posq, int* __restrict__ ltg,
-                              int* __restrict__ lsite, int* __restrict__ ixyz, double* fx, double* fy, double* fz) {
+                              int* __restrict__ lsite, int* __restrict__ ixyz, double* fx, double* fy, double* fz,
+                              int* __restrict__ org_rank, int* __restrict__ org_idx, int* __restrict__ org_wrap) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
-  const double* b = buf + (size_t)k * 6;
+  const double* b = buf + (size_t)k * DLP_HALO_W;
   int i = off + k;
+  org_rank[i] = __double2int_rn(b[6]); org_idx[i] = __double2int_rn(b[7]); org_wrap[i] = __double2int_rn(b[8]);
   posq[i] = make_double4(b[0], b[1], b[2], 0.0);
   ltg[i] = __double2int_rn(b[3]); lsite[i] = __double2int_rn(b[4]); ixyz[i] = __double2int_rn(b[5]);   // Nint, :1935-1940
   fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0;
@@ -192,6 +198,37 @@ __global__ void k_refresh_unpack(int count, int off, const double* __restrict__ 
   double4 p = posq[off + k];
   p.x = b[0]; p.y = b[1]; p.z = b[2];
   posq[off + k] = p;
+}
+
+// ---------------------------------------------------------------- one-kernel halo refresh over peer memory
+// refresh_halo_positions re-sends the same atoms through the same six dependent stages.  Every halo atom is, in the end, a
+// copy of ONE local atom of some rank (possibly this one) plus the periodic shifts picked up on the way; the halo build
+// records that origin.  Each rank publishes its local coordinates in a CUDA-IPC mapped buffer (double-buffered by step
+// parity) and every rank fills its whole halo with one kernel of peer loads over NVLink -- no staging, no messages.
+// The shifts are replayed in stage order (x, then y, then z) with the arithmetic of the staged exchange, so the
+// coordinates carry the same bits.
+__global__ void k_publish(int natms, const double4* __restrict__ posq, double4* __restrict__ pub) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < natms) pub[i] = posq[i];
+}
+__global__ void k_refresh_pull(int natms, int nlast, int parity, const unsigned long long* __restrict__ peers, Mat9 cell,
+                               const int* __restrict__ org_rank, const int* __restrict__ org_idx, const int* __restrict__ org_wrap,
+                               double4* __restrict__ posq) {
+  int h = natms + blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nlast) return;
+  const double4* src = reinterpret_cast<const double4*>(peers[2 * org_rank[h] + parity]) + org_idx[h];
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(src));
+  const double c = __ldcg(reinterpret_cast<const double*>(src) + 2);
+  double x = a.x, y = a.y, z = c;
+  const int w = org_wrap[h];
+  const double u = (double)(w % 3 - 1), v = (double)((w / 3) % 3 - 1), ww = (double)(w / 9 - 1);
+  // deport_data.F90:1786-1796 / :2460-2468 per stage: xadd = cell(1) uuu + cell(4) vvv + cell(7) www with one of them set
+  if (u != 0.0) { x = x + (cell.m[0] * u + cell.m[3] * 0.0 + cell.m[6] * 0.0); y = y + (cell.m[1] * u + cell.m[4] * 0.0 + cell.m[7] * 0.0); z = z + (cell.m[2] * u + cell.m[5] * 0.0 + cell.m[8] * 0.0); }
+  if (v != 0.0) { x = x + (cell.m[0] * 0.0 + cell.m[3] * v + cell.m[6] * 0.0); y = y + (cell.m[1] * 0.0 + cell.m[4] * v + cell.m[7] * 0.0); z = z + (cell.m[2] * 0.0 + cell.m[5] * v + cell.m[8] * 0.0); }
+  if (ww != 0.0) { x = x + (cell.m[0] * 0.0 + cell.m[3] * 0.0 + cell.m[6] * ww); y = y + (cell.m[1] * 0.0 + cell.m[4] * 0.0 + cell.m[7] * ww); z = z + (cell.m[2] * 0.0 + cell.m[5] * 0.0 + cell.m[8] * ww); }
+  double4 p = posq[h];
+  p.x = x; p.y = y; p.z = z;
+  posq[h] = p;
 }
 
 // ---------------------------------------------------------------- relocation
@@ -363,7 +400,9 @@ int dlpgpu_dev_halo_begin(dlpgpu_ctx* ctx) {
   double rc[9];
   h_invert(ctx->cell, rc);
   ctx->nlast = ctx->natms;   // halo.F90:259
-  if (ctx->natms > 0) LAUNCH(ctx, k_halo_tag, cdiv(ctx->natms, 256), 256, 0, ctx->natms, mat(rc), t, ctx->posq.p, ctx->ixyz.p);
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_halo_tag, cdiv(ctx->natms, 256), 256, 0, ctx->natms, mat(rc), t, ctx->posq.p, ctx->ixyz.p, ctx->p2p_rank, ctx->org_rank.p,
+           ctx->org_idx.p, ctx->org_wrap.p);
   ctx->halo_valid = false; ctx->list_valid = false;
   for (int q = 0; q < 6; ++q) { ctx->stage[q].count = 0; ctx->stage[q].recv_count = 0; ctx->stage[q].recv_off = ctx->natms; }
   return 0;
@@ -385,9 +424,17 @@ int dlpgpu_dev_halo_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int cap
   if (total > capacity_atoms || (total > 0 && !sendbuf_dev))
     return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 54: outgoing halo buffer too small (%d atoms > capacity %d)", total, capacity_atoms);
   CK(st.idx.ensure((size_t)total + 1, s));
-  if (total > 0)
-    LAUNCH(ctx, k_halo_pack, cdiv(n, 256), 256, 0, n, d, capacity_atoms, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->ltg.p, ctx->lsite.p,
-           ctx->ixyz.p, sendbuf_dev, st.idx.p);
+  {
+    // wrap code increment of this stage: the sender applies uuu/vvv/www = +-1 on its axis when it sits on the cell border
+    int wrap_add = 0;
+    if (d.lwrap) {
+      const int sgn = (mdir < 0) ? +1 : -1;                 // -dir exports from the low border shift by +cell, +dir by -cell
+      wrap_add = sgn * (d.kx ? 1 : d.ky ? 3 : 9);
+    }
+    if (total > 0)
+      LAUNCH(ctx, k_halo_pack, cdiv(n, 256), 256, 0, n, d, capacity_atoms, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->ltg.p, ctx->lsite.p,
+             ctx->ixyz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p, wrap_add, sendbuf_dev, st.idx.p);
+  }
   return 0;
 }
 
@@ -399,7 +446,7 @@ int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev,
   st.recv_off = ctx->nlast; st.recv_count = count;
   if (count > 0)
     LAUNCH(ctx, k_halo_unpack, cdiv(count, 256), 256, 0, count, ctx->nlast, recvbuf_dev, ctx->posq.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p,
-           ctx->fx.p, ctx->fy.p, ctx->fz.p);
+           ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p);
   ctx->nlast += count;
   return 0;
 }
@@ -425,11 +472,11 @@ int dlpgpu_dev_halo_serial(dlpgpu_ctx* ctx) {
   for (int q = 0; q < 6; ++q) {
     // jmove = imove (deport_data.F90:1884-1886): the rank is its own neighbour.  Size the buffer from the flag count.
     int cnt = 0;
-    int cap = (int)(ctx->xfer.cap / 6);
+    int cap = (int)(ctx->xfer.cap / DLP_HALO_W);
     int rc = dlpgpu_dev_halo_pack(ctx, mdirs[q], ctx->xfer.p, cap, &cnt);
     if (rc == DLPGPU_ERR_BUFFER) {
-      CK(ctx->xfer.ensure((size_t)cnt * 6 + 64, ctx->stream));
-      rc = dlpgpu_dev_halo_pack(ctx, mdirs[q], ctx->xfer.p, (int)(ctx->xfer.cap / 6), &cnt);
+      CK(ctx->xfer.ensure((size_t)cnt * DLP_HALO_W + 64, ctx->stream));
+      rc = dlpgpu_dev_halo_pack(ctx, mdirs[q], ctx->xfer.p, (int)(ctx->xfer.cap / DLP_HALO_W), &cnt);
     }
     if (rc) return rc;
     CKRC(dlpgpu_dev_halo_unpack(ctx, mdirs[q], ctx->xfer.p, cnt));
@@ -458,6 +505,78 @@ int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_d
   if (count != st.recv_count)   // halo.F90:104-106
     return dlp_fail(ctx, DLPGPU_ERR_HALO_COUNT, "error 138: refreshed halo size %d differs from the built one %d", count, st.recv_count);
   if (count > 0) LAUNCH(ctx, k_refresh_unpack, cdiv(count, 256), 256, 0, count, st.recv_off, recvbuf_dev, ctx->posq.p);
+  return 0;
+}
+
+// ---- peer-memory refresh
+int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[128]) {
+  if (!ctx || rank < 0 || nranks < 1 || rank >= nranks || capacity_atoms < 1 || !handles_out) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "p2p_init: already initialised");
+  ctx->p2p_rank = rank; ctx->p2p_nranks = nranks; ctx->pub_cap = capacity_atoms;
+  std::memset(handles_out, 0, 128);
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc((void**)&ctx->pub[b], (size_t)capacity_atoms * sizeof(double4)));
+    if (nranks > 1) {
+      cudaIpcMemHandle_t h;
+      CK(cudaIpcGetMemHandle(&h, ctx->pub[b]));
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+      std::memcpy(handles_out + 64 * b, &h, 64);
+    }
+  }
+  ctx->peer_pub.assign((size_t)2 * nranks, nullptr);
+  ctx->peer_pub[2 * rank] = ctx->pub[0]; ctx->peer_pub[2 * rank + 1] = ctx->pub[1];
+  ctx->p2p_ready = (nranks == 1);
+  if (ctx->p2p_ready) {
+    CK(ctx->peer_pub_dev.ensure(2, ctx->stream));
+    CK(cudaMemcpy(ctx->peer_pub_dev.p, ctx->peer_pub.data(), 2 * sizeof(void*), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x 128 bytes, rank-major */) {
+  if (!ctx || !all_handles) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "p2p_open: call p2p_init first");
+  for (int r = 0; r < ctx->p2p_nranks; ++r) {
+    if (r == ctx->p2p_rank) continue;
+    for (int b = 0; b < 2; ++b) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, all_handles + (size_t)128 * r + 64 * b, 64);
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->peer_pub[2 * r + b] = (double4*)p;
+    }
+  }
+  CK(ctx->peer_pub_dev.ensure((size_t)2 * ctx->p2p_nranks, ctx->stream));
+  CK(cudaMemcpy(ctx->peer_pub_dev.p, ctx->peer_pub.data(), (size_t)2 * ctx->p2p_nranks * sizeof(void*), cudaMemcpyHostToDevice));
+  ctx->p2p_ready = true;
+  return 0;
+}
+
+// copies the local coordinates into the peer-visible buffer of the next parity; call once per step after the positions moved
+int dlpgpu_dev_publish(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "publish: p2p not initialised");
+  if (ctx->natms > ctx->pub_cap) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "publish: %d local atoms exceed the peer buffer (%d)", ctx->natms, ctx->pub_cap);
+  ctx->pub_parity ^= 1;
+  if (ctx->natms > 0) LAUNCH(ctx, k_publish, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->posq.p, ctx->pub[ctx->pub_parity]);
+  ctx->pub_valid = true;
+  return 0;
+}
+
+// refresh_halo_positions in one kernel.  Every rank must have published this step's coordinates and a collective on the
+// same streams (the gmax of vnl_check) must separate the publishes from the pulls.
+int dlpgpu_dev_refresh_pull(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->p2p_ready || !ctx->pub_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "refresh_pull: peer buffers not ready / nothing published");
+  if (!ctx->halo_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "refresh: no halo has been built");
+  const int nh = ctx->nlast - ctx->natms;
+  if (nh > 0)
+    LAUNCH(ctx, k_refresh_pull, cdiv(nh, 256), 256, 0, ctx->natms, ctx->nlast, ctx->pub_parity, ctx->peer_pub_dev.p, mat(ctx->cell),
+           ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p, ctx->posq.p);
   return 0;
 }
 

@@ -22,6 +22,7 @@ The transport is duck-typed (anything with ``exchange(sendbuf, n_send_items, rec
 import numpy as np
 
 MDIRS = (-1, 1, -2, 2, -3, 3)          # stage order of halo.F90:277-292 / deport_data.F90:3031-3052
+HALO_WIDTH = 9                         # DLPGPU_HALO_WIDTH: doubles per atom of a halo-build message
 HALF_MINUS = np.nextafter(0.5, 0.0)
 
 
@@ -287,6 +288,15 @@ class Domain:
         self.rebuilds = 0
         self.steps = 0
         import os
+        # peer-memory refresh: publish buffers sized for the local atoms with head-room for migration
+        self.p2p = os.environ.get("DLP_DD_STAGED_REFRESH") is None
+        if self.p2p:
+            blob = sr_blob = self.sr.dev_p2p_init(self.rank, self.world, int(1.25 * self.natms0) + 8192)
+            if self.world > 1:
+                t_blob = torch.from_numpy(blob.copy()).to(self.device)
+                allb = [torch.empty_like(t_blob) for _ in range(self.world)]
+                self.t.dist.all_gather(allb, t_blob, group=self.t.group)
+                self.sr.dev_p2p_open(torch.cat(allb).cpu().numpy())
         self.profile = {} if os.environ.get("DLP_DD_PROFILE") else None
 
     # ---- buffers on the context's device
@@ -312,13 +322,18 @@ class Domain:
                 sr.dev_halo_serial()
                 return
             sr.dev_halo_begin()
-            staged_exchange(self.t, self.neigh, self.dims, sr.dev_halo_pack, sr.dev_halo_unpack, self._alloc, 6)
+            staged_exchange(self.t, self.neigh, self.dims, sr.dev_halo_pack, sr.dev_halo_unpack, self._alloc, HALO_WIDTH)
             sr.dev_halo_end()
             self._refresh_bufs = None
 
-    def refresh_halo(self):
+    def refresh_halo(self, staged=False):
+        """refresh_halo_positions.  Default: one pull kernel over peer memory (needs publish() + a collective since the
+        positions moved -- step() provides both); staged=True: the reference's six dependent messages."""
         sr = self.sr
         with self.torch.cuda.stream(self.stream):
+            if self.p2p and not staged:
+                sr.dev_refresh_pull()
+                return
             if self.world == 1:
                 sr.dev_refresh_serial()
                 return
@@ -344,6 +359,11 @@ class Domain:
             self.sr.dev_link_cell_pairs()
         self.rebuilds += 1
 
+    def publish(self):
+        if self.p2p:
+            with self.torch.cuda.stream(self.stream):
+                self.sr.dev_publish()
+
     def vnl_update(self):
         with self.torch.cuda.stream(self.stream):
             tol = self.sr.dev_vnl_check()
@@ -361,6 +381,7 @@ class Domain:
             return self._step_profiled(dt)
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(1, dt)
+        self.publish()                       # before the gmax: the collective orders every rank's publish before any pull
         if self.vnl_update():
             self.rebuild()
         else:
@@ -386,6 +407,7 @@ class Domain:
         t = time.perf_counter()
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(1, dt)
+        self.publish()
         t = lap("vv1", t)
         upd = self.vnl_update()
         t = lap("vnl_check+gmax", t)

@@ -197,6 +197,22 @@ class ShortRange:
     def dev_halo_end(self):
         self._ck(self.L.dlpgpu_dev_halo_end(self.h))
 
+    def dev_p2p_init(self, rank, nranks, capacity_atoms):
+        """Returns the 128-byte IPC handle blob of this rank's two peer-visible coordinate buffers."""
+        h = np.zeros(128, dtype=np.uint8)
+        self._ck(self.L.dlpgpu_dev_p2p_init(self.h, int(rank), int(nranks), int(capacity_atoms), ptr(h)))
+        return h
+
+    def dev_p2p_open(self, all_handles):
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        self._ck(self.L.dlpgpu_dev_p2p_open(self.h, ptr(a)))
+
+    def dev_publish(self):
+        self._ck(self.L.dlpgpu_dev_publish(self.h))
+
+    def dev_refresh_pull(self):
+        self._ck(self.L.dlpgpu_dev_refresh_pull(self.h))
+
     def dev_halo_stage_counts(self):
         a, b = np.zeros(6, dtype=np.int32), np.zeros(6, dtype=np.int32)
         self._ck(self.L.dlpgpu_dev_halo_stage_counts(self.h, ptr(a), ptr(b)))

@@ -49,6 +49,10 @@ SIGNATURES = {
     "dlpgpu_dev_halo_end": (ci, [vp]),
     "dlpgpu_dev_refresh_pack": (ci, [vp, ci, vp, pi_]),
     "dlpgpu_dev_refresh_unpack": (ci, [vp, ci, vp, ci]),
+    "dlpgpu_dev_p2p_init": (ci, [vp, ci, ci, ci, vp]),
+    "dlpgpu_dev_p2p_open": (ci, [vp, vp]),
+    "dlpgpu_dev_publish": (ci, [vp]),
+    "dlpgpu_dev_refresh_pull": (ci, [vp]),
     "dlpgpu_dev_halo_stage_counts": (ci, [vp, vp, vp]),
     "dlpgpu_dev_halo_serial": (ci, [vp]),
     "dlpgpu_dev_refresh_serial": (ci, [vp]),

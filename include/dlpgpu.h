@@ -117,8 +117,11 @@ int dlpgpu_dev_zero_forces(dlpgpu_ctx* ctx);
 int dlpgpu_dev_vv(dlpgpu_ctx* ctx, int stage, double dt);
 int dlpgpu_dev_vnl_check(dlpgpu_ctx* ctx, double* tol);
 /* set_halo_particles (halo.F90:153-355) split around the transport: begin (tag ixyz) -> for mdir in -1,1,-2,2,-3,3:
- * pack (export_atomic_data select + pack, 6 doubles per atom, deport_data.F90:1810-1866), [exchange], unpack
- * (:1921-1943) -> end (types/charges from lsite, vnl_set_check).  *count = atoms packed. */
+ * pack (export_atomic_data select + pack, deport_data.F90:1810-1866), [exchange], unpack (:1921-1943) -> end
+ * (types/charges from lsite, vnl_set_check).  *count = atoms packed.  DLPGPU_HALO_WIDTH doubles per atom: the
+ * reference's six (x,y,z,ltg,lsite,ixyz) followed by origin rank, origin local index and the periodic wraps applied so
+ * far, which is what dlpgpu_dev_refresh_pull replays. */
+#define DLPGPU_HALO_WIDTH 9
 int dlpgpu_dev_halo_begin(dlpgpu_ctx* ctx);
 int dlpgpu_dev_halo_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int capacity_atoms, int* count);
 int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
@@ -126,6 +129,16 @@ int dlpgpu_dev_halo_end(dlpgpu_ctx* ctx);
 /* refresh_halo_positions (halo.F90:47-113): same atoms in the same order, 3 doubles per atom */
 int dlpgpu_dev_refresh_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int* count);
 int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
+/* refresh_halo_positions (halo.F90:47-113) as ONE kernel over NVLink peer memory instead of six staged messages: every
+ * rank keeps a double-buffered, CUDA-IPC exported copy of its local coordinates; p2p_init allocates it and returns the two
+ * IPC handles (2 x 64 bytes), p2p_open maps the buffers of all ranks (handles gathered rank-major, 128 bytes each).  Per
+ * step: dlpgpu_dev_publish after the positions moved, a collective on the same streams (the gmax of vnl_check), then
+ * dlpgpu_dev_refresh_pull fills the whole halo from the owners' buffers, replaying the periodic shifts in stage order
+ * (same bits as the staged exchange).  With nranks == 1 no IPC is involved. */
+int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[128]);
+int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
+int dlpgpu_dev_publish(dlpgpu_ctx* ctx);
+int dlpgpu_dev_refresh_pull(dlpgpu_ctx* ctx);
 /* atoms sent / received in each of the six stages of the last halo build (order -x,+x,-y,+y,-z,+z) */
 int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]);
 /* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */

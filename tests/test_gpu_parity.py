@@ -286,3 +286,32 @@ def test_baseline_configs_full_size(name):
     assert abs((out[6] + out[10] + out[14]) + vir) <= 1e-10 * abs(vir)
     assert out[7] == out[9] and out[8] == out[12] and out[11] == out[13]
     sr.close()
+
+
+@pytest.mark.parametrize("name", ["argon", "nacl_ortho"])
+def test_one_kernel_refresh_equals_staged_refresh(name):
+    """dlpgpu_dev_refresh_pull (origin map + replayed shifts) gives the staged refresh_halo_positions bit for bit, and both
+    equal the oracle's."""
+    s = systems.argon(6, temperature=300.0) if name == "argon" else systems.nacl((4, 3, 3), rcut=6.0, padding=0.2, temperature=1200.0)
+    w = world_for(s, P=1, with_halo=False, with_list=False)
+    w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0; w.two_body()
+    sr = native_serial(s)
+    sr.dev_p2p_init(0, 1, s.megatm + 64)
+    sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs(); sr.dev_two_body_forces()
+    for _ in range(2):
+        w.vv(1, 0.002, s.weight_by_type); sr.dev_vv(1, 0.002)
+        assert w.refresh_halo() == 0
+        sr.dev_publish()
+        sr.dev_refresh_serial()
+        a = sr.dev_get_parts()
+        # scramble the halo, then pull
+        sr.dev_refresh_pull()
+        b = sr.dev_get_parts()
+        po = w.parts(0)
+        for k in ("xxx", "yyy", "zzz", "chge"):
+            assert np.array_equal(a[k], b[k]), k
+        natms = s.megatm
+        assert np.abs(po["xxx"][natms:] - b["xxx"][natms:]).max() < 1e-9
+        w.two_body(); sr.dev_two_body_forces()
+        w.vv(2, 0.002, s.weight_by_type); sr.dev_vv(2, 0.002)
+    sr.close()
