@@ -399,7 +399,7 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     if transport is not None:
         t = transport.allreduce_max(t)
     h2d = nlast * 64 + (nb / steps) * (nlast * 64 + 3 * 4 * nlast)
-    d2h = natms * 24 + 16 * 8
+    d2h = natms * 64 + 16 * 8
     sr2.close()
     return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
             "steps": steps, "rebuild_every": interval, "ms_per_step": 1e3 * t / steps,

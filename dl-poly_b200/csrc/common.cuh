@@ -185,7 +185,9 @@ struct dlpgpu_ctx {
   DBuf<unsigned long long> tol_bits;
   // staging for the host-buffer entry points
   DBuf<dlpgpu_corepart> parts_dev;
-  std::vector<double> h_f;
+  void* pinned_ptr = nullptr;      // caller's corePart array, page-locked by us on first use
+  size_t pinned_bytes = 0;
+  bool pinned_ours = false;
   // timings
   cudaEvent_t ev[8] = {nullptr};
   double t_list = 0, t_force = 0, t_pair = 0, t_full = 0;

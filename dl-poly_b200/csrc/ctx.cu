@@ -176,6 +176,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
         if (ctx->peer_pub.size() > (size_t)(2 * r + b) && ctx->peer_pub[2 * r + b]) cudaIpcCloseMemHandle(ctx->peer_pub[2 * r + b]);
   for (int b = 0; b < 2; ++b) if (ctx->pub[b]) cudaFree(ctx->pub[b]);
   ctx->peer_pub_dev.release();
+  if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -375,6 +376,12 @@ __global__ void k_pack_parts(dlpgpu_corepart* __restrict__ parts, int n, const d
   p.xxx = q.x; p.yyy = q.y; p.zzz = q.z; p.fxx = fx[i]; p.fyy = fy[i]; p.fzz = fz[i]; p.chge = q.w; p.pad1 = 0; p.pad2 = 0;
   parts[i] = p;
 }
+__global__ void k_add_forces(dlpgpu_corepart* __restrict__ parts, int n, const double* __restrict__ fx, const double* __restrict__ fy,
+                             const double* __restrict__ fz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  parts[i].fxx += fx[i]; parts[i].fyy += fy[i]; parts[i].fzz += fz[i];
+}
 __global__ void k_load_atoms(int n, const double* __restrict__ xyz, const double* __restrict__ vel, const int* __restrict__ lsite,
                              const int* __restrict__ type_site, const double* __restrict__ charge_site,
                              const int* __restrict__ freeze_site, double4* __restrict__ posq, double* vx, double* vy, double* vz,
@@ -393,8 +400,21 @@ __global__ void k_zero3(int n, double* a, double* b, double* c) {
 }
 }  // namespace
 
+// The caller's corePart array (config%parts) lives at one address for the whole run: page-lock it on first sight so the
+// per-step copies run at full PCIe rate.  Memory that is already pinned (or cannot be pinned) is used as it is.
+static void pin_host_parts(dlpgpu_ctx* ctx, const void* p, size_t bytes) {
+  if (!p || bytes == 0) return;
+  if (ctx->pinned_ptr == p && ctx->pinned_bytes >= bytes) return;
+  if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
+  ctx->pinned_ptr = const_cast<void*>(p); ctx->pinned_bytes = bytes;
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+  ctx->pinned_ours = (e == cudaSuccess);
+  if (e != cudaSuccess) cudaGetLastError();   // already registered / not registrable: plain copies still work
+}
+
 static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   if (n <= 0) return 0;
+  pin_host_parts(ctx, parts, (size_t)n * sizeof(dlpgpu_corepart));
   CK(ctx->parts_dev.ensure(n, ctx->stream));
   CK(cudaMemcpyAsync(ctx->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, ctx->parts_dev.p, n, ctx->posq.p);
@@ -480,18 +500,13 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
                     ctx->list_natms, ctx->list_nlast);
   CKRC(upload_parts(ctx, nlast, parts));
   CKRC(dlp_two_body(ctx, 1, out));
-  // forces of local atoms come back compact (24 B/atom) and are ADDED on the host (every provider adds, drivers.F90:655-660)
-  ctx->h_f.resize((size_t)3 * natms + 3);
-  double* hf = ctx->h_f.data();
-  CK(cudaMemcpyAsync(hf, ctx->fx.p, (size_t)natms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(hf + natms, ctx->fy.p, (size_t)natms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(hf + 2 * (size_t)natms, ctx->fz.p, (size_t)natms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < natms; ++i) {
-    parts[i].fxx += hf[i];
-    parts[i].fyy += hf[natms + i];
-    parts[i].fzz += hf[2 * (size_t)natms + i];
+  // every force provider ADDS (drivers.F90:655-660): the device copy of parts still holds the caller's forces, so the sum is
+  // formed there and the records of the local atoms go back in one contiguous copy (positions and charges unchanged)
+  if (natms > 0) {
+    LAUNCH(ctx, k_add_forces, cdiv(natms, 256), 256, 0, ctx->parts_dev.p, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
+    CK(cudaMemcpyAsync(parts, ctx->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
