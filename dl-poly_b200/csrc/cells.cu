@@ -234,9 +234,17 @@ __global__ void k_loc_slot(int nlast, const int* __restrict__ is_local, const in
 __global__ void k_gather_posq(int nlast, const int* __restrict__ at_list, const double4* __restrict__ posq, double4* __restrict__ posq_s) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nlast) posq_s[s] = posq[at_list[s]];
+  else if (s == nlast) posq_s[s] = make_double4(1e15, 1e15, 1e15, 0.0);   // the sentinel partner of padded list rows
 }
 
 // ---------------------------------------------------------------- list kernels
+// The pair kernels read rows in passes of 16 or 32 entries without bounds checks and gather one pass ahead: every row is
+// padded from its length n up to roundup32(n) + 32 with a sentinel partner (sorted slot nlast: see k_gather_posq).
+#define DLP_ROW_PAD 64
+__device__ __forceinline__ void dlp_pad_row(unsigned* row, int n, unsigned sentinel, int lane, int nlanes) {
+  const int end = ((n + 31) & ~31) + 32;
+  for (int k = n + lane; k < end; k += nlanes) row[k] = sentinel;
+}
 __device__ __forceinline__ double pair_rsq(const double4& a, double xi, double yi, double zi) {
   // neighbours.F90:991-992  rsq = (xxt(jj)-x_i)**2 + (yyt(jj)-y_i)**2 + (zzt(jj)-z_i)**2   (left-to-right, no FMA)
   double dx = a.x - xi, dy = a.y - yi, dz = a.z - zi;
@@ -386,7 +394,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
                            const int* __restrict__ frz_s, const int* __restrict__ type_s, const int* __restrict__ pair_k, int ntypes,
                            const int* __restrict__ xb, const int* __restrict__ excl,
                            unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
-                           int* __restrict__ status) {
+                           int* __restrict__ status, unsigned sentinel) {
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (t >= natms) return;
@@ -444,7 +452,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
         unsigned m = __ballot_sync(DLP_FULL, ok), mx = __ballot_sync(DLP_FULL, isx);
         if (ok) {
           int ll = cnt + __popc(m & ((1u << lane) - 1));
-          if (ll < pitch) row[ll] = entry; else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
+          if (ll < pitch - DLP_ROW_PAD) row[ll] = entry; else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
         }
         if (isx) {
           int ll = xcnt + __popc(mx & ((1u << lane) - 1));
@@ -456,6 +464,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
     }
   }
   if (lane == 0) { nnbr[t] = cnt; nxnbr[t] = xcnt; }
+  dlp_pad_row(row, min(cnt, pitch - DLP_ROW_PAD), sentinel, lane, 32);
 }
 
 
@@ -477,7 +486,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             const int* __restrict__ cell_s, const int* __restrict__ slot_rank, const double4* __restrict__ posq_s,
             const int2* __restrict__ info_s, const int* __restrict__ pair_k, int ntypes, const int* __restrict__ excl,
             unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
-            int* __restrict__ status, unsigned long long* __restrict__ cnt64) {
+            int* __restrict__ status, unsigned long long* __restrict__ cnt64, unsigned sentinel) {
   __shared__ double4 s_pi[LC_WARPS][32];
   __shared__ int2 s_info[LC_WARPS][32];
   __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
@@ -589,7 +598,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             const int kc = pk_smem ? s_pk[kidx] : (pair_k ? pair_k[kidx] + 1 : 0);
             const unsigned entry = jbits | ((unsigned)kc << DLP_K_SHIFT) | ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
             const int ll = ca + __popc(m & ltmask);
-            if (ll < pitch) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
+            if (ll < pitch - DLP_ROW_PAD) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
             else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
           }
           if (lane == 0) s_cnt[wid][a] = ca + __popc(m);
@@ -633,7 +642,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
           const unsigned entry = (unsigned)jj | ((unsigned)kc << DLP_K_SHIFT) | (halo_j ? DLP_F_HALO : 0u) |
                                  ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
           const int ll = ca + __popc(m & ((1u << lane) - 1));
-          if (ll < pitch) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
+          if (ll < pitch - DLP_ROW_PAD) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
           else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
         }
         if (lane == a) cnt += __popc(m);
@@ -651,6 +660,8 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
     }
     }
     if (lane < na) { nnbr[t0 + lane] = cnt; nxnbr[t0 + lane] = xcnt; written += cnt; }
+    for (int a = 0; a < na; ++a)   // sentinel padding the pair kernel relies on
+      dlp_pad_row(nbr + (size_t)(t0 + a) * pitch, min(__shfl_sync(DLP_FULL, cnt, a), pitch - DLP_ROW_PAD), sentinel, lane, 32);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) written += __shfl_xor_sync(DLP_FULL, written, d);
@@ -666,7 +677,7 @@ __global__ void k_bg_copy(int n, const double4* __restrict__ posq, double* xbg, 
 
 int dlp_gather_sorted(dlpgpu_ctx* ctx) {
   int n = ctx->list_nlast;
-  if (n > 0) LAUNCH(ctx, k_gather_posq, cdiv(n, 256), 256, 0, n, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
+  if (n > 0) LAUNCH(ctx, k_gather_posq, cdiv(n + 1, 256), 256, 0, n, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
   return 0;
 }
 
@@ -717,11 +728,12 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nlast, nullptr));
   if (nlast > 0) {
     LAUNCH(ctx, k_loc_slot, cdiv(nlast, 256), 256, 0, nlast, ctx->flag.p, ctx->scan_out.p, ctx->loc_slot.p);
-    LAUNCH(ctx, k_gather_posq, cdiv(nlast, 256), 256, 0, nlast, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
+    LAUNCH(ctx, k_gather_posq, cdiv(nlast + 1, 256), 256, 0, nlast, ctx->at_list.p, ctx->posq.p, ctx->posq_s.p);
   }
   ctx->list_natms = natms; ctx->list_nlast = nlast;
   // device-internal lists
-  ctx->pitch = ((ctx->max_list + 31) / 32) * 32;
+  ctx->pitch = ((ctx->max_list + 31) / 32) * 32 + DLP_ROW_PAD;   // room for the sentinel padding (see dlp_pad_row)
+  const unsigned sentinel = (unsigned)nlast | DLP_F_HALO;   // slot nlast of posq_s: a chargeless point 1e15 A away
   ctx->xpitch = ctx->lbook ? ((ctx->max_exclude + 31) / 32) * 32 : 0;
   const int wpb = 8;   // warps per block
   if (natms > 0) {
@@ -729,13 +741,13 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
     CK(ctx->xnbr.ensure((size_t)natms * std::max(ctx->xpitch, 1) + 1, s));
     cudaEventRecord(ctx->ev[2], s);
     if (ctx->force_mode == 0) {
-      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
+      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 256, s));
       LAUNCH(ctx, k_list_dev<false>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
              ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
              ctx->gid_s.p, ctx->frz_s.p, ctx->type_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->st_xb.p, ctx->excl.p,
-             ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+             ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, sentinel);
     } else {
-      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 1, s));
+      CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 256, s));
       // semi-ball rows (dy,dz) with their half x-extent, for the warp-per-cell kernel
       std::vector<LCRow> hrows;
       const int nlp = g.nlp, W = 2 * nlp + 1;
@@ -754,7 +766,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
-               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p
+               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel
         if (simple) LAUNCH(ctx, k_list_cell<true>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
         else LAUNCH(ctx, k_list_cell<false>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
 #undef DLP_LC_ARGS
@@ -762,7 +774,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
                ctx->max_exclude, ctx->excl_by_gid, ctx->loc_slot.p, ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, ctx->posq_s.p,
                ctx->gid_s.p, ctx->frz_s.p, ctx->type_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->st_xb.p, ctx->excl.p,
-               ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p);
+               ctx->nbr.p, ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, sentinel);
       }
     }
     cudaEventRecord(ctx->ev[3], s);

@@ -109,10 +109,14 @@ struct dlpgpu_ctx {
   // quadratic-form tables of the pair kernel: [max_vdw][max_grid+1] then [ew_n+1] entries {g_f, g_e, h_f, h_e}
   DBuf<double> tab4;
   size_t tab4_entries = 0;
+  // k_pair_v2 layout: [g units: table 0 = Ewald (or zeros), table k = vdW potential k, then 2 zero entries][h units likewise]
+  DBuf<double> tab2;
+  int tab2_ne = 0, tab2_ts = 0, tab2_zero = 0;
   int ew_off = 0;
   bool tab4_valid = false;
   std::vector<double> h_vdw_f, h_vdw_e, h_ew_d, h_ew_e;   // host copies the tab4 build reads
   int tpr_override = 0;
+  int variant = 0;         // DLPGPU_VARIANT: timing experiments of the pair kernel (development only)
   bool no_fast = false;    // DLPGPU_NO_FAST=1: always use the general pair kernel
 
   // sites (native mode)

@@ -471,6 +471,181 @@ k_pair_fast(FParams P, const int* __restrict__ loc_slot, const double4* __restri
   }
 }
 
+// ---------------------------------------------------------------- fast path, second generation
+// Same pair arithmetic as k_pair_fast, re-organised around what ncu showed on B200 (profiles/r1_s3_pair_fast_ionic1m.txt:
+// issue slots 54 % busy, 178 instructions per pair of which 66 fp64; stalls on branch resolution, the XU pipe (F2I / I2F)
+// and fixed-latency waits at 4 warps per scheduler):
+//  * rows are padded by the list build to a multiple of 16 entries (+16) with a sentinel partner that sits 1e15 A away, so
+//    the loop body carries no bounds predicates and prefetches unconditionally;
+//  * out-of-cutoff pairs are not masked arithmetically: their table index is redirected to an all-zero entry, so every term
+//    comes out as an exact 0 (one integer select instead of a dozen 64-bit selects);
+//  * table 0 is the Ewald table and the vdW table of potential k sits at index k (kc of the list entry is k, 0 = none), so
+//    the index is kc * stride + l without decrement / clamp;
+//  * l = Int(r * rdr) and Real(l) come from one DADD with round-down against 2^52 (exact for 0 <= r * rdr < 2^31) instead of
+//    F2I + I2F on the quarter-rate XU pipe; rsqrt is MUFU.RSQ64H + one cubic correction without the library's range branch;
+//  * the vdW virial is not accumulated: vir_vdw + vir_coul = -trace(stress) term by term.
+struct P2 {
+  int natms, pitch, ne, ts, zero;
+  double rdr_v, rdr_e, thr_vdw, thr_coul, scaling;
+};
+
+__device__ __forceinline__ double rsqrt_fast(double x) {   // x normal, positive; ~1 ulp
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = __fma_rn(-(y0 * y0), x, 1.0);
+  const double s = __fma_rn(e, 0.375, 0.5);
+  return __fma_rn(s, y0 * e, y0);
+}
+
+template <int VT, int EW, int SG>
+__device__ __forceinline__ void pair2(const P2& P, const double2* __restrict__ sG, const double2* __restrict__ sH, const double4& pi,
+                                      double qi_s, unsigned e, const double4& pj, double& fix, double& fiy, double& fiz, double* acc,
+                                      double* __restrict__ fneg) {
+  constexpr double MAGIC = 4503599627370496.0;   // 2^52
+  const double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;             // two_body.F90:348-350
+  const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+  const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
+  const bool in_v = VT && kc != 0 && rsq < P.thr_vdw;                         // vdw.F90:1892 (Sqrt(rsq) < rvdw, see sqrt_threshold)
+  const bool in_c = EW && rsq < P.thr_coul;                                   // ewald_spole.F90:133 (a zero charge gives exact zeros)
+  const double ri = rsqrt_fast(rsq);
+  const double rrr = rsq * ri;                                                // two_body.F90:351 to ~1 ulp
+  const double r_rsq = ri * ri;
+  const double tt = rrr * P.rdr_v;                                            // vdw.F90:1909-1910
+  const double m = __dadd_rd(tt, MAGIC);
+  const int l = max(__double2loint(m), 1);                                    // r < one grid step does not occur
+  const double ppp = tt - (m - MAGIC);
+  // energy / virial / stress ownership: local partner or halo partner with idi < ltg(jatm)  (vdw.F90:1948)
+  const double w = ((e & (DLP_F_HALO | DLP_F_ECNT)) != DLP_F_HALO) ? 1.0 : 0.0;
+  double gamma = 0.0;
+  if (VT) {
+    const int u = in_v ? kc * P.ts + l : P.zero;
+    const double2 a = sG[u], b = sG[u + 1], h = sH[u];
+    gamma = __fma_rn(ppp, __fma_rn(ppp, h.x, (b.x - a.x) - h.x), a.x) * r_rsq;             // :1914-1921
+    const double ev = __fma_rn(ppp, __fma_rn(ppp, h.y, (b.y - a.y) - h.y), a.y);           // :1953-1960
+    acc[0] = __fma_rn(w, ev, acc[0]);
+  }
+  if (EW) {
+    int lc = l;
+    double pc = ppp;
+    if (!SG) {
+      const double te = rrr * P.rdr_e;                                        // ewald_spole.F90:140-146
+      const double me = __dadd_rd(te, MAGIC);
+      lc = max(__double2loint(me), 1);
+      pc = te - (me - MAGIC);
+    }
+    const int u = in_c ? lc : P.zero;
+    const double2 a = sG[u], b = sG[u + 1], h = sH[u];
+    const double prefac = qi_s * pj.w;
+    const double gc = prefac * __fma_rn(pc, __fma_rn(pc, h.x, (b.x - a.x) - h.x), a.x);
+    const double ec = prefac * __fma_rn(pc, __fma_rn(pc, h.y, (b.y - a.y) - h.y), a.y);     // :168-174
+    acc[1] = __fma_rn(w, ec, acc[1]);
+    if (VT) acc[2] = __fma_rn(w * rsq, gc, acc[2]);                                       // :189 (the vdW virial follows from the trace)
+    gamma += gc;
+  }
+  const double f1 = gamma * x, f2 = gamma * y, f3 = gamma * z;
+  fix += f1; fiy += f2; fiz += f3;
+  const double wx = w * x, wy = w * y, wz = w * z;
+  acc[3] = __fma_rn(wx, f1, acc[3]); acc[4] = __fma_rn(wx, f2, acc[4]); acc[5] = __fma_rn(wx, f3, acc[5]);
+  acc[6] = __fma_rn(wy, f2, acc[6]); acc[7] = __fma_rn(wy, f3, acc[7]); acc[8] = __fma_rn(wz, f3, acc[8]);
+  // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161); local partners only
+  if ((e & DLP_F_HALO) == 0u && (in_v || in_c)) {
+    double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
+    atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3);
+  }
+}
+
+template <int TPR, int VT, int EW, int SG>
+__global__ void __launch_bounds__(512, 1)
+k_pair_v2(P2 P, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
+          const int* __restrict__ nnbr, const double2* __restrict__ tab, double* __restrict__ fpos, double* __restrict__ fneg,
+          double* __restrict__ partial) {
+  extern __shared__ __align__(16) double2 s_tab[];
+  for (int k = threadIdx.x; k < 2 * P.ne; k += 512) s_tab[k] = tab[k];
+  __syncthreads();
+  const double2* sG = s_tab;
+  const double2* sH = s_tab + P.ne;
+  constexpr int RPB = 512 / TPR;
+  const int lg = threadIdx.x % TPR;
+  const int grp = threadIdx.x / TPR;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+
+  for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
+    const int t = min(base + grp, P.natms - 1);             // surplus groups of the last pass redo the last row and drop it
+    const bool rowlive = base + grp < P.natms;
+    const double4 pi = posq_s[loc_slot[t]];
+    const int npad = rowlive ? (nnbr[t] + 2 * TPR - 1) & ~(2 * TPR - 1) : 0;   // rows are sentinel-padded past npad + 2 TPR (dlp_pad_row)
+    const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    const unsigned* row = nbr + (size_t)t * P.pitch + lg;
+    // software pipeline, unrolled twice so the rotation needs no register moves: list entries are fetched two passes
+    // ahead, partner coordinates one pass ahead (one pass = 2 TPR entries of the row, two per lane)
+    unsigned ea = row[0], eb = row[TPR];
+    unsigned ec = row[2 * TPR], ed = row[3 * TPR];
+    double4 pa = ld_posq(posq_s + (ea & DLP_J_MASK)), pb = ld_posq(posq_s + (eb & DLP_J_MASK));
+    for (int k = 0; k < npad; k += 4 * TPR) {
+      {
+        const double4 pc = ld_posq(posq_s + (ec & DLP_J_MASK)), pd = ld_posq(posq_s + (ed & DLP_J_MASK));
+        const unsigned e0 = ea, e1 = eb;
+        ea = row[4 * TPR]; eb = row[5 * TPR];
+        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        pa = pc; pb = pd;
+      }
+      if (k + 2 * TPR >= npad) break;
+      {
+        const double4 pc = ld_posq(posq_s + (ea & DLP_J_MASK)), pd = ld_posq(posq_s + (eb & DLP_J_MASK));
+        const unsigned e0 = ec, e1 = ed;
+        ec = row[6 * TPR]; ed = row[7 * TPR];
+        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        pa = pc; pb = pd;
+      }
+      row += 4 * TPR;
+    }
+#pragma unroll
+    for (int d = TPR / 2; d > 0; d >>= 1) {
+      fix += __shfl_xor_sync(DLP_FULL, fix, d);
+      fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
+      fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
+    }
+    if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
+  }
+  __shared__ double red[16][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0.0;
+    for (int w = 0; w < 16; ++w) v += red[w][threadIdx.x];
+    red[0][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    // partial[] keeps the 12-slot layout of k_pair_forces: 0 engvdw, 1 virvdw, 2 engcpe_rl, 3 vircpe_rl, 4..5 exclusion terms
+    // (none here), 6..11 stress.  sum over pairs of w gamma rsq = trace(stress): vdW virial = -(trace - coulomb part).
+    const double trace = red[0][3] + red[0][6] + red[0][8];
+    const double vc = (VT && EW) ? red[0][2] : (EW ? trace : 0.0);
+    double v = 0.0;
+    switch (threadIdx.x) {
+      case 0: v = red[0][0]; break;
+      case 1: v = VT ? -(trace - vc) : 0.0; break;
+      case 2: v = red[0][1]; break;
+      case 3: v = -vc; break;
+      case 4: case 5: v = 0.0; break;
+      default: v = red[0][threadIdx.x - 3];
+    }
+    partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
+  }
+}
+
 // half mode epilogue: f(i) (+)= [row sum of atom i] - [what its partners' rows pushed onto it]
 __global__ void k_scatter_half(int natms, int zero_forces, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
                                const double* __restrict__ fpos, const double* __restrict__ fneg, double* fx, double* fy, double* fz) {
@@ -556,6 +731,29 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->tab4.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->tab4_entries = nv + ne;
+  {   // k_pair_v2 layout
+    const int tsz = std::max(vt ? ts : 0, ctx->ew_on ? ctx->ew_n + 1 : 0);
+    const int ntab = 1 + (vt ? ctx->max_vdw : 0);
+    const int NE = ntab * tsz + 2;
+    std::vector<double> t2((size_t)NE * 4, 0.0);   // g units [0, NE), h units [NE, 2 NE), each {force, energy}
+    auto put = [&](int tb, const double* f, const double* e, int n) {
+      for (int l = 0; l <= n; ++l) {
+        const size_t u = (size_t)tb * tsz + l;
+        t2[2 * u] = f[l]; t2[2 * u + 1] = e[l];
+        if (l + 2 <= n) {
+          t2[2 * (NE + u)] = ((f[l + 2] - f[l + 1]) - (f[l + 1] - f[l])) * 0.5;
+          t2[2 * (NE + u) + 1] = ((e[l + 2] - e[l + 1]) - (e[l + 1] - e[l])) * 0.5;
+        }
+      }
+    };
+    if (ne) put(0, ctx->h_ew_d.data(), ctx->h_ew_e.data(), ctx->ew_n);
+    for (int k = 0; vt && k < ctx->max_vdw; ++k)
+      put(1 + k, ctx->h_vdw_f.data() + (size_t)k * ts, ctx->h_vdw_e.data() + (size_t)k * ts, ctx->max_grid);
+    CK(ctx->tab2.ensure(t2.size(), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tab2.p, t2.data(), t2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tab2_ne = NE; ctx->tab2_ts = tsz; ctx->tab2_zero = ntab * tsz;
+  }
   ctx->tab4_valid = true;
   return 0;
 }
@@ -599,7 +797,28 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   cudaEventRecord(ctx->ev[6], s);
   const bool fast = P.half && use_smem && !ctx->no_fast && !(P.lbook && P.ew_on) && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) &&
                     (P.vdw_on || P.ew_on) && (tpr == 8 || tpr == 16);
-  if (natms > 0 && fast) {
+  const size_t smem2 = (size_t)ctx->tab2_ne * 32;
+  const bool fast2 = fast && ctx->variant < 100 && smem2 + 2048 <= 227 * 1024;
+  if (natms > 0 && fast2) {
+    P2 Q{};
+    Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;
+    Q.rdr_v = P.vdw_on ? ctx->vdw_rdr : ctx->ew_rdr; Q.rdr_e = ctx->ew_rdr; Q.thr_vdw = ctx->thr_vdw; Q.thr_coul = ctx->thr_coul;
+    Q.scaling = ctx->scaling;
+    const double2* t2 = reinterpret_cast<const double2*>(ctx->tab2.p);
+#define DLP_V2(T, V, E, S)                                                                                                     \
+  do {                                                                                                                         \
+    CK(cudaFuncSetAttribute(k_pair_v2<T, V, E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                   \
+    LAUNCH(ctx, (k_pair_v2<T, V, E, S>), blocks, 512, smem2, Q, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, t2, fpos, fneg, \
+           ctx->partial.p);                                                                                                    \
+  } while (0)
+    const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0, sg = (!v || !e || P.same_grid) ? 1 : 0;
+    if (tpr == 8) {
+      if (v && e) { if (sg) DLP_V2(8, 1, 1, 1); else DLP_V2(8, 1, 1, 0); } else if (v) DLP_V2(8, 1, 0, 1); else DLP_V2(8, 0, 1, 1);
+    } else {
+      if (v && e) { if (sg) DLP_V2(16, 1, 1, 1); else DLP_V2(16, 1, 1, 0); } else if (v) DLP_V2(16, 1, 0, 1); else DLP_V2(16, 0, 1, 1);
+    }
+#undef DLP_V2
+  } else if (natms > 0 && fast) {
     const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
 #define DLP_FAST(T, V, E)                                                                                                      \
   do {                                                                                                                         \
