@@ -491,7 +491,6 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   __shared__ int2 s_info[LC_WARPS][32];
   __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
   __shared__ int s_pre[LC_WARPS][LC_MAXRUN + 1];   // candidates before run r
-  __shared__ int s_cnt[LC_WARPS][32];
   __shared__ int s_pk[256];                        // (type_i, type_j) -> vdW potential index + 1, when ntypes <= 16
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool pk_smem = pair_k != nullptr && ntypes <= 16;
@@ -547,6 +546,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   }
   const int total = s_pre[wid][LC_MAXRUN];
   long long written = 0;
+  int ovf = 0;   // longest row that did not fit (error 106), reported once per warp
   for (int a0 = s_own0; a0 < s_own1; a0 += 32) {   // atoms of the cell, 32 at a time (one pass unless the cell is crowded)
     const int na = min(32, s_own1 - a0);
     int cnt = 0, xcnt = 0;
@@ -565,16 +565,21 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
     __syncwarp();
     const int t0 = slot_rank[a0];
     if (SIMPLE) {
-      s_cnt[wid][lane] = 0;
+      // lean inner loop (ncu: the first version spent 118 instructions per 32 tests; this one keeps the per-atom work to the
+      // distance test, one ballot, one shuffle and the store): lane = candidate; everything that depends on the candidate
+      // only -- its vdW potential index against every possible type of the cell's atoms (6 bits each, ntypes <= 5), the
+      // ordering rule (jj > ii or jj before the cell) as an integer threshold -- is formed once per 32 candidates.
+      if (lane < na) s_info[wid][lane].y = 6 * ((s_info[wid][lane].y & 0xffff) - 1);   // shift of type_i in the packed kc word
       __syncwarp();
       const unsigned ltmask = (1u << lane) - 1u;
+      const int cap = pitch - DLP_ROW_PAD;
+      unsigned* const row0 = nbr + (size_t)t0 * pitch;
       for (int c0 = 0; c0 < total; c0 += 32) {
         const int c = c0 + lane;
-        const bool valid = c < total;
-        int jj = 0x7fffffff;
-        double4 pj = make_double4(1e300, 1e300, 1e300, 0);
+        int jj = -1;
+        double4 pj = make_double4(1e300, 1e300, 1e300, 0);   // lanes without a candidate sit at 1e300: never within the cutoff
         int2 infj = make_int2(0, 0);
-        if (valid) {   // largest run r with pre[r] <= c
+        if (c < total) {   // largest run r with pre[r] <= c
           int lo = 0, hi = LC_MAXRUN - 1;
           while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[wid][mid] <= c) lo = mid; else hi = mid - 1; }
           jj = s_run0[wid][lo] + (c - s_pre[wid][lo]);
@@ -582,30 +587,32 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
         }
         const bool halo_j = (infj.y >> 17) & 1;
         const unsigned jbits = (unsigned)jj | (halo_j ? DLP_F_HALO : 0u);
-        const int tj = (infj.y & 0xffff) - 1;
-        const bool before = jj < s_own0;
+        const int gid_j = halo_j ? infj.x : 0;               // energy ownership: halo partner and idi < ltg(jatm); gids are >= 1
+        unsigned kcp = 0;
+        if (pair_k != nullptr && jj >= 0) {
+          const int tj = (infj.y & 0xffff) - 1;
+          for (int ti = 0; ti < ntypes; ++ti) kcp |= (unsigned)s_pk[ti * ntypes + tj] << (6 * ti);
+        }
+        // (jj > ii || jj < s_own0) with ii = a0 + a  <=>  jrel > a
+        const int jrel = jj < 0 ? -1 : (jj < s_own0 ? 0x7fffffff : jj - a0);
         // nlp == 2: the only stencil entry with the "no distance check" flag is the cell itself (neighbours.F90:537, :922-943)
-        const bool own_nir = g.nir_r2 > 0 && valid && jj >= s_own0 && jj < s_own1;
+        const double rc_eff = (g.nir_r2 > 0 && jj >= s_own0 && jj < s_own1) ? 1e301 : g.rcsq;
         for (int a = 0; a < na; ++a) {
           const double4 pi = s_pi[wid][a];
-          const bool acc = (own_nir || pair_rsq(pj, pi.x, pi.y, pi.z) <= g.rcsq) && (jj > a0 + a || before);   // invalid lanes sit at 1e300
+          const bool acc = pair_rsq(pj, pi.x, pi.y, pi.z) <= rc_eff && jrel > a;
           const unsigned m = __ballot_sync(DLP_FULL, acc);
           if (m == 0u) continue;
-          const int ca = s_cnt[wid][a];
+          const int ca = __shfl_sync(DLP_FULL, cnt, a);
           if (acc) {
             const int2 infi = s_info[wid][a];
-            const int kidx = ((infi.y & 0xffff) - 1) * ntypes + tj;
-            const int kc = pk_smem ? s_pk[kidx] : (pair_k ? pair_k[kidx] + 1 : 0);
-            const unsigned entry = jbits | ((unsigned)kc << DLP_K_SHIFT) | ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
+            const unsigned entry = jbits | (((kcp >> infi.y) & 63u) << DLP_K_SHIFT) | ((infi.x < gid_j) ? DLP_F_ECNT : 0u);
             const int ll = ca + __popc(m & ltmask);
-            if (ll < pitch - DLP_ROW_PAD) nbr[(size_t)(t0 + a) * pitch + ll] = entry;
-            else { atomicOr(&status[0], 1); atomicMax(&status[1], ll + 1); }
+            if (ll < cap) row0[(size_t)a * pitch + ll] = entry;
+            else ovf = max(ovf, ll + 1);
           }
-          if (lane == 0) s_cnt[wid][a] = ca + __popc(m);
+          if (lane == a) cnt += __popc(m);
         }
-        __syncwarp();
       }
-      cnt = s_cnt[wid][lane];
     } else
     {
     for (int c0 = 0; c0 < total; c0 += 32) {
@@ -663,6 +670,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
     for (int a = 0; a < na; ++a)   // sentinel padding the pair kernel relies on
       dlp_pad_row(nbr + (size_t)(t0 + a) * pitch, min(__shfl_sync(DLP_FULL, cnt, a), pitch - DLP_ROW_PAD), sentinel, lane, 32);
   }
+  if (ovf > 0) { atomicOr(&status[0], 1); atomicMax(&status[1], ovf); }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) written += __shfl_xor_sync(DLP_FULL, written, d);
   if (lane == 0) atomicAdd(&cnt64[0], (unsigned long long)written);
@@ -762,7 +770,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
         CK(ctx->st_rows.ensure(hrows.size() * 3 + 3, s));
         CK(cudaMemcpyAsync(ctx->st_rows.p, hrows.data(), hrows.size() * sizeof(LCRow), cudaMemcpyHostToDevice, s));
         const int ncd = g.nlx * g.nly * g.nlz;
-        const bool simple = !ctx->lbook && ctx->megfrz <= 1 && g.nir_r2 <= 1;
+        const bool simple = !ctx->lbook && ctx->megfrz <= 1 && g.nir_r2 <= 1 && ctx->ntypes <= 5;
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \

@@ -112,10 +112,12 @@ struct dlpgpu_ctx {
   // k_pair_v2 layout: [g units: table 0 = Ewald (or zeros), table k = vdW potential k, then 2 zero entries][h units likewise]
   DBuf<double> tab2;
   int tab2_ne = 0, tab2_ts = 0, tab2_zero = 0;
+  cudaTextureObject_t tab2_tex = 0;   // the same buffer as 16-byte texels: table reads through the texture pipe (see pair2)
   int ew_off = 0;
   bool tab4_valid = false;
   std::vector<double> h_vdw_f, h_vdw_e, h_ew_d, h_ew_e;   // host copies the tab4 build reads
   int tpr_override = 0;
+  int tx_override = -1;    // DLPGPU_TX: which table reads of k_pair_v2 go through the texture pipe (tuning knob)
   int variant = 0;         // DLPGPU_VARIANT: timing experiments of the pair kernel (development only)
   bool no_fast = false;    // DLPGPU_NO_FAST=1: always use the general pair kernel
 

@@ -146,6 +146,7 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   if (const char* e = getenv("DLPGPU_TPR")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) ctx->tpr_override = v; }   // tuning knob
   if (const char* e = getenv("DLPGPU_VARIANT")) ctx->variant = atoi(e);
+  if (const char* e = getenv("DLPGPU_TX")) ctx->tx_override = atoi(e);
   if (const char* e = getenv("DLPGPU_NO_FAST")) ctx->no_fast = atoi(e) != 0;
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
@@ -169,6 +170,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   for (auto* b : db) b->release();
   ctx->vdw_tab.release(); ctx->ew_tab.release(); ctx->posq.release(); ctx->posq_s.release();
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
+  if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
   for (int r = 0; r < ctx->p2p_nranks; ++r)

@@ -497,8 +497,30 @@ __device__ __forceinline__ double rsqrt_fast(double x) {   // x normal, positive
   return __fma_rn(s, y0 * e, y0);
 }
 
-template <int VT, int EW, int SG>
-__device__ __forceinline__ void pair2(const P2& P, const double2* __restrict__ sG, const double2* __restrict__ sH, const double4& pi,
+// Cache policy of the pair kernel: the list is streamed once per step (no L1 allocation, first out of L2), partner
+// coordinates are re-read ~2 x 112 times per step (kept in L1 and L2).
+__device__ __forceinline__ unsigned ld_entry(const unsigned* p, unsigned long long pol) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double4 ld_posq_keep(const double4* p, unsigned long long pol) {
+  double4 v;
+  asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
+__device__ __forceinline__ double2 tex_unit(cudaTextureObject_t tex, int u) {
+  const int4 v = tex1Dfetch<int4>(tex, u);
+  return make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+}
+
+// TX bit 0: the three Ewald-table reads go through the texture pipe, bit 1: the h unit of the vdW table does.  On B200 a
+// random 16-byte texture fetch costs ~20 clk per warp on the TEX data pipe and overlaps completely with LDS.128 traffic
+// (~10 clk per warp on the LSU data pipe, which the coordinate gathers and the REDs also load): scripts/ubench2.cu.
+template <int VT, int EW, int SG, int X = 0, int TX = 0>
+__device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, const double2* __restrict__ sG, const double2* __restrict__ sH, const double4& pi,
                                       double qi_s, unsigned e, const double4& pj, double& fix, double& fiy, double& fiz, double* acc,
                                       double* __restrict__ fneg) {
   constexpr double MAGIC = 4503599627370496.0;   // 2^52
@@ -518,8 +540,11 @@ __device__ __forceinline__ void pair2(const P2& P, const double2* __restrict__ s
   const double w = ((e & (DLP_F_HALO | DLP_F_ECNT)) != DLP_F_HALO) ? 1.0 : 0.0;
   double gamma = 0.0;
   if (VT) {
-    const int u = in_v ? kc * P.ts + l : P.zero;
-    const double2 a = sG[u], b = sG[u + 1], h = sH[u];
+    int u = in_v ? kc * P.ts + l : P.zero;
+    if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
+    double2 a, b, h;
+    if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else { a = sG[u]; b = sG[u + 1]; h = (TX & 2) ? tex_unit(tex, P.ne + u) : sH[u]; }
     gamma = __fma_rn(ppp, __fma_rn(ppp, h.x, (b.x - a.x) - h.x), a.x) * r_rsq;             // :1914-1921
     const double ev = __fma_rn(ppp, __fma_rn(ppp, h.y, (b.y - a.y) - h.y), a.y);           // :1953-1960
     acc[0] = __fma_rn(w, ev, acc[0]);
@@ -533,8 +558,12 @@ __device__ __forceinline__ void pair2(const P2& P, const double2* __restrict__ s
       lc = max(__double2loint(me), 1);
       pc = te - (me - MAGIC);
     }
-    const int u = in_c ? lc : P.zero;
-    const double2 a = sG[u], b = sG[u + 1], h = sH[u];
+    int u = in_c ? lc : P.zero;
+    if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
+    double2 a, b, h;
+    if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else if (TX & 1) { a = tex_unit(tex, u); b = tex_unit(tex, u + 1); h = tex_unit(tex, P.ne + u); }
+    else { a = sG[u]; b = sG[u + 1]; h = sH[u]; }
     const double prefac = qi_s * pj.w;
     const double gc = prefac * __fma_rn(pc, __fma_rn(pc, h.x, (b.x - a.x) - h.x), a.x);
     const double ec = prefac * __fma_rn(pc, __fma_rn(pc, h.y, (b.y - a.y) - h.y), a.y);     // :168-174
@@ -548,23 +577,26 @@ __device__ __forceinline__ void pair2(const P2& P, const double2* __restrict__ s
   acc[3] = __fma_rn(wx, f1, acc[3]); acc[4] = __fma_rn(wx, f2, acc[4]); acc[5] = __fma_rn(wx, f3, acc[5]);
   acc[6] = __fma_rn(wy, f2, acc[6]); acc[7] = __fma_rn(wy, f3, acc[7]); acc[8] = __fma_rn(wz, f3, acc[8]);
   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161); local partners only
-  if ((e & DLP_F_HALO) == 0u && (in_v || in_c)) {
+  if (!(X & 1) && (e & DLP_F_HALO) == 0u && (in_v || in_c)) {
     double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
     atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3);
   }
 }
 
-template <int TPR, int VT, int EW, int SG>
-__global__ void __launch_bounds__(512, 1)
-k_pair_v2(P2 P, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
+template <int TPR, int VT, int EW, int SG, int X = 0, int TX = 0, int NT = 512>
+__global__ void __launch_bounds__(NT, 1)
+k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
           const int* __restrict__ nnbr, const double2* __restrict__ tab, double* __restrict__ fpos, double* __restrict__ fneg,
           double* __restrict__ partial) {
   extern __shared__ __align__(16) double2 s_tab[];
-  for (int k = threadIdx.x; k < 2 * P.ne; k += 512) s_tab[k] = tab[k];
+  for (int k = threadIdx.x; k < 2 * P.ne; k += NT) s_tab[k] = tab[k];
   __syncthreads();
   const double2* sG = s_tab;
   const double2* sH = s_tab + P.ne;
-  constexpr int RPB = 512 / TPR;
+  unsigned long long pol_stream, pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  constexpr int RPB = NT / TPR;
   const int lg = threadIdx.x % TPR;
   const int grp = threadIdx.x / TPR;
   double acc[9];
@@ -581,29 +613,35 @@ k_pair_v2(P2 P, const int* __restrict__ loc_slot, const double4* __restrict__ po
     const unsigned* row = nbr + (size_t)t * P.pitch + lg;
     // software pipeline, unrolled twice so the rotation needs no register moves: list entries are fetched two passes
     // ahead, partner coordinates one pass ahead (one pass = 2 TPR entries of the row, two per lane)
-    unsigned ea = row[0], eb = row[TPR];
-    unsigned ec = row[2 * TPR], ed = row[3 * TPR];
-    double4 pa = ld_posq(posq_s + (ea & DLP_J_MASK)), pb = ld_posq(posq_s + (eb & DLP_J_MASK));
+#define LE(i) ((X & 16) ? row[(i) * TPR] : ld_entry(row + (i) * TPR, pol_stream))
+#define ld_posq(a) ((X & 16) ? ld_posq(a) : ld_posq_keep(a, pol_keep))
+    unsigned ea = LE(0), eb = LE(1);
+    unsigned ec = LE(2), ed = LE(3);
+#define GA(e) ((X & 4) ? (posq_s + ((blockIdx.x * NT + threadIdx.x + ((e) & 0xff)) % (unsigned)P.natms)) : (posq_s + ((e) & DLP_J_MASK)))
+    double4 pa = ld_posq(GA(ea)), pb = ld_posq(GA(eb));
     for (int k = 0; k < npad; k += 4 * TPR) {
       {
-        const double4 pc = ld_posq(posq_s + (ec & DLP_J_MASK)), pd = ld_posq(posq_s + (ed & DLP_J_MASK));
+        const double4 pc = ld_posq(GA(ec)), pd = ld_posq(GA(ed));
         const unsigned e0 = ea, e1 = eb;
-        ea = row[4 * TPR]; eb = row[5 * TPR];
-        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        ea = LE(4); eb = LE(5);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
         pa = pc; pb = pd;
       }
       if (k + 2 * TPR >= npad) break;
       {
-        const double4 pc = ld_posq(posq_s + (ea & DLP_J_MASK)), pd = ld_posq(posq_s + (eb & DLP_J_MASK));
+        const double4 pc = ld_posq(GA(ea)), pd = ld_posq(GA(eb));
         const unsigned e0 = ec, e1 = ed;
-        ec = row[6 * TPR]; ed = row[7 * TPR];
-        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair2<VT, EW, SG>(P, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        ec = LE(6); ed = LE(7);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
         pa = pc; pb = pd;
       }
       row += 4 * TPR;
     }
+#undef ld_posq
+#undef LE
+#undef GA
 #pragma unroll
     for (int d = TPR / 2; d > 0; d >>= 1) {
       fix += __shfl_xor_sync(DLP_FULL, fix, d);
@@ -612,7 +650,7 @@ k_pair_v2(P2 P, const int* __restrict__ loc_slot, const double4* __restrict__ po
     }
     if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
   }
-  __shared__ double red[16][9];
+  __shared__ double red[NT / 32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -624,7 +662,7 @@ k_pair_v2(P2 P, const int* __restrict__ loc_slot, const double4* __restrict__ po
   __syncthreads();
   if (threadIdx.x < 9) {
     double v = 0.0;
-    for (int w = 0; w < 16; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < NT / 32; ++w) v += red[w][threadIdx.x];
     red[0][threadIdx.x] = v;
   }
   __syncthreads();
@@ -753,6 +791,13 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->tab2.p, t2.data(), t2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tab2_ne = NE; ctx->tab2_ts = tsz; ctx->tab2_zero = ntab * tsz;
+    if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ctx->tab2.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<int4>(); rd.res.linear.sizeInBytes = (size_t)NE * 32;
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    CK(cudaCreateTextureObject(&ctx->tab2_tex, &rd, &td, nullptr));
   }
   ctx->tab4_valid = true;
   return 0;
@@ -782,7 +827,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   // threads per row from the mean row length: the group width that wastes the fewest lanes on the last pass
   long long pairs_hint = ctx->list_entries;
   double mean = natms > 0 ? (double)pairs_hint / natms : 0.0;
-  int tpr = mean > 64.0 ? 8 : 16;   // measured on B200: long (ionic) rows run best 8 lanes wide, short (LJ) rows 16 wide
+  (void)mean;
+  int tpr = 8;   // measured on B200 with k_pair_v2: 8 lanes per row beat 16 for long (NaCl, 1.44 vs 1.53 ms) and short (argon, 0.44 vs 0.53 ms) rows
   if (ctx->tpr_override) tpr = ctx->tpr_override;
   const int NT = 512;
   int blocks = std::max(1, std::min(cdiv(natms, NT / tpr), ctx->sm_count * bps));
@@ -796,27 +842,49 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   }
   cudaEventRecord(ctx->ev[6], s);
   const bool fast = P.half && use_smem && !ctx->no_fast && !(P.lbook && P.ew_on) && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) &&
-                    (P.vdw_on || P.ew_on) && (tpr == 8 || tpr == 16);
+                    (P.vdw_on || P.ew_on) && tpr == 8;
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
-  const bool fast2 = fast && ctx->variant < 100 && smem2 + 2048 <= 227 * 1024;
+  const bool fast2 = fast && ctx->variant != 100 && smem2 + 2048 <= 227 * 1024;
   if (natms > 0 && fast2) {
     P2 Q{};
     Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;
     Q.rdr_v = P.vdw_on ? ctx->vdw_rdr : ctx->ew_rdr; Q.rdr_e = ctx->ew_rdr; Q.thr_vdw = ctx->thr_vdw; Q.thr_coul = ctx->thr_coul;
     Q.scaling = ctx->scaling;
     const double2* t2 = reinterpret_cast<const double2*>(ctx->tab2.p);
-#define DLP_V2(T, V, E, S)                                                                                                     \
+#define DLP_V2(V, E, S, TXV)                                                                                                   \
   do {                                                                                                                         \
-    CK(cudaFuncSetAttribute(k_pair_v2<T, V, E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));                   \
-    LAUNCH(ctx, (k_pair_v2<T, V, E, S>), blocks, 512, smem2, Q, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, t2, fpos, fneg, \
-           ctx->partial.p);                                                                                                    \
+    CK(cudaFuncSetAttribute(k_pair_v2<8, V, E, S, 0, TXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));           \
+    LAUNCH(ctx, (k_pair_v2<8, V, E, S, 0, TXV>), blocks, 512, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, \
+           t2, fpos, fneg, ctx->partial.p);                                                                                    \
+  } while (0)
+#define DLP_V2X(XV, NTV)                                                                                                       \
+  do {                                                                                                                         \
+    const int blocks_x = std::max(1, std::min(cdiv(natms, (NTV) / 8), ctx->sm_count));                                          \
+    CK(ctx->partial.ensure((size_t)blocks_x * 12 + 16, s));                                                                     \
+    CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, ((XV) & 255), ((XV) >> 8), NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, ((XV) & 255), ((XV) >> 8), NTV>), blocks_x, NTV, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, \
+           ctx->nbr.p, ctx->nnbr.p, t2, fpos, fneg, ctx->partial.p);                                                            \
   } while (0)
     const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0, sg = (!v || !e || P.same_grid) ? 1 : 0;
-    if (tpr == 8) {
-      if (v && e) { if (sg) DLP_V2(8, 1, 1, 1); else DLP_V2(8, 1, 1, 0); } else if (v) DLP_V2(8, 1, 0, 1); else DLP_V2(8, 0, 1, 1);
+    // vdW h unit through the texture pipe: measured on B200 (1 M NaCl ions) 1.393 ms against 1.440 ms with all six reads in LDS
+    const int tx = ctx->tx_override >= 0 ? ctx->tx_override : (v ? 2 : 0);   // argon: 0.418 against 0.437 ms
+    if (ctx->variant > 0 && ctx->variant != 100 && v && e && sg) {   // timing experiments only (DLPGPU_VARIANT): results are not meaningful
+      const int xv = ctx->variant & 0xfff, ntc = ctx->variant >> 12;
+#define DLP_V2N(XV) do { if (ntc == 0) DLP_V2X(XV, 512); else if (ntc == 1) DLP_V2X(XV, 640); else DLP_V2X(XV, 768); } while (0)
+      switch (xv) {
+        case 1: DLP_V2N(1); break; case 2: DLP_V2N(2); break; case 4: DLP_V2N(4); break; case 8: DLP_V2N(8); break;
+        case 256: DLP_V2N(256); break;
+        default: DLP_V2N(0);
+      }
+    } else if (v && e) {
+      if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
+    } else if (v) {
+      if (tx == 2) DLP_V2(1, 0, 1, 2); else DLP_V2(1, 0, 1, 0);
     } else {
-      if (v && e) { if (sg) DLP_V2(16, 1, 1, 1); else DLP_V2(16, 1, 1, 0); } else if (v) DLP_V2(16, 1, 0, 1); else DLP_V2(16, 0, 1, 1);
+      if (tx == 1) DLP_V2(0, 1, 1, 1); else DLP_V2(0, 1, 1, 0);
     }
+#undef DLP_V2X
+#undef DLP_V2N
 #undef DLP_V2
   } else if (natms > 0 && fast) {
     const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
