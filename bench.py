@@ -332,9 +332,9 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread; restatement "
                          "of the reference algorithm (oracle/), not the reference binary" % (what, info["steps"], info["rebuilds"], info["cores"])}
-    if rank == 0 and dom.profile is not None:
-        sys.stderr.write("phase profile (ms per step, synchronised phases): %s\n" %
-                         {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()})
+    if dom.profile is not None:
+        sys.stderr.write("rank %d phase profile (ms per step, synchronised phases): %s\n" % (rank,
+                         {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()}))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

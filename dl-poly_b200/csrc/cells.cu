@@ -607,7 +607,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             const int2 infi = s_info[wid][a];
             const unsigned entry = jbits | (((kcp >> infi.y) & 63u) << DLP_K_SHIFT) | ((infi.x < gid_j) ? DLP_F_ECNT : 0u);
             const int ll = ca + __popc(m & ltmask);
-            if (ll < cap) row0[(size_t)a * pitch + ll] = entry;
+            if (ll < cap) row0[(unsigned)(a * pitch + ll)] = entry;   // 32-bit offset inside the cell's block of rows
             else ovf = max(ovf, ll + 1);
           }
           if (lane == a) cnt += __popc(m);

@@ -147,6 +147,15 @@ struct dlpgpu_ctx {
   bool p2p_ready = false, pub_valid = false;
   std::vector<double4*> peer_pub;   // [2 * nranks]
   DBuf<unsigned long long> peer_pub_dev;   // the same table on the device
+  // fused device-side exchange (dlpgpu_dev_xchg_*): one CUDA-IPC exported region with the gmax mailboxes and the per-stage
+  // receive buffers of migration and halo build, the peers' regions, and the device-resident atom counts
+  char* xr = nullptr;
+  int xr_rank = 0, xr_nranks = 0, xr_cap_r = 0, xr_cap_h = 0;
+  bool xr_ready = false;
+  std::vector<char*> peer_xr;
+  DBuf<unsigned long long> peer_xr_dev;
+  DBuf<int> dcnt;
+  DBuf<unsigned long long> gmax_out;
   DBuf<double> xbg, ybg, zbg;
   bool have_bg = false;
 

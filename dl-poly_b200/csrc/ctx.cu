@@ -179,6 +179,10 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
         if (ctx->peer_pub.size() > (size_t)(2 * r + b) && ctx->peer_pub[2 * r + b]) cudaIpcCloseMemHandle(ctx->peer_pub[2 * r + b]);
   for (int b = 0; b < 2; ++b) if (ctx->pub[b]) cudaFree(ctx->pub[b]);
   ctx->peer_pub_dev.release();
+  for (int r = 0; r < ctx->xr_nranks; ++r)
+    if (r != ctx->xr_rank && ctx->peer_xr.size() > (size_t)r && ctx->peer_xr[r]) cudaIpcCloseMemHandle(ctx->peer_xr[r]);
+  if (ctx->xr) cudaFree(ctx->xr);
+  ctx->peer_xr_dev.release(); ctx->dcnt.release(); ctx->gmax_out.release();
   if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);

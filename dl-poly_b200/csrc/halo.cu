@@ -347,6 +347,263 @@ __global__ void k_count_nonzero(int n, const int* __restrict__ ixyz, int* __rest
 
 Mat9 mat(const double* a) { Mat9 m; for (int i = 0; i < 9; ++i) m.m[i] = a[i]; return m; }
 
+// ================================================================ fused device-side exchange over peer memory
+// relocate_particles + set_halo_particles of one rebuild -- twelve dependent stages -- and the gmax of vnl_check without a
+// single host round trip between the stages and without NCCL: every rank owns a CUDA-IPC exported region holding, per
+// stage, a receive buffer of fixed capacity and a header {sequence number, atom count}.  The sender's pack kernel writes
+// the payload straight into the RECEIVER's buffer over NVLink (or into its own when the decomposition has one domain in
+// that direction, deport_data.F90:1884-1886), a one-thread kernel publishes count + sequence with a system-scope release,
+// and the receiver's unpack kernel spins on its own header with acquire loads before it appends the atoms.  natms / nlast
+// live on the device while the twelve stages run (kernels are launched over host-side upper bounds and read the live
+// counts), the host learns them with ONE synchronisation at the end.  Selection rules, payloads, ordering and the periodic
+// shifts are those of the staged routines above (same device functions), so local indices and bits agree with them.
+struct XHdr { unsigned long long seq; long long count; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// true when the header carries `seq`; gives up after a few seconds and raises DCNT_ERR bit 2 (a peer died / lost lock-step)
+__device__ bool x_wait(const unsigned long long* seq_word, unsigned long long seq, int* err) {
+  for (long long it = 0; it < 4000000LL; ++it) {
+    if (ld_acquire_sys(seq_word) == seq) return true;
+    if ((it & 1023) == 1023 && (*(volatile int*)err & 4)) return false;   // somebody already gave up: do not wait again
+    __nanosleep(200);
+  }
+  atomicOr(err, 4);
+  return false;
+}
+// device counts block
+#define DC_NATMS 0
+#define DC_NLAST 1
+#define DC_ERR 2      // bit 0: migration buffer overflow (error 43), 1: halo buffer overflow (54), 2: wait timeout, 3: atom arrays full
+#define DC_LOST 3
+#define DC_HSENT 8
+#define DC_HRECV 16
+#define DC_HOFF 24
+#define DC_RSENT 32
+#define DC_RRECV 40
+#define DC_WORDS 64
+
+__global__ void k_x_reloc_tag(const int* __restrict__ dc, Mat9 rcell, DomI D, const double4* __restrict__ posq, int* __restrict__ ixyz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dc[DC_NATMS]) return;
+  const double half_plus = 0.50000000000000011102230246251565404236316680908203125;
+  const double half_minus = 0.499999999999999944488848768742172978818416595458984375;
+  double4 p = posq[i];
+  double x = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;
+  double y = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
+  double z = rcell.m[2] * p.x + rcell.m[5] * p.y + rcell.m[8] * p.z;
+  int ipx = __double2int_rz((x + 0.5) * (double)D.nx), ipy = __double2int_rz((y + 0.5) * (double)D.ny), ipz = __double2int_rz((z + 0.5) * (double)D.nz);
+  int v = 0;   // deport_data.F90:2981-3025
+  if (D.idx == 0) { if (x < -half_plus) v += 1; } else { if (ipx < D.idx) v += 1; }
+  if (D.idx == D.nx - 1) { if (x >= half_minus) v += 2; } else { if (ipx > D.idx) v += 2; }
+  if (D.idy == 0) { if (y < -half_plus) v += 10; } else { if (ipy < D.idy) v += 10; }
+  if (D.idy == D.ny - 1) { if (y >= half_minus) v += 20; } else { if (ipy > D.idy) v += 20; }
+  if (D.idz == 0) { if (z < -half_plus) v += 100; } else { if (ipz < D.idz) v += 100; }
+  if (D.idz == D.nz - 1) { if (z >= half_minus) v += 200; } else { if (ipz > D.idz) v += 200; }
+  ixyz[i] = v;
+}
+__global__ void k_x_reloc_flag(const int* __restrict__ dc, int nub, Dir d, const int* __restrict__ ixyz, int* __restrict__ leave) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nub) return;
+  int f = 0;
+  if (i < dc[DC_NATMS]) {
+    int v = ixyz[i];
+    if (v != 0) {
+      int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
+      if (ix * d.kx + iy * d.ky + iz * d.kz == d.jxyz) f = 1;
+    }
+  }
+  leave[i] = f;
+}
+__global__ void k_x_reloc_pack(const int* __restrict__ dc, const int* __restrict__ tot, Dir d, int cap, const int* __restrict__ leave,
+                               const int* __restrict__ lpos, const double4* __restrict__ posq, const double* __restrict__ vx,
+                               const double* __restrict__ vy, const double* __restrict__ vz, const double* __restrict__ fx,
+                               const double* __restrict__ fy, const double* __restrict__ fz, const int* __restrict__ ltg,
+                               const int* __restrict__ lsite, const int* __restrict__ ixyz, double* __restrict__ buf, int* __restrict__ hole_pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = dc[DC_NATMS];
+  if (i >= n || !leave[i]) return;
+  const int k_stay = n - *tot;
+  int k = lpos[i];
+  if (k >= cap) return;                  // overflow is reported by k_x_reloc_sent
+  if (i < k_stay) hole_pos[k] = i;
+  double4 p = posq[i];
+  double* b = buf + (size_t)k * 12;
+  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
+  b[3] = vx[i]; b[4] = vy[i]; b[5] = vz[i];
+  b[6] = fx[i]; b[7] = fy[i]; b[8] = fz[i];
+  b[9] = (double)ltg[i]; b[10] = (double)lsite[i]; b[11] = (double)(ixyz[i] - d.jxyz);
+}
+__global__ void k_x_reloc_restack(const int* __restrict__ dc, const int* __restrict__ tot, int cap, const int* __restrict__ leave,
+                                  const int* __restrict__ lpos, const int* __restrict__ hole_pos, double4* __restrict__ posq, double* vx,
+                                  double* vy, double* vz, double* fx, double* fy, double* fz, int* ltg, int* lsite, int* ixyz) {
+  const int n = dc[DC_NATMS], total = *tot;
+  if (total > cap) return;
+  const int k_stay = n - total;
+  int j = k_stay + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || leave[j]) return;
+  int r = k_stay - 1 - (j - lpos[j]);   // deport_data.F90:822-925, see k_reloc_restack
+  int dst = hole_pos[r];
+  posq[dst] = posq[j];
+  vx[dst] = vx[j]; vy[dst] = vy[j]; vz[dst] = vz[j];
+  fx[dst] = fx[j]; fy[dst] = fy[j]; fz[dst] = fz[j];
+  ltg[dst] = ltg[j]; lsite[dst] = lsite[j]; ixyz[dst] = ixyz[j];
+}
+// one thread: the stage's leavers are gone from the local range; count + sequence go to the receiver's header
+__global__ void k_x_sent(int is_halo, int q, const int* __restrict__ tot, int cap, int* __restrict__ dc, XHdr* dst_hdr, unsigned long long seq) {
+  int total = *tot;
+  if (total > cap) { atomicOr(&dc[DC_ERR], is_halo ? 2 : 1); total = cap; }
+  if (is_halo) dc[DC_HSENT + q] = total;
+  else { dc[DC_RSENT + q] = total; dc[DC_NATMS] -= *tot > cap ? 0 : total; dc[DC_NLAST] = dc[DC_NATMS]; }
+  dst_hdr->count = total;
+  __threadfence_system();
+  st_release_sys(&dst_hdr->seq, seq);
+}
+__global__ void k_x_reloc_recv(const XHdr* __restrict__ hdr, unsigned long long seq, const double* __restrict__ buf, int capacity,
+                               int* __restrict__ dc, double4* __restrict__ posq, double* vx, double* vy, double* vz, double* fx, double* fy,
+                               double* fz, int* ltg, int* lsite, int* ixyz) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = x_wait(&hdr->seq, seq, &dc[DC_ERR]) ? (int)hdr->count : 0;
+  __syncthreads();
+  const int off = dc[DC_NATMS];
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= s_count || off + k >= capacity) return;
+  const double* b = buf + (size_t)k * 12;
+  int i = off + k;
+  posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
+  vx[i] = __ldcg(b + 3); vy[i] = __ldcg(b + 4); vz[i] = __ldcg(b + 5);
+  fx[i] = __ldcg(b + 6); fy[i] = __ldcg(b + 7); fz[i] = __ldcg(b + 8);
+  ltg[i] = __double2int_rn(__ldcg(b + 9)); lsite[i] = __double2int_rn(__ldcg(b + 10)); ixyz[i] = __double2int_rn(__ldcg(b + 11));
+}
+__global__ void k_x_recvd(int is_halo, int q, const XHdr* __restrict__ hdr, unsigned long long seq, int capacity, int* __restrict__ dc) {
+  int count = (ld_acquire_sys(&hdr->seq) == seq) ? (int)hdr->count : 0;
+  const int off = is_halo ? dc[DC_NLAST] : dc[DC_NATMS];
+  if (off + count > capacity) { atomicOr(&dc[DC_ERR], 8); count = capacity - off; }
+  if (is_halo) { dc[DC_HOFF + q] = off; dc[DC_HRECV + q] = count; dc[DC_NLAST] = off + count; }
+  else { dc[DC_RRECV + q] = count; dc[DC_NATMS] = off + count; dc[DC_NLAST] = off + count; }
+}
+__global__ void k_x_reloc_end(int* dc, const int* __restrict__ ixyz, const int* __restrict__ lsite,
+                              const int* __restrict__ type_site, const double* __restrict__ charge_site, const int* __restrict__ freeze_site,
+                              double4* __restrict__ posq, int* __restrict__ ltype, int* __restrict__ lfrzn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *(volatile int*)&dc[DC_NATMS]) return;
+  if (ixyz[i] != 0) atomicAdd(&dc[DC_LOST], 1);       // deport_data.F90:3056-3058
+  int s = lsite[i] - 1;
+  ltype[i] = type_site[s]; posq[i].w = charge_site[s]; lfrzn[i] = freeze_site[s];   // :3062-3069
+}
+__global__ void k_x_halo_tag(const int* __restrict__ dc, Mat9 rcell, HaloThr t, const double4* __restrict__ posq, int* __restrict__ ixyz,
+                             int my_rank, int* __restrict__ org_rank, int* __restrict__ org_idx, int* __restrict__ org_wrap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dc[DC_NATMS]) return;
+  org_rank[i] = my_rank; org_idx[i] = i; org_wrap[i] = 13;
+  double4 p = posq[i];
+  double x = rcell.m[0] * p.x + rcell.m[3] * p.y + rcell.m[6] * p.z;   // halo.F90:265-267
+  double y = rcell.m[1] * p.x + rcell.m[4] * p.y + rcell.m[7] * p.z;
+  double z = rcell.m[2] * p.x + rcell.m[5] * p.y + rcell.m[8] * p.z;
+  int v = 0;
+  if (x <= t.ecwx) v += 1;
+  if (x >= t.cwx) v += 2;
+  if (y <= t.ecwy) v += 10;
+  if (y >= t.cwy) v += 20;
+  if (z <= t.ecwz) v += 100;
+  if (z >= t.cwz) v += 200;
+  ixyz[i] = v;
+}
+__global__ void k_x_halo_flag(const int* __restrict__ dc, int nub, Dir d, const int* __restrict__ ixyz, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nub) return;
+  flag[i] = (i < dc[DC_NLAST] && halo_sel(ixyz[i], d) != 0) ? 1 : 0;
+}
+__global__ void k_x_halo_pack(const int* __restrict__ dc, Dir d, int cap, const int* __restrict__ flag, const int* __restrict__ pos,
+                              const double4* __restrict__ posq, const int* __restrict__ ltg, const int* __restrict__ lsite,
+                              const int* __restrict__ ixyz, const int* __restrict__ org_rank, const int* __restrict__ org_idx,
+                              const int* __restrict__ org_wrap, int wrap_add, double* __restrict__ buf, int* __restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dc[DC_NLAST] || !flag[i]) return;
+  int k = pos[i];
+  if (k >= cap) return;
+  idx[k] = i;
+  double4 p = posq[i];
+  double* b = buf + (size_t)k * DLP_HALO_W;
+  b[6] = (double)org_rank[i]; b[7] = (double)org_idx[i]; b[8] = (double)(org_wrap[i] + wrap_add);
+  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:1836-1844
+  b[3] = (double)ltg[i];
+  b[4] = (double)lsite[i];
+  int v = ixyz[i];
+  b[5] = (double)(v - (halo_sel(v, d) == 1 ? d.jxyz : d.kxyz));            // :1853
+}
+__global__ void k_x_halo_recv(const XHdr* __restrict__ hdr, unsigned long long seq, const double* __restrict__ buf, int capacity,
+                              int* __restrict__ dc, double4* __restrict__ posq, int* __restrict__ ltg, int* __restrict__ lsite,
+                              int* __restrict__ ixyz, double* fx, double* fy, double* fz, int* __restrict__ org_rank,
+                              int* __restrict__ org_idx, int* __restrict__ org_wrap) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = x_wait(&hdr->seq, seq, &dc[DC_ERR]) ? (int)hdr->count : 0;
+  __syncthreads();
+  const int off = dc[DC_NLAST];
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= s_count || off + k >= capacity) return;
+  const double* b = buf + (size_t)k * DLP_HALO_W;
+  int i = off + k;
+  org_rank[i] = __double2int_rn(__ldcg(b + 6)); org_idx[i] = __double2int_rn(__ldcg(b + 7)); org_wrap[i] = __double2int_rn(__ldcg(b + 8));
+  posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
+  ltg[i] = __double2int_rn(__ldcg(b + 3)); lsite[i] = __double2int_rn(__ldcg(b + 4)); ixyz[i] = __double2int_rn(__ldcg(b + 5));   // Nint, :1935-1940
+  fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0;
+}
+__global__ void k_x_halo_end(const int* __restrict__ dc, const int* __restrict__ lsite, const int* __restrict__ type_site,
+                             const double* __restrict__ charge_site, const int* __restrict__ freeze_site, double4* __restrict__ posq,
+                             int* __restrict__ ltype, int* __restrict__ lfrzn, double* xbg, double* ybg, double* zbg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dc[DC_NLAST]) return;
+  double4 p = posq[i];
+  if (i >= dc[DC_NATMS]) {   // halo.F90:296-302
+    int s = lsite[i] - 1;
+    ltype[i] = type_site[s]; p.w = charge_site[s]; lfrzn[i] = freeze_site[s];
+    posq[i] = p;
+  }
+  xbg[i] = p.x; ybg[i] = p.y; zbg[i] = p.z;   // vnl_set_check, halo.F90:315 / neighbours.F90:337-341
+}
+// gmax of vnl_check (neighbours.F90:176) through the peers' mailboxes: lane r writes this rank's value into rank r's slot
+// and waits for rank r's value in its own.  Slots alternate with the parity of the sequence number.
+__global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const unsigned long long* __restrict__ tol_bits,
+                         const unsigned long long* __restrict__ peers, size_t off_gm, unsigned long long* __restrict__ out, int* __restrict__ dc) {
+  const int r = threadIdx.x;
+  unsigned long long v = 0;
+  if (r < nranks) {
+    const unsigned long long mine = *tol_bits;
+    const size_t slot = ((seq & 1) * (size_t)nranks);
+    XHdr* dst = reinterpret_cast<XHdr*>(peers[r] + off_gm) + slot + rank;
+    dst->count = (long long)mine;
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    const XHdr* src = reinterpret_cast<const XHdr*>(peers[rank] + off_gm) + slot + r;
+    if (x_wait(&src->seq, seq, &dc[DC_ERR])) v = (unsigned long long)src->count;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(DLP_FULL, v, d); v = o > v ? o : v; }   // non-negative doubles order like their bits
+  if (r == 0) *out = v;
+}
+
+static size_t x_align(size_t v) { return (v + 255) & ~(size_t)255; }
+struct XLayout { size_t off_gm, off_hdr, off_rbuf, off_hbuf, bytes; };
+static XLayout x_layout(int nranks, int cap_r, int cap_h) {
+  XLayout L;
+  L.off_gm = 0;
+  L.off_hdr = x_align((size_t)2 * nranks * sizeof(XHdr));
+  L.off_rbuf = x_align(L.off_hdr + 12 * sizeof(XHdr));
+  L.off_hbuf = x_align(L.off_rbuf + (size_t)6 * cap_r * 12 * sizeof(double));
+  L.bytes = x_align(L.off_hbuf + (size_t)6 * cap_h * DLP_HALO_W * sizeof(double));
+  return L;
+}
+
+
 }  // namespace
 
 int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol) {
@@ -677,6 +934,210 @@ int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now) {
   if (natms_now) *natms_now = n;
   if (st[2] != 0)   // deport_data.F90:3056-3058: an atom still wants to leave after the six stages
     return dlp_fail(ctx, DLPGPU_ERR_LOST_ATOMS, "error 58: %d atoms moved further than one domain in a single relocation", st[2]);
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[64]) {
+  if (!ctx || rank < 0 || nranks < 1 || nranks > 32 || rank >= nranks || cap_reloc_atoms < 1 || cap_halo_atoms < 1 || !handle_out) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->xr) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_init: already initialised");
+  const XLayout L = x_layout(nranks, cap_reloc_atoms, cap_halo_atoms);
+  CK(cudaMalloc((void**)&ctx->xr, L.bytes));
+  CK(cudaMemset(ctx->xr, 0, L.bytes));
+  CK(cudaDeviceSynchronize());
+  ctx->xr_rank = rank; ctx->xr_nranks = nranks; ctx->xr_cap_r = cap_reloc_atoms; ctx->xr_cap_h = cap_halo_atoms;
+  std::memset(handle_out, 0, 64);
+  if (nranks > 1) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xr));
+    std::memcpy(handle_out, &h, 64);
+  }
+  ctx->peer_xr.assign(nranks, nullptr);
+  ctx->peer_xr[rank] = ctx->xr;
+  CK(ctx->dcnt.ensure(DC_WORDS, ctx->stream));
+  CK(cudaMemset(ctx->dcnt.p, 0, DC_WORDS * sizeof(int)));
+  CK(ctx->gmax_out.ensure(2, ctx->stream));
+  ctx->xr_ready = false;
+  if (nranks == 1) {
+    CK(ctx->peer_xr_dev.ensure(1, ctx->stream));
+    CK(cudaMemcpy(ctx->peer_xr_dev.p, ctx->peer_xr.data(), sizeof(void*), cudaMemcpyHostToDevice));
+    ctx->xr_ready = true;
+  }
+  return 0;
+}
+
+int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x 64 bytes */) {
+  if (!ctx || !all_handles) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xr) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_open: call xchg_init first");
+  for (int r = 0; r < ctx->xr_nranks; ++r) {
+    if (r == ctx->xr_rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, all_handles + (size_t)64 * r, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_xr[r] = (char*)p;
+  }
+  CK(ctx->peer_xr_dev.ensure((size_t)ctx->xr_nranks, ctx->stream));
+  CK(cudaMemcpy(ctx->peer_xr_dev.p, ctx->peer_xr.data(), (size_t)ctx->xr_nranks * sizeof(void*), cudaMemcpyHostToDevice));
+  ctx->xr_ready = true;
+  return 0;
+}
+
+// vnl_check + gmax (neighbours.F90:123-182) with the reduction done by the GPUs themselves
+int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol) {
+  if (!ctx || !tol) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xr_ready) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_gmax: exchange region not ready");
+  if (!ctx->have_bg) return dlp_fail(ctx, DLPGPU_ERR_STATE, "vnl_check: no checkpoint");
+  cudaStream_t s = ctx->stream;
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
+           ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  const XLayout L = x_layout(ctx->xr_nranks, ctx->xr_cap_r, ctx->xr_cap_h);
+  LAUNCH(ctx, k_x_gmax, 1, 32, 0, ctx->xr_rank, ctx->xr_nranks, seq, ctx->tol_bits.p, ctx->peer_xr_dev.p, L.off_gm, ctx->gmax_out.p, ctx->dcnt.p);
+  unsigned long long bits = 0;
+  int err = 0;
+  CK(cudaMemcpyAsync(&bits, ctx->gmax_out.p, sizeof bits, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&err, ctx->dcnt.p + DC_ERR, sizeof err, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (err & 4) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_gmax: timed out waiting for a peer (ranks out of lock-step)");
+  double r;
+  std::memcpy(&r, &bits, sizeof r);
+  *tol = r;
+  return 0;
+}
+
+// relocate_particles (deport_data.F90:2870-3202) + set_halo_particles (halo.F90:153-355) + vnl_set_check in one enqueue
+int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long long seq, int* natms_out, int* nlast_out) {
+  if (!ctx || !neigh) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xr_ready) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: exchange region not ready");
+  if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: sites not set");
+  cudaStream_t s = ctx->stream;
+  const int nr = ctx->xr_nranks, cap_r = ctx->xr_cap_r, cap_h = ctx->xr_cap_h;
+  const XLayout L = x_layout(nr, cap_r, cap_h);
+  const bool multi = ctx->nx * ctx->ny * ctx->nz > 1;
+  const int mdirs[6] = {-1, 1, -2, 2, -3, 3};
+  const int ub_total = ctx->natms + (multi ? 6 * cap_r : 0) + 6 * cap_h + 16;
+  CKRC(dlp_ensure_atoms(ctx, ub_total));
+  const int capacity = ctx->capacity;
+  CK(ctx->flag.ensure((size_t)ub_total + 2, s)); CK(ctx->scan_out.ensure((size_t)ub_total + 2, s));
+  CK(ctx->hole_pos.ensure((size_t)cap_r + 1, s));
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  int* dc = ctx->dcnt.p;
+  int h_dc[DC_WORDS];
+  std::memset(h_dc, 0, sizeof h_dc);
+  h_dc[DC_NATMS] = ctx->natms; h_dc[DC_NLAST] = ctx->natms;
+  CK(cudaMemcpyAsync(dc, h_dc, sizeof h_dc, cudaMemcpyHostToDevice, s));
+  ctx->halo_valid = false; ctx->list_valid = false;
+  int nub = ctx->natms;   // host-side upper bound of the live natms / nlast
+  auto hdr_of = [&](int r, int stage) { return reinterpret_cast<XHdr*>(ctx->peer_xr[r] + L.off_hdr) + stage; };
+  auto rbuf_of = [&](int r, int q) { return reinterpret_cast<double*>(ctx->peer_xr[r] + L.off_rbuf) + (size_t)q * cap_r * 12; };
+  auto hbuf_of = [&](int r, int q) { return reinterpret_cast<double*>(ctx->peer_xr[r] + L.off_hbuf) + (size_t)q * cap_h * DLP_HALO_W; };
+  const int me = ctx->xr_rank;
+  // ---- relocate_particles
+  if (!multi) {
+    if (ctx->natms > 0 && ctx->imcon != 0)
+      LAUNCH(ctx, k_pbcshift, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p);   // deport_data.F90:3190
+  } else {
+    DomI D{ctx->nx, ctx->ny, ctx->nz, ctx->idx, ctx->idy, ctx->idz};
+    if (nub > 0) LAUNCH(ctx, k_x_reloc_tag, cdiv(nub, 256), 256, 0, dc, mat(rc), D, ctx->posq.p, ctx->ixyz.p);
+    for (int q = 0; q < 6; ++q) {
+      const Dir d = dir_settings(ctx, mdirs[q]);
+      const int dst = neigh[q];
+      if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
+      LAUNCH(ctx, k_x_reloc_flag, cdiv(nub + 1, 256), 256, 0, dc, nub, d, ctx->ixyz.p, ctx->flag.p);
+      CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nub, nullptr));
+      const int* tot = ctx->scan_out.p + nub;
+      if (nub > 0) {
+        LAUNCH(ctx, k_x_reloc_pack, cdiv(nub, 256), 256, 0, dc, tot, d, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->vx.p, ctx->vy.p,
+               ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p, rbuf_of(dst, q), ctx->hole_pos.p);
+        LAUNCH(ctx, k_x_reloc_restack, cdiv(cap_r, 256), 256, 0, dc, tot, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, ctx->posq.p,
+               ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
+      }
+      LAUNCH(ctx, k_x_sent, 1, 1, 0, 0, q, tot, cap_r, dc, hdr_of(dst, q), seq);
+      LAUNCH(ctx, k_x_reloc_recv, cdiv(cap_r, 256), 256, 0, hdr_of(me, q), seq, rbuf_of(me, q), capacity, dc, ctx->posq.p, ctx->vx.p, ctx->vy.p,
+             ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
+      LAUNCH(ctx, k_x_recvd, 1, 1, 0, 0, q, hdr_of(me, q), seq, capacity, dc);
+      nub = std::min(nub + cap_r, capacity);
+    }
+    LAUNCH(ctx, k_x_reloc_end, cdiv(nub, 256), 256, 0, dc, ctx->ixyz.p, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p,
+           ctx->freeze_site.p, ctx->posq.p, ctx->ltype.p, ctx->lfrzn.p);
+  }
+  // ---- set_halo_particles: thresholds of halo.F90:190-249 (see dlpgpu_dev_halo_begin)
+  {
+    double cut = ctx->rx + 1.0e-6;
+    double w3[3];
+    h_widths(ctx->cell, w3);
+    double nxr = (double)ctx->nx, nyr = (double)ctx->ny, nzr = (double)ctx->nz;
+    int nlx = (int)(w3[0] / (cut * nxr)), nly = (int)(w3[1] / (cut * nyr)), nlz = (int)(w3[2] / (cut * nzr));
+    if (nlx * nly * nlz == 0) return dlp_fail(ctx, DLPGPU_ERR_LINK_CELLS, "error 307: domain narrower than cutoff_extended");
+    double xdc = (double)(nlx * ctx->nx), ydc = (double)(nly * ctx->ny), zdc = (double)(nlz * ctx->nz);
+    double cwx = 1.0 / xdc, cwy = 1.0 / ydc, cwz = 1.0 / zdc;
+    double ecwx = std::max(cwx, ctx->ecw[0]), ecwy = std::max(cwy, ctx->ecw[1]), ecwz = std::max(cwz, ctx->ecw[2]);
+    double nx_recip = 1.0 / nxr, ny_recip = 1.0 / nyr, nz_recip = 1.0 / nzr;
+    const double zero_plus = DBL_MIN;
+    HaloThr t;
+    t.ecwx = std::nextafter((-0.5 + ecwx) + (double)ctx->idx * nx_recip, DBL_MAX) + zero_plus;
+    t.ecwy = std::nextafter((-0.5 + ecwy) + (double)ctx->idy * ny_recip, DBL_MAX) + zero_plus;
+    t.ecwz = std::nextafter((-0.5 + ecwz) + (double)ctx->idz * nz_recip, DBL_MAX) + zero_plus;
+    t.cwx = std::nextafter((-0.5 - cwx) + (double)(ctx->idx + 1) * nx_recip, -DBL_MAX) - zero_plus - (nlx == 1 ? cwx * 1.0e-10 : 0.0);
+    t.cwy = std::nextafter((-0.5 - cwy) + (double)(ctx->idy + 1) * ny_recip, -DBL_MAX) - zero_plus - (nly == 1 ? cwy * 1.0e-10 : 0.0);
+    t.cwz = std::nextafter((-0.5 - cwz) + (double)(ctx->idz + 1) * nz_recip, -DBL_MAX) - zero_plus - (nlz == 1 ? cwz * 1.0e-10 : 0.0);
+    if (nub > 0)
+      LAUNCH(ctx, k_x_halo_tag, cdiv(nub, 256), 256, 0, dc, mat(rc), t, ctx->posq.p, ctx->ixyz.p, ctx->p2p_rank, ctx->org_rank.p, ctx->org_idx.p,
+             ctx->org_wrap.p);
+  }
+  for (int q = 0; q < 6; ++q) {
+    const Dir d = dir_settings(ctx, mdirs[q]);
+    const int dst = neigh[q];
+    if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
+    HaloStage& st = ctx->stage[q];
+    st.lwrap = d.lwrap != 0; st.shift[0] = d.xadd; st.shift[1] = d.yadd; st.shift[2] = d.zadd;
+    CK(st.idx.ensure((size_t)cap_h + 1, s));
+    int wrap_add = 0;
+    if (d.lwrap) wrap_add = ((mdirs[q] < 0) ? +1 : -1) * (d.kx ? 1 : d.ky ? 3 : 9);
+    LAUNCH(ctx, k_x_halo_flag, cdiv(nub + 1, 256), 256, 0, dc, nub, d, ctx->ixyz.p, ctx->flag.p);
+    CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nub, nullptr));
+    const int* tot = ctx->scan_out.p + nub;
+    if (nub > 0)
+      LAUNCH(ctx, k_x_halo_pack, cdiv(nub, 256), 256, 0, dc, d, cap_h, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->ltg.p, ctx->lsite.p,
+             ctx->ixyz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p, wrap_add, hbuf_of(dst, q), st.idx.p);
+    LAUNCH(ctx, k_x_sent, 1, 1, 0, 1, q, tot, cap_h, dc, hdr_of(dst, 6 + q), seq);
+    LAUNCH(ctx, k_x_halo_recv, cdiv(cap_h, 256), 256, 0, hdr_of(me, 6 + q), seq, hbuf_of(me, q), capacity, dc, ctx->posq.p, ctx->ltg.p,
+           ctx->lsite.p, ctx->ixyz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p);
+    LAUNCH(ctx, k_x_recvd, 1, 1, 0, 1, q, hdr_of(me, 6 + q), seq, capacity, dc);
+    nub = std::min(nub + cap_h, capacity);
+  }
+  if (nub > 0)
+    LAUNCH(ctx, k_x_halo_end, cdiv(nub, 256), 256, 0, dc, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p, ctx->freeze_site.p, ctx->posq.p,
+           ctx->ltype.p, ctx->lfrzn.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p);
+  CK(cudaMemcpyAsync(h_dc, dc, sizeof h_dc, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  ctx->natms = h_dc[DC_NATMS]; ctx->nlast = h_dc[DC_NLAST];
+  if (natms_out) *natms_out = ctx->natms;
+  if (nlast_out) *nlast_out = ctx->nlast;
+  if (h_dc[DC_ERR] & 4) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: timed out waiting for a peer (ranks out of lock-step)");
+  if (h_dc[DC_ERR] & 1) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 43: outgoing migration buffer too small (capacity %d atoms per stage)", cap_r);
+  if (h_dc[DC_ERR] & 2) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 54: outgoing halo buffer too small (capacity %d atoms per stage)", cap_h);
+  if (h_dc[DC_ERR] & 8) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "xchg_rebuild: atom arrays full (%d)", capacity);
+  if (h_dc[DC_LOST] != 0)
+    return dlp_fail(ctx, DLPGPU_ERR_LOST_ATOMS, "error 58: %d atoms moved further than one domain in a single relocation", h_dc[DC_LOST]);
+  for (int q = 0; q < 6; ++q) {
+    ctx->stage[q].count = h_dc[DC_HSENT + q]; ctx->stage[q].recv_off = h_dc[DC_HOFF + q]; ctx->stage[q].recv_count = h_dc[DC_HRECV + q];
+  }
+  ctx->have_bg = true;
+  ctx->halo_valid = true;
   return 0;
 }
 

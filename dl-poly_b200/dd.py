@@ -258,6 +258,25 @@ def staged_exchange(transport, neighbours, dims, pack, unpack, alloc, width, sel
     return bufs
 
 
+def exchange_capacities(sysm, dims, safety=2.0):
+    """Per-stage receive capacities (atoms) of the fused device-side exchange, identical on every rank: the halo slab of
+    the widest face (link-cell width w = domain width / Int(domain width / cutoff_extended), halo.F90:219-239, grown by the
+    halo layers already received in the earlier directions) at the mean density, times ``safety``; migration: a layer of
+    one padding thickness across that face (an atom moves less than padding / 2 between rebuilds, neighbours.F90:182)."""
+    cell = np.asarray(sysm.cell, dtype=np.float64).reshape(3, 3)
+    vol = abs(np.linalg.det(cell))
+    rho = sysm.megatm / vol
+    wid = [w / d for w, d in zip(cell_widths(cell), dims)]
+    rx = sysm.rcut + sysm.padding
+    lw = [wd / max(int(wd / (rx + 1.0e-6)), 1) for wd in wid]
+    full = [wd + 2.0 * l for wd, l in zip(wid, lw)]
+    face = max(full[1] * full[2] * lw[0], full[0] * full[2] * lw[1], full[0] * full[1] * lw[2])
+    cap_h = int(safety * rho * face) + 4096
+    area = max(wid[1] * wid[2], wid[0] * wid[2], wid[0] * wid[1])
+    cap_r = int(safety * rho * area * max(sysm.padding, 0.05 * rx)) + 4096
+    return cap_r, cap_h
+
+
 class Domain:
     """One DL_POLY domain resident on one GPU."""
 
@@ -297,6 +316,19 @@ class Domain:
                 allb = [torch.empty_like(t_blob) for _ in range(self.world)]
                 self.t.dist.all_gather(allb, t_blob, group=self.t.group)
                 self.sr.dev_p2p_open(torch.cat(allb).cpu().numpy())
+        # fused device-side exchange (migration + halo build + gmax over peer memory, no NCCL, one host sync per rebuild)
+        self.xchg = self.p2p and os.environ.get("DLP_DD_STAGED_EXCHANGE") is None
+        self.rseq = 0
+        self.gseq = 0
+        if self.xchg:
+            cap_r, cap_h = exchange_capacities(sysm, self.dims)
+            blob = self.sr.dev_xchg_init(self.rank, self.world, cap_r, cap_h)
+            if self.world > 1:
+                t_blob = torch.from_numpy(blob.copy()).to(self.device)
+                allb = [torch.empty_like(t_blob) for _ in range(self.world)]
+                self.t.dist.all_gather(allb, t_blob, group=self.t.group)
+                self.sr.dev_xchg_open(torch.cat(allb).cpu().numpy())
+                self.t.barrier()
         self.profile = {} if os.environ.get("DLP_DD_PROFILE") else None
 
     # ---- buffers on the context's device
@@ -353,6 +385,14 @@ class Domain:
 
     # ---- md_vv around the path
     def rebuild(self):
+        if self.xchg:
+            self.rseq += 1
+            with self.torch.cuda.stream(self.stream):
+                self.sr.dev_xchg_rebuild(self.neigh, self.rseq)
+                self._refresh_bufs = None
+                self.sr.dev_link_cell_pairs()
+            self.rebuilds += 1
+            return
         self.relocate()
         self.set_halo()
         with self.torch.cuda.stream(self.stream):
@@ -365,6 +405,11 @@ class Domain:
                 self.sr.dev_publish()
 
     def vnl_update(self):
+        if self.xchg:
+            self.gseq += 1
+            with self.torch.cuda.stream(self.stream):
+                tol = self.sr.dev_xchg_gmax(self.gseq)      # gmax over the GPUs' mailboxes, neighbours.F90:176
+            return self.sr.vnl_update(tol)
         with self.torch.cuda.stream(self.stream):
             tol = self.sr.dev_vnl_check()
             tol = self.t.allreduce_max(tol)                 # gmax, neighbours.F90:176
@@ -411,7 +456,16 @@ class Domain:
         t = lap("vv1", t)
         upd = self.vnl_update()
         t = lap("vnl_check+gmax", t)
-        if upd:
+        if upd and self.xchg:
+            self.rseq += 1
+            with self.torch.cuda.stream(self.stream):
+                sr.dev_xchg_rebuild(self.neigh, self.rseq)
+            t = lap("relocate+set_halo (fused)", t)
+            with self.torch.cuda.stream(self.stream):
+                sr.dev_link_cell_pairs()
+            t = lap("link_cell_pairs", t)
+            self.rebuilds += 1
+        elif upd:
             self.relocate(); t = lap("relocate", t)
             self.set_halo(); t = lap("set_halo", t)
             with self.torch.cuda.stream(self.stream):

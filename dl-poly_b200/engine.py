@@ -213,6 +213,29 @@ class ShortRange:
     def dev_refresh_pull(self):
         self._ck(self.L.dlpgpu_dev_refresh_pull(self.h))
 
+    def dev_xchg_init(self, rank, nranks, cap_reloc_atoms, cap_halo_atoms):
+        """Allocates the peer-visible exchange region (gmax mailboxes + per-stage receive buffers); returns its 64-byte IPC handle."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self.L.dlpgpu_dev_xchg_init(self.h, int(rank), int(nranks), int(cap_reloc_atoms), int(cap_halo_atoms), ptr(h)))
+        return h
+
+    def dev_xchg_open(self, all_handles):
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        self._ck(self.L.dlpgpu_dev_xchg_open(self.h, ptr(a)))
+
+    def dev_xchg_rebuild(self, neigh, seq):
+        """relocate_particles + set_halo_particles + vnl_set_check as one device-side exchange; returns (natms, nlast)."""
+        nb = np.ascontiguousarray(neigh, dtype=np.int32)
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self.L.dlpgpu_dev_xchg_rebuild(self.h, ptr(nb), C.c_ulonglong(int(seq)), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def dev_xchg_gmax(self, seq):
+        """vnl_check + gmax: the largest displacement over all ranks, reduced by the GPUs through their mailboxes."""
+        tol = C.c_double(0.0)
+        self._ck(self.L.dlpgpu_dev_xchg_gmax(self.h, C.c_ulonglong(int(seq)), C.byref(tol)))
+        return tol.value
+
     def dev_halo_stage_counts(self):
         a, b = np.zeros(6, dtype=np.int32), np.zeros(6, dtype=np.int32)
         self._ck(self.L.dlpgpu_dev_halo_stage_counts(self.h, ptr(a), ptr(b)))

@@ -53,6 +53,10 @@ SIGNATURES = {
     "dlpgpu_dev_p2p_open": (ci, [vp, vp]),
     "dlpgpu_dev_publish": (ci, [vp]),
     "dlpgpu_dev_refresh_pull": (ci, [vp]),
+    "dlpgpu_dev_xchg_init": (ci, [vp, ci, ci, ci, ci, vp]),
+    "dlpgpu_dev_xchg_open": (ci, [vp, vp]),
+    "dlpgpu_dev_xchg_rebuild": (ci, [vp, vp, C.c_ulonglong, pi_, pi_]),
+    "dlpgpu_dev_xchg_gmax": (ci, [vp, C.c_ulonglong, pd_]),
     "dlpgpu_dev_halo_stage_counts": (ci, [vp, vp, vp]),
     "dlpgpu_dev_halo_serial": (ci, [vp]),
     "dlpgpu_dev_refresh_serial": (ci, [vp]),

@@ -139,6 +139,19 @@ int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atom
 int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
 int dlpgpu_dev_publish(dlpgpu_ctx* ctx);
 int dlpgpu_dev_refresh_pull(dlpgpu_ctx* ctx);
+/* relocate_particles + set_halo_particles (+ vnl_set_check) and the gmax of vnl_check as device-side exchanges over NVLink
+ * peer memory: no NCCL, no host synchronisation between the twelve dependent stages of a rebuild.  xchg_init allocates this
+ * rank's CUDA-IPC exported region (gmax mailboxes + one fixed-capacity receive buffer and {sequence, count} header per
+ * stage; capacities in atoms per stage, identical on every rank) and returns its 64-byte handle; xchg_open maps the regions
+ * of all ranks (handles gathered rank-major).  xchg_rebuild enqueues everything and synchronises ONCE at the end (natms /
+ * nlast live on the device meanwhile); neigh = map(1:6) of domains.F90:206-211 (0-based ranks; the rank itself where the
+ * decomposition has one domain in that direction).  seq must be a fresh, rank-uniform sequence number per call (ranks run
+ * in lock-step: every rank calls xchg_rebuild / xchg_gmax in the same order).  Errors: 43 / 54 (a stage exceeded its
+ * capacity), 58 (lost atoms), 9002 on a peer time-out.  With nranks == 1 no IPC is involved. */
+int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[64]);
+int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
+int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long long seq, int* natms, int* nlast);
+int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol);
 /* atoms sent / received in each of the six stages of the last halo build (order -x,+x,-y,+y,-z,+z) */
 int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]);
 /* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */
