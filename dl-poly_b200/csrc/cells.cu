@@ -574,15 +574,15 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
       const unsigned ltmask = (1u << lane) - 1u;
       const int cap = pitch - DLP_ROW_PAD;
       unsigned* const row0 = nbr + (size_t)t0 * pitch;
+      int run = 0;
       for (int c0 = 0; c0 < total; c0 += 32) {
         const int c = c0 + lane;
         int jj = -1;
         double4 pj = make_double4(1e300, 1e300, 1e300, 0);   // lanes without a candidate sit at 1e300: never within the cutoff
         int2 infj = make_int2(0, 0);
-        if (c < total) {   // largest run r with pre[r] <= c
-          int lo = 0, hi = LC_MAXRUN - 1;
-          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[wid][mid] <= c) lo = mid; else hi = mid - 1; }
-          jj = s_run0[wid][lo] + (c - s_pre[wid][lo]);
+        if (c < total) {   // run of candidate c: the lane's candidates only move forward, so its run index does too
+          while (s_pre[wid][run + 1] <= c) ++run;          // pre[LC_MAXRUN] = total > c ends the walk
+          jj = s_run0[wid][run] + (c - s_pre[wid][run]);
           pj = posq_s[jj]; infj = info_s[jj];
         }
         const bool halo_j = (infj.y >> 17) & 1;

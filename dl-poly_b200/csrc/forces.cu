@@ -563,7 +563,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
     else if (TX & 1) { a = tex_unit(tex, u); b = tex_unit(tex, u + 1); h = tex_unit(tex, P.ne + u); }
-    else { a = sG[u]; b = sG[u + 1]; h = sH[u]; }
+    else { a = sG[u]; b = sG[u + 1]; h = (TX & 4) ? tex_unit(tex, P.ne + u) : sH[u]; }
     const double prefac = qi_s * pj.w;
     const double gc = prefac * __fma_rn(pc, __fma_rn(pc, h.x, (b.x - a.x) - h.x), a.x);
     const double ec = prefac * __fma_rn(pc, __fma_rn(pc, h.y, (b.y - a.y) - h.y), a.y);     // :168-174
@@ -877,7 +877,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
         default: DLP_V2N(0);
       }
     } else if (v && e) {
-      if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
+      if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else if (tx == 6) DLP_V2(1, 1, 1, 6); else if (tx == 4) DLP_V2(1, 1, 1, 4); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
     } else if (v) {
       if (tx == 2) DLP_V2(1, 0, 1, 2); else DLP_V2(1, 0, 1, 0);
     } else {
