@@ -314,7 +314,8 @@ def run_gpu(args):
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                "traffic": traffic, "kernel": "k_pair_forces (two_body_forces pair loop)",
+                "traffic": traffic, "kernel": "k_pair_v2 (two_body_forces pair loop: vdW + real-space Ewald, half list, fp64)",
+                "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written by one launch)" if traffic else None,
                 "kernel_ms_avg": pair_ms_avg, "flop_per_atom_step": flop_as, "listed_pairs_per_atom": n_l,
                 "peak_source": "DFMA micro-benchmark run in this process (dlpgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "whole_step": {"achieved": flop_as * value / world / 1e12, "frac": flop_as * value / world / 1e12 / fp64_peak},

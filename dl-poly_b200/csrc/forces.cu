@@ -302,10 +302,13 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
 }
 
 __global__ void k_final_reduce(int nblocks, const double* __restrict__ partial, double* __restrict__ out) {
-  int k = threadIdx.x;
-  if (k >= 12) return;
+  // one warp per quantity (12 warps): lane-strided partial sums, then a shuffle tree -- a fixed order for a given grid
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double v = 0.0;
-  for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * 12 + k];
+  for (int b = lane; b < nblocks; b += 32) v += partial[(size_t)b * 12 + k];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
+  if (lane != 0) return;
   if (k < 6) out[k] = v;
   else {
     // strs1,2,3,5,6,9 -> stress(1:9) symmetric (vdw.F90:2014-2022)
@@ -907,7 +910,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   if (natms > 0 && P.half)
     LAUNCH(ctx, k_scatter_half, cdiv(natms, 256), 256, 0, natms, zero_forces, ctx->loc_slot.p, ctx->at_list.p, fpos, fneg, ctx->fx.p,
            ctx->fy.p, ctx->fz.p);
-  LAUNCH(ctx, k_final_reduce, 1, 32, 0, natms > 0 ? blocks : 0, ctx->partial.p, ctx->out_dev.p);
+  LAUNCH(ctx, k_final_reduce, 1, 12 * 32, 0, natms > 0 ? blocks : 0, ctx->partial.p, ctx->out_dev.p);
   cudaEventRecord(ctx->ev[5], s);
   if (out) {
     CK(cudaMemcpyAsync(out, ctx->out_dev.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
