@@ -114,7 +114,7 @@ def _rocksalt(ncell, a, seed, jitter):
 
 
 def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=False, force_shift=False, ewald=True,
-         jitter=0.3, temperature=1200.0, spme_precision=1.0e-6):
+         jitter=0.3, temperature=1200.0, spme_precision=1.0e-6, rvdw=None, vdw_pairs=((1, 1), (1, 2), (2, 2))):
     """C2/C4/C5-ionic: molten NaCl, 8*ncell^3 ions at the TEST01 density (V=963,882.2 A^3 for 27,000 ions).
     tabfile=True builds the three pair tables through a TABLE-format round trip (C4)."""
     nc = np.array(_n3(ncell), dtype=np.float64)
@@ -122,20 +122,25 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
     a = (963882.2 * 8.0 / 27000.0) ** (1.0 / 3.0)             # rock-salt cell edge at the TEST01 density
     L = nc * a
     xyz, species = _rocksalt(ncell, a, seed, jitter)
-    ff = tables.ForceField(2, rcut, rcut, force_shift=force_shift, direct=direct)
+    # rvdw < rcut (control.F90:1499-1543) gives the vdW and Ewald tables different grids; vdw_pairs selects which type
+    # pairs carry a vdW potential at all (the others interact through the Ewald term only)
+    ff = tables.ForceField(2, rcut if rvdw is None else rvdw, rcut, force_shift=force_shift, direct=direct)
     if tabfile:
         g = ff.mxgrid
         ngrid = g                                             # = max(1004, nint(rcut/0.01)+4): no re-gridding
         delpot = rcut / float(g - 4)
         r = np.arange(1, ngrid + 1, dtype=np.float64) * delpot
         for (ai, aj), p in _BHM.items():
+            if (ai, aj) not in vdw_pairs:
+                continue
             e, gm = tables.pot_energy(tables.VDW_BHM, p, r)
             tp = tables.regrid_table(e, delpot, rcut, g, is_force=False)
             tf = tables.regrid_table(gm, delpot, rcut, g, is_force=True)
             ff.add_table(ai, aj, tp, tf)
     else:
         for (ai, aj), p in _BHM.items():
-            ff.add(ai, aj, "bhm", p)
+            if (ai, aj) in vdw_pairs:
+                ff.add(ai, aj, "bhm", p)
     if ewald:
         ff.set_ewald(precision=spme_precision)
     ff.finalize()

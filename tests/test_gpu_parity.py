@@ -91,6 +91,18 @@ def test_nacl_table_file_force_shift():
     check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, tabfile=True, force_shift=True), 1)
 
 
+def test_nacl_vdw_cutoff_below_rcut_separate_grids():
+    """rvdw < rcut: the vdW and Ewald tables have different grid spacings (the pair kernel's separate-grid instantiation)."""
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, rvdw=6.5), 1, mode=1)
+
+
+def test_nacl_ewald_only_and_partial_vdw():
+    """No vdW potential at all (Ewald-only instantiation), and a force field where only Na-Cl carries one (entries with
+    potential index 0 next to tabulated ones)."""
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, vdw_pairs=()), 1, mode=1)
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, vdw_pairs=((1, 2),)), 1, mode=1)
+
+
 def test_nacl_bhm_direct():
     check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, direct=True), 1)
 
