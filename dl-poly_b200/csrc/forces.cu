@@ -542,11 +542,22 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
   // energy / virial / stress ownership: local partner or halo partner with idi < ltg(jatm)  (vdw.F90:1948)
   const double w = ((e & (DLP_F_HALO | DLP_F_ECNT)) != DLP_F_HALO) ? 1.0 : 0.0;
   double gamma = 0.0;
+  // TX bit 3 (needs VT, EW, one grid and rvdw == rcut): the second differences of BOTH tables come as one float4 texel
+  // {h_vdw_force, h_vdw_energy, h_ewald_force, h_ewald_energy} indexed by (potential, l): 5 instead of 6 table reads, and
+  // half the shared memory.  |h| <= ~2e-3 |g| on these grids, so the fp32 rounding of h moves a pair term by < 4e-11 relative.
+  double2 h_v4 = make_double2(0.0, 0.0), h_c4 = make_double2(0.0, 0.0);
+  if (TX & 8) {
+    const int uh = in_c ? (in_v ? kc : 0) * P.ts + l : P.zero;
+    const float4 h4 = tex1Dfetch<float4>(tex, uh);
+    h_v4 = make_double2((double)h4.x, (double)h4.y);
+    h_c4 = make_double2((double)h4.z, (double)h4.w);
+  }
   if (VT) {
     int u = in_v ? kc * P.ts + l : P.zero;
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = h_v4; }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 2) ? tex_unit(tex, P.ne + u) : sH[u]; }
     gamma = __fma_rn(ppp, __fma_rn(ppp, h.x, (b.x - a.x) - h.x), a.x) * r_rsq;             // :1914-1921
     const double ev = __fma_rn(ppp, __fma_rn(ppp, h.y, (b.y - a.y) - h.y), a.y);           // :1953-1960
@@ -565,6 +576,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = h_c4; }
     else if (TX & 1) { a = tex_unit(tex, u); b = tex_unit(tex, u + 1); h = tex_unit(tex, P.ne + u); }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 4) ? tex_unit(tex, P.ne + u) : sH[u]; }
     const double prefac = qi_s * pj.w;
@@ -592,7 +604,7 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
           const int* __restrict__ nnbr, const double2* __restrict__ tab, double* __restrict__ fpos, double* __restrict__ fneg,
           double* __restrict__ partial) {
   extern __shared__ __align__(16) double2 s_tab[];
-  for (int k = threadIdx.x; k < 2 * P.ne; k += NT) s_tab[k] = tab[k];
+  for (int k = threadIdx.x; k < ((TX & 8) ? 1 : 2) * P.ne; k += NT) s_tab[k] = tab[k];
   __syncthreads();
   const double2* sG = s_tab;
   const double2* sH = s_tab + P.ne;
@@ -794,6 +806,26 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->tab2.p, t2.data(), t2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tab2_ne = NE; ctx->tab2_ts = tsz; ctx->tab2_zero = ntab * tsz;
+    // float4 {h_vdw_force, h_vdw_energy, h_ewald_force, h_ewald_energy} per (potential k = 0..n, l); k = 0: no vdW
+    if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
+    if (vt && ne) {
+      std::vector<float> h4((size_t)NE * 4, 0.0f);
+      for (int k = 0; k < ntab; ++k)
+        for (int l = 0; l < tsz; ++l) {
+          const size_t u = (size_t)k * tsz + l;
+          if (k > 0) { h4[4 * u] = (float)t2[2 * (NE + u)]; h4[4 * u + 1] = (float)t2[2 * (NE + u) + 1]; }
+          h4[4 * u + 2] = (float)t2[2 * (NE + l)]; h4[4 * u + 3] = (float)t2[2 * (NE + l) + 1];
+        }
+      CK(ctx->tab2h.ensure(h4.size(), ctx->stream));
+      CK(cudaMemcpyAsync(ctx->tab2h.p, h4.data(), h4.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaResourceDesc rdh = {};
+      rdh.resType = cudaResourceTypeLinear; rdh.res.linear.devPtr = ctx->tab2h.p;
+      rdh.res.linear.desc = cudaCreateChannelDesc<float4>(); rdh.res.linear.sizeInBytes = (size_t)NE * 16;
+      cudaTextureDesc tdh = {};
+      tdh.readMode = cudaReadModeElementType;
+      CK(cudaCreateTextureObject(&ctx->tab2h_tex, &rdh, &tdh, nullptr));
+    }
     if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ctx->tab2.p;
@@ -870,7 +902,9 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   } while (0)
     const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0, sg = (!v || !e || P.same_grid) ? 1 : 0;
     // vdW h unit through the texture pipe: measured on B200 (1 M NaCl ions) 1.393 ms against 1.440 ms with all six reads in LDS
-    const int tx = ctx->tx_override >= 0 ? ctx->tx_override : (v ? 2 : 0);   // argon: 0.418 against 0.437 ms
+    // measured on B200, 1 M NaCl ions: all reads in LDS 1.438 ms, vdW h through the texture pipe 1.394 ms, combined fp32 h texel 1.264 ms
+    const bool can8 = v && e && sg && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul;
+    const int tx = ctx->tx_override >= 0 ? ctx->tx_override : (can8 ? 8 : (v ? 2 : 0));   // argon: 0.418 against 0.437 ms
     if (ctx->variant > 0 && ctx->variant != 100 && v && e && sg) {   // timing experiments only (DLPGPU_VARIANT): results are not meaningful
       const int xv = ctx->variant & 0xfff, ntc = ctx->variant >> 12;
 #define DLP_V2N(XV) do { if (ntc == 0) DLP_V2X(XV, 512); else if (ntc == 1) DLP_V2X(XV, 640); else DLP_V2X(XV, 768); } while (0)
@@ -880,7 +914,12 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
         default: DLP_V2N(0);
       }
     } else if (v && e) {
-      if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else if (tx == 6) DLP_V2(1, 1, 1, 6); else if (tx == 4) DLP_V2(1, 1, 1, 4); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
+      if (sg && tx == 8 && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul) {
+        const size_t smem8 = (size_t)ctx->tab2_ne * 16;
+        CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+               t2, fpos, fneg, ctx->partial.p);
+      } else if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else if (tx == 6) DLP_V2(1, 1, 1, 6); else if (tx == 4) DLP_V2(1, 1, 1, 4); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
     } else if (v) {
       if (tx == 2) DLP_V2(1, 0, 1, 2); else DLP_V2(1, 0, 1, 0);
     } else {
