@@ -321,161 +321,9 @@ __global__ void k_final_reduce(int nblocks, const double* __restrict__ partial, 
 }
 
 // ---------------------------------------------------------------- fast path
-// Tabulated vdW (VT = 1) and / or tabulated real-space Ewald (EW = 1), half list, tables in shared memory, no force
-// shift, no exclusion rows: the configurations the BASELINE sizes run.  Same arithmetic as k_pair_forces; the body is
-// straight-line (out-of-range pairs are masked, not branched around) and every lane works on two pairs at a time, so
-// the two independent dependency chains hide the fp64 / LDS / MUFU latencies at 16 warps per SM.
-struct PairOut { double gamma, ev, vv, ec, vc; };
-
-template <int VT, int EW>
-__device__ __forceinline__ PairOut pair_terms(const FParams& P, const double2* s_tab, unsigned e, bool live, double qi_s, bool coul_i,
-                                              double qj, double rsq_in) {
-  const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
-  const bool in_v = VT && live && kc != 0 && rsq_in < P.thr_vdw;                       // vdw.F90:1892
-  const bool in_c = EW && live && coul_i && fabs(qj) > ZERO_PLUS && rsq_in < P.thr_coul;   // ewald_spole.F90:133
-  const double rsq = (in_v || in_c) ? rsq_in : 1.0;                                    // masked pairs compute on a harmless value
-  const double r_rrr = rsqrt(rsq);
-  const double rrr = rsq * r_rrr;
-  const double r_rsq = r_rrr * r_rrr;
-  PairOut o;
-  o.gamma = 0.0; o.ev = 0.0; o.vv = 0.0; o.ec = 0.0; o.vc = 0.0;
-  int l = 1;
-  double ppp = 0.0;
-  if (VT) {
-    const double tt = rrr * P.vdw_rdr;                                                 // vdw.F90:1909-1910
-    l = max(__double2int_rz(tt), 1);                                                   // r < one grid step does not occur
-    ppp = tt - (double)l;
-    const int u = max(kc - 1, 0) * P.tstride + l;
-    const double2 a = s_tab[u], h = s_tab[P.tab_ne + u], b = s_tab[u + 1];
-    const double gam = (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x)) * r_rsq;        // :1914-1921
-    const double eng = a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y);                  // :1953-1960
-    o.gamma = in_v ? gam : 0.0;
-    o.ev = in_v ? eng : 0.0;
-    o.vv = o.gamma * rsq;
-  }
-  if (EW) {
-    if (!(VT && P.same_grid)) {
-      const double tt = rrr * P.ew_rdr;                                                // ewald_spole.F90:140-146
-      l = max(__double2int_rz(tt), 1);
-      ppp = tt - (double)l;
-    }
-    const int u = P.ew_off + l;
-    const double2 a = s_tab[u], h = s_tab[P.tab_ne + u], b = s_tab[u + 1];
-    const double prefac = in_c ? qi_s * qj : 0.0;
-    const double gd = prefac * (a.x + ppp * (((b.x - a.x) - h.x) + ppp * h.x));
-    o.ec = prefac * (a.y + ppp * (((b.y - a.y) - h.y) + ppp * h.y));                   // :168-174
-    o.vc = gd * rsq;                                                                   // :189
-    o.gamma += gd;
-  }
-  return o;
-}
-
-template <int TPR, int VT, int EW>
-__global__ void __launch_bounds__(512, 1)
-k_pair_fast(FParams P, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
-            const int* __restrict__ nnbr, const Tab4* __restrict__ tab4_g, double* __restrict__ fpos, double* __restrict__ fneg,
-            double* __restrict__ partial) {
-  extern __shared__ __align__(16) double2 s_tab[];
-  {   // Tab4 entries are split into a g-array and an h-array of 16-byte units, so that consecutive l fall into consecutive
-      // bank groups (an interleaved layout would put every g-unit on an even group and double the conflicts)
-    const double2* gv = reinterpret_cast<const double2*>(tab4_g);
-    for (int k = threadIdx.x; k < P.tab_ne; k += 512) { s_tab[k] = gv[2 * k]; s_tab[P.tab_ne + k] = gv[2 * k + 1]; }
-    __syncthreads();
-  }
-  constexpr int RPB = 512 / TPR;
-  const int lg = threadIdx.x % TPR;
-  const int grp = threadIdx.x / TPR;
-  double acc[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-
-  for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
-    const int t = base + grp;
-    const bool rowlive = t < P.natms;
-    int n = 0;
-    double4 pi = make_double4(0, 0, 0, 0);
-    if (rowlive) { pi = posq_s[loc_slot[t]]; n = nnbr[t]; }
-    const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
-    const bool coul_i = EW && !(fabs(qi_s) < ZERO_PLUS);                      // :117
-    double fix = 0.0, fiy = 0.0, fiz = 0.0;
-    const unsigned* row = nbr + (size_t)t * P.pitch;
-    int k = lg;
-    unsigned ea = (k < n) ? row[k] : 0u, eb = (k + TPR < n) ? row[k + TPR] : 0u;
-    unsigned ea_nx = (k + 2 * TPR < n) ? row[k + 2 * TPR] : 0u, eb_nx = (k + 3 * TPR < n) ? row[k + 3 * TPR] : 0u;
-    double4 pa = pi, pb = pi;
-    if (k < n) pa = ld_posq(posq_s + (ea & DLP_J_MASK));
-    if (k + TPR < n) pb = ld_posq(posq_s + (eb & DLP_J_MASK));
-    for (; k < n; k += 2 * TPR) {
-      const unsigned e0 = ea, e1 = eb;
-      const double4 p0 = pa, p1 = pb;
-      const bool live0 = true, live1 = (k + TPR) < n;
-      // prefetch: entries two passes ahead, coordinates one pass ahead
-      const unsigned ea_n2 = (k + 4 * TPR < n) ? row[k + 4 * TPR] : 0u, eb_n2 = (k + 5 * TPR < n) ? row[k + 5 * TPR] : 0u;
-      if (k + 2 * TPR < n) pa = ld_posq(posq_s + (ea_nx & DLP_J_MASK));
-      if (k + 3 * TPR < n) pb = ld_posq(posq_s + (eb_nx & DLP_J_MASK));
-      ea = ea_nx; eb = eb_nx; ea_nx = ea_n2; eb_nx = eb_n2;
-
-      const double x0 = pi.x - p0.x, y0 = pi.y - p0.y, z0 = pi.z - p0.z;      // two_body.F90:348-350
-      const double x1 = pi.x - p1.x, y1 = pi.y - p1.y, z1 = pi.z - p1.z;
-      const double rsq0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(y0, y0)), __dmul_rn(z0, z0));
-      const double rsq1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, x1), __dmul_rn(y1, y1)), __dmul_rn(z1, z1));
-      const PairOut o0 = pair_terms<VT, EW>(P, s_tab, e0, live0, qi_s, coul_i, p0.w, rsq0);
-      const PairOut o1 = pair_terms<VT, EW>(P, s_tab, e1, live1, qi_s, coul_i, p1.w, rsq1);
-      const bool h0 = (e0 & DLP_F_HALO) != 0, h1 = (e1 & DLP_F_HALO) != 0;
-      const double w0 = h0 ? ((e0 & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0;
-      const double w1 = h1 ? ((e1 & DLP_F_ECNT) ? 1.0 : 0.0) : 1.0;
-      const double f0x = o0.gamma * x0, f0y = o0.gamma * y0, f0z = o0.gamma * z0;
-      const double f1x = o1.gamma * x1, f1y = o1.gamma * y1, f1z = o1.gamma * z1;
-      fix += f0x; fiy += f0y; fiz += f0z;
-      fix += f1x; fiy += f1y; fiz += f1z;
-      if (VT) { acc[0] += w0 * o0.ev; acc[1] -= w0 * o0.vv; acc[0] += w1 * o1.ev; acc[1] -= w1 * o1.vv; }
-      if (EW) { acc[2] += w0 * o0.ec; acc[3] -= w0 * o0.vc; acc[2] += w1 * o1.ec; acc[3] -= w1 * o1.vc; }
-      {
-        const double wx = w0 * x0, wy = w0 * y0, wz = w0 * z0;
-        acc[4] += wx * f0x; acc[5] += wx * f0y; acc[6] += wx * f0z; acc[7] += wy * f0y; acc[8] += wy * f0z; acc[9] += wz * f0z;
-      }
-      {
-        const double wx = w1 * x1, wy = w1 * y1, wz = w1 * z1;
-        acc[4] += wx * f1x; acc[5] += wx * f1y; acc[6] += wx * f1z; acc[7] += wy * f1y; acc[8] += wy * f1z; acc[9] += wz * f1z;
-      }
-      if (!h0 && o0.gamma != 0.0) {   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161)
-        double* q = fneg_ptr(fneg, (int)(e0 & DLP_J_MASK));
-        atomicAdd(q, f0x); atomicAdd(q + 4, f0y); atomicAdd(q + 8, f0z);
-      }
-      if (live1 && !h1 && o1.gamma != 0.0) {
-        double* q = fneg_ptr(fneg, (int)(e1 & DLP_J_MASK));
-        atomicAdd(q, f1x); atomicAdd(q + 4, f1y); atomicAdd(q + 8, f1z);
-      }
-    }
-#pragma unroll
-    for (int d = TPR / 2; d > 0; d >>= 1) {
-      fix += __shfl_xor_sync(DLP_FULL, fix, d);
-      fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
-      fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
-    }
-    if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
-  }
-  __shared__ double red[16][10];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
-    if (lane == 0) red[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 12) {
-    // partial[] keeps the 12-slot layout of k_pair_forces: 0..3 vdw/coul energy+virial, 4..5 exclusion terms (none here), 6..11 stress
-    const int src = threadIdx.x < 4 ? threadIdx.x : (threadIdx.x < 6 ? -1 : threadIdx.x - 2);
-    double v = 0.0;
-    if (src >= 0) for (int w = 0; w < 16; ++w) v += red[w][src];
-    partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
-  }
-}
-
-// ---------------------------------------------------------------- fast path, second generation
-// Same pair arithmetic as k_pair_fast, re-organised around what ncu showed on B200 (profiles/r1_s3_pair_fast_ionic1m.txt:
+// Tabulated vdW (VT) and / or tabulated real-space Ewald (EW), half list, no force shift, no exclusion rows: the configurations
+// the BASELINE sizes run.  Same pair terms as k_pair_forces, organised around what ncu showed for its predecessor on B200
+// (profiles/r1_s3_pair_fast_ionic1m.txt:
 // issue slots 54 % busy, 178 instructions per pair of which 66 fp64; stalls on branch resolution, the XU pipe (F2I / I2F)
 // and fixed-latency waits at 4 warps per scheduler):
 //  * rows are padded by the list build to a multiple of 16 entries (+16) with a sentinel partner that sits 1e15 A away, so
@@ -879,7 +727,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   const bool fast = P.half && use_smem && !ctx->no_fast && !(P.lbook && P.ew_on) && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) &&
                     (P.vdw_on || P.ew_on) && tpr == 8;
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
-  const bool fast2 = fast && ctx->variant != 100 && smem2 + 2048 <= 227 * 1024;
+  const bool fast2 = fast && smem2 + 2048 <= 227 * 1024;
   if (natms > 0 && fast2) {
     P2 Q{};
     Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;
@@ -928,18 +776,6 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
 #undef DLP_V2X
 #undef DLP_V2N
 #undef DLP_V2
-  } else if (natms > 0 && fast) {
-    const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
-#define DLP_FAST(T, V, E)                                                                                                      \
-  do {                                                                                                                         \
-    CK(cudaFuncSetAttribute(k_pair_fast<T, V, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
-    LAUNCH(ctx, (k_pair_fast<T, V, E>), blocks, 512, smem, P, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, t4, fpos, fneg, \
-           ctx->partial.p);                                                                                                    \
-  } while (0)
-    const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0;
-    if (tpr == 8) { if (v && e) DLP_FAST(8, 1, 1); else if (v) DLP_FAST(8, 1, 0); else DLP_FAST(8, 0, 1); }
-    else { if (v && e) DLP_FAST(16, 1, 1); else if (v) DLP_FAST(16, 1, 0); else DLP_FAST(16, 0, 1); }
-#undef DLP_FAST
   } else if (natms > 0) {
     if (tpr == 32) CKRC((launch_pair<32, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
     else if (tpr == 16) CKRC((launch_pair<16, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));

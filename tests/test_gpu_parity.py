@@ -327,3 +327,53 @@ def test_one_kernel_refresh_equals_staged_refresh(name):
         w.two_body(); sr.dev_two_body_forces()
         w.vv(2, 0.002, s.weight_by_type); sr.dev_vv(2, 0.002)
     sr.close()
+
+
+@pytest.mark.parametrize("name", ["argon", "nacl_ortho"])
+def test_fused_device_exchange_equals_staged_serial(name):
+    """dlpgpu_dev_xchg_rebuild (migration + halo build with device-resident counts, one host sync) leaves exactly the atoms,
+    order, tags and checkpoint the staged single-domain routines leave, over a trajectory with atoms crossing the periodic
+    boundary; dlpgpu_dev_xchg_gmax returns vnl_check's tolerance."""
+    s = systems.argon(6, temperature=300.0) if name == "argon" else systems.nacl((4, 3, 3), rcut=6.0, padding=0.2, temperature=1200.0)
+    a, b = native_serial(s), native_serial(s)
+    for sr in (a, b):
+        sr.set_force_mode(0)      # full list, no atomics: forces are bitwise reproducible, so both trajectories stay identical
+    b.dev_p2p_init(0, 1, s.megatm + 64)
+    cap_r, cap_h = dd.exchange_capacities(s, (1, 1, 1))
+    b.dev_xchg_init(0, 1, cap_r, cap_h)
+    neigh = [0] * 6
+    a.dev_relocate_serial(); a.dev_halo_serial()
+    assert b.dev_xchg_rebuild(neigh, 1) == a.dev_counts()
+    seq = 1
+    for step in range(6):
+        for sr in (a, b):
+            sr.dev_link_cell_pairs(); sr.dev_two_body_forces()
+        pa, pb = a.dev_get_parts(), b.dev_get_parts()
+        ia, ib = a.dev_get_ints(), b.dev_get_ints()
+        for k in ("xxx", "yyy", "zzz", "chge", "fxx", "fyy", "fzz"):
+            assert np.array_equal(pa[k], pb[k]), (step, k)
+        for k in ("ltg", "lsite", "ltype", "lfrzn", "ixyz"):
+            assert np.array_equal(ia[k], ib[k]), (step, k)
+        assert a.dev_halo_stage_counts() == b.dev_halo_stage_counts()
+        for sr in (a, b):
+            sr.dev_vv(1, 0.004)
+        seq += 1
+        assert b.dev_xchg_gmax(seq) == a.dev_vnl_check()
+        a.dev_relocate_serial(); a.dev_halo_serial()
+        assert b.dev_xchg_rebuild(neigh, seq) == a.dev_counts()
+        for sr in (a, b):
+            sr.dev_vv(2, 0.004)
+    a.close(); b.close()
+
+
+def test_fused_exchange_reports_a_too_small_stage_buffer():
+    """A halo stage that does not fit its receive buffer is error 54, as in export_atomic_data (deport_data.F90:1869-1877)."""
+    from dl_poly_b200.lib import DlpError
+    s = systems.argon(6, temperature=100.0)
+    sr = native_serial(s)
+    sr.dev_p2p_init(0, 1, s.megatm + 64)
+    sr.dev_xchg_init(0, 1, 64, 16)
+    with pytest.raises(DlpError) as e:
+        sr.dev_xchg_rebuild([0] * 6, 1)
+    assert e.value.code == 54
+    sr.close()
