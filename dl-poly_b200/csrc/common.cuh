@@ -112,6 +112,7 @@ struct dlpgpu_ctx {
   // k_pair_v2 layout: [g units: table 0 = Ewald (or zeros), table k = vdW potential k, then 2 zero entries][h units likewise]
   DBuf<double> tab2;
   int tab2_ne = 0, tab2_ts = 0, tab2_zero = 0;
+  DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
   cudaTextureObject_t tab2_tex = 0;   // the same buffer as 16-byte texels: table reads through the texture pipe (see pair2)

@@ -336,8 +336,8 @@ __global__ void k_final_reduce(int nblocks, const double* __restrict__ partial, 
 //    F2I + I2F on the quarter-rate XU pipe; rsqrt is MUFU.RSQ64H + one cubic correction without the library's range branch;
 //  * the vdW virial is not accumulated: vir_vdw + vir_coul = -trace(stress) term by term.
 struct P2 {
-  int natms, pitch, ne, ts, zero;
-  double rdr_v, rdr_e, thr_vdw, thr_coul, scaling;
+  int natms, pitch, ne, ts, zero, xpitch;
+  double rdr_v, rdr_e, thr_vdw, thr_coul, scaling, alpha, rcut;
 };
 
 __device__ __forceinline__ double rsqrt_fast(double x) {   // x normal, positive; ~1 ulp
@@ -370,6 +370,16 @@ __device__ __forceinline__ double2 tex_unit(cudaTextureObject_t tex, int u) {
 // TX bit 0: the three Ewald-table reads go through the texture pipe, bit 1: the h unit of the vdW table does.  On B200 a
 // random 16-byte texture fetch costs ~20 clk per warp on the TEX data pipe and overlaps completely with LDS.128 traffic
 // (~10 clk per warp on the LSU data pipe, which the coordinate gathers and the REDs also load): scripts/ubench2.cu.
+// TX bit 3: each fp32 second difference is completed to ~33 significant bits by a signed 8-bit correction (in units of
+// 2^-8 ulp of the fp32 value) that the table build parks in the 8 lowest mantissa bits of the unit's g value -- a 2^-44
+// relative perturbation of g itself.  Energies and virials are summed over ~1e8 pairs and a fp32 rounding error of h is the
+// same for every pair that falls into the same grid interval (perfect lattices!), so plain fp32 costs up to ~1e-10 of a total.
+__device__ __forceinline__ double h_exact(float h32, double g_unit) {
+  const int q = (int)(signed char)(__double2loint(g_unit) & 0xff);
+  const float p2 = __int_as_float(__float_as_int(h32) & 0x7f800000);          // 2^exponent(h32)
+  return __fma_rn((double)((float)q * p2), 4.656612873077392578125e-10, (double)h32);   // + q 2^(e-31)
+}
+
 template <int VT, int EW, int SG, int X = 0, int TX = 0>
 __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, const double2* __restrict__ sG, const double2* __restrict__ sH, const double4& pi,
                                       double qi_s, unsigned e, const double4& pj, double& fix, double& fiy, double& fiz, double* acc,
@@ -393,19 +403,17 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
   // TX bit 3 (needs VT, EW, one grid and rvdw == rcut): the second differences of BOTH tables come as one float4 texel
   // {h_vdw_force, h_vdw_energy, h_ewald_force, h_ewald_energy} indexed by (potential, l): 5 instead of 6 table reads, and
   // half the shared memory.  |h| <= ~2e-3 |g| on these grids, so the fp32 rounding of h moves a pair term by < 4e-11 relative.
-  double2 h_v4 = make_double2(0.0, 0.0), h_c4 = make_double2(0.0, 0.0);
+  float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (TX & 8) {
     const int uh = in_c ? (in_v ? kc : 0) * P.ts + l : P.zero;
-    const float4 h4 = tex1Dfetch<float4>(tex, uh);
-    h_v4 = make_double2((double)h4.x, (double)h4.y);
-    h_c4 = make_double2((double)h4.z, (double)h4.w);
+    h4 = tex1Dfetch<float4>(tex, uh);
   }
   if (VT) {
     int u = in_v ? kc * P.ts + l : P.zero;
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
-    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = h_v4; }
+    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = make_double2(h_exact(h4.x, a.x), h_exact(h4.y, a.y)); }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 2) ? tex_unit(tex, P.ne + u) : sH[u]; }
     gamma = __fma_rn(ppp, __fma_rn(ppp, h.x, (b.x - a.x) - h.x), a.x) * r_rsq;             // :1914-1921
     const double ev = __fma_rn(ppp, __fma_rn(ppp, h.y, (b.y - a.y) - h.y), a.y);           // :1953-1960
@@ -424,7 +432,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
-    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = h_c4; }
+    else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = make_double2(h_exact(h4.z, a.x), h_exact(h4.w, a.y)); }
     else if (TX & 1) { a = tex_unit(tex, u); b = tex_unit(tex, u + 1); h = tex_unit(tex, P.ne + u); }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 4) ? tex_unit(tex, P.ne + u) : sH[u]; }
     const double prefac = qi_s * pj.w;
@@ -446,11 +454,48 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
   }
 }
 
-template <int TPR, int VT, int EW, int SG, int X = 0, int TX = 0, int NT = 512>
+// one excluded pair of two_body.F90:555-606 -> ewald_excl_forces (ewald_spole.F90:479-679), the reference's statements as
+// in k_pair_forces; returns the force components, adds the weighted energy / virial / stress terms
+__device__ __forceinline__ bool excl_pair(double alpha, double rcut, double chgea, const double4& pi, const double4& pj, double w,
+                                          double& f1, double& f2, double& f3, double& eng, double& vir, double* st) {
+  const double xxt = pi.x - pj.x, yyt = pi.y - pj.y, zzt = pi.z - pj.z;
+  const double rsq0 = __dadd_rn(__dadd_rn(__dmul_rn(xxt, xxt), __dmul_rn(yyt, yyt)), __dmul_rn(zzt, zzt));
+  const double rrr = sqrt(rsq0);                                              // two_body.F90:576
+  double chgprd = pj.w;
+  if (!(fabs(chgprd) > ZERO_PLUS && rrr < rcut)) return false;                // ewald_spole.F90:570
+  const double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429,
+               pp = 0.3275911, r10 = 0.1, r216 = 1.0 / 216.0, r42 = 1.0 / 42.0, rr3 = 1.0 / 3.0;
+  const double sqrpi = 1.7724538509055159;                                    // Sqrt(pi), constants.F90:56
+  chgprd = chgprd * chgea;
+  const double rsq = __dmul_rn(rrr, rrr);
+  const double alpr = __dmul_rn(rrr, alpha);
+  const double alpr2 = __dmul_rn(alpr, alpr);
+  double erfr, egamma;
+  if (alpr < 1.0e-2) {                                                        // :587-595
+    erfr = 2.0 * chgprd * (alpha / sqrpi) * (1.0 + alpr2 * (-rr3 + alpr2 * (r10 + alpr2 * (-r42 + alpr2 * r216))));
+    egamma = -4.0 * chgprd * ((alpha * (alpha * alpha)) / sqrpi) * (rr3 + alpr2 * (-2.0 * r10 + alpr2 * (3.0 * r42 - 4.0 * alpr2 * r216)));
+  } else {                                                                    // :601-607
+    const double ar = alpha * rrr;
+    const double exp1 = exp(-(ar * ar));
+    const double tt = 1.0 / (1.0 + pp * alpha * rrr);
+    erfr = chgprd * (1.0 - tt * (a1 + tt * (a2 + tt * (a3 + tt * (a4 + tt * a5)))) * exp1) / rrr;
+    egamma = -(erfr - 2.0 * chgprd * (alpha / sqrpi) * exp1) / rsq;
+  }
+  f1 = egamma * xxt; f2 = egamma * yyt; f3 = egamma * zzt;
+  eng -= w * erfr;
+  vir += w * (egamma * rsq);
+  const double wx = w * xxt, wy = w * yyt, wz = w * zzt;
+  st[0] += wx * f1; st[1] += wx * f2; st[2] += wx * f3; st[3] += wy * f2; st[4] += wy * f3; st[5] += wz * f3;
+  return true;
+}
+
+// XC: rows also carry excluded partners (bonded systems with Ewald): their correction terms are evaluated after the row's
+// main loop, a few pairs per row
+template <int TPR, int VT, int EW, int SG, int X = 0, int TX = 0, int NT = 512, int XC = 0>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
           const int* __restrict__ nnbr, const double2* __restrict__ tab, double* __restrict__ fpos, double* __restrict__ fneg,
-          double* __restrict__ partial) {
+          double* __restrict__ partial, const unsigned* __restrict__ xnbr = nullptr, const int* __restrict__ nxnbr = nullptr) {
   extern __shared__ __align__(16) double2 s_tab[];
   for (int k = threadIdx.x; k < ((TX & 8) ? 1 : 2) * P.ne; k += NT) s_tab[k] = tab[k];
   __syncthreads();
@@ -465,6 +510,7 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   double acc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  double xeng = 0.0, xvir = 0.0;   // exclusion terms: engcpe_ex, sum of w egamma rsq
 
   for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
     const int t = min(base + grp, P.natms - 1);             // surplus groups of the last pass redo the last row and drop it
@@ -505,6 +551,23 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
 #undef ld_posq
 #undef LE
 #undef GA
+    if (XC && rowlive) {
+      const int nx = nxnbr[t];
+      if (nx > 0 && fabs(pi.w) > ZERO_PLUS) {                                 // ewald_spole.F90:541
+        const unsigned* xrow = xnbr + (size_t)t * P.xpitch;
+        for (int kx = lg; kx < nx; kx += TPR) {
+          const unsigned e = xrow[kx];
+          const int j = (int)(e & DLP_J_MASK);
+          const bool halo = (e & DLP_F_HALO) != 0;
+          const double w = (halo && !(e & DLP_F_ECNT)) ? 0.0 : 1.0;
+          double f1, f2, f3;
+          if (excl_pair(P.alpha, P.rcut, qi_s, pi, posq_s[j], w, f1, f2, f3, xeng, xvir, acc + 3)) {
+            fix += f1; fiy += f2; fiz += f3;
+            if (!halo) { double* q = fneg_ptr(fneg, j); atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3); }
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int d = TPR / 2; d > 0; d >>= 1) {
       fix += __shfl_xor_sync(DLP_FULL, fix, d);
@@ -513,17 +576,17 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
     }
     if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
   }
-  __shared__ double red[NT / 32][9];
+  __shared__ double red[NT / 32][11];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    double v = acc[k];
+  for (int k = 0; k < 11; ++k) {
+    double v = k < 9 ? acc[k] : (k == 9 ? xeng : xvir);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
     if (lane == 0) red[warp][k] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 9) {
+  if (threadIdx.x < 11) {
     double v = 0.0;
     for (int w = 0; w < NT / 32; ++w) v += red[w][threadIdx.x];
     red[0][threadIdx.x] = v;
@@ -532,7 +595,7 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   if (threadIdx.x < 12) {
     // partial[] keeps the 12-slot layout of k_pair_forces: 0 engvdw, 1 virvdw, 2 engcpe_rl, 3 vircpe_rl, 4..5 exclusion terms
     // (none here), 6..11 stress.  sum over pairs of w gamma rsq = trace(stress): vdW virial = -(trace - coulomb part).
-    const double trace = red[0][3] + red[0][6] + red[0][8];
+    const double trace = red[0][3] + red[0][6] + red[0][8] - (XC ? red[0][10] : 0.0);   // without the excluded pairs' part
     const double vc = (VT && EW) ? red[0][2] : (EW ? trace : 0.0);
     double v = 0.0;
     switch (threadIdx.x) {
@@ -540,7 +603,8 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
       case 1: v = VT ? -(trace - vc) : 0.0; break;
       case 2: v = red[0][1]; break;
       case 3: v = -vc; break;
-      case 4: case 5: v = 0.0; break;
+      case 4: v = XC ? red[0][9] : 0.0; break;       // engcpe_ex
+      case 5: v = XC ? -red[0][10] : 0.0; break;     // vircpe_ex
       default: v = red[0][threadIdx.x - 3];
     }
     partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
@@ -664,6 +728,26 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
           if (k > 0) { h4[4 * u] = (float)t2[2 * (NE + u)]; h4[4 * u + 1] = (float)t2[2 * (NE + u) + 1]; }
           h4[4 * u + 2] = (float)t2[2 * (NE + l)]; h4[4 * u + 3] = (float)t2[2 * (NE + l) + 1];
         }
+      // g units with the 8-bit completion of the fp32 energy second difference in the low mantissa bits of g_energy
+      std::vector<double> gs(t2.begin(), t2.begin() + (size_t)NE * 2);
+      for (int k = 0; k < ntab; ++k)
+        for (int l = 0; l < tsz; ++l) {
+          const size_t u = (size_t)k * tsz + l;
+          for (int c = 0; c < 2; ++c) {   // force, energy
+            const double hd = (k > 0) ? t2[2 * (NE + u) + c] : t2[2 * (NE + l) + c];
+            const float hf = (k > 0) ? h4[4 * u + c] : h4[4 * u + 2 + c];
+            unsigned fb; std::memcpy(&fb, &hf, 4);
+            const int eb = (int)((fb >> 23) & 0xff);
+            long q = 0;
+            if (eb >= 40 && eb < 255) q = std::lrint((hd - (double)hf) / std::ldexp(1.0, eb - 127 - 31));
+            q = std::max(-128L, std::min(127L, q));
+            unsigned long long gb; std::memcpy(&gb, &gs[2 * u + c], 8);
+            gb = (gb & ~0xffULL) | (unsigned long long)(q & 0xff);
+            std::memcpy(&gs[2 * u + c], &gb, 8);
+          }
+        }
+      CK(ctx->tab2s.ensure(gs.size(), ctx->stream));
+      CK(cudaMemcpyAsync(ctx->tab2s.p, gs.data(), gs.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       CK(ctx->tab2h.ensure(h4.size(), ctx->stream));
       CK(cudaMemcpyAsync(ctx->tab2h.p, h4.data(), h4.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
@@ -724,16 +808,18 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
     fpos = ctx->fsx.p; fneg = ctx->fsy.p;
   }
   cudaEventRecord(ctx->ev[6], s);
-  const bool fast = P.half && use_smem && !ctx->no_fast && !(P.lbook && P.ew_on) && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) &&
-                    (P.vdw_on || P.ew_on) && tpr == 8;
+  const bool xc = P.lbook && P.ew_on;   // rows carry excluded partners: the fast kernel has them for the vdW + Ewald, one-grid case
+  const bool fast = P.half && use_smem && !ctx->no_fast && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
+                    tpr == 8 && (!xc || (P.vdw_on && P.ew_on && P.same_grid));
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
   const bool fast2 = fast && smem2 + 2048 <= 227 * 1024;
   if (natms > 0 && fast2) {
     P2 Q{};
     Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;
     Q.rdr_v = P.vdw_on ? ctx->vdw_rdr : ctx->ew_rdr; Q.rdr_e = ctx->ew_rdr; Q.thr_vdw = ctx->thr_vdw; Q.thr_coul = ctx->thr_coul;
-    Q.scaling = ctx->scaling;
+    Q.scaling = ctx->scaling; Q.alpha = ctx->alpha; Q.rcut = ctx->rcut; Q.xpitch = P.xpitch;
     const double2* t2 = reinterpret_cast<const double2*>(ctx->tab2.p);
+    const double2* t2s = reinterpret_cast<const double2*>(ctx->tab2s.p);   // g units carrying the fp32-h completion bits (TX 8)
 #define DLP_V2(V, E, S, TXV)                                                                                                   \
   do {                                                                                                                         \
     CK(cudaFuncSetAttribute(k_pair_v2<8, V, E, S, 0, TXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));           \
@@ -762,11 +848,22 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
         default: DLP_V2N(0);
       }
     } else if (v && e) {
-      if (sg && tx == 8 && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul) {
+      if (xc) {   // sg is guaranteed by `fast`
+        if (can8 && tx == 8) {
+          const size_t smem8 = (size_t)ctx->tab2_ne * 16;
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 8, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 8, 512, 1>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p,
+                 ctx->nnbr.p, t2s, fpos, fneg, ctx->partial.p, ctx->xnbr.p, ctx->nxnbr.p);
+        } else {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 2, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 2, 512, 1>), blocks, 512, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p,
+                 ctx->nnbr.p, t2, fpos, fneg, ctx->partial.p, ctx->xnbr.p, ctx->nxnbr.p);
+        }
+      } else if (sg && tx == 8 && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul) {
         const size_t smem8 = (size_t)ctx->tab2_ne * 16;
         CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
         LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
-               t2, fpos, fneg, ctx->partial.p);
+               t2s, fpos, fneg, ctx->partial.p);
       } else if (sg) { if (tx == 2) DLP_V2(1, 1, 1, 2); else if (tx == 6) DLP_V2(1, 1, 1, 6); else if (tx == 4) DLP_V2(1, 1, 1, 4); else DLP_V2(1, 1, 1, 0); } else { if (tx == 2) DLP_V2(1, 1, 0, 2); else DLP_V2(1, 1, 0, 0); }
     } else if (v) {
       if (tx == 2) DLP_V2(1, 0, 1, 2); else DLP_V2(1, 0, 1, 0);
