@@ -208,6 +208,9 @@ struct dlpgpu_ctx {
   bool pinned_ours = false;
   // timings
   cudaEvent_t ev[8] = {nullptr};
+  cudaEvent_t ev_res = nullptr;     // behind the asynchronous result copy of dlpgpu_dev_two_body_forces(out = NULL)
+  double* out_pinned = nullptr;
+  bool res_pending = false;
   double t_list = 0, t_force = 0, t_pair = 0, t_full = 0;
 };
 

@@ -144,6 +144,7 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  cudaEventCreate(&ctx->ev_res);
   if (const char* e = getenv("DLPGPU_TPR")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) ctx->tpr_override = v; }   // tuning knob
   if (const char* e = getenv("DLPGPU_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("DLPGPU_TX")) ctx->tx_override = atoi(e);
@@ -187,6 +188,8 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->peer_xr_dev.release(); ctx->dcnt.release(); ctx->gmax_out.release();
   if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
+  if (ctx->out_pinned) cudaFreeHost(ctx->out_pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;

@@ -890,6 +890,12 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->t_force = ms;
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->t_pair = ms;
+    ctx->res_pending = false;
+  } else {   // asynchronous call: the sums travel to a pinned buffer behind the kernels; dlpgpu_dev_fetch_results collects them
+    if (!ctx->out_pinned) CK(cudaMallocHost((void**)&ctx->out_pinned, 16 * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->out_pinned, ctx->out_dev.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev_res, s));
+    ctx->res_pending = true;
   }
   CK(cudaGetLastError());
   return 0;
@@ -901,6 +907,19 @@ int dlpgpu_dev_two_body_forces(dlpgpu_ctx* ctx, int zero_forces, double out[16])
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   return dlp_two_body(ctx, zero_forces, out);
+}
+
+int dlpgpu_dev_fetch_results(dlpgpu_ctx* ctx, double out[16]) {
+  if (!ctx || !out) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->res_pending) return dlp_fail(ctx, DLPGPU_ERR_STATE, "fetch_results: no asynchronous two_body_forces call is pending");
+  CK(cudaEventSynchronize(ctx->ev_res));
+  std::memcpy(out, ctx->out_pinned, 16 * sizeof(double));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->t_force = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->t_pair = ms;
+  ctx->res_pending = false;
+  return 0;
 }
 
 int dlpgpu_dev_vv(dlpgpu_ctx* ctx, int stage, double dt) {

@@ -306,6 +306,9 @@ class Domain:
         self._refresh_bufs = None
         self.rebuilds = 0
         self.steps = 0
+        self._pending = False
+        self.last_out = None
+        self.acc = {"pair_ms": 0.0, "force_ms": 0.0, "force_calls": 0, "list_ms": 0.0, "list_builds": 0}
         import os
         # peer-memory refresh: publish buffers sized for the local atoms with head-room for migration
         self.p2p = os.environ.get("DLP_DD_STAGED_REFRESH") is None
@@ -392,12 +395,14 @@ class Domain:
                 self._refresh_bufs = None
                 self.sr.dev_link_cell_pairs()
             self.rebuilds += 1
+            self.acc["list_ms"] += self.sr.last_timings()["list_ms"]; self.acc["list_builds"] += 1
             return
         self.relocate()
         self.set_halo()
         with self.torch.cuda.stream(self.stream):
             self.sr.dev_link_cell_pairs()
         self.rebuilds += 1
+        self.acc["list_ms"] += self.sr.last_timings()["list_ms"]; self.acc["list_builds"] += 1
 
     def publish(self):
         if self.p2p:
@@ -417,21 +422,49 @@ class Domain:
 
     def forces(self):
         with self.torch.cuda.stream(self.stream):
-            return self.sr.dev_two_body_forces(zero_forces=True)
+            out = self.sr.dev_two_body_forces(zero_forces=True)
+        self._account()
+        return out
 
-    def step(self, dt):
-        """One velocity-Verlet step with the short-range path as the only force provider."""
+    def _account(self):
+        t = self.sr.last_timings()
+        self.acc["pair_ms"] += t["pair_kernel_ms"]; self.acc["force_ms"] += t["force_ms"]; self.acc["force_calls"] += 1
+
+    def collect(self):
+        """Energies / virial / stress of the last lazily issued force call (see step(lazy=True)); None if none is pending."""
+        if not self._pending:
+            return self.last_out
+        with self.torch.cuda.stream(self.stream):
+            self.last_out = self.sr.dev_fetch_results()
+        self._pending = False
+        self._account()
+        return self.last_out
+
+    def step(self, dt, lazy=False):
+        """One velocity-Verlet step with the short-range path as the only force provider.  lazy=True does not wait for the
+        step's energies: they are collected behind the NEXT host synchronisation (the gmax of the following step, or
+        collect()), so a step costs one host round trip instead of two; the return value is then the previous step's sums."""
         sr = self.sr
         if self.profile is not None:
             return self._step_profiled(dt)
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(1, dt)
         self.publish()                       # before the gmax: the collective orders every rank's publish before any pull
-        if self.vnl_update():
+        upd = self.vnl_update()              # host synchronisation: everything enqueued before it has completed
+        prev = self.collect() if self._pending else self.last_out
+        if upd:
             self.rebuild()
         else:
             self.refresh_halo()
+        if lazy:
+            with self.torch.cuda.stream(self.stream):
+                sr.dev_two_body_forces_async(zero_forces=True)
+                sr.dev_vv(2, dt)
+            self._pending = True
+            self.steps += 1
+            return prev
         out = self.forces()
+        self.last_out = out
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(2, dt)
         self.steps += 1

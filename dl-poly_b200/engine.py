@@ -278,6 +278,15 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_two_body_forces(self.h, int(bool(zero_forces)), ptr(out)))
         return out
 
+    def dev_two_body_forces_async(self, zero_forces=True):
+        """Enqueues two_body_forces without waiting for the sums; collect them with dev_fetch_results()."""
+        self._ck(self.L.dlpgpu_dev_two_body_forces(self.h, int(bool(zero_forces)), None))
+
+    def dev_fetch_results(self):
+        out = np.zeros(16)
+        self._ck(self.L.dlpgpu_dev_fetch_results(self.h, ptr(out)))
+        return out
+
     def dev_list_pairs(self):
         n = C.c_longlong(0)
         self._ck(self.L.dlpgpu_dev_list_pairs(self.h, C.byref(n)))

@@ -67,6 +67,7 @@ SIGNATURES = {
     "dlpgpu_dev_relocate_end": (ci, [vp, pi_]),
     "dlpgpu_dev_link_cell_pairs": (ci, [vp, ci, pi_]),
     "dlpgpu_dev_two_body_forces": (ci, [vp, ci, vp]),
+    "dlpgpu_dev_fetch_results": (ci, [vp, vp]),
     "dlpgpu_dev_list_pairs": (ci, [vp, C.POINTER(C.c_longlong)]),
     "dlpgpu_dev_get_parts": (ci, [vp, vp, ci]),
     "dlpgpu_dev_get_ints": (ci, [vp, ci, vp, vp, vp, vp, vp]),

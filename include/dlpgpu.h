@@ -168,6 +168,9 @@ int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now);
  * reference-format half list on the device (for dlpgpu_dev_get_list). */
 int dlpgpu_dev_link_cell_pairs(dlpgpu_ctx* ctx, int want_ref_list, int* ibig);
 int dlpgpu_dev_two_body_forces(dlpgpu_ctx* ctx, int zero_forces, double out[16]);
+/* out == NULL above enqueues the call without waiting; the sums are collected later (after any later synchronisation of the
+ * context's stream they are already there) -- one host round trip per MD step instead of two */
+int dlpgpu_dev_fetch_results(dlpgpu_ctx* ctx, double out[16]);
 /* pairs in the reference's half list for this domain (local-local once + local-halo), counted from the device list */
 int dlpgpu_dev_list_pairs(dlpgpu_ctx* ctx, long long* pairs);
 /* read-back (tests, diagnostics) */
