@@ -816,7 +816,7 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
 int dlp_vnl_set_check(dlpgpu_ctx* ctx) {
   int n = ctx->nlast;
   if (n > 0) LAUNCH(ctx, k_bg_copy, cdiv(n, 256), 256, 0, n, ctx->posq.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p);
-  ctx->have_bg = true;
+  ctx->have_bg = true; ctx->tol_fresh = false;
   return 0;
 }
 

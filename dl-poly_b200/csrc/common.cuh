@@ -148,6 +148,7 @@ struct dlpgpu_ctx {
   int pub_cap = 0, pub_parity = 0;
   int p2p_rank = 0, p2p_nranks = 0;
   bool p2p_ready = false, pub_valid = false;
+  bool tol_fresh = false, pub_fresh = false;   // left behind by the fused velocity-Verlet stage 1 (dlp_vv1_fused)
   std::vector<double4*> peer_pub;   // [2 * nranks]
   DBuf<unsigned long long> peer_pub_dev;   // the same table on the device
   // fused device-side exchange (dlpgpu_dev_xchg_*): one CUDA-IPC exported region with the gmax mailboxes and the per-stage
@@ -246,4 +247,5 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]);
 int dlp_build_tab4(dlpgpu_ctx* ctx);
 // halo.cu
 int dlp_vnl_set_check(dlpgpu_ctx* ctx);
+extern "C" int dlp_vv1_fused(dlpgpu_ctx* ctx, double dt);
 int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol);

@@ -430,6 +430,7 @@ static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   CK(ctx->parts_dev.ensure(n, ctx->stream));
   CK(cudaMemcpyAsync(ctx->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, ctx->parts_dev.p, n, ctx->posq.p);
+  ctx->tol_fresh = false; ctx->pub_fresh = false;
   return 0;
 }
 
@@ -458,7 +459,7 @@ int dlpgpu_dev_load_atoms(dlpgpu_ctx* ctx, int natms, const double* xyz, const d
   CK(cudaStreamSynchronize(ctx->stream));
   tx.release(); tv.release();
   ctx->natms = natms; ctx->nlast = natms;
-  ctx->list_valid = false; ctx->halo_valid = false; ctx->have_bg = false;
+  ctx->list_valid = false; ctx->halo_valid = false; ctx->have_bg = false; ctx->tol_fresh = false; ctx->pub_fresh = false;
   return 0;
 }
 

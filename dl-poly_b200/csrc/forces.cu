@@ -926,6 +926,7 @@ int dlpgpu_dev_vv(dlpgpu_ctx* ctx, int stage, double dt) {
   if (!ctx || (stage != 1 && stage != 2)) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "vv: sites not set");
+  if (stage == 1) return dlp_vv1_fused(ctx, dt);
   if (ctx->natms > 0)
     LAUNCH(ctx, k_vv, cdiv(ctx->natms, 256), 256, 0, ctx->natms, stage, dt, ctx->lsite.p, ctx->weight_site.p, ctx->posq.p, ctx->vx.p,
            ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p);

@@ -76,13 +76,8 @@ void h_widths(const double* aaa0, double* w3) {   // dcell bbb(7:9), numerics.F9
 struct Mat9 { double m[9]; };
 
 // ---------------------------------------------------------------- vnl_check
-__global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const double4* __restrict__ posq, const double* __restrict__ xbg,
-                          const double* __restrict__ ybg, const double* __restrict__ zbg, unsigned long long* __restrict__ tol_bits) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double r = 0.0;
-  if (i < natms) {
-    double4 p = posq[i];
-    double x = p.x - xbg[i], y = p.y - ybg[i], z = p.z - zbg[i];   // neighbours.F90:157-161
+__device__ __forceinline__ double vnl_displacement(int imcon, const Mat9& cell, const Mat9& rcell, double x, double y, double z) {
+  {
     if (imcon == 1) {                                              // numerics.F90:1553-1563
       double aaa = 1.0 / cell.m[0];
       x = x - cell.m[0] * round(aaa * x) ; y = y - cell.m[0] * round(aaa * y); z = z - cell.m[0] * round(aaa * z);
@@ -98,11 +93,48 @@ __global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const dou
       y = cell.m[1] * xss + cell.m[4] * yss + cell.m[7] * zss;
       z = cell.m[2] * xss + cell.m[5] * yss + cell.m[8] * zss;
     }
-    r = sqrt(x * x + y * y + z * z);                               // :166
+    return sqrt(x * x + y * y + z * z);                            // :166
+  }
+}
+__global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const double4* __restrict__ posq, const double* __restrict__ xbg,
+                          const double* __restrict__ ybg, const double* __restrict__ zbg, unsigned long long* __restrict__ tol_bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0;
+  if (i < natms) {
+    double4 p = posq[i];
+    r = vnl_displacement(imcon, cell, rcell, p.x - xbg[i], p.y - ybg[i], p.z - zbg[i]);   // neighbours.F90:157-161
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
   if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));   // r >= 0: bits are order-preserving
+}
+// velocity-Verlet stage 1 (nve.F90:163-173, same contraction as forces.cu::k_vv) fused with what always follows it in the
+// native driver: the displacement test of vnl_check on the new positions and the copy into the peer-visible buffer of the
+// one-kernel halo refresh -- one pass over the atoms instead of three
+__global__ void k_vv1_fused(int natms, double dt, int imcon, Mat9 cell, Mat9 rcell, const int* __restrict__ lsite,
+                            const double* __restrict__ weight_site, double4* __restrict__ posq, double* vx, double* vy, double* vz,
+                            const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                            const double* __restrict__ xbg, const double* __restrict__ ybg, const double* __restrict__ zbg,
+                            unsigned long long* __restrict__ tol_bits, double4* __restrict__ pub) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0;
+  if (i < natms) {
+    const double hstep = 0.5 * dt;
+    const double rm = 1.0 / weight_site[lsite[i] - 1];
+    const double tmp = hstep * rm;
+    const double a = __fma_rn(tmp, fx[i], vx[i]), b = __fma_rn(tmp, fy[i], vy[i]), c = __fma_rn(tmp, fz[i], vz[i]);
+    vx[i] = a; vy[i] = b; vz[i] = c;
+    double4 p = posq[i];
+    p.x = __fma_rn(dt, a, p.x); p.y = __fma_rn(dt, b, p.y); p.z = __fma_rn(dt, c, p.z);
+    posq[i] = p;
+    if (pub) pub[i] = p;
+    if (tol_bits) r = vnl_displacement(imcon, cell, rcell, p.x - xbg[i], p.y - ybg[i], p.z - zbg[i]);
+  }
+  if (tol_bits) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
+    if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));
+  }
 }
 
 // ---------------------------------------------------------------- halo build
@@ -611,10 +643,13 @@ int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol) {
   if (!ctx->have_bg) return dlp_fail(ctx, DLPGPU_ERR_STATE, "vnl_check: no checkpoint");
   double rc[9];
   h_invert(ctx->cell, rc);
-  CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
-  if (ctx->natms > 0)
-    LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
-           ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  if (!ctx->tol_fresh) {   // otherwise the fused velocity-Verlet stage 1 already left the maximum there
+    CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
+    if (ctx->natms > 0)
+      LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
+             ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  }
+  ctx->tol_fresh = false;
   unsigned long long bits = 0;
   CK(cudaMemcpyAsync(&bits, ctx->tol_bits.p, sizeof bits, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -818,7 +853,9 @@ int dlpgpu_dev_publish(dlpgpu_ctx* ctx) {
   if (!ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "publish: p2p not initialised");
   if (ctx->natms > ctx->pub_cap) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "publish: %d local atoms exceed the peer buffer (%d)", ctx->natms, ctx->pub_cap);
   ctx->pub_parity ^= 1;
-  if (ctx->natms > 0) LAUNCH(ctx, k_publish, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->posq.p, ctx->pub[ctx->pub_parity]);
+  if (ctx->natms > 0 && !ctx->pub_fresh)   // the fused velocity-Verlet stage 1 may have filled the buffer of the next parity already
+    LAUNCH(ctx, k_publish, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->posq.p, ctx->pub[ctx->pub_parity]);
+  ctx->pub_fresh = false;
   ctx->pub_valid = true;
   return 0;
 }
@@ -865,6 +902,7 @@ int dlpgpu_dev_relocate_serial(dlpgpu_ctx* ctx) {
     LAUNCH(ctx, k_pbcshift, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p);
   ctx->nlast = ctx->natms;
   ctx->halo_valid = false; ctx->list_valid = false;
+  ctx->tol_fresh = false; ctx->pub_fresh = false;
   return 0;
 }
 
@@ -877,6 +915,7 @@ int dlpgpu_dev_relocate_begin(dlpgpu_ctx* ctx) {
   ctx->nlast = ctx->natms;
   if (ctx->natms > 0) LAUNCH(ctx, k_reloc_tag, cdiv(ctx->natms, 256), 256, 0, ctx->natms, mat(rc), D, ctx->posq.p, ctx->ixyz.p);
   ctx->halo_valid = false; ctx->list_valid = false;
+  ctx->tol_fresh = false; ctx->pub_fresh = false;
   return 0;
 }
 
@@ -997,10 +1036,13 @@ int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol) {
   cudaStream_t s = ctx->stream;
   double rc[9];
   h_invert(ctx->cell, rc);
-  CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
-  if (ctx->natms > 0)
-    LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
-           ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  if (!ctx->tol_fresh) {
+    CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
+    if (ctx->natms > 0)
+      LAUNCH(ctx, k_vnl_tol, cdiv(ctx->natms, 256), 256, 0, ctx->natms, ctx->imcon, mat(ctx->cell), mat(rc), ctx->posq.p, ctx->xbg.p,
+             ctx->ybg.p, ctx->zbg.p, ctx->tol_bits.p);
+  }
+  ctx->tol_fresh = false;
   const XLayout L = x_layout(ctx->xr_nranks, ctx->xr_cap_r, ctx->xr_cap_h);
   LAUNCH(ctx, k_x_gmax, 1, 32, 0, ctx->xr_rank, ctx->xr_nranks, seq, ctx->tol_bits.p, ctx->peer_xr_dev.p, L.off_gm, ctx->gmax_out.p, ctx->dcnt.p);
   unsigned long long bits = 0;
@@ -1039,6 +1081,7 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   h_dc[DC_NATMS] = ctx->natms; h_dc[DC_NLAST] = ctx->natms;
   CK(cudaMemcpyAsync(dc, h_dc, sizeof h_dc, cudaMemcpyHostToDevice, s));
   ctx->halo_valid = false; ctx->list_valid = false;
+  ctx->tol_fresh = false; ctx->pub_fresh = false;
   int nub = ctx->natms;   // host-side upper bound of the live natms / nlast
   auto hdr_of = [&](int r, int stage) { return reinterpret_cast<XHdr*>(ctx->peer_xr[r] + L.off_hdr) + stage; };
   auto rbuf_of = [&](int r, int q) { return reinterpret_cast<double*>(ctx->peer_xr[r] + L.off_rbuf) + (size_t)q * cap_r * 12; };
@@ -1138,6 +1181,23 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   }
   ctx->have_bg = true;
   ctx->halo_valid = true;
+  return 0;
+}
+
+// velocity-Verlet stage 1 + vnl_check displacement maximum + publish in one pass (see k_vv1_fused); called by dlpgpu_dev_vv
+int dlp_vv1_fused(dlpgpu_ctx* ctx, double dt) {
+  cudaStream_t s = ctx->stream;
+  const bool want_tol = ctx->have_bg;
+  const bool want_pub = ctx->pub[0] != nullptr && ctx->natms <= ctx->pub_cap;
+  double rc[9];
+  h_invert(ctx->cell, rc);
+  if (want_tol) CK(cudaMemsetAsync(ctx->tol_bits.p, 0, sizeof(unsigned long long), s));
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_vv1_fused, cdiv(ctx->natms, 256), 256, 0, ctx->natms, dt, ctx->imcon, mat(ctx->cell), mat(rc), ctx->lsite.p, ctx->weight_site.p,
+           ctx->posq.p, ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p,
+           want_tol ? ctx->tol_bits.p : nullptr, want_pub ? ctx->pub[ctx->pub_parity ^ 1] : nullptr);
+  ctx->tol_fresh = want_tol;
+  ctx->pub_fresh = want_pub;
   return 0;
 }
 
