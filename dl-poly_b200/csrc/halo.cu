@@ -440,86 +440,177 @@ __global__ void k_x_reloc_tag(const int* __restrict__ dc, Mat9 rcell, DomI D, co
   if (D.idz == D.nz - 1) { if (z >= half_minus) v += 200; } else { if (ipz > D.idz) v += 200; }
   ixyz[i] = v;
 }
-__global__ void k_x_reloc_flag(const int* __restrict__ dc, int nub, Dir d, const int* __restrict__ ixyz, int* __restrict__ leave) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > nub) return;
-  int f = 0;
-  if (i < dc[DC_NATMS]) {
-    int v = ixyz[i];
-    if (v != 0) {
-      int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
-      if (ix * d.kx + iy * d.ky + iz * d.kz == d.jxyz) f = 1;
+// ---- stage kernels: count -> pack (+ signal) -> [restack] -> receive (+ bookkeeping): 3 launches per halo stage, 4 per
+// migration stage.  A block owns XB_N consecutive atoms, eight per thread, so packed order = ascending local index (the
+// reference's buffer order).  The last block to finish (a ticket in the counts block) does the one-thread work.
+#define XB_T 512
+#define XB_A 8
+#define XB_N (XB_T * XB_A)
+#define DC_TICKET 4
+#define DC_NOLD 5
+#define DC_TOT 6
+
+__device__ __forceinline__ int reloc_sel(int v, const Dir& d) {   // deport_data.F90:254-274
+  if (v == 0) return 0;
+  int ix = v % 10, iy = (v - ix) % 100, iz = (v - (ix + iy)) % 1000;
+  return (ix * d.kx + iy * d.ky + iz * d.kz == d.jxyz) ? 1 : 0;
+}
+__device__ __forceinline__ int x_block_sum(int v, int* s_w) {   // sum over the block, returned to every thread
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DLP_FULL, v, o);
+  __syncthreads();
+  if (lane == 0) s_w[w] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < XB_T / 32; ++k) t += s_w[k];
+  return t;
+}
+template <int HALO>
+__global__ void __launch_bounds__(XB_T) k_x_count(const int* __restrict__ dc, Dir d, const int* __restrict__ ixyz, int* __restrict__ blocksum) {
+  __shared__ int s_w[XB_T / 32];
+  const int n = HALO ? dc[DC_NLAST] : dc[DC_NATMS];
+  const int base = blockIdx.x * XB_N + threadIdx.x;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) {
+    const int i = base + j * XB_T;
+    if (i < n) c += HALO ? (halo_sel(ixyz[i], d) != 0) : reloc_sel(ixyz[i], d);
+  }
+  const int t = x_block_sum(c, s_w);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = t;
+}
+struct XAtoms {   // the per-atom arrays a stage moves
+  double4* posq; double *vx, *vy, *vz, *fx, *fy, *fz;
+  int *ltg, *lsite, *ixyz, *org_rank, *org_idx, *org_wrap;
+};
+template <int HALO>
+__global__ void __launch_bounds__(XB_T)
+k_x_pack(int* __restrict__ dc, Dir d, int cap, int q, const int* __restrict__ blocksum, XAtoms A, int wrap_add, double* __restrict__ buf,
+         int* __restrict__ idx_or_hole, int* __restrict__ leave, int* __restrict__ lpos, XHdr* dst_hdr, unsigned long long seq) {
+  __shared__ int s_w[XB_T / 32];
+  __shared__ int s_last;
+  const int n = HALO ? dc[DC_NLAST] : dc[DC_NATMS];
+  // atoms selected in the blocks before this one, and in all blocks
+  int before = 0, all = 0;
+  for (int k = threadIdx.x; k < gridDim.x; k += XB_T) { const int v = blocksum[k]; all += v; if (k < blockIdx.x) before += v; }
+  before = x_block_sum(before, s_w);
+  const int total = x_block_sum(all, s_w);
+  const int k_stay = n - total;
+  // XB_A passes over XB_T consecutive atoms each (adjacent threads = adjacent atoms = adjacent buffer records); the packed
+  // position of an atom = selected atoms before it: blocks before, passes before, warps before, lanes before
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int run = before;
+  for (int j = 0; j < XB_A; ++j) {
+    const int i = blockIdx.x * XB_N + j * XB_T + threadIdx.x;
+    int code = 0;
+    if (i < n) code = HALO ? halo_sel(A.ixyz[i], d) : reloc_sel(A.ixyz[i], d);
+    const unsigned m = __ballot_sync(DLP_FULL, code != 0);
+    __syncthreads();
+    if (lane == 0) s_w[w] = __popc(m);
+    __syncthreads();
+    int wbase = 0, tot_j = 0;
+#pragma unroll
+    for (int k = 0; k < XB_T / 32; ++k) { const int v = s_w[k]; tot_j += v; if (k < w) wbase += v; }
+    const int k = run + wbase + __popc(m & ((1u << lane) - 1u));
+    run += tot_j;
+    if (i >= n) continue;
+    if (!HALO) { leave[i] = code ? 1 : 0; lpos[i] = k; }   // what the restack reads
+    if (!code || k >= cap) continue;
+    const double4 p = A.posq[i];
+    if (HALO) {
+      idx_or_hole[k] = i;
+      double* b = buf + (size_t)k * DLP_HALO_W;
+      b[6] = (double)A.org_rank[i]; b[7] = (double)A.org_idx[i]; b[8] = (double)(A.org_wrap[i] + wrap_add);
+      if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+      else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:1836-1844
+      b[3] = (double)A.ltg[i];
+      b[4] = (double)A.lsite[i];
+      b[5] = (double)(A.ixyz[i] - (code == 1 ? d.jxyz : d.kxyz));              // :1853
+    } else {
+      if (i < k_stay) idx_or_hole[k] = i;       // holes below the new natms are the first ones (ascending)
+      double* b = buf + (size_t)k * 12;
+      if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+      else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
+      b[3] = A.vx[i]; b[4] = A.vy[i]; b[5] = A.vz[i];
+      b[6] = A.fx[i]; b[7] = A.fy[i]; b[8] = A.fz[i];
+      b[9] = (double)A.ltg[i]; b[10] = (double)A.lsite[i]; b[11] = (double)(A.ixyz[i] - d.jxyz);
     }
   }
-  leave[i] = f;
+  // the last block publishes count + sequence to the receiver and settles the local counts.  The barrier orders the
+  // block's payload stores before thread 0's system-scope fence (cumulative), the ticket chains the blocks.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(&dc[DC_TICKET], 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    dc[DC_TICKET] = 0;
+    int sent = total;
+    if (total > cap) { atomicOr(&dc[DC_ERR], HALO ? 2 : 1); sent = cap; }
+    if (HALO) dc[DC_HSENT + q] = sent;
+    else {
+      dc[DC_RSENT + q] = sent; dc[DC_NOLD] = n; dc[DC_TOT] = total;
+      if (total <= cap) { dc[DC_NATMS] = k_stay; dc[DC_NLAST] = k_stay; }
+    }
+    dst_hdr->count = sent;
+    __threadfence_system();
+    st_release_sys(&dst_hdr->seq, seq);
+  }
 }
-__global__ void k_x_reloc_pack(const int* __restrict__ dc, const int* __restrict__ tot, Dir d, int cap, const int* __restrict__ leave,
-                               const int* __restrict__ lpos, const double4* __restrict__ posq, const double* __restrict__ vx,
-                               const double* __restrict__ vy, const double* __restrict__ vz, const double* __restrict__ fx,
-                               const double* __restrict__ fy, const double* __restrict__ fz, const int* __restrict__ ltg,
-                               const int* __restrict__ lsite, const int* __restrict__ ixyz, double* __restrict__ buf, int* __restrict__ hole_pos) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = dc[DC_NATMS];
-  if (i >= n || !leave[i]) return;
-  const int k_stay = n - *tot;
-  int k = lpos[i];
-  if (k >= cap) return;                  // overflow is reported by k_x_reloc_sent
-  if (i < k_stay) hole_pos[k] = i;
-  double4 p = posq[i];
-  double* b = buf + (size_t)k * 12;
-  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
-  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
-  b[3] = vx[i]; b[4] = vy[i]; b[5] = vz[i];
-  b[6] = fx[i]; b[7] = fy[i]; b[8] = fz[i];
-  b[9] = (double)ltg[i]; b[10] = (double)lsite[i]; b[11] = (double)(ixyz[i] - d.jxyz);
-}
-__global__ void k_x_reloc_restack(const int* __restrict__ dc, const int* __restrict__ tot, int cap, const int* __restrict__ leave,
-                                  const int* __restrict__ lpos, const int* __restrict__ hole_pos, double4* __restrict__ posq, double* vx,
-                                  double* vy, double* vz, double* fx, double* fy, double* fz, int* ltg, int* lsite, int* ixyz) {
-  const int n = dc[DC_NATMS], total = *tot;
+__global__ void k_x_reloc_restack(const int* __restrict__ dc, int cap, const int* __restrict__ leave, const int* __restrict__ lpos,
+                                  const int* __restrict__ hole_pos, XAtoms A) {
+  const int n = dc[DC_NOLD], total = dc[DC_TOT];
   if (total > cap) return;
   const int k_stay = n - total;
   int j = k_stay + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n || leave[j]) return;
   int r = k_stay - 1 - (j - lpos[j]);   // deport_data.F90:822-925, see k_reloc_restack
   int dst = hole_pos[r];
-  posq[dst] = posq[j];
-  vx[dst] = vx[j]; vy[dst] = vy[j]; vz[dst] = vz[j];
-  fx[dst] = fx[j]; fy[dst] = fy[j]; fz[dst] = fz[j];
-  ltg[dst] = ltg[j]; lsite[dst] = lsite[j]; ixyz[dst] = ixyz[j];
+  A.posq[dst] = A.posq[j];
+  A.vx[dst] = A.vx[j]; A.vy[dst] = A.vy[j]; A.vz[dst] = A.vz[j];
+  A.fx[dst] = A.fx[j]; A.fy[dst] = A.fy[j]; A.fz[dst] = A.fz[j];
+  A.ltg[dst] = A.ltg[j]; A.lsite[dst] = A.lsite[j]; A.ixyz[dst] = A.ixyz[j];
 }
-// one thread: the stage's leavers are gone from the local range; count + sequence go to the receiver's header
-__global__ void k_x_sent(int is_halo, int q, const int* __restrict__ tot, int cap, int* __restrict__ dc, XHdr* dst_hdr, unsigned long long seq) {
-  int total = *tot;
-  if (total > cap) { atomicOr(&dc[DC_ERR], is_halo ? 2 : 1); total = cap; }
-  if (is_halo) dc[DC_HSENT + q] = total;
-  else { dc[DC_RSENT + q] = total; dc[DC_NATMS] -= *tot > cap ? 0 : total; dc[DC_NLAST] = dc[DC_NATMS]; }
-  dst_hdr->count = total;
-  __threadfence_system();
-  st_release_sys(&dst_hdr->seq, seq);
-}
-__global__ void k_x_reloc_recv(const XHdr* __restrict__ hdr, unsigned long long seq, const double* __restrict__ buf, int capacity,
-                               int* __restrict__ dc, double4* __restrict__ posq, double* vx, double* vy, double* vz, double* fx, double* fy,
-                               double* fz, int* ltg, int* lsite, int* ixyz) {
-  __shared__ int s_count;
+template <int HALO>
+__global__ void k_x_recv(const XHdr* __restrict__ hdr, unsigned long long seq, const double* __restrict__ buf, int capacity, int q,
+                         int* __restrict__ dc, XAtoms A) {
+  __shared__ int s_count, s_last;
   if (threadIdx.x == 0) s_count = x_wait(&hdr->seq, seq, &dc[DC_ERR]) ? (int)hdr->count : 0;
   __syncthreads();
-  const int off = dc[DC_NATMS];
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= s_count || off + k >= capacity) return;
-  const double* b = buf + (size_t)k * 12;
-  int i = off + k;
-  posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
-  vx[i] = __ldcg(b + 3); vy[i] = __ldcg(b + 4); vz[i] = __ldcg(b + 5);
-  fx[i] = __ldcg(b + 6); fy[i] = __ldcg(b + 7); fz[i] = __ldcg(b + 8);
-  ltg[i] = __double2int_rn(__ldcg(b + 9)); lsite[i] = __double2int_rn(__ldcg(b + 10)); ixyz[i] = __double2int_rn(__ldcg(b + 11));
-}
-__global__ void k_x_recvd(int is_halo, int q, const XHdr* __restrict__ hdr, unsigned long long seq, int capacity, int* __restrict__ dc) {
-  int count = (ld_acquire_sys(&hdr->seq) == seq) ? (int)hdr->count : 0;
-  const int off = is_halo ? dc[DC_NLAST] : dc[DC_NATMS];
-  if (off + count > capacity) { atomicOr(&dc[DC_ERR], 8); count = capacity - off; }
-  if (is_halo) { dc[DC_HOFF + q] = off; dc[DC_HRECV + q] = count; dc[DC_NLAST] = off + count; }
-  else { dc[DC_RRECV + q] = count; dc[DC_NATMS] = off + count; dc[DC_NLAST] = off + count; }
+  const int off = HALO ? dc[DC_NLAST] : dc[DC_NATMS];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < s_count && off + k < capacity) {
+    const int i = off + k;
+    if (HALO) {
+      const double* b = buf + (size_t)k * DLP_HALO_W;
+      A.org_rank[i] = __double2int_rn(__ldcg(b + 6)); A.org_idx[i] = __double2int_rn(__ldcg(b + 7)); A.org_wrap[i] = __double2int_rn(__ldcg(b + 8));
+      A.posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
+      A.ltg[i] = __double2int_rn(__ldcg(b + 3)); A.lsite[i] = __double2int_rn(__ldcg(b + 4)); A.ixyz[i] = __double2int_rn(__ldcg(b + 5));   // Nint, :1935-1940
+      A.fx[i] = 0.0; A.fy[i] = 0.0; A.fz[i] = 0.0;
+    } else {
+      const double* b = buf + (size_t)k * 12;
+      A.posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
+      A.vx[i] = __ldcg(b + 3); A.vy[i] = __ldcg(b + 4); A.vz[i] = __ldcg(b + 5);
+      A.fx[i] = __ldcg(b + 6); A.fy[i] = __ldcg(b + 7); A.fz[i] = __ldcg(b + 8);
+      A.ltg[i] = __double2int_rn(__ldcg(b + 9)); A.lsite[i] = __double2int_rn(__ldcg(b + 10)); A.ixyz[i] = __double2int_rn(__ldcg(b + 11));
+    }
+  }
+  // every block has read `off` before it takes a ticket; the last one appends the received atoms to the counts
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&dc[DC_TICKET], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    dc[DC_TICKET] = 0;
+    int count = s_count;
+    if (off + count > capacity) { atomicOr(&dc[DC_ERR], 8); count = capacity - off; }
+    if (HALO) { dc[DC_HOFF + q] = off; dc[DC_HRECV + q] = count; dc[DC_NLAST] = off + count; }
+    else { dc[DC_RRECV + q] = count; dc[DC_NATMS] = off + count; dc[DC_NLAST] = off + count; }
+  }
 }
 __global__ void k_x_reloc_end(int* dc, const int* __restrict__ ixyz, const int* __restrict__ lsite,
                               const int* __restrict__ type_site, const double* __restrict__ charge_site, const int* __restrict__ freeze_site,
@@ -547,47 +638,6 @@ __global__ void k_x_halo_tag(const int* __restrict__ dc, Mat9 rcell, HaloThr t, 
   if (z <= t.ecwz) v += 100;
   if (z >= t.cwz) v += 200;
   ixyz[i] = v;
-}
-__global__ void k_x_halo_flag(const int* __restrict__ dc, int nub, Dir d, const int* __restrict__ ixyz, int* __restrict__ flag) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > nub) return;
-  flag[i] = (i < dc[DC_NLAST] && halo_sel(ixyz[i], d) != 0) ? 1 : 0;
-}
-__global__ void k_x_halo_pack(const int* __restrict__ dc, Dir d, int cap, const int* __restrict__ flag, const int* __restrict__ pos,
-                              const double4* __restrict__ posq, const int* __restrict__ ltg, const int* __restrict__ lsite,
-                              const int* __restrict__ ixyz, const int* __restrict__ org_rank, const int* __restrict__ org_idx,
-                              const int* __restrict__ org_wrap, int wrap_add, double* __restrict__ buf, int* __restrict__ idx) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dc[DC_NLAST] || !flag[i]) return;
-  int k = pos[i];
-  if (k >= cap) return;
-  idx[k] = i;
-  double4 p = posq[i];
-  double* b = buf + (size_t)k * DLP_HALO_W;
-  b[6] = (double)org_rank[i]; b[7] = (double)org_idx[i]; b[8] = (double)(org_wrap[i] + wrap_add);
-  if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
-  else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:1836-1844
-  b[3] = (double)ltg[i];
-  b[4] = (double)lsite[i];
-  int v = ixyz[i];
-  b[5] = (double)(v - (halo_sel(v, d) == 1 ? d.jxyz : d.kxyz));            // :1853
-}
-__global__ void k_x_halo_recv(const XHdr* __restrict__ hdr, unsigned long long seq, const double* __restrict__ buf, int capacity,
-                              int* __restrict__ dc, double4* __restrict__ posq, int* __restrict__ ltg, int* __restrict__ lsite,
-                              int* __restrict__ ixyz, double* fx, double* fy, double* fz, int* __restrict__ org_rank,
-                              int* __restrict__ org_idx, int* __restrict__ org_wrap) {
-  __shared__ int s_count;
-  if (threadIdx.x == 0) s_count = x_wait(&hdr->seq, seq, &dc[DC_ERR]) ? (int)hdr->count : 0;
-  __syncthreads();
-  const int off = dc[DC_NLAST];
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= s_count || off + k >= capacity) return;
-  const double* b = buf + (size_t)k * DLP_HALO_W;
-  int i = off + k;
-  org_rank[i] = __double2int_rn(__ldcg(b + 6)); org_idx[i] = __double2int_rn(__ldcg(b + 7)); org_wrap[i] = __double2int_rn(__ldcg(b + 8));
-  posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
-  ltg[i] = __double2int_rn(__ldcg(b + 3)); lsite[i] = __double2int_rn(__ldcg(b + 4)); ixyz[i] = __double2int_rn(__ldcg(b + 5));   // Nint, :1935-1940
-  fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0;
 }
 __global__ void k_x_halo_end(const int* __restrict__ dc, const int* __restrict__ lsite, const int* __restrict__ type_site,
                              const double* __restrict__ charge_site, const int* __restrict__ freeze_site, double4* __restrict__ posq,
@@ -1083,6 +1133,9 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   ctx->halo_valid = false; ctx->list_valid = false;
   ctx->tol_fresh = false; ctx->pub_fresh = false;
   int nub = ctx->natms;   // host-side upper bound of the live natms / nlast
+  CK(ctx->scan_tmp.ensure((size_t)cdiv(ub_total, XB_N) + 64, s));   // per-block selection counts of a stage
+  XAtoms A{ctx->posq.p, ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p,
+           ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p};
   auto hdr_of = [&](int r, int stage) { return reinterpret_cast<XHdr*>(ctx->peer_xr[r] + L.off_hdr) + stage; };
   auto rbuf_of = [&](int r, int q) { return reinterpret_cast<double*>(ctx->peer_xr[r] + L.off_rbuf) + (size_t)q * cap_r * 12; };
   auto hbuf_of = [&](int r, int q) { return reinterpret_cast<double*>(ctx->peer_xr[r] + L.off_hbuf) + (size_t)q * cap_h * DLP_HALO_W; };
@@ -1098,19 +1151,12 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
       const Dir d = dir_settings(ctx, mdirs[q]);
       const int dst = neigh[q];
       if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
-      LAUNCH(ctx, k_x_reloc_flag, cdiv(nub + 1, 256), 256, 0, dc, nub, d, ctx->ixyz.p, ctx->flag.p);
-      CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nub, nullptr));
-      const int* tot = ctx->scan_out.p + nub;
-      if (nub > 0) {
-        LAUNCH(ctx, k_x_reloc_pack, cdiv(nub, 256), 256, 0, dc, tot, d, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->vx.p, ctx->vy.p,
-               ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p, rbuf_of(dst, q), ctx->hole_pos.p);
-        LAUNCH(ctx, k_x_reloc_restack, cdiv(cap_r, 256), 256, 0, dc, tot, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, ctx->posq.p,
-               ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
-      }
-      LAUNCH(ctx, k_x_sent, 1, 1, 0, 0, q, tot, cap_r, dc, hdr_of(dst, q), seq);
-      LAUNCH(ctx, k_x_reloc_recv, cdiv(cap_r, 256), 256, 0, hdr_of(me, q), seq, rbuf_of(me, q), capacity, dc, ctx->posq.p, ctx->vx.p, ctx->vy.p,
-             ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p);
-      LAUNCH(ctx, k_x_recvd, 1, 1, 0, 0, q, hdr_of(me, q), seq, capacity, dc);
+      const int nb = std::max(1, cdiv(nub, XB_N));
+      LAUNCH(ctx, k_x_count<0>, nb, XB_T, 0, dc, d, ctx->ixyz.p, ctx->scan_tmp.p);
+      LAUNCH(ctx, k_x_pack<0>, nb, XB_T, 0, dc, d, cap_r, q, ctx->scan_tmp.p, A, 0, rbuf_of(dst, q), ctx->hole_pos.p, ctx->flag.p, ctx->scan_out.p,
+             hdr_of(dst, q), seq);
+      LAUNCH(ctx, k_x_reloc_restack, cdiv(cap_r, 256), 256, 0, dc, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, A);
+      LAUNCH(ctx, k_x_recv<0>, cdiv(cap_r, 256), 256, 0, hdr_of(me, q), seq, rbuf_of(me, q), capacity, q, dc, A);
       nub = std::min(nub + cap_r, capacity);
     }
     LAUNCH(ctx, k_x_reloc_end, cdiv(nub, 256), 256, 0, dc, ctx->ixyz.p, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p,
@@ -1149,16 +1195,11 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
     CK(st.idx.ensure((size_t)cap_h + 1, s));
     int wrap_add = 0;
     if (d.lwrap) wrap_add = ((mdirs[q] < 0) ? +1 : -1) * (d.kx ? 1 : d.ky ? 3 : 9);
-    LAUNCH(ctx, k_x_halo_flag, cdiv(nub + 1, 256), 256, 0, dc, nub, d, ctx->ixyz.p, ctx->flag.p);
-    CKRC(dlp_exclusive_scan(ctx, ctx->flag.p, ctx->scan_out.p, nub, nullptr));
-    const int* tot = ctx->scan_out.p + nub;
-    if (nub > 0)
-      LAUNCH(ctx, k_x_halo_pack, cdiv(nub, 256), 256, 0, dc, d, cap_h, ctx->flag.p, ctx->scan_out.p, ctx->posq.p, ctx->ltg.p, ctx->lsite.p,
-             ctx->ixyz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p, wrap_add, hbuf_of(dst, q), st.idx.p);
-    LAUNCH(ctx, k_x_sent, 1, 1, 0, 1, q, tot, cap_h, dc, hdr_of(dst, 6 + q), seq);
-    LAUNCH(ctx, k_x_halo_recv, cdiv(cap_h, 256), 256, 0, hdr_of(me, 6 + q), seq, hbuf_of(me, q), capacity, dc, ctx->posq.p, ctx->ltg.p,
-           ctx->lsite.p, ctx->ixyz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p);
-    LAUNCH(ctx, k_x_recvd, 1, 1, 0, 1, q, hdr_of(me, 6 + q), seq, capacity, dc);
+    const int nb = std::max(1, cdiv(nub, XB_N));
+    LAUNCH(ctx, k_x_count<1>, nb, XB_T, 0, dc, d, ctx->ixyz.p, ctx->scan_tmp.p);
+    LAUNCH(ctx, k_x_pack<1>, nb, XB_T, 0, dc, d, cap_h, q, ctx->scan_tmp.p, A, wrap_add, hbuf_of(dst, q), st.idx.p, nullptr, nullptr,
+           hdr_of(dst, 6 + q), seq);
+    LAUNCH(ctx, k_x_recv<1>, cdiv(cap_h, 256), 256, 0, hdr_of(me, 6 + q), seq, hbuf_of(me, q), capacity, q, dc, A);
     nub = std::min(nub + cap_h, capacity);
   }
   if (nub > 0)

@@ -508,6 +508,7 @@ class Domain:
         else:
             self.refresh_halo(); t = lap("refresh_halo", t)
         out = self.forces(); t = lap("two_body_forces", t)
+        self.last_out = out
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(2, dt)
         t = lap("vv2", t)
