@@ -42,11 +42,17 @@ FLOP_EWALD = 56      # ewald_spole.F90:133-197, in-cutoff charged pair
 FLOP_EXCL = 50       # ewald_spole.F90:570-649, excluded pair
 
 
-def make_system(workload, dims, per_gpu_cells=None):
+def make_system(workload, dims, per_gpu_cells=None, strong=False):
     import _pkg
     _pkg.load()
     from dl_poly_b200 import systems
     dx, dy, dz = dims
+    if strong:      # BASELINE configs[4] strong scaling: the 8M-atom box is fixed, the domains shrink with N
+        if workload in ("ionic", "table"):
+            return systems.nacl(per_gpu_cells or 100, seed=1005, tabfile=(workload == "table"))
+        if workload == "lj":
+            return systems.argon(per_gpu_cells or 126, seed=1005)
+        raise SystemExit("--strong applies to the ionic / table / lj workloads")
     if workload in ("ionic", "table"):
         c = per_gpu_cells or 50
         return systems.nacl((c * dx, c * dy, c * dz), seed=1005, tabfile=(workload == "table"))
@@ -66,6 +72,11 @@ def workload_name(workload, sysm, n):
          "lj": "C5-LJ weak scaling: argon 12-6 (tabulated), rc 8.5 A, padding 0.3 A",
          "c1": "C1 argon 32,000", "c2": "C2 NaCl 27,000", "c3": "C3 SPC/E 216,000"}[workload]
     return "%s; %d atoms on %d GPU(s)" % (d, sysm.megatm, n)
+
+
+def workload_label(args, sysm, n):
+    w = workload_name(args.workload, sysm, n)
+    return w.replace("weak scaling", "strong scaling (fixed 8M-atom box)") if args.strong else w
 
 
 def flop_per_atom_step(sysm, listed_pairs_per_atom):
@@ -247,7 +258,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         transport = dd.TorchTransport(torch.device("cuda", local))
     dims = DIMS[world]
-    sysm = make_system(args.workload, dims, args.cells_per_gpu)
+    sysm = make_system(args.workload, dims, args.cells_per_gpu, strong=args.strong)
     dom = dd.Domain(sysm, device=local, transport=transport)
     sr = dom.sr
     if args.force_mode is not None:
@@ -339,9 +350,9 @@ def run_gpu(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, sysm, world), "domains": list(dims), "atoms": natoms_total,
+            "config": {"workload": workload_label(args, sysm, world), "domains": list(dims), "atoms": natoms_total,
                        "rcut": sysm.rcut, "padding": sysm.padding, "timestep_ps": dt,
                        "rebuilds_in_timed_region": dom.rebuilds if transport is None else int(round(tot[4] / world)),
                        "list_build_ms_total": list_ms_tot, "force_call_ms_total": force_ms_tot,
@@ -418,6 +429,7 @@ def main():
     ap.add_argument("--dt", type=float, default=0.001, help="timestep in ps")
     ap.add_argument("--force-mode", type=int, default=None, choices=[0, 1])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the fixed 8M-atom box of BASELINE configs[4] on N GPUs")
     args = ap.parse_args()
     if args.gpus not in DIMS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
