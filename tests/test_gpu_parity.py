@@ -377,3 +377,34 @@ def test_fused_exchange_reports_a_too_small_stage_buffer():
         sr.dev_xchg_rebuild([0] * 6, 1)
     assert e.value.code == 54
     sr.close()
+
+
+def test_c4_table_1m_fast_kernel_against_general_kernel(monkeypatch):
+    """BASELINE configs[3] at its per-GPU size (1,000,000 ions, TABLE-file vdW + real-space Ewald): the fast pair kernel
+    (fp32-completed second differences, texture path, Newton 3 with REDs) against the general kernel that follows the
+    reference statement by statement, plus the size-independent properties: Newton's third law over the periodic box,
+    virial == -trace(stress), symmetric stress."""
+    s = systems.by_name("c4")
+    fast = native_serial(s)
+    monkeypatch.setenv("DLPGPU_NO_FAST", "1")
+    slow = native_serial(s)
+    monkeypatch.delenv("DLPGPU_NO_FAST")
+    res = []
+    for sr in (fast, slow):
+        sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs()
+        out = sr.dev_two_body_forces()
+        natms, _ = sr.dev_counts()
+        res.append((out, parts_forces(sr.dev_get_parts(), natms)))
+    (of, ff), (og, fg) = res
+    assert fast.dev_list_pairs() == slow.dev_list_pairs()
+    a, b = force_errors(ff, fg)
+    assert a <= FORCE_TOL
+    for k in range(4):
+        assert abs(of[k] - og[k]) <= ENERGY_TOL * abs(og[k]), (k, of[k], og[k])
+    for k in range(6, 15):
+        assert abs(of[k] - og[k]) <= ENERGY_TOL * np.abs(og[6:15]).max(), (k, of[k], og[k])
+    assert np.abs(ff.sum(0)).max() <= 1e-9 * np.abs(ff).sum()
+    vir = of[1] + of[3] + of[5]
+    assert abs((of[6] + of[10] + of[14]) + vir) <= 1e-10 * abs(vir)
+    assert of[7] == of[9] and of[8] == of[12] and of[11] == of[13]
+    fast.close(); slow.close()
