@@ -402,15 +402,17 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     nb = 0
     t0 = time.perf_counter()
     for s in range(steps):
-        if s % interval == 0:
+        built = s % interval == 0
+        if built:
             sr2.link_cell_pairs(natms, nlast, parts, ints["ltype"], ints["ltg"], ints["lfrzn"], **kw)
             nb += 1
-        sr2.two_body_forces(natms, nlast, parts)
+        # calculate_forces calls the two back to back (drivers.F90:675-679): on a rebuild step the records are already there
+        sr2.two_body_forces(natms, nlast, parts, unchanged_since_list=built)
     torch.cuda.synchronize()
     t = time.perf_counter() - t0
     if transport is not None:
         t = transport.allreduce_max(t)
-    h2d = nlast * 64 + (nb / steps) * (nlast * 64 + 3 * 4 * nlast)
+    h2d = nlast * 64 + (nb / steps) * (3 * 4 * nlast)      # parts every step (once on rebuild steps too) + the three int arrays per rebuild
     d2h = natms * 64 + 16 * 8
     sr2.close()
     return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),

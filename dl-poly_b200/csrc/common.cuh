@@ -207,6 +207,8 @@ struct dlpgpu_ctx {
   void* pinned_ptr = nullptr;      // caller's corePart array, page-locked by us on first use
   size_t pinned_bytes = 0;
   bool pinned_ours = false;
+  int parts_resident = 0;          // records of the caller's parts array currently mirrored in parts_dev (set by link_cell_pairs)
+  bool parts_current = false;      // dlpgpu_parts_unchanged_since_list: the next two_body_forces may skip its upload
   // timings
   cudaEvent_t ev[8] = {nullptr};
   cudaEvent_t ev_res = nullptr;     // behind the asynchronous result copy of dlpgpu_dev_two_body_forces(out = NULL)

@@ -431,6 +431,7 @@ static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   CK(cudaMemcpyAsync(ctx->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, ctx->parts_dev.p, n, ctx->posq.p);
   ctx->tol_fresh = false; ctx->pub_fresh = false;
+  ctx->parts_resident = 0; ctx->parts_current = false;
   return 0;
 }
 
@@ -480,6 +481,7 @@ int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_c
   ctx->natms = 0; ctx->nlast = 0;
   CKRC(dlp_ensure_atoms(ctx, nlast + 16));
   CKRC(upload_parts(ctx, nlast, parts));
+  ctx->parts_resident = nlast;
   CK(cudaMemcpyAsync(ctx->ltype.p, ltype, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->ltg.p, ltg, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if (lfrzn) CK(cudaMemcpyAsync(ctx->lfrzn.p, lfrzn, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -511,7 +513,12 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
   if (natms != ctx->list_natms || nlast != ctx->list_nlast)
     return dlp_fail(ctx, DLPGPU_ERR_HALO_COUNT, "two_body_forces: natms/nlast (%d/%d) differ from the list build (%d/%d)", natms, nlast,
                     ctx->list_natms, ctx->list_nlast);
-  CKRC(upload_parts(ctx, nlast, parts));
+  if (ctx->parts_current && ctx->parts_resident >= nlast) {
+    // the records link_cell_pairs uploaded (and unpacked into the device arrays) are still the caller's
+  } else {
+    CKRC(upload_parts(ctx, nlast, parts));
+  }
+  ctx->parts_current = false;
   CKRC(dlp_two_body(ctx, 1, out));
   // every force provider ADDS (drivers.F90:655-660): the device copy of parts still holds the caller's forces, so the sum is
   // formed there and the records of the local atoms go back in one contiguous copy (positions and charges unchanged)
@@ -520,6 +527,14 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
     CK(cudaMemcpyAsync(parts, ctx->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  if (!ctx->list_valid || ctx->parts_resident < ctx->list_nlast)
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "parts_unchanged_since_list: no list build has uploaded the parts array");
+  ctx->parts_current = true;
   return 0;
 }
 

@@ -109,9 +109,12 @@ class ShortRange:
         self._ck(rc)
         return out
 
-    def two_body_forces(self, natms, nlast, parts):
-        """Adds the pair forces into parts['fxx','fyy','fzz'][:natms]; returns the 16 partial sums of the C ABI."""
+    def two_body_forces(self, natms, nlast, parts, unchanged_since_list=False):
+        """Adds the pair forces into parts['fxx','fyy','fzz'][:natms]; returns the 16 partial sums of the C ABI.
+        unchanged_since_list: the caller asserts parts has not been written since link_cell_pairs (skips the upload)."""
         assert parts.dtype == COREPART and parts.flags.c_contiguous
+        if unchanged_since_list:
+            self._ck(self.L.dlpgpu_parts_unchanged_since_list(self.h))
         out = np.zeros(16)
         self._ck(self.L.dlpgpu_two_body_forces(self.h, int(natms), int(nlast), ptr(parts), ptr(out)))
         return out

@@ -112,6 +112,11 @@ Module dlp_gpu_binding
       Real(c_double), Intent(Out)  :: out(16)
       Integer(c_int)               :: rc
     End Function
+    Function dlpgpu_parts_unchanged_since_list(ctx) Bind(C, name='dlpgpu_parts_unchanged_since_list') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value :: ctx
+      Integer(c_int)     :: rc
+    End Function
     Function dlpgpu_vnl_check(ctx, natms, parts, tol) Bind(C, name='dlpgpu_vnl_check') Result(rc)
       Import :: c_ptr, c_int, c_double
       Type(c_ptr), Value           :: ctx
@@ -253,15 +258,21 @@ Contains
     Call check(rc, 'link_cell_pairs')
   End Subroutine link_cell_pairs_gpu
 
-  Subroutine two_body_pairs_gpu(config, stats, engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex)
+  Subroutine two_body_pairs_gpu(config, stats, engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex, list_just_built)
     !! replaces the two Do i = 1, config%natms loops of two_body_forces: forces are ADDED into config%parts(1:natms)%f,
     !! the six per-rank partial sums feed the existing gsum buffer (two_body.F90:708-729) and the nine stress
     !! contributions are added to stats%stress exactly where vdw_forces / ewald_real_forces add theirs.
     Type(configuration_type), Intent(InOut), Target :: config
     Type(stats_type),         Intent(InOut)         :: stats
     Real(Kind=wp),            Intent(InOut)         :: engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex
+    Logical, Optional,        Intent(In   )         :: list_just_built   !! = neigh%update: link_cell_pairs_gpu ran in this
+                                                                         !! calculate_forces and parts is untouched since
 
     Real(c_double) :: out(16)
+
+    If (Present(list_just_built)) Then
+      If (list_just_built) Call check(dlpgpu_parts_unchanged_since_list(ctx), 'parts_unchanged_since_list')
+    End If
 
     Call check(dlpgpu_two_body_forces(ctx, Int(config%natms, c_int), Int(config%nlast, c_int), c_loc(config%parts), out), &
                'two_body_forces')

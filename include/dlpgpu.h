@@ -94,6 +94,11 @@ int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_c
  * of parts(1:natms) are incremented.  out[0..5] = engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex;
  * out[6..14] = this rank's contribution to stats%stress(1:9); out[15] = 0. */
 int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepart* parts, double out[16]);
+/* The caller asserts that parts(1:nlast) has not been written since the last dlpgpu_link_cell_pairs (calculate_forces calls
+ * link_cell_pairs and two_body_forces back to back, drivers.F90:675-679 then two_body_forces): the next
+ * dlpgpu_two_body_forces then works on the copy that call left on the device and skips its own 64 nlast-byte upload.
+ * One-shot: the assertion is consumed by the next dlpgpu_two_body_forces. */
+int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
 /* neighbours.F90:157-171: tol = max_i |r_i - r_bg,i| (minimum image) over parts(1:natms); caller does gmax + test */
 int dlpgpu_vnl_check(dlpgpu_ctx* ctx, int natms, const dlpgpu_corepart* parts, double* tol);
 int dlpgpu_vnl_set_check(dlpgpu_ctx* ctx, int nlast, const dlpgpu_corepart* parts);

@@ -52,7 +52,14 @@ def check_dropin(s, P, ranks=None, mode=0):
         assert np.array_equal(cells["which_cell"], wc)
         assert np.array_equal(cells["lct_start"] + 1, ls)                # 0-based slots vs Fortran 1-based
         assert np.array_equal(cells["at_list"] + 1, al)
-        out = sr.two_body_forces(d["natms"], d["nlast"], parts)
+        parts_again = parts.copy()
+        # the call sequence of calculate_forces: the records link_cell_pairs uploaded are reused ...
+        out = sr.two_body_forces(d["natms"], d["nlast"], parts, unchanged_since_list=True)
+        # ... and the plain call (own upload) gives the same forces and sums up to the order of the atomic adds
+        out_again = sr.two_body_forces(d["natms"], d["nlast"], parts_again)
+        assert np.allclose(out_again, out, rtol=1e-12, atol=1e-12 * np.abs(out).max())
+        fa, fb = parts_forces(parts_again, d["natms"]), parts_forces(parts, d["natms"])
+        assert np.abs(fa - fb).max() <= 1e-12 * np.abs(fb).max()
         fo = parts_forces(d["parts"], d["natms"])
         fg = parts_forces(parts, d["natms"])
         a, b = force_errors(fg, fo)
