@@ -103,6 +103,9 @@ struct dlpgpu_ctx {
   DBuf<double> vdw_par;    // [max_vdw][10] param(1:7), afs, bfs, pad
   // ewald
   bool ew_on = false;
+  int coul_kind = 0;        // DLPGPU_COUL_*: direct-space Coulomb variant instead of Ewald (coul_spole.F90)
+  bool coul_damp = false;
+  double coul_fs = 0, coul_es = 0, coul_rf[3] = {0, 0, 0};
   double alpha = 0, scaling = 0, ew_rdr = 0, thr_coul = 0;
   int ew_n = 0;
   DBuf<double2> ew_tab;    // [ew_n+1] {erfc_deriv, erfc}

@@ -290,6 +290,7 @@ int dlpgpu_set_ewald(dlpgpu_ctx* ctx, int active, double alpha, double scaling, 
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->tab4_valid = false;
+  ctx->coul_kind = 0; ctx->coul_damp = false;
   if (!active) { ctx->ew_on = false; return 0; }
   if (!erfc_tab || !erfc_deriv_tab || nsamples < 10) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_ewald: tables missing");
   ctx->alpha = alpha; ctx->scaling = scaling; ctx->ew_n = nsamples; ctx->ew_rdr = recip_spacing;
@@ -301,6 +302,30 @@ int dlpgpu_set_ewald(dlpgpu_ctx* ctx, int active, double alpha, double scaling, 
   CK(cudaMemcpyAsync(ctx->ew_tab.p, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->ew_on = true;
+  return 0;
+}
+
+int dlpgpu_set_coulomb(dlpgpu_ctx* ctx, int kind, int damp, double scaling, double force_shift, double energy_shift,
+                       const double reaction_field[3], int nsamples, const double* erfc_tab, const double* erfc_deriv_tab,
+                       double recip_spacing) {
+  if (!ctx || kind < DLPGPU_COUL_CP || kind > DLPGPU_COUL_RFP) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->tab4_valid = false;
+  ctx->ew_on = false;
+  ctx->coul_kind = kind; ctx->coul_damp = damp != 0 && (kind == DLPGPU_COUL_FSCP || kind == DLPGPU_COUL_RFP);
+  ctx->scaling = scaling; ctx->coul_fs = force_shift; ctx->coul_es = energy_shift;
+  for (int k = 0; k < 3; ++k) ctx->coul_rf[k] = reaction_field ? reaction_field[k] : 0.0;
+  if (ctx->coul_damp) {
+    if (!erfc_tab || !erfc_deriv_tab || nsamples < 10) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_coulomb: damped variant without erfc tables");
+    ctx->ew_n = nsamples; ctx->ew_rdr = recip_spacing;
+    std::vector<double2> t((size_t)nsamples + 1);
+    for (int i = 0; i <= nsamples; ++i) t[i] = make_double2(erfc_deriv_tab[i], erfc_tab[i]);
+    ctx->h_ew_d.assign(erfc_deriv_tab, erfc_deriv_tab + nsamples + 1);
+    ctx->h_ew_e.assign(erfc_tab, erfc_tab + nsamples + 1);
+    CK(ctx->ew_tab.ensure(t.size(), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ew_tab.p, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return 0;
 }
 

@@ -18,6 +18,8 @@ struct FParams {
   int natms, pitch, xpitch, max_grid, max_vdw, ew_n, tstride, ew_off, tab_ne;
   int vdw_on, vdw_direct, vdw_fshift, ew_on, half, zero_forces, lbook, same_grid;
   double rvdw, r_rvdw, vdw_rdr, rcut, ew_rdr, alpha, scaling, thr_vdw, thr_coul;
+  int coul_kind, coul_tab;   // direct-space Coulomb variant (coul_spole.F90) instead of Ewald; coul_tab: damped (erfc tables present)
+  double coul_fs, coul_es, rf0, rf1, rf2;
 };
 
 constexpr double ZERO_PLUS = 2.2250738585072014e-308;   // Tiny(1.0_wp), constants.F90:189
@@ -100,7 +102,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
   extern __shared__ __align__(16) double2 s_tab[];   // Tab4 entries as pairs of double2: [2e] = lo, [2e+1] = hi
   if (SMEM) {
     const double2* gv = reinterpret_cast<const double2*>(tab4_g);
-    const int n2 = 2 * (P.ew_off + (P.ew_on ? P.ew_n + 1 : 0));
+    const int n2 = 2 * (P.ew_off + ((P.ew_on || P.coul_tab) ? P.ew_n + 1 : 0));
     for (int k = threadIdx.x; k < n2; k += NT) s_tab[k] = gv[k];
     __syncthreads();
   }
@@ -119,7 +121,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
     double4 pi = make_double4(0, 0, 0, 0);
     if (live) { ii = loc_slot[t]; pi = posq_s[ii]; n = nnbr[t]; }
     const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
-    const bool coul_i = P.ew_on && !(fabs(qi_s) < ZERO_PLUS);                 // :117
+    const bool coul_i = (P.ew_on || P.coul_kind) && !(fabs(qi_s) < ZERO_PLUS);  // :117 / coul_spole.F90:218
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
     const unsigned* row = nbr + (size_t)t * P.pitch;
     // software pipeline: list entries are fetched two passes ahead, partner coordinates one pass ahead
@@ -184,7 +186,26 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
         acc[0] += w * eng;
         acc[1] -= w * (gam * rsq);
       }
-      if (in_c) {
+      if (in_c && P.coul_kind && !P.coul_tab) {   // coul_spole.F90: undamped direct-space variants, analytic
+        const double chgprd = qi_s * pj.w;
+        double egamma, coul, virterm;
+        if (P.coul_kind == DLPGPU_COUL_CP) {                                  // coul_cp_forces :647-649, vircpe = -engcpe :722
+          coul = chgprd * r_rrr; egamma = coul * r_rsq; virterm = coul;
+        } else if (P.coul_kind == DLPGPU_COUL_DDDP) {                         // coul_dddp_forces :812-815, vircpe = -2 engcpe :890
+          coul = chgprd * r_rsq; egamma = 2.0 * coul * r_rsq; virterm = 2.0 * coul;
+        } else if (P.coul_kind == DLPGPU_COUL_FSCP) {                         // coul_fscp_forces :262, :301
+          egamma = chgprd * (r_rsq - P.coul_fs) * r_rrr;
+          coul = chgprd * (r_rrr + P.coul_fs * rrr + P.coul_es);
+          virterm = egamma * rsq;
+        } else {                                                              // coul_rfp_forces :474, :507
+          egamma = chgprd * (r_rsq * r_rrr - P.rf0);
+          coul = chgprd * (r_rrr + P.rf2 * rsq - P.rf1);
+          virterm = egamma * rsq;
+        }
+        gamma += egamma;
+        acc[2] += w * coul;
+        acc[3] -= w * virterm;
+      } else if (in_c) {
         const double prefac = qi_s * pj.w;
         if (!(P.same_grid && in_v && !P.vdw_direct)) {
           const double tt = rrr * P.ew_rdr;                                   // ewald_spole.F90:140-146
@@ -203,9 +224,16 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
           gd = interp3(ew_raw[0].x * rrr, ew_raw[1].x, ew_raw[2].x, ppp);
           ge = interp3(ew_raw[0].y * rrr, ew_raw[1].y, ew_raw[2].y, ppp);
         }
-        const double erf_gamma = prefac * gd;
+        double erf_gamma = prefac * gd, e_comp = prefac * ge;                  // ewald_spole.F90:140-174
+        if (P.coul_kind == DLPGPU_COUL_FSCP) {                                // damped coul_fscp_forces :260, :296
+          erf_gamma = (gd - P.coul_fs * r_rrr) * prefac;
+          e_comp = (ge + P.coul_fs * rrr + P.coul_es) * prefac;
+        } else if (P.coul_kind == DLPGPU_COUL_RFP) {                          // damped coul_rfp_forces :471-472, :504-505
+          erf_gamma = (gd - P.coul_fs * r_rrr - P.rf0) * prefac;
+          e_comp = (ge + P.coul_fs * rrr + P.coul_es + P.rf2 * (rsq - P.rcut * P.rcut)) * prefac;
+        }
         gamma += erf_gamma;
-        acc[2] += w * (prefac * ge);                                          // :168-174
+        acc[2] += w * e_comp;
         acc[3] -= w * (erf_gamma * rsq);                                      // :189
       }
       const double f1 = gamma * xxt, f2 = gamma * yyt, f3 = gamma * zzt;
@@ -677,7 +705,8 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
   const int ts = ctx->max_grid + 1;
   const bool vt = ctx->vdw_on && !ctx->vdw_direct && !ctx->h_vdw_f.empty();
   const size_t nv = vt ? (size_t)ctx->max_vdw * ts : 0;
-  const size_t ne = ctx->ew_on ? (size_t)ctx->ew_n + 1 : 0;
+  const bool have_ew_tab = ctx->ew_on || (ctx->coul_kind && ctx->coul_damp);   // Ewald or a damped direct-space variant
+  const size_t ne = have_ew_tab ? (size_t)ctx->ew_n + 1 : 0;
   ctx->ew_off = (int)nv;
   std::vector<double> t((nv + ne) * 4 + 4, 0.0);
   auto fill = [&](double* dst, const double* f, const double* e, int n) {   // n+1 entries 0..n
@@ -697,7 +726,7 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->tab4_entries = nv + ne;
   {   // k_pair_v2 layout
-    const int tsz = std::max(vt ? ts : 0, ctx->ew_on ? ctx->ew_n + 1 : 0);
+    const int tsz = std::max(vt ? ts : 0, have_ew_tab ? ctx->ew_n + 1 : 0);
     const int ntab = 1 + (vt ? ctx->max_vdw : 0);
     const int NE = ntab * tsz + 2;
     std::vector<double> t2((size_t)NE * 4, 0.0);   // g units [0, NE), h units [NE, 2 NE), each {force, energy}
@@ -785,6 +814,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   P.vdw_on = ctx->vdw_on; P.vdw_direct = ctx->vdw_direct; P.vdw_fshift = ctx->vdw_fshift; P.ew_on = ctx->ew_on;
   P.half = ctx->force_mode == 1; P.zero_forces = zero_forces; P.lbook = ctx->lbook;
   P.same_grid = ctx->vdw_on && ctx->ew_on && ctx->vdw_rdr == ctx->ew_rdr;
+  P.coul_kind = ctx->coul_kind; P.coul_tab = (ctx->coul_kind && ctx->coul_damp) ? 1 : 0;
+  P.coul_fs = ctx->coul_fs; P.coul_es = ctx->coul_es; P.rf0 = ctx->coul_rf[0]; P.rf1 = ctx->coul_rf[1]; P.rf2 = ctx->coul_rf[2];
   P.rvdw = ctx->rvdw; P.r_rvdw = ctx->rvdw > 0 ? 1.0 / ctx->rvdw : 0.0; P.vdw_rdr = ctx->vdw_rdr; P.rcut = ctx->rcut;
   P.ew_rdr = ctx->ew_rdr; P.alpha = ctx->alpha; P.scaling = ctx->scaling; P.thr_vdw = ctx->thr_vdw; P.thr_coul = ctx->thr_coul;
   // shared-memory tables when they fit
@@ -809,7 +840,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   }
   cudaEventRecord(ctx->ev[6], s);
   const bool xc = P.lbook && P.ew_on;   // rows carry excluded partners: the fast kernel has them for the vdW + Ewald, one-grid case
-  const bool fast = P.half && use_smem && !ctx->no_fast && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
+  const bool fast = P.half && use_smem && !ctx->no_fast && !P.coul_kind && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
                     tpr == 8 && (!xc || (P.vdw_on && P.ew_on && P.same_grid));
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
   const bool fast2 = fast && smem2 + 2048 <= 227 * 1024;

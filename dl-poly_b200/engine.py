@@ -80,6 +80,16 @@ class ShortRange:
             d = np.ascontiguousarray(ff.erfc_deriv, dtype=np.float64)
             self._ck(self.L.dlpgpu_set_ewald(self.h, 1, float(ff.alpha), float(ff.scaling), int(ff.ew_n), ptr(e), ptr(d),
                                              float(ff.ew_recip)))
+        elif getattr(ff, "coul_kind", 0):
+            rf = np.ascontiguousarray(ff.coul_rf, dtype=np.float64)
+            if ff.coul_damp:
+                e = np.ascontiguousarray(ff.erfc, dtype=np.float64)
+                d = np.ascontiguousarray(ff.erfc_deriv, dtype=np.float64)
+                self._ck(self.L.dlpgpu_set_coulomb(self.h, int(ff.coul_kind), 1, float(ff.scaling), float(ff.coul_force_shift),
+                                                   float(ff.coul_energy_shift), ptr(rf), int(ff.ew_n), ptr(e), ptr(d), float(ff.ew_recip)))
+            else:
+                self._ck(self.L.dlpgpu_set_coulomb(self.h, int(ff.coul_kind), 0, float(ff.scaling), float(ff.coul_force_shift),
+                                                   float(ff.coul_energy_shift), ptr(rf), 0, None, None, 0.0))
         else:
             self._ck(self.L.dlpgpu_set_ewald(self.h, 0, 0.0, 0.0, 0, None, None, 0.0))
 

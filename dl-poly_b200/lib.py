@@ -30,6 +30,7 @@ SIGNATURES = {
     "dlpgpu_set_cutoffs": (ci, [vp, cd, cd, cd]),
     "dlpgpu_set_vdw": (ci, [vp, ci, vp, ci, ci, vp, ci, vp, vp, cd, ci, ci, vp, vp, vp]),
     "dlpgpu_set_ewald": (ci, [vp, ci, cd, cd, ci, vp, vp, cd]),
+    "dlpgpu_set_coulomb": (ci, [vp, ci, ci, cd, cd, cd, vp, ci, vp, vp, cd]),
     "dlpgpu_link_cell_pairs": (ci, [vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, pi_]),
     "dlpgpu_two_body_forces": (ci, [vp, ci, ci, vp, vp]),
     "dlpgpu_parts_unchanged_since_list": (ci, [vp]),

@@ -114,7 +114,8 @@ def _rocksalt(ncell, a, seed, jitter):
 
 
 def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=False, force_shift=False, ewald=True,
-         jitter=0.3, temperature=1200.0, spme_precision=1.0e-6, rvdw=None, vdw_pairs=((1, 1), (1, 2), (2, 2))):
+         jitter=0.3, temperature=1200.0, spme_precision=1.0e-6, rvdw=None, vdw_pairs=((1, 1), (1, 2), (2, 2)),
+         coulomb=None, eps=1.0, damping=0.0):
     """C2/C4/C5-ionic: molten NaCl, 8*ncell^3 ions at the TEST01 density (V=963,882.2 A^3 for 27,000 ions).
     tabfile=True builds the three pair tables through a TABLE-format round trip (C4)."""
     nc = np.array(_n3(ncell), dtype=np.float64)
@@ -141,7 +142,9 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
         for (ai, aj), p in _BHM.items():
             if (ai, aj) in vdw_pairs:
                 ff.add(ai, aj, "bhm", p)
-    if ewald:
+    if coulomb is not None:       # "coul" | "dddp" | "fscp" | "rfp": the direct-space variants of coul_spole.F90 instead of Ewald
+        ff.set_coulomb(coulomb, eps=eps, damping=damping)
+    elif ewald:
         ff.set_ewald(precision=spme_precision)
     ff.finalize()
     cell = np.diag(L)
@@ -149,7 +152,8 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
                   [22.9898, 35.453], ff, rcut, padding, temperature=temperature, seed=seed)
 
 
-def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0e-6, temperature=0.0):
+def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0e-6, temperature=0.0, coulomb=None, eps=1.0,
+               damping=0.0):
     """C3: SPC/E water, 3*nmol atoms, rigid geometry 1.0 A / 109.47 deg, random orientations, O-O LJ, exclusions =
     the two other atoms of the molecule."""
     L = (nmol / 0.0334) ** (1.0 / 3.0)
@@ -173,7 +177,10 @@ def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0
     lsite = np.tile(np.array([1, 2, 3], dtype=np.int32), nmol)
     ff = tables.ForceField(2, rcut, rcut)
     ff.add(1, 1, "lj", [65.0, 3.166])
-    ff.set_ewald(precision=spme_precision)
+    if coulomb is not None:
+        ff.set_coulomb(coulomb, eps=eps, damping=damping)
+    else:
+        ff.set_ewald(precision=spme_precision)
     ff.finalize()
     gid = np.arange(1, n + 1, dtype=np.int32).reshape(nmol, 3)
     excl = np.zeros((n, 3), dtype=np.int32)

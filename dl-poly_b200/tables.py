@@ -220,6 +220,8 @@ class ForceField:
         self.pots = []                                              # [(keypot, param7)]
         self.mxgrid = max_grid(self.rvdw)
         self.ew_active = False
+        self.coul_kind = 0
+        self.coul_damp = False
         self.alpha = 0.0
         self.scaling = 0.0
         self.eps = 1.0
@@ -252,6 +254,34 @@ class ForceField:
         self.eps = eps
         self.alpha = ewald_alpha(precision, self.rcut) if alpha is None else float(alpha)
         self.scaling = R4PIE0 / eps                                # two_body.F90:188
+
+    COUL_KINDS = {"coul": 1, "dddp": 2, "fscp": 3, "rfp": 4}   # coul_cp / coul_dddp / coul_fscp / coul_rfp_forces
+
+    def set_coulomb(self, kind, eps=1.0, damping=0.0):
+        """The direct-space Coulomb variants of coul_spole.F90 (two_body.F90:480-514).  damping > 0 (fscp, rfp only) is the
+        Fennell-Gezelter damped form through erfc tables generated with alpha = damping (coul_spole.F90:186-202, :407-417)."""
+        self.ew_active = False
+        self.coul_kind = self.COUL_KINDS[kind]
+        self.coul_damp = damping > 0.0 and self.coul_kind in (3, 4)
+        self.eps = float(eps)
+        self.scaling = R4PIE0 / eps
+        self.alpha = float(damping)
+        rc = self.rcut
+        self.coul_force_shift, self.coul_energy_shift = 0.0, 0.0
+        self.coul_rf = np.zeros(3)
+        if self.coul_kind == 4:
+            b0 = 2.0 * (eps - 1.0) / (2.0 * eps + 1.0)
+            self.coul_rf[0] = b0 / rc ** 3
+            self.coul_rf[1] = (1.0 + 0.5 * b0) / rc
+            self.coul_rf[2] = 0.5 * self.coul_rf[0]
+        if self.coul_damp:
+            self.erfc, self.erfc_deriv, self.ew_recip = erfcgen(rc, self.alpha)
+            self.ew_n = len(self.erfc) - 1
+            self.coul_force_shift = self.erfc_deriv[self.ew_n - 4] * rc            # end_sample = table(nsamples - 4), numerics.F90:245
+            self.coul_energy_shift = -(self.erfc[self.ew_n - 4] + self.coul_force_shift * rc)
+        elif self.coul_kind == 3:
+            self.coul_force_shift = 1.0 / rc ** 2
+            self.coul_energy_shift = -2.0 / rc
 
     def finalize(self):
         n_vdw = len(self.pots)

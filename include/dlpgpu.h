@@ -81,6 +81,19 @@ int dlpgpu_set_vdw(dlpgpu_ctx* ctx, int ntypes, const int* vdw_list, int max_vdw
  * (numerics.F90:235).  active=0 switches electrostatics off (coul_method off). */
 int dlpgpu_set_ewald(dlpgpu_ctx* ctx, int active, double alpha, double scaling, int nsamples, const double* erfc_tab,
                      const double* erfc_deriv_tab, double recip_spacing);
+/* The direct-space Coulomb variants of coul_spole.F90, dispatched at two_body.F90:480-514 instead of the Ewald term:
+ * kind 1 = coul_cp_forces (1/r), 2 = coul_dddp_forces (distance-dependent dielectric), 3 = coul_fscp_forces (force-shifted),
+ * 4 = coul_rfp_forces (reaction field).  scaling = r4pie0/eps; force_shift / energy_shift = electro%force_shift /
+ * energy_shift (coul_spole.F90:186-202); reaction_field = electro%reaction_field(0:2) (:407-409).  damp != 0 (kinds 3, 4):
+ * the damped forms read electro%erfc / erfc_deriv (generated with alpha = electro%damping), passed like dlpgpu_set_ewald's.
+ * Replaces any earlier dlpgpu_set_ewald. */
+#define DLPGPU_COUL_CP 1
+#define DLPGPU_COUL_DDDP 2
+#define DLPGPU_COUL_FSCP 3
+#define DLPGPU_COUL_RFP 4
+int dlpgpu_set_coulomb(dlpgpu_ctx* ctx, int kind, int damp, double scaling, double force_shift, double energy_shift,
+                       const double reaction_field[3], int nsamples, const double* erfc_tab, const double* erfc_deriv_tab,
+                       double recip_spacing);
 
 /* ---------------------------------------------------------------- drop-in entry points (host buffers) */
 /* neighbours.F90:356-1306.  parts(1:nlast), ltype/ltg/lfrzn(1:nlast), list_excl(0:max_exclude,1:natms) (may be NULL

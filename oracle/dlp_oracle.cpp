@@ -436,6 +436,15 @@ struct Vdw {
   double& tf(int i, int k) { return tab_force[(size_t)(k - 1) * (max_grid + 1) + i]; }
   const double* par(int k) const { return &param[(size_t)(k - 1) * 7] - 1; }  // 1-based view
 };
+// coul_spole.F90: the direct-space Coulomb variants of two_body.F90:480-514 (everything except Ewald)
+enum { COUL_NONE = 0, COUL_CP = 1, COUL_DDDP = 2, COUL_FSCP = 3, COUL_RFP = 4 };
+struct Coulomb {
+  int kind = COUL_NONE;
+  bool damp = false;                       // electro%damp: Fennell-Gezelter damping through the erfc tables of `Ewald`
+  double scaling = 0.0;                    // r4pie0/eps
+  double force_shift = 0.0, energy_shift = 0.0;   // coul_spole.F90:186-202 / :413-414
+  double rf[3] = {0, 0, 0};                // electro%reaction_field(0:2), :407-409
+};
 struct Ewald {
   bool active = false;
   double alpha = 0.0, scaling = 0.0;   // scaling = r4pie0/eps (two_body.F90:188)
@@ -612,6 +621,7 @@ struct World {
   double ecw[4] = {0, 0, 0, 0};          // SPME negative-direction halo widths (reduced); 0 => link-cell width
   Vdw vdw;
   Ewald ew;
+  Coulomb coul;
   Sites sites;
   int max_exclude = 0;
   std::vector<int> excl_global;          // (0:max_exclude, 1:megatm) by global id
@@ -1384,6 +1394,87 @@ Acc ewald_real_forces_coul(World& w, Dom& dom, int iatm, const double* x_pos, co
   return {engcpe_rl, vircpe_rl};
 }
 
+// numerics.F90:265-290 calc_interp (the electro%calc_erfc / calc_erfc_deriv of the damped variants)
+static inline double interp3_table(const double* t, double recip_spacing, double r) {
+  int nsi = f_int(r * recip_spacing);
+  double diff = r * recip_spacing - (double)nsi;
+  double p1 = t[nsi], p2 = t[nsi + 1], p3 = t[nsi + 2];
+  if (nsi == 0) p1 = p1 * r;
+  double tm1 = p1 + (p2 - p1) * diff;
+  double tm2 = p2 + (p3 - p2) * (diff - 1.0);
+  return tm1 + (tm2 - tm1) * diff * 0.5;
+}
+
+// coul_spole.F90:567-729 coul_cp_forces, :731-897 coul_dddp_forces, :141-350 coul_fscp_forces, :352-565 coul_rfp_forces
+Acc coul_direct_forces(World& w, Dom& dom, int iatm, const double* xxt, const double* yyt, const double* zzt, const double* rrt) {
+  const Coulomb& c = w.coul;
+  const Ewald& e = w.ew;   // tables of the damped variants
+  double engcpe = 0.0, vircpe = 0.0;
+  double st[7] = {0};
+  CorePart* parts = dom.parts.data();
+  int idi = dom.ltg[iatm];
+  double chgea = parts[iatm].chge;
+  if (!(std::fabs(chgea) > zero_plus)) return {0.0, 0.0};
+  chgea = chgea * c.scaling;
+  double fix = parts[iatm].fxx, fiy = parts[iatm].fyy, fiz = parts[iatm].fzz;
+  const double cutoff_2 = w.rcut * w.rcut;
+  for (int m = 1; m <= dom.L(0, iatm); ++m) {
+    int jatm = dom.L(m, iatm);
+    double chgprd = parts[jatm].chge;
+    double rrr = rrt[m];
+    if (std::fabs(chgprd) > zero_plus && rrr < w.rcut) {
+      chgprd = chgprd * chgea;
+      double rsq = rrr * rrr;
+      double egamma = 0.0, coul = 0.0;
+      switch (c.kind) {
+        case COUL_CP:                                             // :647-649
+          coul = chgprd / rrr;
+          egamma = coul / (rrr * rrr);
+          break;
+        case COUL_DDDP:                                           // :812-815
+          coul = chgprd / rsq;
+          egamma = 2.0 * coul / rsq;
+          break;
+        case COUL_FSCP:                                           // :258-262
+          if (c.damp) egamma = (interp3_table(e.erfc_deriv.data(), e.recip_spacing, rrr) - c.force_shift / rrr) * chgprd;
+          else egamma = chgprd * (1.0 / rsq - c.force_shift) / rrr;
+          break;
+        case COUL_RFP:                                            // :470-475
+          if (c.damp) egamma = (interp3_table(e.erfc_deriv.data(), e.recip_spacing, rrr) - c.force_shift / rrr - c.rf[0]) * chgprd;
+          else egamma = chgprd * (1.0 / rsq / rrr - c.rf[0]);
+          break;
+      }
+      double fx = egamma * xxt[m], fy = egamma * yyt[m], fz = egamma * zzt[m];
+      fix = fix + fx; fiy = fiy + fy; fiz = fiz + fz;
+      if (jatm <= dom.natms) {
+        parts[jatm].fxx = parts[jatm].fxx - fx;
+        parts[jatm].fyy = parts[jatm].fyy - fy;
+        parts[jatm].fzz = parts[jatm].fzz - fz;
+      }
+      if (jatm <= dom.natms || idi < dom.ltg[jatm]) {
+        if (c.kind == COUL_FSCP) {                                // :292-301
+          if (c.damp) coul = (interp3_table(e.erfc.data(), e.recip_spacing, rrr) + c.force_shift * rrr + c.energy_shift) * chgprd;
+          else coul = chgprd * (1.0 / rrr + c.force_shift * rrr + c.energy_shift);
+        } else if (c.kind == COUL_RFP) {                          // :503-508
+          if (c.damp) coul = (interp3_table(e.erfc.data(), e.recip_spacing, rrr) + c.force_shift * rrr + c.energy_shift +
+                              c.rf[2] * (rsq - cutoff_2)) * chgprd;
+          else coul = chgprd * (1.0 / rrr + c.rf[2] * rsq - c.rf[1]);
+        }
+        engcpe = engcpe + coul;
+        if (c.kind == COUL_FSCP || c.kind == COUL_RFP) vircpe = vircpe - egamma * rsq;
+        st[1] += xxt[m] * fx; st[2] += xxt[m] * fy; st[3] += xxt[m] * fz;
+        st[4] += yyt[m] * fy; st[5] += yyt[m] * fz; st[6] += zzt[m] * fz;
+      }
+    }
+  }
+  parts[iatm].fxx = fix; parts[iatm].fyy = fiy; parts[iatm].fzz = fiz;
+  if (c.kind == COUL_CP) vircpe = -engcpe;                         // :722
+  if (c.kind == COUL_DDDP) vircpe = -2.0 * engcpe;                 // :890
+  double* s = dom.stress;
+  s[1] += st[1]; s[2] += st[2]; s[3] += st[3]; s[4] += st[2]; s[5] += st[4]; s[6] += st[5]; s[7] += st[3]; s[8] += st[5]; s[9] += st[6];
+  return {engcpe, vircpe};
+}
+
 // ewald_spole.F90:479-679 ewald_excl_forces
 Acc ewald_excl_forces(World& w, Dom& dom, int iatm, const double* xxt, const double* yyt, const double* zzt, const double* rrt) {
   const double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429,
@@ -1464,6 +1555,9 @@ void two_body_forces(World& w, Dom& dom) {
     }
     if (w.ew.active) {
       Acc a = ewald_real_forces_coul(w, dom, i, xxt.data(), yyt.data(), zzt.data(), rrt.data());
+      engcpe_rl = engcpe_rl + a.eng; vircpe_rl = vircpe_rl + a.vir;
+    } else if (w.coul.kind != COUL_NONE) {   // two_body.F90:480-514
+      Acc a = coul_direct_forces(w, dom, i, xxt.data(), yyt.data(), zzt.data(), rrt.data());
       engcpe_rl = engcpe_rl + a.eng; vircpe_rl = vircpe_rl + a.vir;
     }
   }
@@ -1750,6 +1844,20 @@ void ora_world_set_ewald(void* h, int active, double alpha, double scaling, int 
   Ewald& e = w->ew;
   e.active = active != 0; e.alpha = alpha; e.scaling = scaling; e.nsamples = nsamples; e.recip_spacing = recip_spacing;
   if (active) { e.erfc.assign(erfc_t, erfc_t + nsamples + 1); e.erfc_deriv.assign(deriv_t, deriv_t + nsamples + 1); }
+}
+// direct-space Coulomb variant (kind 1..4 as COUL_*); damped variants carry the erfc tables generated with alpha = damping
+void ora_world_set_coulomb(void* h, int kind, int damp, double scaling, double force_shift, double energy_shift, const double* rf3,
+                           int nsamples, const double* erfc_t, const double* deriv_t, double recip_spacing) {
+  World* w = (World*)h;
+  Coulomb& c = w->coul;
+  c.kind = kind; c.damp = damp != 0; c.scaling = scaling; c.force_shift = force_shift; c.energy_shift = energy_shift;
+  for (int k = 0; k < 3; ++k) c.rf[k] = rf3 ? rf3[k] : 0.0;
+  Ewald& e = w->ew;
+  e.active = false;
+  if (c.damp) {
+    e.nsamples = nsamples; e.recip_spacing = recip_spacing;
+    e.erfc.assign(erfc_t, erfc_t + nsamples + 1); e.erfc_deriv.assign(deriv_t, deriv_t + nsamples + 1);
+  }
 }
 // exclusions by global id: rows (0:max_exclude) for gid 1..megatm ; row[0]=count, sorted ascending ids
 void ora_world_set_excl(void* h, int max_exclude, const int* excl /* (max_exclude+1)*megatm */, int megatm) {

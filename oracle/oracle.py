@@ -211,6 +211,17 @@ class World:
             e, d = _d(ff.erfc), _d(ff.erfc_deriv)
             self.L.ora_world_set_ewald(self.h, C.c_int(1), C.c_double(ff.alpha), C.c_double(ff.scaling), C.c_int(ff.ew_n),
                                        _vp(e), _vp(d), C.c_double(ff.ew_recip))
+        elif getattr(ff, "coul_kind", 0):
+            rf = _d(ff.coul_rf)
+            if ff.coul_damp:
+                e, d = _d(ff.erfc), _d(ff.erfc_deriv)
+                self.L.ora_world_set_coulomb(self.h, C.c_int(ff.coul_kind), C.c_int(1), C.c_double(ff.scaling),
+                                             C.c_double(ff.coul_force_shift), C.c_double(ff.coul_energy_shift), _vp(rf),
+                                             C.c_int(ff.ew_n), _vp(e), _vp(d), C.c_double(ff.ew_recip))
+            else:
+                self.L.ora_world_set_coulomb(self.h, C.c_int(ff.coul_kind), C.c_int(0), C.c_double(ff.scaling),
+                                             C.c_double(ff.coul_force_shift), C.c_double(ff.coul_energy_shift), _vp(rf),
+                                             C.c_int(0), None, None, C.c_double(0.0))
 
     def set_excl(self, excl):
         e = _i(excl)

@@ -110,6 +110,15 @@ def test_nacl_ewald_only_and_partial_vdw():
     check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, vdw_pairs=((1, 2),)), 1, mode=1)
 
 
+@pytest.mark.parametrize("kind,eps,damping", [("coul", 1.0, 0.0), ("dddp", 2.5, 0.0), ("fscp", 1.0, 0.0), ("fscp", 1.0, 0.2),
+                                              ("rfp", 78.0, 0.0), ("rfp", 5.0, 0.25)])
+def test_direct_space_coulomb_variants(kind, eps, damping):
+    """coul_spole.F90: coul_cp / coul_dddp / coul_fscp / coul_rfp_forces (undamped and Fennell-Gezelter damped) instead of the
+    Ewald term, with vdW tables next to them; SPC/E checks that excluded pairs simply drop out (no Ewald correction)."""
+    check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, coulomb=kind, eps=eps, damping=damping), 1, mode=1)
+    check_dropin(systems.spce_water(512, rcut=8.0, padding=0.2, coulomb=kind, eps=eps, damping=damping), 1, mode=1)
+
+
 def test_nacl_bhm_direct():
     check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, direct=True), 1)
 

@@ -193,3 +193,43 @@ def test_read_config_fold_matches_oracle_load_bits(oracle):
         for r in range(P):
             assert np.array_equal(np.sort(w.ints(r)["ltg"][:w.counts(r)["natms"]]), np.nonzero(owner == r)[0] + 1)
             assert list(w.dd(r)[1][:6]) == dd.face_neighbours(r, *dims)
+
+
+@pytest.mark.parametrize("kind,eps", [("coul", 1.0), ("dddp", 2.5), ("fscp", 1.0), ("rfp", 78.0)])
+def test_direct_coulomb_variants_against_numpy_brute_force(oracle, kind, eps):
+    """coul_spole.F90 restatement (coul_cp / coul_dddp / coul_fscp / coul_rfp_forces, undamped) against an independent
+    O(N^2) minimum-image evaluation of the closed forms in numpy: energy, virial, per-atom forces."""
+    s = systems.nacl(2, rcut=5.0, padding=0.2, coulomb=kind, eps=eps, vdw_pairs=())
+    w = world_for(s, P=1)
+    out = w.two_body()
+    n = s.megatm
+    xyz = w.parts(0)[:n]
+    pos = np.stack([xyz["xxx"], xyz["yyy"], xyz["zzz"]], 1)
+    q = s.charge_site[s.lsite - 1]
+    L = s.cell[0]
+    d = pos[:, None, :] - pos[None, :, :]
+    d -= L * np.rint(d / L)
+    r = np.sqrt((d ** 2).sum(-1))
+    iu = np.triu_indices(n, 1)
+    rr, dd = r[iu], d[iu]
+    m = rr < s.rcut
+    rr, dd, ii, jj = rr[m], dd[m], iu[0][m], iu[1][m]
+    qq = q[ii] * q[jj] * tables.R4PIE0 / eps
+    rc = s.rcut
+    if kind == "coul":
+        e, g = qq / rr, qq / rr ** 3
+    elif kind == "dddp":
+        e, g = qq / rr ** 2, 2.0 * qq / rr ** 4
+    elif kind == "fscp":
+        e, g = qq * (1.0 / rr + rr / rc ** 2 - 2.0 / rc), qq * (1.0 / rr ** 2 - 1.0 / rc ** 2) / rr
+    else:
+        b0 = 2.0 * (eps - 1.0) / (2.0 * eps + 1.0)
+        e, g = qq * (1.0 / rr + 0.5 * b0 * rr ** 2 / rc ** 3 - (1.0 + 0.5 * b0) / rc), qq * (1.0 / rr ** 3 - b0 / rc ** 3)
+    vir = {"coul": -e.sum(), "dddp": -2.0 * e.sum()}.get(kind, -(g * rr ** 2).sum())
+    f = np.zeros((n, 3))
+    np.add.at(f, ii, g[:, None] * dd)
+    np.add.at(f, jj, -g[:, None] * dd)
+    assert abs(out[2] - e.sum()) <= 1e-11 * np.abs(e).sum()
+    assert abs(out[3] - vir) <= 1e-11 * np.abs(g * rr ** 2).sum()
+    fo = np.stack([xyz["fxx"], xyz["fyy"], xyz["fzz"]], 1)
+    assert np.abs(fo - f).max() <= 1e-10 * np.abs(f).max()
