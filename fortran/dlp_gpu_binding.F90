@@ -25,7 +25,8 @@ Module dlp_gpu_binding
   Use configuration,   Only: configuration_type
   Use constants,       Only: r4pie0
   Use domains,         Only: domains_type
-  Use electrostatic,   Only: electrostatic_type
+  Use electrostatic,   Only: electrostatic_type, ELECTROSTATIC_COULOMB, ELECTROSTATIC_DDDP, &
+                             ELECTROSTATIC_COULOMB_FORCE_SHIFT, ELECTROSTATIC_COULOMB_REACTION_FIELD
   Use errors_warnings, Only: error
   Use ewald,           Only: ewald_type
   Use neighbours,      Only: neighbours_type
@@ -92,6 +93,16 @@ Module dlp_gpu_binding
       Type(c_ptr), Value    :: ctx
       Integer(c_int), Value :: active, nsamples
       Real(c_double), Value :: alpha, scaling, recip_spacing
+      Type(c_ptr), Value    :: erfc_tab, erfc_deriv_tab
+      Integer(c_int)        :: rc
+    End Function
+    Function dlpgpu_set_coulomb(ctx, kind, damp, scaling, force_shift, energy_shift, reaction_field, nsamples, erfc_tab, &
+                                erfc_deriv_tab, recip_spacing) Bind(C, name='dlpgpu_set_coulomb') Result(rc)
+      Import :: c_ptr, c_int, c_double
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int), Value :: kind, damp, nsamples
+      Real(c_double), Value :: scaling, force_shift, energy_shift, recip_spacing
+      Real(c_double)        :: reaction_field(3)
       Type(c_ptr), Value    :: erfc_tab, erfc_deriv_tab
       Integer(c_int)        :: rc
     End Function
@@ -187,7 +198,7 @@ Contains
 
     Real(Kind=wp)  :: recip_spacing
     Type(c_ptr)    :: p_pot, p_frc, p_par, p_afs, p_bfs
-    Integer(c_int) :: fs, dr
+    Integer(c_int) :: fs, dr, kind
 
     p_pot = c_null_ptr; p_frc = c_null_ptr; p_par = c_null_ptr; p_afs = c_null_ptr; p_bfs = c_null_ptr
     If (Allocated(vdws%tab_potential)) p_pot = c_loc(vdws%tab_potential)   ! (0:max_grid, 1:max_vdw), column-major
@@ -204,7 +215,28 @@ Contains
                                 c_loc(vdws%ltp), Int(vdws%max_grid, c_int), p_pot, p_frc, vdws%cutoff, fs, dr, p_par, p_afs, &
                                 p_bfs), 'set_vdw')
     End If
-    If (electro%erfc%initialised) Then
+    If (Any(electro%key == [ELECTROSTATIC_COULOMB, ELECTROSTATIC_DDDP, ELECTROSTATIC_COULOMB_FORCE_SHIFT, &
+                            ELECTROSTATIC_COULOMB_REACTION_FIELD])) Then
+      ! coul_spole.F90: the direct-space variants dispatched at two_body.F90:480-514.  force_shift / energy_shift /
+      ! reaction_field are set by the reference's own first call (coul_spole.F90:186-202, :407-417); call this routine after
+      ! them or reproduce those statements here.  Damped forms pass the erfc tables generated with electro%damping.
+      Select Case (electro%key)
+      Case (ELECTROSTATIC_COULOMB);                kind = 1
+      Case (ELECTROSTATIC_DDDP);                   kind = 2
+      Case (ELECTROSTATIC_COULOMB_FORCE_SHIFT);    kind = 3
+      Case Default;                                kind = 4
+      End Select
+      If (electro%damp .and. kind >= 3) Then
+        recip_spacing = 1.0_wp / (rcut / Real(electro%erfc%nsamples - 4, wp))
+        Call check(dlpgpu_set_coulomb(ctx, kind, 1_c_int, r4pie0 / eps, electro%force_shift, electro%energy_shift, &
+                                      electro%reaction_field(0:2), Int(electro%erfc%nsamples, c_int), &
+                                      table_base(electro%erfc%table), table_base(electro%erfc_deriv%table), recip_spacing), &
+                   'set_coulomb')
+      Else
+        Call check(dlpgpu_set_coulomb(ctx, kind, 0_c_int, r4pie0 / eps, electro%force_shift, electro%energy_shift, &
+                                      electro%reaction_field(0:2), 0_c_int, c_null_ptr, c_null_ptr, 0.0_c_double), 'set_coulomb')
+      End If
+    Else If (electro%erfc%initialised) Then
       ! interp_table%recip_spacing is private: recompute it with the statements of init_interp_table (numerics.F90:237-238).
       ! The C side reads element i of the array as table(i); table(1:nsamples) has no element 0, so pass the address one
       ! element before table(1) -- it is never dereferenced for r >= spacing.
