@@ -202,6 +202,8 @@ struct dlpgpu_ctx {
   HaloStage stage[6];
   bool halo_valid = false;
   // reductions
+  DBuf<int> rdf_list;                 // rdf%list on the device (dlpgpu_rdf_collect)
+  DBuf<unsigned long long> rdf_hist;
   DBuf<double> partial;    // [blocks][16]
   DBuf<double> out_dev;    // [16]
   DBuf<unsigned long long> tol_bits;

@@ -639,6 +639,50 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   }
 }
 
+// rdfs.F90:146-212 rdf_collect / :880-946 rdf_excl_collect over the device rows: one warp per row, a per-block histogram in
+// shared memory (counts are integers, so the sums are exact in any order).  The distance is the reference's
+// Sqrt(xxt**2 + yyt**2 + zzt**2) (IEEE, unfused) because the bin index Int(rrr * rdelr) has to agree bit for bit.
+__global__ void k_rdf_collect(int natms, int pitch, int xpitch, int lbook, int ntypes, int n_pairs, int max_grid, double rcut,
+                              double rdelr, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s,
+                              const int2* __restrict__ info_s, const unsigned* __restrict__ nbr, const int* __restrict__ nnbr,
+                              const unsigned* __restrict__ xnbr, const int* __restrict__ nxnbr, const int* __restrict__ rdf_list,
+                              unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned s_hist[];
+  const int nbin = n_pairs * max_grid;
+  for (int k = threadIdx.x; k < nbin; k += blockDim.x) s_hist[k] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < natms; t += gridDim.x * wpb) {
+    const int ii = loc_slot[t];
+    const double4 pi = posq_s[ii];
+    const int ai = info_s[ii].y & 0xffff;
+    for (int pass = 0; pass < (lbook ? 2 : 1); ++pass) {
+      const unsigned* row = pass ? xnbr + (size_t)t * xpitch : nbr + (size_t)t * pitch;
+      const int n = pass ? nxnbr[t] : nnbr[t];
+      for (int k = lane; k < n; k += 32) {
+        const unsigned e = row[k];
+        if ((e & (DLP_F_HALO | DLP_F_ECNT)) == DLP_F_HALO) continue;          // jatm <= natms .or. idi < ltg(jatm)
+        const int j = (int)(e & DLP_J_MASK);
+        const int aj = info_s[j].y & 0xffff;
+        const int hi = max(ai, aj), lo = min(ai, aj);
+        const int kk = rdf_list[(hi * (hi - 1)) / 2 + lo - 1];
+        if (kk <= 0 || kk > n_pairs) continue;
+        const double4 pj = posq_s[j];
+        const double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;
+        const double rrr = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        if (rrr < rcut) {
+          const int ll = min(1 + __double2int_rz(__dmul_rn(rrr, rdelr)), max_grid);
+          atomicAdd(&s_hist[(kk - 1) * max_grid + ll - 1], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nbin; k += blockDim.x)
+    if (s_hist[k]) atomicAdd(&hist[k], (unsigned long long)s_hist[k]);
+}
+
 // half mode epilogue: f(i) (+)= [row sum of atom i] - [what its partners' rows pushed onto it]
 __global__ void k_scatter_half(int natms, int zero_forces, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
                                const double* __restrict__ fpos, const double* __restrict__ fneg, double* fx, double* fy, double* fz) {
@@ -938,6 +982,34 @@ int dlpgpu_dev_two_body_forces(dlpgpu_ctx* ctx, int zero_forces, double out[16])
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   return dlp_two_body(ctx, zero_forces, out);
+}
+
+int dlpgpu_rdf_collect(dlpgpu_ctx* ctx, int ntypes, const int* rdf_list, int n_pairs, int max_grid, double* rdf) {
+  if (!ctx || !rdf_list || !rdf || ntypes < 1 || n_pairs < 1 || max_grid < 1) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->list_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "rdf_collect: no valid neighbour list");
+  if (ctx->force_mode != 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "rdf_collect needs the half list (force mode 1)");
+  const size_t nbin = (size_t)n_pairs * max_grid;
+  if (nbin * sizeof(unsigned) > 200 * 1024) return dlp_fail(ctx, DLPGPU_ERR_ARG, "rdf_collect: %d x %d bins do not fit shared memory", n_pairs, max_grid);
+  cudaStream_t s = ctx->stream;
+  const int nkey = ntypes * (ntypes + 1) / 2;
+  CK(ctx->rdf_list.ensure(nkey, s)); CK(ctx->rdf_hist.ensure(nbin, s));
+  CK(cudaMemcpyAsync(ctx->rdf_list.p, rdf_list, nkey * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->rdf_hist.p, 0, nbin * sizeof(unsigned long long), s));
+  const int natms = ctx->list_natms;
+  if (natms > 0) {
+    const int threads = 256, blocks = std::min(cdiv(natms, threads / 32), ctx->sm_count * 4);
+    CK(cudaFuncSetAttribute(k_rdf_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbin * sizeof(unsigned))));
+    LAUNCH(ctx, k_rdf_collect, blocks, threads, nbin * sizeof(unsigned), natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->lbook, ntypes, n_pairs,
+           max_grid, ctx->rcut, (double)max_grid / ctx->rcut, ctx->loc_slot.p, ctx->posq_s.p, ctx->info_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->rdf_list.p, ctx->rdf_hist.p);
+  }
+  std::vector<unsigned long long> h(nbin);
+  CK(cudaMemcpyAsync(h.data(), ctx->rdf_hist.p, nbin * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  for (size_t k = 0; k < nbin; ++k) rdf[k] += (double)h[k];
+  return 0;
 }
 
 int dlpgpu_dev_fetch_results(dlpgpu_ctx* ctx, double out[16]) {

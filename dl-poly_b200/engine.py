@@ -129,6 +129,15 @@ class ShortRange:
         self._ck(self.L.dlpgpu_two_body_forces(self.h, int(natms), int(nlast), ptr(parts), ptr(out)))
         return out
 
+    def rdf_collect(self, ntypes, rdf_list, n_pairs, max_grid, rdf=None):
+        """rdf_collect + rdf_excl_collect on the device list; rdf: (n_pairs, max_grid) float64 counts, incremented."""
+        lst = np.ascontiguousarray(rdf_list, dtype=np.int32)
+        if rdf is None:
+            rdf = np.zeros((n_pairs, max_grid))
+        assert rdf.dtype == np.float64 and rdf.flags.c_contiguous and rdf.shape == (n_pairs, max_grid)
+        self._ck(self.L.dlpgpu_rdf_collect(self.h, int(ntypes), ptr(lst), int(n_pairs), int(max_grid), ptr(rdf)))
+        return rdf
+
     def vnl_check(self, natms, parts):
         tol = C.c_double(0.0)
         self._ck(self.L.dlpgpu_vnl_check(self.h, int(natms), ptr(parts), C.byref(tol)))

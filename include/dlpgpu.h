@@ -112,6 +112,12 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
  * dlpgpu_two_body_forces then works on the copy that call left on the device and skips its own 64 nlast-byte upload.
  * One-shot: the assertion is consumed by the next dlpgpu_two_body_forces. */
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
+/* rdfs.F90:146-212 rdf_collect and :880-946 rdf_excl_collect for the atoms and list of the last dlpgpu_two_body_forces /
+ * dlpgpu_dev_two_body_forces call (two_body_forces calls them inside its loops, two_body.F90:523, :581):
+ * rdf_list(1:ntypes(ntypes+1)/2) = rdf%list (0 or > n_pairs: pair not collected), rdf = rdf%rdf(1:max_grid,1:n_pairs)
+ * column-major on the host, INCREMENTED by this rank's counts.  Frozen-frozen pairs (rdf_frzn_collect) are not kept on the
+ * device and stay with the caller. */
+int dlpgpu_rdf_collect(dlpgpu_ctx* ctx, int ntypes, const int* rdf_list, int n_pairs, int max_grid, double* rdf);
 /* neighbours.F90:157-171: tol = max_i |r_i - r_bg,i| (minimum image) over parts(1:natms); caller does gmax + test */
 int dlpgpu_vnl_check(dlpgpu_ctx* ctx, int natms, const dlpgpu_corepart* parts, double* tol);
 int dlpgpu_vnl_set_check(dlpgpu_ctx* ctx, int nlast, const dlpgpu_corepart* parts);

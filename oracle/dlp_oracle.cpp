@@ -1532,6 +1532,36 @@ Acc ewald_excl_forces(World& w, Dom& dom, int iatm, const double* xxt, const dou
   return {engcpe_ex, vircpe_ex};
 }
 
+// rdfs.F90:146-212 rdf_collect (active pairs) and :880-946 rdf_excl_collect (excluded pairs), as two_body_forces calls them
+// (two_body.F90:523, :581) with the same distance arrays.  rdf(ll,kk) is (1:max_grid, 1:n_pairs), column-major, counts.
+void rdf_collect_domain(World& w, Dom& dom, const int* rdf_list /*1-based keys*/, int n_pairs, int max_grid, double* rdf) {
+  const double rdelr = (double)max_grid / w.rcut;
+  CorePart* parts = dom.parts.data();
+  auto collect = [&](int iatm, int first, int count) {
+    int idi = dom.ltg[iatm], ai = dom.ltype[iatm];
+    for (int m = 1; m <= count; ++m) {
+      int jatm = dom.L(first + m, iatm);
+      int aj = dom.ltype[jatm];
+      if (jatm <= dom.natms || idi < dom.ltg[jatm]) {
+        int keyrdf = (std::max(ai, aj) * (std::max(ai, aj) - 1)) / 2 + std::min(ai, aj);
+        int kk = rdf_list[keyrdf - 1];
+        if (kk > 0 && kk <= n_pairs) {
+          double xx = parts[iatm].xxx - parts[jatm].xxx, yy = parts[iatm].yyy - parts[jatm].yyy, zz = parts[iatm].zzz - parts[jatm].zzz;
+          double rrr = std::sqrt(xx * xx + yy * yy + zz * zz);
+          if (rrr < w.rcut) {
+            int ll = std::min(1 + f_int(rrr * rdelr), max_grid);
+            rdf[(size_t)(kk - 1) * max_grid + (ll - 1)] += 1.0;
+          }
+        }
+      }
+    }
+  };
+  for (int i = 1; i <= dom.natms; ++i) {
+    collect(i, 0, dom.L(0, i));                                         // rdf_collect
+    if (w.lbook) collect(i, dom.L(0, i), dom.L(-1, i) - dom.L(0, i));   // rdf_excl_collect
+  }
+}
+
 // two_body.F90:339-525 + :552-606 : the two outer loops (per domain).  Forces are ADDED into parts%f.
 void two_body_forces(World& w, Dom& dom) {
   const int ml = dom.max_list;
@@ -1973,6 +2003,10 @@ int ora_world_two_body(void* h, int nthreads, int zero_forces, double* out15) {
     }
   }
   return 0;
+}
+void ora_world_rdf_collect(void* h, const int* rdf_list, int n_pairs, int max_grid, double* rdf /* max_grid*n_pairs, += */) {
+  World* w = (World*)h;
+  for (Dom& d : w->d) rdf_collect_domain(*w, d, rdf_list, n_pairs, max_grid, rdf);
 }
 // per-domain accessors
 void ora_dom_counts(void* h, int rank, int* out /*natms,nlast,max_list,max_exclude,nlx,nly,nlz,nlp,ncells,nsbcll,ibig*/) {

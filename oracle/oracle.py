@@ -263,6 +263,13 @@ class World:
         self.L.ora_world_two_body(self.h, C.c_int(nthreads), C.c_int(int(zero_forces)), _vp(out))
         return out
 
+    def rdf_collect(self, rdf_list, n_pairs, max_grid):
+        """rdf_collect + rdf_excl_collect over every domain; returns the counts as (n_pairs, max_grid)."""
+        lst = _i(rdf_list)
+        rdf = np.zeros((n_pairs, max_grid))
+        self.L.ora_world_rdf_collect(self.h, _vp(lst), C.c_int(n_pairs), C.c_int(max_grid), _vp(rdf))
+        return rdf
+
     def vv(self, stage, dt, weight_by_type):
         wt = _d(weight_by_type)
         self.L.ora_world_vv(self.h, C.c_int(stage), C.c_double(dt), _vp(wt))

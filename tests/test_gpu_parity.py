@@ -424,3 +424,31 @@ def test_c4_table_1m_fast_kernel_against_general_kernel(monkeypatch):
     assert abs((of[6] + of[10] + of[14]) + vir) <= 1e-10 * abs(vir)
     assert of[7] == of[9] and of[8] == of[12] and of[11] == of[13]
     fast.close(); slow.close()
+
+
+@pytest.mark.parametrize("which,P", [("nacl", 1), ("nacl", 8), ("water", 1)])
+def test_rdf_collect_counts_are_exact(which, P):
+    """rdf_collect / rdf_excl_collect (rdfs.F90:146-212, :880-946) on the device list: integer pair counts per (bin, type
+    pair), summed over the domains, equal the oracle's exactly (bin index from the reference's IEEE distance)."""
+    s = systems.nacl(8 if P > 1 else 4, rcut=8.0, padding=0.2) if which == "nacl" else systems.spce_water(512, rcut=8.0, padding=0.2)
+    w = world_for(s, P=P)
+    nt = s.ff.ntypes
+    nkey = nt * (nt + 1) // 2
+    rdf_list = np.arange(1, nkey + 1, dtype=np.int32)       # every type pair collected, kk = key
+    if which == "water":
+        rdf_list[1] = 0                                     # ... except O-H
+    n_pairs, max_grid = nkey, 250
+    ref = w.rdf_collect(rdf_list, n_pairs, max_grid)
+    got = np.zeros((n_pairs, max_grid))
+    for r in range(P):
+        d = domain_inputs(w, r)
+        sr = make_sr(s, d["dd"])
+        sr.set_force_mode(1)
+        parts = d["parts"].copy()
+        sr.link_cell_pairs(d["natms"], d["nlast"], parts, d["ltype"], d["ltg"], d["lfrzn"], lbook=s.lbook, megfrz=s.megfrz,
+                           list_excl=d["list_excl"], max_list=d["max_list"], want_list=False)
+        sr.two_body_forces(d["natms"], d["nlast"], parts)
+        sr.rdf_collect(nt, rdf_list, n_pairs, max_grid, got)
+        sr.close()
+    assert ref.sum() > 1000
+    assert np.array_equal(got, ref)
