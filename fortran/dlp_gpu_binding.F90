@@ -25,6 +25,7 @@ Module dlp_gpu_binding
   Use configuration,   Only: configuration_type
   Use constants,       Only: r4pie0
   Use domains,         Only: domains_type
+  Use rdfs,            Only: rdf_type
   Use electrostatic,   Only: electrostatic_type, ELECTROSTATIC_COULOMB, ELECTROSTATIC_DDDP, &
                              ELECTROSTATIC_COULOMB_FORCE_SHIFT, ELECTROSTATIC_COULOMB_REACTION_FIELD
   Use errors_warnings, Only: error
@@ -122,6 +123,13 @@ Module dlp_gpu_binding
       Type(c_ptr), Value           :: parts
       Real(c_double), Intent(Out)  :: out(16)
       Integer(c_int)               :: rc
+    End Function
+    Function dlpgpu_rdf_collect(ctx, ntypes, rdf_list, n_pairs, max_grid, rdf) Bind(C, name='dlpgpu_rdf_collect') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int), Value :: ntypes, n_pairs, max_grid
+      Type(c_ptr), Value    :: rdf_list, rdf
+      Integer(c_int)        :: rc
     End Function
     Function dlpgpu_parts_unchanged_since_list(ctx) Bind(C, name='dlpgpu_parts_unchanged_since_list') Result(rc)
       Import :: c_ptr, c_int
@@ -313,6 +321,17 @@ Contains
     engcpe_ex = engcpe_ex + out(5); vircpe_ex = vircpe_ex + out(6)
     stats%stress(1:9) = stats%stress(1:9) + out(7:15)
   End Subroutine two_body_pairs_gpu
+
+  Subroutine rdf_collect_gpu(ntpatm, rdf)
+    !! replaces the per-atom Call rdf_collect / rdf_excl_collect inside two_body_forces (two_body.F90:523, :581) on steps with
+    !! l_do_rdf: the counts of this rank's pairs are added to rdf%rdf(1:max_grid, 1:n_pairs).  Call after two_body_pairs_gpu.
+    !! (rdf%tmp_rdf block statistics and rdf_frzn_collect stay on the host path.)
+    Integer,        Intent(In   )         :: ntpatm
+    Type(rdf_type), Intent(InOut), Target :: rdf
+
+    Call check(dlpgpu_rdf_collect(ctx, Int(ntpatm, c_int), c_loc(rdf%list), Int(rdf%n_pairs, c_int), Int(rdf%max_grid, c_int), &
+                                  c_loc(rdf%rdf)), 'rdf_collect')
+  End Subroutine rdf_collect_gpu
 
   Function dlp_gpu_vnl_tolerance(config) Result(tol)
     !! neighbours.F90:157-171: max_i |r_i - r_bg,i| over the local atoms; the caller keeps gmax and the comparison
