@@ -40,7 +40,7 @@ Module dlp_gpu_binding
 
   Type(c_ptr), Save :: ctx = c_null_ptr
 
-  Public :: dlp_gpu_init, dlp_gpu_finalise, dlp_gpu_set_forcefield, link_cell_pairs_gpu, two_body_pairs_gpu, &
+  Public :: dlp_gpu_init, dlp_gpu_finalise, dlp_gpu_set_forcefield, link_cell_pairs_gpu, two_body_pairs_gpu, rdf_collect_gpu, &
             dlp_gpu_vnl_tolerance
 
   Interface
