@@ -411,7 +411,7 @@ __device__ __forceinline__ double h_exact(float h32, double g_unit) {
 template <int VT, int EW, int SG, int X = 0, int TX = 0>
 __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, const double2* __restrict__ sG, const double2* __restrict__ sH, const double4& pi,
                                       double qi_s, unsigned e, const double4& pj, double& fix, double& fiy, double& fiz, double* acc,
-                                      double* __restrict__ fneg) {
+                                      double* __restrict__ fneg, bool second = false) {
   constexpr double MAGIC = 4503599627370496.0;   // 2^52
   const double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;             // two_body.F90:348-350
   const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
@@ -476,7 +476,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
   acc[3] = __fma_rn(wx, f1, acc[3]); acc[4] = __fma_rn(wx, f2, acc[4]); acc[5] = __fma_rn(wx, f3, acc[5]);
   acc[6] = __fma_rn(wy, f2, acc[6]); acc[7] = __fma_rn(wy, f3, acc[7]); acc[8] = __fma_rn(wz, f3, acc[8]);
   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161); local partners only
-  if (!(X & 1) && (e & DLP_F_HALO) == 0u && (in_v || in_c)) {
+  if (!(X & 1) && !((X & 32) && second) && (e & DLP_F_HALO) == 0u && (in_v || in_c)) {
     double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
     atomicAdd(q, f1); atomicAdd(q + 4, f2); atomicAdd(q + 8, f3);
   }
@@ -555,23 +555,23 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
     unsigned ea = LE(0), eb = LE(1);
     unsigned ec = LE(2), ed = LE(3);
 #define GA(e) ((X & 4) ? (posq_s + ((blockIdx.x * NT + threadIdx.x + ((e) & 0xff)) % (unsigned)P.natms)) : (posq_s + ((e) & DLP_J_MASK)))
-    double4 pa = ld_posq(GA(ea)), pb = ld_posq(GA(eb));
+    double4 pa = ld_posq(GA(ea)), pb = (X & 32) ? pa : ld_posq(GA(eb));
     for (int k = 0; k < npad; k += 4 * TPR) {
       {
-        const double4 pc = ld_posq(GA(ec)), pd = ld_posq(GA(ed));
+        const double4 pc = ld_posq(GA(ec)), pd = (X & 32) ? pc : ld_posq(GA(ed));
         const unsigned e0 = ea, e1 = eb;
         ea = LE(4); eb = LE(5);
         pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg, true);
         pa = pc; pb = pd;
       }
       if (k + 2 * TPR >= npad) break;
       {
-        const double4 pc = ld_posq(GA(ea)), pd = ld_posq(GA(eb));
+        const double4 pc = ld_posq(GA(ea)), pd = (X & 32) ? pc : ld_posq(GA(eb));
         const unsigned e0 = ec, e1 = ed;
         ec = LE(6); ed = LE(7);
         pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
+        pair2<VT, EW, SG, X, TX>(P, tex, sG, sH, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg, true);
         pa = pc; pb = pd;
       }
       row += 4 * TPR;
@@ -917,6 +917,18 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
     if (ctx->variant > 0 && ctx->variant != 100 && v && e && sg) {   // timing experiments only (DLPGPU_VARIANT): results are not meaningful
       const int xv = ctx->variant & 0xfff, ntc = ctx->variant >> 12;
 #define DLP_V2N(XV) do { if (ntc == 0) DLP_V2X(XV, 512); else if (ntc == 1) DLP_V2X(XV, 640); else DLP_V2X(XV, 768); } while (0)
+      if (xv == 32 || xv == 0x800) {   // on the default fp32-h layout: 32 = one gather + one RED triple per two pairs (emulates 2 x 1 clusters)
+        const size_t smem8 = (size_t)ctx->tab2_ne * 16;
+        if (xv == 32) {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 32, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+                 t2s, fpos, fneg, ctx->partial.p);
+        } else {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+                 t2s, fpos, fneg, ctx->partial.p);
+        }
+      } else
       switch (xv) {
         case 1: DLP_V2N(1); break; case 2: DLP_V2N(2); break; case 4: DLP_V2N(4); break; case 8: DLP_V2N(8); break;
         case 256: DLP_V2N(256); break;
