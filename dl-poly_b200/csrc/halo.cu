@@ -443,8 +443,8 @@ __global__ void k_x_reloc_tag(const int* __restrict__ dc, Mat9 rcell, DomI D, co
 // ---- stage kernels: count -> pack (+ signal) -> [restack] -> receive (+ bookkeeping): 3 launches per halo stage, 4 per
 // migration stage.  A block owns XB_N consecutive atoms, eight per thread, so packed order = ascending local index (the
 // reference's buffer order).  The last block to finish (a ticket in the counts block) does the one-thread work.
-#define XB_T 512
-#define XB_A 8
+#define XB_T 256
+#define XB_A 4
 #define XB_N (XB_T * XB_A)
 #define DC_TICKET 4
 #define DC_NOLD 5
@@ -539,10 +539,11 @@ k_x_pack(int* __restrict__ dc, Dir d, int cap, int q, const int* __restrict__ bl
     }
   }
   // the last block publishes count + sequence to the receiver and settles the local counts.  The barrier orders the
-  // block's payload stores before thread 0's system-scope fence (cumulative), the ticket chains the blocks.
+  // block's payload stores before thread 0's device-scope fence, the ticket chains the blocks, and only the last block pays
+  // for the system-scope fence in front of the release store (fences are cumulative along this chain).
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();
     s_last = (atomicAdd(&dc[DC_TICKET], 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
