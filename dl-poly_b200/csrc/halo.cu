@@ -401,7 +401,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 // true when the header carries `seq`; gives up after a few seconds and raises DCNT_ERR bit 2 (a peer died / lost lock-step)
 __device__ bool x_wait(const unsigned long long* seq_word, unsigned long long seq, int* err) {
-  for (long long it = 0; it < 4000000LL; ++it) {
+  for (long long it = 0; it < 20000000LL; ++it) {   // several seconds
     if (ld_acquire_sys(seq_word) == seq) return true;
     if ((it & 1023) == 1023 && (*(volatile int*)err & 4)) return false;   // somebody already gave up: do not wait again
     __nanosleep(200);

@@ -324,7 +324,7 @@ class Domain:
         self.rseq = 0
         self.gseq = 0
         if self.xchg:
-            cap_r, cap_h = exchange_capacities(sysm, self.dims)
+            cap_r, cap_h = exchange_capacities(sysm, self.dims, safety=float(os.environ.get("DLP_DD_CAP_SAFETY", "2.0")))
             blob = self.sr.dev_xchg_init(self.rank, self.world, cap_r, cap_h)
             if self.world > 1:
                 t_blob = torch.from_numpy(blob.copy()).to(self.device)
