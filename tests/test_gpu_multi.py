@@ -1,4 +1,4 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): scripts/dd_check.py under torch.distributed.run."""
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): tests/dd_check.py under torch.distributed.run."""
 import os
 import subprocess
 import sys
@@ -19,7 +19,7 @@ def test_two_domains_against_oracle(which):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29655", os.path.join(ROOT, "scripts", "dd_check.py"), which]
+           "--master-port", "29655", os.path.join(ROOT, "tests", "dd_check.py"), which]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "OK" in r.stdout
