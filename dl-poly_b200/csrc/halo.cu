@@ -1243,4 +1243,38 @@ int dlp_vv1_fused(dlpgpu_ctx* ctx, double dt) {
   return 0;
 }
 
+// One MD step of the native driver around the path (md_vv, drivers.F90:1910-2290) enqueued from C, so that the device does
+// not wait for an interpreter between the gmax decision and the force kernels: velocity-Verlet stage 1 (+ displacement
+// maximum + publish), gmax through the peers' mailboxes (the step's only host synchronisation), then either
+// relocate_particles + set_halo_particles + link_cell_pairs (neighbours.F90:182 says rebuild) or the one-kernel halo
+// refresh, two_body_forces without waiting for its sums, velocity-Verlet stage 2.  The sums of the PREVIOUS step's force
+// call are handed back (they completed before this step's synchronisation); *have_prev says whether there were any.
+int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned long long gseq, unsigned long long rseq, int* rebuilt,
+                       double out_prev[16], int* have_prev, double* list_ms) {
+  if (!ctx || !neigh || !rebuilt || !out_prev || !have_prev) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->xr_ready) return dlp_fail(ctx, DLPGPU_ERR_STATE, "md_step: exchange region not ready");
+  CKRC(dlpgpu_dev_vv(ctx, 1, dt));
+  if (ctx->pub[0]) CKRC(dlpgpu_dev_publish(ctx));
+  double tol = 0.0;
+  CKRC(dlpgpu_dev_xchg_gmax(ctx, gseq, &tol));
+  *have_prev = 0;
+  if (ctx->res_pending) { CKRC(dlpgpu_dev_fetch_results(ctx, out_prev)); *have_prev = 1; }
+  const double half_minus = 0.499999999999999944488848768742172978818416595458984375;
+  *rebuilt = (tol >= half_minus * ctx->padding) ? 1 : 0;                       // neighbours.F90:182
+  if (list_ms) *list_ms = 0.0;
+  if (*rebuilt) {
+    CKRC(dlpgpu_dev_xchg_rebuild(ctx, neigh, rseq, nullptr, nullptr));
+    int ibig = 0;
+    CKRC(dlp_build_lists(ctx, 0, &ibig));
+    if (list_ms) *list_ms = ctx->t_list;
+  } else if (ctx->pub[0]) {
+    CKRC(dlpgpu_dev_refresh_pull(ctx));
+  } else {
+    CKRC(dlpgpu_dev_refresh_serial(ctx));
+  }
+  CKRC(dlp_two_body(ctx, 1, nullptr));
+  return dlpgpu_dev_vv(ctx, 2, dt);
+}
+
 }  // extern "C"

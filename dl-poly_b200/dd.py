@@ -447,6 +447,22 @@ class Domain:
         sr = self.sr
         if self.profile is not None:
             return self._step_profiled(dt)
+        if lazy and self.xchg and self.p2p:
+            # the whole step is enqueued by the library (dlpgpu_dev_md_step): no interpreter between the gmax decision and
+            # the force kernels
+            self.gseq += 1
+            reb, prev, list_ms = sr.dev_md_step(self.neigh, dt, self.gseq, self.rseq + 1)
+            if prev is not None:
+                self.last_out = prev
+                self._account()
+            if reb:
+                self.rseq += 1
+                self.rebuilds += 1
+                self._refresh_bufs = None
+                self.acc["list_ms"] += list_ms; self.acc["list_builds"] += 1
+            self._pending = True
+            self.steps += 1
+            return self.last_out
         with self.torch.cuda.stream(self.stream):
             sr.dev_vv(1, dt)
         self.publish()                       # before the gmax: the collective orders every rank's publish before any pull

@@ -258,6 +258,20 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_xchg_gmax(self.h, C.c_ulonglong(int(seq)), C.byref(tol)))
         return tol.value
 
+    def dev_md_step(self, neigh, dt, gseq, rseq):
+        """One MD step enqueued from C (see dlpgpu_dev_md_step); returns (rebuilt, previous step's sums or None, list_ms)."""
+        nb = self._neigh_cache.get(tuple(neigh)) if hasattr(self, "_neigh_cache") else None
+        if nb is None:
+            if not hasattr(self, "_neigh_cache"):
+                self._neigh_cache = {}
+                self._step_out = np.zeros(16)
+            nb = np.ascontiguousarray(neigh, dtype=np.int32)
+            self._neigh_cache[tuple(neigh)] = nb
+        reb, have, lms = C.c_int(0), C.c_int(0), C.c_double(0.0)
+        self._ck(self.L.dlpgpu_dev_md_step(self.h, ptr(nb), float(dt), C.c_ulonglong(int(gseq)), C.c_ulonglong(int(rseq)), C.byref(reb),
+                                           ptr(self._step_out), C.byref(have), C.byref(lms)))
+        return bool(reb.value), (self._step_out.copy() if have.value else None), lms.value
+
     def dev_halo_stage_counts(self):
         a, b = np.zeros(6, dtype=np.int32), np.zeros(6, dtype=np.int32)
         self._ck(self.L.dlpgpu_dev_halo_stage_counts(self.h, ptr(a), ptr(b)))

@@ -60,6 +60,7 @@ SIGNATURES = {
     "dlpgpu_dev_xchg_open": (ci, [vp, vp]),
     "dlpgpu_dev_xchg_rebuild": (ci, [vp, vp, C.c_ulonglong, pi_, pi_]),
     "dlpgpu_dev_xchg_gmax": (ci, [vp, C.c_ulonglong, pd_]),
+    "dlpgpu_dev_md_step": (ci, [vp, vp, cd, C.c_ulonglong, C.c_ulonglong, pi_, vp, pi_, pd_]),
     "dlpgpu_dev_halo_stage_counts": (ci, [vp, vp, vp]),
     "dlpgpu_dev_halo_serial": (ci, [vp]),
     "dlpgpu_dev_refresh_serial": (ci, [vp]),

@@ -176,6 +176,13 @@ int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_at
 int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
 int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long long seq, int* natms, int* nlast);
 int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol);
+/* One MD step of the native driver around the path (md_vv, drivers.F90:1910-2290), enqueued from C: dev_vv(1) + publish,
+ * xchg_gmax (the only host synchronisation), then xchg_rebuild + link_cell_pairs when tol >= half_minus * padding
+ * (neighbours.F90:182; *rebuilt = 1, *list_ms = time of the list build) or the one-kernel halo refresh, two_body_forces
+ * without waiting for its sums, dev_vv(2).  out_prev / *have_prev: the sums of the previous step's force call, if one was
+ * pending; collect the last step's with dlpgpu_dev_fetch_results.  gseq / rseq: as for xchg_gmax / xchg_rebuild. */
+int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned long long gseq, unsigned long long rseq,
+                       int* rebuilt, double out_prev[16], int* have_prev, double* list_ms);
 /* atoms sent / received in each of the six stages of the last halo build (order -x,+x,-y,+y,-z,+z) */
 int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]);
 /* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */
