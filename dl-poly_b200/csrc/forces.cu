@@ -884,10 +884,13 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   }
   cudaEventRecord(ctx->ev[6], s);
   const bool xc = P.lbook && P.ew_on;   // rows carry excluded partners: the fast kernel has them for the vdW + Ewald, one-grid case
-  const bool fast = P.half && use_smem && !ctx->no_fast && !P.coul_kind && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
+  const bool fast = P.half && !ctx->no_fast && !P.coul_kind && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
                     tpr == 8 && (!xc || (P.vdw_on && P.ew_on && P.same_grid));
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
-  const bool fast2 = fast && smem2 + 2048 <= 227 * 1024;
+  // the fp32-h layout keeps only the g units in shared memory (16 B per entry): force fields with many potentials still fit
+  const bool can8_pre = P.vdw_on && P.ew_on && P.same_grid && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul &&
+                        (ctx->tx_override < 0 || ctx->tx_override == 8);
+  const bool fast2 = fast && (can8_pre ? smem2 / 2 : smem2) + 2048 <= 227 * 1024;
   if (natms > 0 && fast2) {
     P2 Q{};
     Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;

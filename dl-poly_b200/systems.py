@@ -152,6 +152,31 @@ def nacl(ncell=15, seed=1002, rcut=12.0, padding=0.24, tabfile=False, direct=Fal
                   [22.9898, 35.453], ff, rcut, padding, temperature=temperature, seed=seed)
 
 
+def ionic_mixture(ncell=4, ntypes=4, seed=1010, rcut=8.0, padding=0.2, jitter=0.3, temperature=800.0, spme_precision=1.0e-6):
+    """A rock-salt lattice with ``ntypes`` species (charges alternate +1 / -1) and a tabulated 12-6 potential for EVERY type
+    pair (ntypes (ntypes + 1) / 2 tables) next to real-space Ewald: the force field with many potentials."""
+    nc = np.array(_n3(ncell), dtype=np.float64)
+    n = int(8 * nc.prod())
+    a = 6.2
+    L = nc * a
+    xyz, parity = _rocksalt(ncell, a, seed, jitter)
+    rng = np.random.default_rng(seed + 1)
+    half = ntypes // 2
+    species = np.where(parity == 1, 1 + 2 * rng.integers(0, ntypes - half, n), 2 + 2 * rng.integers(0, half, n)).astype(np.int32)
+    ff = tables.ForceField(ntypes, rcut, rcut)
+    for i in range(1, ntypes + 1):
+        for j in range(i, ntypes + 1):
+            sig = 2.2 + 0.15 * (i + j)
+            eps = 40.0 + 7.0 * i * j
+            ff.add(i, j, "12-6", [4 * eps * sig ** 12, 4 * eps * sig ** 6])
+    ff.set_ewald(precision=spme_precision)
+    ff.finalize()
+    q = [1.0 if t % 2 == 1 else -1.0 for t in range(1, ntypes + 1)]
+    w = [20.0 + 3.0 * t for t in range(1, ntypes + 1)]
+    return System("mixture-%d-%dtypes" % (n, ntypes), np.diag(L), xyz, species, list(range(1, ntypes + 1)), q, w, ff, rcut, padding,
+                  temperature=temperature, seed=seed)
+
+
 def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0e-6, temperature=0.0, coulomb=None, eps=1.0,
                damping=0.0):
     """C3: SPC/E water, 3*nmol atoms, rigid geometry 1.0 A / 109.47 deg, random orientations, O-O LJ, exclusions =

@@ -119,6 +119,13 @@ def test_direct_space_coulomb_variants(kind, eps, damping):
     check_dropin(systems.spce_water(512, rcut=8.0, padding=0.2, coulomb=kind, eps=eps, damping=damping), 1, mode=1)
 
 
+def test_many_potentials_fit_the_fp32_h_layout():
+    """Four species = ten vdW tables + Ewald: 424 KB in the fp64 table layout, 212 KB of g units in the fp32-h layout -- the
+    fast kernel still applies; five species (16 tables) fall back to the general kernel with tables in global memory."""
+    check_dropin(systems.ionic_mixture(4, ntypes=4), 1, mode=1)
+    check_dropin(systems.ionic_mixture(3, ntypes=5), 1, mode=1)
+
+
 def test_nacl_bhm_direct():
     check_dropin(systems.nacl(4, rcut=8.0, padding=0.2, direct=True), 1)
 
