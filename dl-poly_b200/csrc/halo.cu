@@ -1254,6 +1254,8 @@ int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned 
   if (!ctx || !neigh || !rebuilt || !out_prev || !have_prev) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->xr_ready) return dlp_fail(ctx, DLPGPU_ERR_STATE, "md_step: exchange region not ready");
+  if (ctx->nx * ctx->ny * ctx->nz > 1 && !(ctx->pub[0] && ctx->p2p_ready))
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "md_step: several domains need the peer-memory halo refresh (p2p_init / p2p_open)");
   CKRC(dlpgpu_dev_vv(ctx, 1, dt));
   if (ctx->pub[0]) CKRC(dlpgpu_dev_publish(ctx));
   double tol = 0.0;
