@@ -312,13 +312,26 @@ class Domain:
         import os
         # peer-memory refresh: publish buffers sized for the local atoms with head-room for migration
         self.p2p = os.environ.get("DLP_DD_STAGED_REFRESH") is None
+        def all_ok(ok):
+            """True only if the step succeeded on every rank (peer memory is all-or-nothing across the ranks)."""
+            return ok if self.world == 1 else self.t.allreduce_max(0.0 if ok else 1.0) == 0.0
+
+        def gather_blobs(blob):
+            t_blob = torch.from_numpy(blob.copy()).to(self.device)
+            allb = [torch.empty_like(t_blob) for _ in range(self.world)]
+            self.t.dist.all_gather(allb, t_blob, group=self.t.group)
+            return torch.cat(allb).cpu().numpy()
+
+        from .lib import DlpError
         if self.p2p:
-            blob = sr_blob = self.sr.dev_p2p_init(self.rank, self.world, int(1.25 * self.natms0) + 8192)
+            blob = self.sr.dev_p2p_init(self.rank, self.world, int(1.25 * self.natms0) + 8192)
             if self.world > 1:
-                t_blob = torch.from_numpy(blob.copy()).to(self.device)
-                allb = [torch.empty_like(t_blob) for _ in range(self.world)]
-                self.t.dist.all_gather(allb, t_blob, group=self.t.group)
-                self.sr.dev_p2p_open(torch.cat(allb).cpu().numpy())
+                allb = gather_blobs(blob)
+                try:
+                    self.sr.dev_p2p_open(allb); ok = True
+                except DlpError:
+                    ok = False          # no CUDA-IPC peer access between these GPUs: fall back to the NCCL message path
+                self.p2p = all_ok(ok)
         # fused device-side exchange (migration + halo build + gmax over peer memory, no NCCL, one host sync per rebuild)
         self.xchg = self.p2p and os.environ.get("DLP_DD_STAGED_EXCHANGE") is None
         self.rseq = 0
@@ -327,10 +340,12 @@ class Domain:
             cap_r, cap_h = exchange_capacities(sysm, self.dims, safety=float(os.environ.get("DLP_DD_CAP_SAFETY", "2.0")))
             blob = self.sr.dev_xchg_init(self.rank, self.world, cap_r, cap_h)
             if self.world > 1:
-                t_blob = torch.from_numpy(blob.copy()).to(self.device)
-                allb = [torch.empty_like(t_blob) for _ in range(self.world)]
-                self.t.dist.all_gather(allb, t_blob, group=self.t.group)
-                self.sr.dev_xchg_open(torch.cat(allb).cpu().numpy())
+                allb = gather_blobs(blob)
+                try:
+                    self.sr.dev_xchg_open(allb); ok = True
+                except DlpError:
+                    ok = False
+                self.xchg = all_ok(ok)
                 self.t.barrier()
         self.profile = {} if os.environ.get("DLP_DD_PROFILE") else None
 
