@@ -479,7 +479,7 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
 #define LC_MAXRUN 96
 struct LCRow { int dy, dz, b; };
 
-template <bool SIMPLE>   // SIMPLE: no exclusion lists, no frozen pairs, nlp < 3 -- the lean inner loop
+template <int SIMPLE>   // 1: no exclusion lists, no frozen pairs, nlp < 3 -- the lean inner loop; 2: the lean loop with exclusion lists
 __global__ void __launch_bounds__(LC_WARPS * 32)
 k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid, int nrows,
             const LCRow* __restrict__ rows, const int* __restrict__ at_list, const int* __restrict__ lct_start,
@@ -491,6 +491,8 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   __shared__ int2 s_info[LC_WARPS][32];
   __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
   __shared__ int s_pre[LC_WARPS][LC_MAXRUN + 1];   // candidates before run r
+  __shared__ int s_exn[LC_WARPS][32];                       // exclusion count / list of the cell's atoms (SIMPLE == 2)
+  __shared__ unsigned long long s_exp[LC_WARPS][32];
   __shared__ int s_pk[256];                        // (type_i, type_j) -> vdW potential index + 1, when ntypes <= 16
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool pk_smem = pair_k != nullptr && ntypes <= 16;
@@ -570,7 +572,9 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
       // only -- its vdW potential index against every possible type of the cell's atoms (6 bits each, ntypes <= 5), the
       // ordering rule (jj > ii or jj before the cell) as an integer threshold -- is formed once per 32 candidates.
       if (lane < na) s_info[wid][lane].y = 6 * ((s_info[wid][lane].y & 0xffff) - 1);   // shift of type_i in the packed kc word
+      if (SIMPLE == 2) { s_exn[wid][lane] = lane < na ? nex_l : 0; s_exp[wid][lane] = (unsigned long long)(size_t)ex_l; }
       __syncwarp();
+      unsigned* const xrow0 = xnbr + (size_t)t0 * xpitch;
       const unsigned ltmask = (1u << lane) - 1u;
       const int cap = pitch - DLP_ROW_PAD;
       unsigned* const row0 = nbr + (size_t)t0 * pitch;
@@ -600,10 +604,28 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
         for (int a = 0; a < na; ++a) {
           const double4 pi = s_pi[wid][a];
           const bool acc = pair_rsq(pj, pi.x, pi.y, pi.z) <= rc_eff && jrel > a;
-          const unsigned m = __ballot_sync(DLP_FULL, acc);
+          unsigned m = __ballot_sync(DLP_FULL, acc);
           if (m == 0u) continue;
+          bool isx = false;
+          if (SIMPLE == 2) {   // partners on the atom's exclusion list go to its xnbr row (neighbours.F90:1229-1251)
+            const int nex = s_exn[wid][a];
+            if (nex > 0) {
+              if (acc) isx = excl_match(infj.x, nex, reinterpret_cast<const int*>((size_t)s_exp[wid][a]));
+              const unsigned mx = __ballot_sync(DLP_FULL, isx);
+              if (mx) {
+                const int cxa = __shfl_sync(DLP_FULL, xcnt, a);
+                if (isx) {
+                  const unsigned entry = jbits | ((s_info[wid][a].x < gid_j) ? DLP_F_ECNT : 0u);
+                  const int ll = cxa + __popc(mx & ltmask);
+                  if (ll < xpitch) xrow0[(unsigned)(a * xpitch + ll)] = entry; else atomicOr(&status[0], 2);
+                }
+                if (lane == a) xcnt += __popc(mx);
+                m &= ~mx;
+              }
+            }
+          }
           const int ca = __shfl_sync(DLP_FULL, cnt, a);
-          if (acc) {
+          if (acc && !isx) {
             const int2 infi = s_info[wid][a];
             const unsigned entry = jbits | (((kcp >> infi.y) & 63u) << DLP_K_SHIFT) | ((infi.x < gid_j) ? DLP_F_ECNT : 0u);
             const int ll = ca + __popc(m & ltmask);
@@ -770,13 +792,15 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
         CK(ctx->st_rows.ensure(hrows.size() * 3 + 3, s));
         CK(cudaMemcpyAsync(ctx->st_rows.p, hrows.data(), hrows.size() * sizeof(LCRow), cudaMemcpyHostToDevice, s));
         const int ncd = g.nlx * g.nly * g.nlz;
-        const bool simple = !ctx->lbook && ctx->megfrz <= 1 && g.nir_r2 <= 1 && ctx->ntypes <= 5;
+        const bool lean = ctx->megfrz <= 1 && g.nir_r2 <= 1 && ctx->ntypes <= 5;
+        const bool simple = lean && !ctx->lbook;
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
                ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel
-        if (simple) LAUNCH(ctx, k_list_cell<true>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else LAUNCH(ctx, k_list_cell<false>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        if (simple) LAUNCH(ctx, k_list_cell<1>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (lean) LAUNCH(ctx, k_list_cell<2>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else LAUNCH(ctx, k_list_cell<0>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
 #undef DLP_LC_ARGS
       } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
