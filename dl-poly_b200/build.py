@@ -17,6 +17,34 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--st
 EXTRA = {"ctx.cu": ["-fmad=false"], "cells.cu": ["-fmad=false"], "halo.cu": ["-fmad=false"], "forces.cu": []}
 
 
+HOST = os.path.join(HERE, "host")
+HOST_OUT = os.path.join(HOST, "_build")
+HOST_LIB = os.path.join(HOST_OUT, "libdlpoly_host.so")
+HOST_CHECK = os.path.join(HOST_OUT, "dlpoly_check")
+CXX = os.environ.get("CXX", "g++")
+# -ffp-contract=off: the host-side table generators and decisions follow the reference's un-fused IEEE arithmetic
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-Wall", "-I", os.path.join(HERE, "..", "include")]
+
+
+def build_host(force=False):
+    """The C++ host side above the C ABI (host/dlpoly_host.cpp -> libdlpoly_host.so) and its check driver (dlpoly_check)."""
+    srcs = [os.path.join(HOST, f) for f in ("dlpoly_host.cpp", "dlpoly_host.hpp", "dlpoly_check.cpp")] + [OUT]
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_CHECK) and \
+            all(os.path.getmtime(s) <= min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_CHECK)) for s in srcs):
+        return HOST_CHECK
+    os.makedirs(HOST_OUT, exist_ok=True)
+    link = ["-L", HERE, "-ldlpgpu"]
+    cmds = [[CXX] + HOST_FLAGS + ["-shared", "-o", HOST_LIB, os.path.join(HOST, "dlpoly_host.cpp")] + link + ["-Wl,-rpath,$ORIGIN/../.."],
+            [CXX] + HOST_FLAGS + ["-o", HOST_CHECK, os.path.join(HOST, "dlpoly_check.cpp"), "-L", HOST_OUT, "-ldlpoly_host"] + link +
+            ["-Wl,-rpath,$ORIGIN:$ORIGIN/../.."]]
+    for cmd in cmds:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("host build failed: %s" % " ".join(cmd))
+    return HOST_CHECK
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -27,6 +55,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_host()
         return OUT
     objdir = os.path.join(CSRC, "_obj")
     os.makedirs(objdir, exist_ok=True)
@@ -54,6 +83,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed")
     if verbose:
         print("\n".join(log))
+    build_host(force=True)
     return OUT
 
 

@@ -627,8 +627,10 @@ struct World {
   std::vector<int> excl_global;          // (0:max_exclude, 1:megatm) by global id
   std::vector<Dom> d;
   bool update = true;                    // neigh%update
-  double neighskip[6] = {0};
+  double neighskip[6] = {0, 0, 0, 0, 999999999.0, 0};   // statistics.F90:185-186 (index 0 unused)
   bool newstart = true;
+  bool l_str = true;                     // strict_checks (control.F90:4421-4427: default on)
+  int bspline = 0;                       // > 0 <=> SPME is on (vnl_check's test = 2 % instead of 4 %)
   std::string err;
 };
 
@@ -926,7 +928,77 @@ int refresh_halo_positions(World& w) {
   return 0;
 }
 
-// neighbours.F90:123-296 vnl_check (strict mode: no padding re-tune, l_str=.true.)
+// neighbours.F90:182-284: the update decision, the padding re-tune of the 'no strict' regime and the skip statistics, for a
+// displacement maximum that is already global.  celprp from dcell(cell); dims = (nx, ny, nz); mxnode = nx ny nz.
+// Returns 0, or 307 (the reference's error number).  The KIM clause (:261-266) is outside this path.
+int vnl_decide(bool l_str, double tolg, int bspline, double cutoff, double& padding, double& cutoff_extended, const double* cell,
+               int nx, int ny, int nz, bool& update, bool& newstart, double* ns /*1..5*/, double& width) {
+  update = (tolg >= half_minus * padding);                                   // :182
+  double celprp[11];
+  dcell(cell, celprp);                                                       // :186
+  width = std::min(celprp[7], std::min(celprp[8], celprp[9]));               // :187
+  double cut = cutoff_extended + smalldr;                                    // :191
+  double nx_recip = 1.0 / (double)nx, ny_recip = 1.0 / (double)ny, nz_recip = 1.0 / (double)nz;
+  int mxnode = nx * ny * nz;
+  int ilx = f_int(nx_recip * celprp[7] / cut);                               // :195-197
+  int ily = f_int(ny_recip * celprp[8] / cut);
+  int ilz = f_int(nz_recip * celprp[9] / cut);
+  double m6 = 0.05, m7 = 0.005, m8 = 0.02, m9 = 0.95;                         // :199-202
+  double tol = std::min(m6, m7 * cutoff);                                    // :204
+  double test;
+  if (bspline > 0) test = m8; else test = m8 * 2.0;                          // :206-210
+  cut = std::min(nx_recip * celprp[7], std::min(ny_recip * celprp[8], nz_recip * celprp[9])) - smalldr;   // :212-214
+  if (ilx * ily * ilz == 0) {                                                // :216
+    if (cut < cutoff) return 307;                                            // :217-219
+    else {
+      if (cut < cutoff_extended) {                                           // :221
+        if (l_str) return 307;                                               // :222-224
+        else {
+          if (cut >= cutoff) {                                               // :226-232
+            padding = std::min(m9 * (cut - cutoff), test * cutoff);
+            padding = (double)f_int(100.0 * padding) / 100.0;
+            if (padding < tol) padding = 0.0;
+            cutoff_extended = cutoff + padding;
+            update = true;
+          }
+        }
+      }
+    }
+  } else {                                                                   // :236
+    if (update && (!l_str)) {                                                // :237
+      if (f_int((double)std::min(ilx, std::min(ily, ilz)) / (1.0 + test)) >= 2) {   // :238
+        cut = test * cutoff;
+      } else {
+        if (mxnode > 1) {                                                    // :241-245
+          cut = std::min(m9 * (std::min(nx_recip * celprp[7] / (double)ilx,
+                                        std::min(ny_recip * celprp[8] / (double)ily, nz_recip * celprp[9] / (double)ilz)) -
+                               cutoff - smalldr),
+                         test * cutoff);
+        } else {
+          cut = m9 * (0.5 * width - cutoff - smalldr);                       // :247
+        }
+      }
+      cut = (double)f_int(100.0 * cut) / 100.0;                              // :250
+      if ((!(cut < tol)) && cut - padding > 0.005) {                         // :251-257
+        padding = cut;
+        cutoff_extended = cutoff + padding;
+      }
+    }
+  }
+  if (update) {                                                              // :270-284
+    ns[3] = ns[2] * ns[3];
+    ns[2] = ns[2] + 1.0;
+    ns[3] = ns[3] / ns[2] + ns[1] / ns[2];
+    if (!newstart) ns[4] = std::min(ns[1], ns[4]); else newstart = false;
+    ns[5] = std::max(ns[1], ns[5]);
+    ns[1] = 0.0;
+  } else {
+    ns[1] = ns[1] + 1.0;
+  }
+  return 0;
+}
+
+// neighbours.F90:123-296 vnl_check
 bool vnl_check(World& w, double* tol_out) {
   if (!(w.padding > 0.0)) {   // unconditional_update false => returns leaving update=.true. (neighbours.F90:141)
     w.update = true;
@@ -948,20 +1020,11 @@ bool vnl_check(World& w, double* tol_out) {
       tol = std::max(tol, r);   // Maxval + gmax
     }
   }
-  w.update = (tol >= half_minus * w.padding);
   if (tol_out) *tol_out = tol;
-  // skip statistics neighbours.F90:270-284
-  double* ns = w.neighskip;
-  if (w.update) {
-    ns[3] = ns[2] * ns[3];
-    ns[2] = ns[2] + 1.0;
-    ns[3] = ns[3] / ns[2] + ns[1] / ns[2];
-    if (!w.newstart) ns[4] = std::min(ns[1], ns[4]); else w.newstart = false;
-    ns[5] = std::max(ns[1], ns[5]);
-    ns[1] = 0.0;
-  } else {
-    ns[1] = ns[1] + 1.0;
-  }
+  double width;
+  int rc = vnl_decide(w.l_str, tol, w.bspline, w.rcut, w.padding, w.rx, w.cell, w.d[0].nx, w.d[0].ny, w.d[0].nz, w.update, w.newstart,
+                      w.neighskip, width);
+  if (rc != 0) { w.err = "vnl_check: error 307"; w.update = true; }
   return w.update;
 }
 
@@ -1963,6 +2026,20 @@ int ora_world_set_halo(void* h) {
 }
 int ora_world_refresh_halo(void* h) { return refresh_halo_positions(*(World*)h); }
 int ora_world_vnl_check(void* h, double* tol) { return vnl_check(*(World*)h, tol) ? 1 : 0; }
+void ora_world_set_strict(void* h, int l_str, int bspline) { ((World*)h)->l_str = l_str != 0; ((World*)h)->bspline = bspline; }
+void ora_world_cutoffs(void* h, double* out3) { World* w = (World*)h; out3[0] = w->rcut; out3[1] = w->padding; out3[2] = w->rx; }
+// stateless form of the decision: io = {padding, cutoff_extended}, flags = {update, newstart} (in / out), ns5 = neighskip(1:5)
+int ora_vnl_decide(int l_str, double tolg, int bspline, double cutoff, double* io2, const double* cell9, const int* dims3, int* flags2,
+                   double* ns5, double* width) {
+  bool update = flags2[0] != 0, newstart = flags2[1] != 0;
+  double ns[6] = {0, ns5[0], ns5[1], ns5[2], ns5[3], ns5[4]};
+  double cell[10];
+  for (int i = 1; i <= 9; ++i) cell[i] = cell9[i - 1];
+  int rc = vnl_decide(l_str != 0, tolg, bspline, cutoff, io2[0], io2[1], cell, dims3[0], dims3[1], dims3[2], update, newstart, ns, *width);
+  flags2[0] = update; flags2[1] = newstart;
+  for (int i = 0; i < 5; ++i) ns5[i] = ns[i + 1];
+  return rc;
+}
 void ora_world_neighskip(void* h, double* out5) { for (int i = 0; i < 5; ++i) out5[i] = ((World*)h)->neighskip[i + 1]; }
 
 static void par_for_domains(World* w, int nthreads, void (*fn)(World*, int)) {
