@@ -57,6 +57,34 @@ def test_product_never_imports_the_oracle():
     bad = re.compile(r"^\s*(from|import)\s+\S*oracle|libdlp_oracle|dlp_oracle\.|oracle/|ora_world|ora_dom", re.M)
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not bad.search(txt), "%s references the oracle" % f
+
+
+def test_cpp_host_fails_loudly_without_gpu(tmp_path):
+    """The C++ host side has no CPU fallback either: without a GPU gpu_short_range's constructor raises and the check program
+    exits non-zero with the message."""
+    import subprocess
+    import struct
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dl_poly_b200 import build
+    exe = build.build_host()
+    fin = tmp_path / "in.bundle"
+    import numpy as np
+
+    def rec(name, arr):
+        a = np.ascontiguousarray(arr)
+        dt = b"d" if a.dtype.kind == "f" else b"i"
+        a = a.astype(np.float64 if dt == b"d" else np.int32)
+        return name.encode().ljust(24, b"\0") + dt + b"\0" * 7 + struct.pack("<q", a.size) + a.tobytes()
+
+    recs = [rec("cell", np.diag([30.0, 30.0, 30.0]).reshape(9)), rec("imcon", [1]), rec("megatm", [10]), rec("rcut", [8.0]),
+            rec("rvdw", [8.0]), rec("padding", [0.2]), rec("ntypes", [1]), rec("force_shift", [0]), rec("direct", [0]),
+            rec("pot_pairs", np.array([1, 1, 2])), rec("pot_param", [99.61, 3.405, 0, 0, 0, 0, 0.0]), rec("electro_key", [0]),
+            rec("eps", [1.0]), rec("damping", [0.0]), rec("natms", [0]), rec("nlast", [0])]
+    fin.write_bytes(b"".join(recs))
+    r = subprocess.run([exe, "md", str(fin), str(tmp_path / "out.bundle")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
