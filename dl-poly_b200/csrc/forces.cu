@@ -431,16 +431,22 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
   // TX bit 3 (needs VT, EW, one grid and rvdw == rcut): the second differences of BOTH tables come as one float4 texel
   // {h_vdw_force, h_vdw_energy, h_ewald_force, h_ewald_energy} indexed by (potential, l): 5 instead of 6 table reads, and
   // half the shared memory.  |h| <= ~2e-3 |g| on these grids, so the fp32 rounding of h moves a pair term by < 4e-11 relative.
-  float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = h4;
   if (TX & 8) {
     const int uh = in_c ? (in_v ? kc : 0) * P.ts + l : P.zero;
     h4 = tex1Dfetch<float4>(tex, uh);
+    if (X & 64) {   // timing experiment: the g(l+1) units replaced by a second fp32 texel (first differences) far from the first
+      int ud = uh + (P.ne >> 1);
+      ud -= ud >= P.ne ? P.ne : 0;
+      d4 = tex1Dfetch<float4>(tex, ud);
+    }
   }
   if (VT) {
     int u = in_v ? kc * P.ts + l : P.zero;
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else if ((TX & 8) && (X & 64)) { a = sG[u]; b = make_double2(a.x + (double)d4.x, a.y + (double)d4.y); h = make_double2(h_exact(h4.x, a.x), h_exact(h4.y, a.y)); }
     else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = make_double2(h_exact(h4.x, a.x), h_exact(h4.y, a.y)); }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 2) ? tex_unit(tex, P.ne + u) : sH[u]; }
     gamma = __fma_rn(ppp, __fma_rn(ppp, h.x, (b.x - a.x) - h.x), a.x) * r_rsq;             // :1914-1921
@@ -460,6 +466,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
     if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
+    else if ((TX & 8) && (X & 64)) { a = sG[u]; b = make_double2(a.x + (double)d4.z, a.y + (double)d4.w); h = make_double2(h_exact(h4.z, a.x), h_exact(h4.w, a.y)); }
     else if (TX & 8) { a = sG[u]; b = sG[u + 1]; h = make_double2(h_exact(h4.z, a.x), h_exact(h4.w, a.y)); }
     else if (TX & 1) { a = tex_unit(tex, u); b = tex_unit(tex, u + 1); h = tex_unit(tex, P.ne + u); }
     else { a = sG[u]; b = sG[u + 1]; h = (TX & 4) ? tex_unit(tex, P.ne + u) : sH[u]; }
@@ -920,7 +927,12 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
     if (ctx->variant > 0 && ctx->variant != 100 && v && e && sg) {   // timing experiments only (DLPGPU_VARIANT): results are not meaningful
       const int xv = ctx->variant & 0xfff, ntc = ctx->variant >> 12;
 #define DLP_V2N(XV) do { if (ntc == 0) DLP_V2X(XV, 512); else if (ntc == 1) DLP_V2X(XV, 640); else DLP_V2X(XV, 768); } while (0)
-      if (xv == 32 || xv == 0x800) {   // on the default fp32-h layout: 32 = one gather + one RED triple per two pairs (emulates 2 x 1 clusters)
+      if (xv == 64) {   // fp32-h layout with the g(l+1) units replaced by a second texel (timing only)
+        const size_t smem8 = (size_t)ctx->tab2_ne * 16;
+        CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 64, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+               t2s, fpos, fneg, ctx->partial.p);
+      } else if (xv == 32 || xv == 0x800) {   // on the default fp32-h layout: 32 = one gather + one RED triple per two pairs (emulates 2 x 1 clusters)
         const size_t smem8 = (size_t)ctx->tab2_ne * 16;
         if (xv == 32) {
           CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));

@@ -201,6 +201,23 @@ int mode_host(const Bundle& in, Bundle& out) {
     const double a = ewald_alpha_from_precision(in.has("ew_precision") ? in.d1("ew_precision") : 1.0e-6, in.d1("rcut"));
     out.put("alpha_from_precision", 'd', &a, 1);
   }
+  if (in.has("num_type")) {   // vdw_lrc + the end of two_body_forces on given (already global) partial sums
+    ForceField ff;
+    build_forcefield(in, ff);
+    configuration_type c;
+    c.imcon = in.i1("imcon");
+    c.volm = in.d1("volm");
+    c.sumchg = in.d1("sumchg");
+    vdw_lrc(in.d("num_type"), in.d("numfrz"), ff.vdws, c.imcon, c.volm);
+    out.put("lrc", std::vector<double>{ff.vdws.elrc, ff.vdws.vlrc});
+    const std::vector<double> p = in.d("partial_sums");   // engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex, engcpe_rc, vircpe_rc
+    stats_type st;
+    const std::vector<double> s0 = in.d("stress_in");
+    for (int k = 0; k < 9; ++k) st.stress[k] = s0[k];
+    two_body_totals(st, ff.vdws, ff.electro, ff.ewld, c, in.i1("mxnode"), p[0], p[1], p[6], p[7], p[2], p[3], p[4], p[5]);
+    out.put("totals", std::vector<double>{st.engcpe, st.vircpe, st.engsrp, st.virsrp});
+    out.put("stress_out", 'd', st.stress, 9);
+  }
   if (in.has("vnl_tols")) {   // a sequence of global displacement maxima through vnl_check's decision logic
     configuration_type c;
     neighbours_type n;

@@ -334,6 +334,69 @@ void vdw_table_read(vdw_type& v, const std::string& filename, double engunit) {
   }
 }
 
+// vdw.F90:617-967
+void vdw_lrc(const std::vector<double>& num_type, const std::vector<double>& numfrz, vdw_type& v, int imcon, double volm) {
+  v.elrc = v.vlrc = 0.0;
+  if (v.l_force_shift || imcon == 0 || imcon == 6) return;   // shifted potentials vanish at the cutoff; 3D periodic systems only
+  const double r = v.cutoff, r3 = powi(r, 3), r5 = powi(r, 5), r9 = powi(r, 9);
+  double plrc = 0.0;
+  int ivdw = 0;
+  for (int i = 1; i <= v.ntype_atom; ++i) {
+    for (int j = 1; j <= i; ++j) {
+      const int k = v.list[ivdw++] - 1;
+      const double* p = &v.param[(size_t)7 * k];
+      double eadd = 0.0, padd = 0.0;   // integrals of u r^2 and of (r du/dr) r^2 beyond the cutoff
+      switch (v.ltp[k]) {
+        case VDW_TAB: eadd = p[0]; padd = -p[1]; break;                        // the TABLE file's own corrections
+        case VDW_12_6:
+          eadd = p[0] / (9.0 * r9) - p[1] / (3.0 * r3);
+          padd = 12.0 * p[0] / (9.0 * r9) - 6.0 * p[1] / (3.0 * r3);
+          break;
+        case VDW_LENNARD_JONES:
+          eadd = 4.0 * p[0] * (powi(p[1], 12) / (9.0 * r9) - powi(p[1], 6) / (3.0 * r3));
+          padd = 8.0 * p[0] * (6.0 * powi(p[1], 12) / (9.0 * r9) - powi(p[1], 6) / r3);
+          break;
+        case VDW_BUCKINGHAM:
+          eadd = -p[2] / (3.0 * r3);
+          padd = -2.0 * p[2] / r3;
+          break;
+        case VDW_BORN_HUGGINS_MEYER:
+          eadd = -p[3] / (3.0 * r3) - p[4] / (5.0 * r5);
+          padd = -2.0 * p[3] / r3 - 8.0 * p[4] / (5.0 * r5);
+          break;
+        default: break;                                                        // VDW_NULL: no potential for this pair
+      }
+      if (i != j) { eadd = eadd * 2.0; padd = padd * 2.0; }                    // unlike pairs count twice
+      const double denprd = 2.0 * pi * (num_type[i - 1] * num_type[j - 1] - numfrz[i - 1] * numfrz[j - 1]) / powi(volm, 2);
+      v.elrc = v.elrc + volm * denprd * eadd;
+      plrc = plrc + denprd * padd / 3.0;
+    }
+  }
+  v.vlrc = plrc * (-3.0 * volm);
+}
+
+// two_body.F90:672-790
+void two_body_totals(stats_type& st, const vdw_type& v, const electrostatic_type& el, const ewald_type& ew, const configuration_type& c,
+                     int mxnode, double engvdw, double virvdw, double engcpe_rc, double vircpe_rc, double engcpe_rl, double vircpe_rl,
+                     double engcpe_ex, double vircpe_ex) {
+  double engcpe_nz = 0.0, vircpe_nz = 0.0;
+  if (el.key == ELECTROSTATIC_SPME && std::fabs(c.sumchg) > 1.0e-6) {          // Fuchs, Proc. R. Soc. A 151 (1935) 585
+    const double factor_nz = -0.5 * (pi * r4pie0 / el.eps) * powi(c.sumchg / ew.alpha, 2);
+    engcpe_nz = factor_nz / c.volm;
+    vircpe_nz = -3.0 * engcpe_nz;
+  }
+  const double zero = 0.0;   // core-shell (ch), frozen (fr) and multipole (dt) terms are not part of this path
+  st.engcpe = st.engcpe + engcpe_rc + engcpe_rl + zero + engcpe_ex + zero + engcpe_nz;
+  st.vircpe = st.vircpe + vircpe_rc + vircpe_rl + zero + vircpe_ex + zero + vircpe_nz + zero;
+  st.engsrp = st.engsrp + (engvdw + v.elrc);
+  st.virsrp = st.virsrp + (virvdw + v.vlrc);
+  for (const double corr : {-vircpe_nz / (3.0 * (double)mxnode), -(v.vlrc + 0.0) / (3.0 * (double)mxnode)}) {
+    st.stress[0] = st.stress[0] + corr;
+    st.stress[4] = st.stress[4] + corr;
+    st.stress[8] = st.stress[8] + corr;
+  }
+}
+
 // ---------------------------------------------------------------- electrostatics
 double calc_erfc(double x) {   // numerics.F90:3659-3665 (Abramowitz-Stegun 7.1.26)
   const double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429, pp = 0.3275911;

@@ -78,6 +78,7 @@ struct vdw_type {
   std::vector<double> tab_force;
   std::vector<double> afs, bfs;       // force-shift constants of vdw_forces_direct
   std::vector<std::string> unique_atom;   // sites%unique_atom (labels TABLE entries are matched against)
+  double elrc = 0.0, vlrc = 0.0;      // long-range corrections (vdw_lrc)
 
   void init(int ntype_atom, double rvdw, bool force_shift, bool direct);   // bounds.F90:820 max_grid
   // read_field's vdw block (ffield.F90:3620-3960): one potential per unordered type pair; returns its number
@@ -91,6 +92,8 @@ void pair_potential(int keypot, const double* prm, double r, double& energy, dou
 void vdw_generate(vdw_type& vdws);
 void vdw_direct_fs_generate(vdw_type& vdws);
 void vdw_table_read(vdw_type& vdws, const std::string& filename, double engunit = 1.0);
+// vdw.F90:617-967: num_type / numfrz = atoms / frozen atoms per type over the whole system (after gsum); sets elrc, vlrc
+void vdw_lrc(const std::vector<double>& num_type, const std::vector<double>& numfrz, vdw_type& vdws, int imcon, double volm);
 
 // ---------------------------------------------------------------- electrostatic.F90 / ewald.F90
 struct interp_table {                 // numerics.F90:47-60
@@ -132,9 +135,17 @@ struct stats_type {
 struct configuration_type {
   int imcon = 1, natms = 0, nlast = 0, megatm = 0, megfrz = 0;
   double cell[9] = {0.0};
+  double volm = 0.0, sumchg = 0.0;     // cell volume, total system charge
   std::vector<corePart> parts;         // parts(1:nlast)
   std::vector<int> ltg, lsite, ltype, lfrzn;
 };
+
+// The end of two_body_forces (two_body.F90:672-790) for the terms of this path, AFTER the caller's gsum of the six partial sums
+// (:729): Fuchs' net-charge correction (SPME only), stats%engcpe / vircpe / engsrp / virsrp incl. the long-range corrections,
+// and the per-rank share of the corrections on the stress diagonal.  engcpe_rc / vircpe_rc: the caller's reciprocal-space sums.
+void two_body_totals(stats_type& stats, const vdw_type& vdws, const electrostatic_type& electro, const ewald_type& ewld,
+                     const configuration_type& config, int mxnode, double engvdw, double virvdw, double engcpe_rc, double vircpe_rc,
+                     double engcpe_rl, double vircpe_rl, double engcpe_ex, double vircpe_ex);
 
 // The padding / update decision of vnl_check for a displacement maximum that is already global (after gmax): everything of
 // neighbours.F90:182-284 except the KIM clause.  bspline > 0 <=> SPME is on.  Returns neigh.update.

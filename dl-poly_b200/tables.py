@@ -8,6 +8,7 @@ module mirrors, on the host with numpy,
 * ``vdw_direct_fs_generate`` vdw.F90:969-1049    (force-shift constants afs/bfs)
 * ``vdw_table_read``         vdw.F90:1051-1370   (TABLE file parsing + 3-point re-gridding)
 * ``erfcgen``                electrostatic.F90:88-127 + numerics.F90:215-248,3647-3683 (A&S erfc polynomial)
+* ``vdw_lrc``                vdw.F90:617-967     (long-range corrections elrc / vlrc)
 * sizes/alpha                bounds.F90:811,820,907 ; control.F90:1709-1710
 
 The same arrays (same bits) are handed to the GPU library and, in tests/bench, to the CPU oracle.
@@ -103,6 +104,70 @@ def vdw_direct_fs(keypot, param, rvdw):
     """vdw.F90:1003-1046  afs = dz/rvdw, bfs = -z - dz."""
     z, dz = pot_energy(keypot, param, np.array([rvdw]))
     return float(dz[0]) / rvdw, -float(z[0]) - float(dz[0])
+
+
+def vdw_lrc(ff, num_type, numfrz=None, imcon=1, volm=1.0):
+    """vdw.F90:617-967: long-range corrections (elrc, vlrc) of a finalized ForceField; num_type / numfrz = atoms / frozen
+    atoms per type over the whole system.  TABLE potentials carry theirs in param[0:2] (vdw.F90:1166-1170)."""
+    if ff.force_shift or imcon in (0, 6):
+        return 0.0, 0.0
+    nt = np.asarray(num_type, dtype=np.float64)
+    nf = np.zeros_like(nt) if numfrz is None else np.asarray(numfrz, dtype=np.float64)
+
+    def pw(x, n):
+        return float(_powi(np.array([float(x)]), n)[0])
+
+    r = ff.rvdw
+    r3, r5, r9 = pw(r, 3), pw(r, 5), pw(r, 9)
+    elrc = plrc = 0.0
+    ivdw = 0
+    for i in range(1, ff.ntypes + 1):
+        for j in range(1, i + 1):
+            k = int(ff.vdw_list_c[ivdw]) - 1
+            ivdw += 1
+            p, key = ff.param[k], int(ff.ltp[k])
+            eadd = padd = 0.0
+            if key == VDW_TAB:
+                eadd, padd = p[0], -p[1]
+            elif key == VDW_12_6:
+                eadd = p[0] / (9.0 * r9) - p[1] / (3.0 * r3)
+                padd = 12.0 * p[0] / (9.0 * r9) - 6.0 * p[1] / (3.0 * r3)
+            elif key == VDW_LJ:
+                eadd = 4.0 * p[0] * (pw(p[1], 12) / (9.0 * r9) - pw(p[1], 6) / (3.0 * r3))
+                padd = 8.0 * p[0] * (6.0 * pw(p[1], 12) / (9.0 * r9) - pw(p[1], 6) / r3)
+            elif key == VDW_BUCK:
+                eadd = -p[2] / (3.0 * r3)
+                padd = -2.0 * p[2] / r3
+            elif key == VDW_BHM:
+                eadd = -p[3] / (3.0 * r3) - p[4] / (5.0 * r5)
+                padd = -2.0 * p[3] / r3 - 8.0 * p[4] / (5.0 * r5)
+            if i != j:
+                eadd, padd = eadd * 2.0, padd * 2.0
+            denprd = 2.0 * PI * (nt[i - 1] * nt[j - 1] - nf[i - 1] * nf[j - 1]) / pw(volm, 2)
+            elrc = elrc + volm * denprd * eadd
+            plrc = plrc + denprd * padd / 3.0
+    return float(elrc), float(plrc * (-3.0 * volm))
+
+
+def two_body_totals(out, elrc, vlrc, mxnode=1, spme=False, sumchg=0.0, alpha=0.0, eps=1.0, volm=1.0, engcpe_rc=0.0, vircpe_rc=0.0):
+    """The end of two_body_forces (two_body.F90:672-790) for this path: ``out`` = the 16 partial sums of the C ABI AFTER the
+    caller's gsum.  Returns (engcpe, vircpe, engsrp, virsrp, stress9): Fuchs' net-charge term (SPME, |sumchg| > 1e-6), the
+    long-range corrections, and this rank's share of both on the stress diagonal."""
+    engcpe_nz = vircpe_nz = 0.0
+    if spme and abs(sumchg) > 1.0e-6:
+        q = sumchg / alpha
+        engcpe_nz = (-0.5 * (PI * R4PIE0 / eps) * (q * q)) / volm
+        vircpe_nz = -3.0 * engcpe_nz
+    engcpe = 0.0 + engcpe_rc + out[2] + 0.0 + out[4] + 0.0 + engcpe_nz
+    vircpe = 0.0 + vircpe_rc + out[3] + 0.0 + out[5] + 0.0 + vircpe_nz + 0.0
+    engsrp = 0.0 + (out[0] + elrc)
+    virsrp = 0.0 + (out[1] + vlrc)
+    stress = np.array(out[6:15], dtype=np.float64)
+    for corr in (-vircpe_nz / (3.0 * float(mxnode)), -(vlrc + 0.0) / (3.0 * float(mxnode))):
+        stress[0] += corr
+        stress[4] += corr
+        stress[8] += corr
+    return engcpe, vircpe, engsrp, virsrp, stress
 
 
 def erfc_as(x):

@@ -1788,6 +1788,90 @@ int relocate_particles(World& w) {
 // =============================================================================
 // C API (ctypes).  Plain pointers, 0-based arrays on the outside.
 // =============================================================================
+// ---------------------------------------------------------------- vdw.F90:617-967 vdw_lrc
+// Long-range corrections to energy and virial in a 3D periodic system, for the potentials of this path (TABLE entries carry
+// theirs in param(1:2), vdw.F90:1166-1170).  num_type / numfrz: atoms and frozen atoms per type, already global (gsum, :672).
+// list / ltp / param as in Vdw (1-based views); returns elrc, vlrc.
+void vdw_lrc(int ntype_atom, const int* list /*1..*/, const int* ltp /*1..*/, const double* param /*(1:7,1:max_vdw)*/, double rvdw,
+             bool l_force_shift, int imcon, double volm, const double* num_type /*1..*/, const double* numfrz /*1..*/, double* elrc_out,
+             double* vlrc_out) {
+  double twopi = 2.0 * pi;
+  double plrc = 0.0, elrc = 0.0;                                             // :659-660
+  if (!l_force_shift) {                                                      // :662
+    if (imcon != 0 && imcon != 6) {                                          // :676
+      int ivdw = 0;
+      for (int i = 1; i <= ntype_atom; ++i) {
+        for (int j = 1; j <= i; ++j) {
+          double eadd = 0.0, padd = 0.0;
+          ivdw = ivdw + 1;
+          int k = list[ivdw];
+          int keypot = ltp[k];
+          const double* prm = param + (size_t)(k - 1) * 7 - 1;               // prm[1..7]
+          double r = rvdw;
+          if (keypot == 0) {                                                 // VDW_TAB :691-696
+            eadd = prm[1];
+            padd = -prm[2];
+          } else if (keypot == 1) {                                          // VDW_12_6 :698-707
+            double a = prm[1], b = prm[2];
+            eadd = a / (9.0 * powi(r, 9)) - b / (3.0 * powi(r, 3));
+            padd = 12.0 * a / (9.0 * powi(r, 9)) - 6.0 * b / (3.0 * powi(r, 3));
+          } else if (keypot == 2) {                                          // VDW_LENNARD_JONES :709-718
+            double eps = prm[1], sig = prm[2];
+            eadd = 4.0 * eps * (powi(sig, 12) / (9.0 * powi(r, 9)) - powi(sig, 6) / (3.0 * powi(r, 3)));
+            padd = 8.0 * eps * (6.0 * powi(sig, 12) / (9.0 * powi(r, 9)) - powi(sig, 6) / (powi(r, 3)));
+          } else if (keypot == 4) {                                          // VDW_BUCKINGHAM :735-743
+            double c = prm[3];
+            eadd = -c / (3.0 * powi(r, 3));
+            padd = -2.0 * c / (powi(r, 3));
+          } else if (keypot == 5) {                                          // VDW_BORN_HUGGINS_MEYER :745-754
+            double c = prm[4], d = prm[5];
+            eadd = -c / (3.0 * powi(r, 3)) - d / (5.0 * powi(r, 5));
+            padd = -2.0 * c / (powi(r, 3)) - 8.0 * d / (5.0 * powi(r, 5));
+          }                                                                  // VDW_NULL and the rest: 0
+          if (i != j) {                                                      // :936-939
+            eadd = eadd * 2.0;
+            padd = padd * 2.0;
+          }
+          double denprd = twopi * (num_type[i] * num_type[j] - numfrz[i] * numfrz[j]) / powi(volm, 2);   // :941
+          elrc = elrc + volm * denprd * eadd;                                // :945
+          plrc = plrc + denprd * padd / 3.0;                                 // :946
+        }
+      }
+    }
+  }
+  *elrc_out = elrc;
+  *vlrc_out = plrc * (-3.0 * volm);                                          // :962
+}
+
+// two_body.F90:672-790, the terms this path feeds: in = engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex AFTER gsum
+// (:729), plus the reciprocal-space pair (engcpe_rc, vircpe_rc) the caller's SPME produced (0 without it).  Adds to
+// tot = {engcpe, vircpe, engsrp, virsrp} and to this rank's stress(1:9).
+void two_body_epilogue(const double* in6, double engcpe_rc, double vircpe_rc, bool spme_or_poisson, double sumchg, double alpha, double eps,
+                       double volm, double elrc, double vlrc, int mxnode, double* tot4, double* stress /*1..9*/) {
+  double engcpe_nz = 0.0, vircpe_nz = 0.0;
+  if (spme_or_poisson) {
+    if (std::fabs(sumchg) > 1.0e-6) {                                        // :691-696 (Fuchs)
+      double factor_nz = -0.5 * (pi * r4pie0 / eps) * powi(sumchg / alpha, 2);
+      engcpe_nz = factor_nz / volm;
+      vircpe_nz = -3.0 * engcpe_nz;
+    }
+  }
+  double engvdw = in6[0], virvdw = in6[1], engcpe_rl = in6[2], vircpe_rl = in6[3], engcpe_ex = in6[4], vircpe_ex = in6[5];
+  double engcpe_ch = 0.0, vircpe_ch = 0.0, engcpe_fr = 0.0, vircpe_fr = 0.0, vircpe_dt = 0.0;   // core-shell, frozen, multipoles: not this path
+  tot4[0] = tot4[0] + engcpe_rc + engcpe_rl + engcpe_ch + engcpe_ex + engcpe_fr + engcpe_nz;    // :766
+  tot4[1] = tot4[1] + vircpe_rc + vircpe_rl + vircpe_ch + vircpe_ex + vircpe_fr + vircpe_nz + vircpe_dt;   // :767
+  double tmp = -vircpe_nz / (3.0 * (double)mxnode);                          // :772-775
+  stress[1] = stress[1] + tmp;
+  stress[5] = stress[5] + tmp;
+  stress[9] = stress[9] + tmp;
+  tot4[2] = tot4[2] + (engvdw + elrc);                                       // :780 (no KIM, no metal)
+  tot4[3] = tot4[3] + (virvdw + vlrc);                                       // :781
+  tmp = -(vlrc + 0.0) / (3.0 * (double)mxnode);                              // :787-790
+  stress[1] = stress[1] + tmp;
+  stress[5] = stress[5] + tmp;
+  stress[9] = stress[9] + tmp;
+}
+
 extern "C" {
 
 void ora_dcell(const double* cell9, double* out10) {
@@ -1801,6 +1885,14 @@ void ora_invert(const double* a9, double* b9, double* det) {
   for (int i = 0; i < 9; ++i) a[i + 1] = a9[i];
   invert(a, b, *det);
   for (int i = 0; i < 9; ++i) b9[i] = b[i + 1];
+}
+void ora_vdw_lrc(int ntype_atom, const int* list0, const int* ltp0, const double* param, double rvdw, int l_force_shift, int imcon,
+                 double volm, const double* num_type0, const double* numfrz0, double* elrc, double* vlrc) {
+  vdw_lrc(ntype_atom, list0 - 1, ltp0 - 1, param, rvdw, l_force_shift != 0, imcon, volm, num_type0 - 1, numfrz0 - 1, elrc, vlrc);
+}
+void ora_two_body_epilogue(const double* in6, double engcpe_rc, double vircpe_rc, int spme, double sumchg, double alpha, double eps,
+                           double volm, double elrc, double vlrc, int mxnode, double* tot4, double* stress9) {
+  two_body_epilogue(in6, engcpe_rc, vircpe_rc, spme != 0, sumchg, alpha, eps, volm, elrc, vlrc, mxnode, tot4, stress9 - 1);
 }
 int ora_match(int n, int ind_top, const int* list0) { return match(n, ind_top, list0 - 1) ? 1 : 0; }
 void ora_images(int imcon, const double* cell9, int n, double* x, double* y, double* z) {

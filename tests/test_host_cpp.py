@@ -414,3 +414,98 @@ def test_cpp_host_native_md_against_oracle(tmp_path):
     order_g, order_o = np.argsort(out["ltg"][:c["natms"]]), np.argsort(w.ints(0)["ltg"][:c["natms"]])
     for k in ("xxx", "yyy", "zzz"):
         assert np.abs(parts[k][:c["natms"]][order_g] - po[k][:c["natms"]][order_o]).max() < 1e-7
+
+
+# ---------------------------------------------------------------- CPU: long-range corrections and the end of two_body_forces
+def _ora_lrc(oracle, ff, num_type, numfrz, imcon, volm):
+    import ctypes as C
+    L = oracle.lib()
+    lst, ltp = np.ascontiguousarray(ff.vdw_list_c, dtype=np.int32), np.ascontiguousarray(ff.ltp, dtype=np.int32)
+    par = np.ascontiguousarray(ff.param, dtype=np.float64)
+    nt, nf = np.ascontiguousarray(num_type, dtype=np.float64), np.ascontiguousarray(numfrz, dtype=np.float64)
+    e, v = C.c_double(), C.c_double()
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    L.ora_vdw_lrc(C.c_int(ff.ntypes), vp(lst), vp(ltp), vp(par), C.c_double(ff.rvdw), C.c_int(int(ff.force_shift)), C.c_int(imcon),
+                  C.c_double(volm), vp(nt), vp(nf), C.byref(e), C.byref(v))
+    return e.value, v.value
+
+
+def _ora_epilogue(oracle, sums8, spme, sumchg, alpha, eps, volm, elrc, vlrc, mxnode, stress_in):
+    import ctypes as C
+    L = oracle.lib()
+    in6 = np.ascontiguousarray(sums8[:6], dtype=np.float64)
+    tot, st = np.zeros(4), np.ascontiguousarray(stress_in, dtype=np.float64).copy()
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    L.ora_two_body_epilogue(vp(in6), C.c_double(sums8[6]), C.c_double(sums8[7]), C.c_int(int(spme)), C.c_double(sumchg), C.c_double(alpha),
+                            C.c_double(eps), C.c_double(volm), C.c_double(elrc), C.c_double(vlrc), C.c_int(mxnode), vp(tot), vp(st))
+    return tot, st
+
+
+@pytest.mark.parametrize("name", ["argon_126", "argon_lj", "nacl_bhm", "buck", "argon_shifted", "slab"])
+def test_vdw_lrc_and_two_body_totals(oracle, tmp_path, name):
+    """vdw_lrc (vdw.F90:617-967) and the end of two_body_forces (two_body.F90:672-790): the oracle's restatement is pinned by
+    numerical integration of the potential beyond the cutoff (elrc = 2 pi N_i N_j / V * int u r^2 dr, vlrc from r du/dr); the
+    C++ and Python hosts equal the oracle bit for bit."""
+    from scipy.integrate import quad
+    s, spec = {
+        "argon_126": lambda: (systems.argon(4), SPEC_AR_126),
+        "argon_lj": lambda: (systems.argon(4, form="lj"), SPEC_AR_LJ),
+        "nacl_bhm": lambda: (systems.nacl(3, rcut=9.0, padding=0.2), SPEC_NACL),
+        "buck": lambda: (systems.nacl(3, rcut=9.0, padding=0.2, vdw_pairs=()), [(1, 2, "buck", [1.0e5, 0.31, 650.0]), (2, 2, "buck", [2.2e5, 0.29, 2800.0])]),
+        "argon_shifted": lambda: (systems.argon(4, form="lj", force_shift=True), SPEC_AR_LJ),
+        "slab": lambda: (systems.argon(4), SPEC_AR_126),
+    }[name]()
+    if name == "buck":
+        ff = tables.ForceField(2, 9.0, 9.0)
+        for ai, aj, form, p in spec:
+            ff.add(ai, aj, form, p)
+        ff.set_ewald(precision=1e-6)
+        s.ff = ff.finalize()
+    imcon = 6 if name == "slab" else s.imcon
+    types = s.type_site[s.lsite - 1]
+    num_type = np.bincount(types, minlength=s.ff.ntypes + 1)[1:].astype(np.float64)
+    numfrz = np.zeros_like(num_type)
+    if name == "nacl_bhm":
+        numfrz[:] = [3.0, 5.0]
+    sumchg = 0.0 if name != "buck" else 2.0                     # a net charge switches Fuchs' correction on
+    e_o, v_o = _ora_lrc(oracle, s.ff, num_type, numfrz, imcon, s.volume)
+    # second opinion: numerical integration of every pair's analytic form beyond rvdw
+    e_q = v_q = 0.0
+    if not s.ff.force_shift and imcon not in (0, 6):
+        for ai, aj, form, p in spec:
+            pp = np.zeros(7); pp[:len(p)] = p
+            u = lambda r: float(tables.pot_energy(tables.KEYPOT[form], pp, np.array([r]))[0][0]) * r * r
+            g = lambda r: float(tables.pot_energy(tables.KEYPOT[form], pp, np.array([r]))[1][0]) * r * r
+            mult = 1.0 if ai == aj else 2.0
+            # the reference drops the exponential tails of buck / bhm: integrate the dispersion part only
+            if form in ("buck", "bhm"):
+                c6, d8 = (pp[2], 0.0) if form == "buck" else (pp[3], pp[4])
+                u = lambda r, c6=c6, d8=d8: (-c6 / r ** 6 - d8 / r ** 8) * r * r
+                g = lambda r, c6=c6, d8=d8: (-6.0 * c6 / r ** 6 - 8.0 * d8 / r ** 8) * r * r
+            dens = 2.0 * np.pi * (num_type[ai - 1] * num_type[aj - 1] - numfrz[ai - 1] * numfrz[aj - 1]) / s.volume ** 2
+            e_q += s.volume * dens * mult * quad(u, s.ff.rvdw, np.inf, epsabs=0, epsrel=1e-12)[0]
+            v_q += -s.volume * dens * mult * quad(g, s.ff.rvdw, np.inf, epsabs=0, epsrel=1e-12)[0]
+    assert abs(e_o - e_q) <= 1e-9 * max(abs(e_q), 1e-300) and abs(v_o - v_q) <= 1e-9 * max(abs(v_q), 1e-300)
+    if name in ("argon_shifted", "slab"):
+        assert (e_o, v_o) == (0.0, 0.0)
+    else:
+        assert e_o < 0.0 and v_o > 0.0                            # attractive dispersion tail beyond the cutoff (virial = -r dU/dr)
+    assert tables.vdw_lrc(s.ff, num_type, numfrz, imcon, s.volume) == (e_o, v_o)
+    # the end of two_body_forces on made-up partial sums
+    rng = np.random.default_rng(17)
+    sums8 = rng.normal(0.0, 1.0e5, 8)
+    stress_in = rng.normal(0.0, 1.0e4, 9)
+    mxnode = 8
+    spme = s.ff.ew_active
+    tot_o, st_o = _ora_epilogue(oracle, sums8, spme, sumchg, s.ff.alpha, s.ff.eps, s.volume, e_o, v_o, mxnode, stress_in)
+    recs = ff_records(s, spec)
+    recs.update(imcon=[imcon], num_type=num_type, numfrz=numfrz, volm=[s.volume], sumchg=[sumchg], partial_sums=sums8, stress_in=stress_in,
+                mxnode=[mxnode])
+    out = run_check("host", recs, tmp_path)
+    assert tuple(out["lrc"]) == (e_o, v_o)
+    assert np.array_equal(out["totals"], tot_o) and np.array_equal(out["stress_out"], st_o)
+    py = tables.two_body_totals(np.concatenate([sums8[:6], stress_in, [0.0]]), e_o, v_o, mxnode, spme, sumchg, s.ff.alpha, s.ff.eps, s.volume,
+                                sums8[6], sums8[7])
+    assert np.array_equal(np.array(py[:4]), tot_o) and np.array_equal(py[4], st_o)
+    if name == "buck":
+        assert tot_o[0] != sums8[6] + sums8[2] + sums8[4]         # the net-charge term is in
