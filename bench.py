@@ -218,6 +218,8 @@ def run_reference(args):
         return
     sample, what = sample_system(args.workload)
     v, info = cpu_trajectory(sample, None, args.steps, min(args.warmup, 3), args.dt, budget_s=150.0)
+    # the reference's serial path (one domain, one core) next to the MPI-equivalent one, on a few steps of the same sample
+    vs, infos = cpu_trajectory(sample, 1, min(args.steps, 6), 1, args.dt, budget_s=20.0)
     dims = DIMS[args.gpus]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps"],
@@ -229,7 +231,8 @@ def run_reference(args):
                          "sample": "%s; %d MD steps on %d host threads (one reference domain per thread), %d rebuilds; "
                                    "oracle/dlp_oracle.cpp is a restatement of the reference algorithm, not the reference "
                                    "binary (the reference is Fortran; no Fortran compiler in this image)"
-                                   % (what, info["steps"], info["cores"], info["rebuilds"])},
+                                   % (what, info["steps"], info["cores"], info["rebuilds"]),
+                         "serial": {"value": vs, "unit": UNIT, "cores": 1, "steps": infos["steps"]}},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -344,6 +347,8 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread; restatement "
                          "of the reference algorithm (oracle/), not the reference binary" % (what, info["steps"], info["rebuilds"], info["cores"])}
+        vs, infos = cpu_trajectory(sample, 1, 6, 1, dt, budget_s=8.0)     # the serial path: one domain on one core
+        cpu["serial"] = {"value": vs, "unit": UNIT, "cores": 1, "steps": infos["steps"]}
     if dom.profile is not None:
         sys.stderr.write("rank %d phase profile (ms per step, synchronised phases): %s\n" % (rank,
                          {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()}))
