@@ -463,7 +463,7 @@ __device__ __forceinline__ void pair2(const P2& P, cudaTextureObject_t tex, cons
       pc = te - (me - MAGIC);
     }
     int u = in_c ? lc : P.zero;
-    if (X & 2) u = (u & ~7) | (threadIdx.x & 7);
+    if (X & (2 | 128)) u = min((u & ~7) | (threadIdx.x & 7), P.ne - 2);
     double2 a, b, h;
     if (X & 8) { a = make_double2(ppp, rsq); b = make_double2(ri, rrr); h = make_double2(rsq, ppp); }
     else if ((TX & 8) && (X & 64)) { a = sG[u]; b = make_double2(a.x + (double)d4.z, a.y + (double)d4.w); h = make_double2(h_exact(h4.z, a.x), h_exact(h4.w, a.y)); }
@@ -927,11 +927,25 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
     if (ctx->variant > 0 && ctx->variant != 100 && v && e && sg) {   // timing experiments only (DLPGPU_VARIANT): results are not meaningful
       const int xv = ctx->variant & 0xfff, ntc = ctx->variant >> 12;
 #define DLP_V2N(XV) do { if (ntc == 0) DLP_V2X(XV, 512); else if (ntc == 1) DLP_V2X(XV, 640); else DLP_V2X(XV, 768); } while (0)
-      if (xv == 64) {   // fp32-h layout with the g(l+1) units replaced by a second texel (timing only)
-        const size_t smem8 = (size_t)ctx->tab2_ne * 16;
-        CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 64, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
-               t2s, fpos, fneg, ctx->partial.p);
+      if (xv == 64 || xv == 128 || xv == 0x801) {
+        // fp32-h layout, timing only.  64: the g(l+1) units replaced by a second texel; 128: conflict-free index for the Ewald
+        // reads only (what an 8-fold interleaved copy of the Ewald table would give); 0x801: the default kernel.  DLPGPU_SMEM_PAD
+        // (KB) adds unused dynamic shared memory, i.e. takes that much away from the L1 cache.
+        const char* pe = getenv("DLPGPU_SMEM_PAD");
+        const size_t smem8 = (size_t)ctx->tab2_ne * 16 + (pe ? (size_t)atoi(pe) * 1024 : 0);
+        if (xv == 64) {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 64, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+                 t2s, fpos, fneg, ctx->partial.p);
+        } else if (xv == 128) {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 128, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+                 t2s, fpos, fneg, ctx->partial.p);
+        } else {
+          CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 0, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+                 t2s, fpos, fneg, ctx->partial.p);
+        }
       } else if (xv == 32 || xv == 0x800) {   // on the default fp32-h layout: 32 = one gather + one RED triple per two pairs (emulates 2 x 1 clusters)
         const size_t smem8 = (size_t)ctx->tab2_ne * 16;
         if (xv == 32) {
