@@ -547,6 +547,9 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   for (int k = 0; k < 9; ++k) acc[k] = 0.0;
   double xeng = 0.0, xvir = 0.0;   // exclusion terms: engcpe_ex, sum of w egamma rsq
 
+  // rows are dealt to the blocks pass by pass (block b takes rows b RPB ... of every window of gridDim.x RPB rows), so the
+  // SMs work on one compact slab of the box at a time and share its coordinates and j-side accumulators in L2: giving each
+  // block one long run of consecutive rows instead costs 35 % (1.73 against 1.28 ms on 1 M NaCl ions, scripts/chunk_probe.py)
   for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
     const int t = min(base + grp, P.natms - 1);             // surplus groups of the last pass redo the last row and drop it
     const bool rowlive = base + grp < P.natms;
