@@ -169,6 +169,8 @@ def test_golden_fixture_matches_oracle(oracle):
         if not fn.endswith(".json"):
             continue
         g = json.load(open(os.path.join(GOLD, fn)))
+        if "generator" not in g:
+            continue
         s = getattr(systems, g["generator"])(**g["kwargs"])
         w = world_for(s, P=g["P"])
         out = w.two_body()
@@ -261,3 +263,20 @@ def test_rdf_collect_against_numpy_histogram(oracle):
     assert got.sum() == ref.sum() == m.sum()
     # a pair sitting within an ulp of a bin edge may fall either way between the two distance evaluations
     assert np.abs(got - ref).sum() <= 4
+
+
+def test_golden_host_logic_matches_oracle(oracle):
+    """tests/golden/host_logic.json: the oracle's vdw_lrc, end-of-two_body_forces and vnl_check decision answers, frozen."""
+    import test_host_cpp as th
+    g = json.load(open(os.path.join(GOLD, "host_logic.json")))
+    s = systems.nacl(3, rcut=9.0, padding=0.2)
+    num_type = [float((s.type_site[s.lsite - 1] == t).sum()) for t in (1, 2)]
+    e, v = th._ora_lrc(oracle, s.ff, num_type, [3.0, 5.0], 1, s.volume)
+    assert [e, v] == g["vdw_lrc_nacl_216_rc9_frozen_3_5"]
+    a = systems.argon(4)
+    assert list(th._ora_lrc(oracle, a.ff, [float(a.megatm)], [0.0], 1, a.volume)) == g["vdw_lrc_argon_256"]
+    tot, st = th._ora_epilogue(oracle, [1.0e5, -2.0e5, -3.0e6, 2.5e6, 4.0e3, -5.0e3, -7.0e5, 6.0e5], True, 2.0, 0.3, 1.0, 5000.0, e, v, 8,
+                               np.arange(9.0))
+    assert list(tot) == g["epilogue_totals"] and list(st) == g["epilogue_stress"]
+    rows, kodes = th._ora_vnl_trace(oracle, False, 0, 8.5, 0.1, np.diag([114.39] * 3).reshape(9), [1, 1, 1], g["vnl_tols"])
+    assert kodes == g["vnl_kodes"] and np.array_equal(rows, np.array(g["vnl_trace_nostrict_argon"]))
