@@ -201,6 +201,17 @@ int mode_host(const Bundle& in, Bundle& out) {
     const double a = ewald_alpha_from_precision(in.has("ew_precision") ? in.d1("ew_precision") : 1.0e-6, in.d1("rcut"));
     out.put("alpha_from_precision", 'd', &a, 1);
   }
+  if (in.has("fold_xyz")) {   // read_config: fold + domain assignment
+    std::vector<double> xyz = in.d("fold_xyz");
+    std::vector<int> owner;
+    domains_type dom;
+    double cp[10];
+    dcell(cell.data(), cp);
+    map_domains(in.i1("imcon"), cp[6], cp[7], cp[8], 0, in.i1("mxnode"), dom);
+    read_config_fold(xyz, cell.data(), dom, owner);
+    out.put("folded_xyz", xyz);
+    out.put("owner", owner);
+  }
   if (in.has("num_type")) {   // vdw_lrc + the end of two_body_forces on given (already global) partial sums
     ForceField ff;
     build_forcefield(in, ff);
@@ -338,7 +349,10 @@ int mode_md(const Bundle& in, Bundle& out) {
     const int rc = dlpgpu_set_force_mode(gpu.handle(), in.i1("force_mode"));
     if (rc) error(rc, dlpgpu_last_error(gpu.handle()));
   }
-  gpu.dev_load(in.d("xyz"), in.has("vel") ? in.d("vel") : std::vector<double>(), in.i("ltg"), in.i("lsite"));
+  std::vector<double> xyz = in.d("xyz");   // CONFIG positions: folded into the cell like read_config does
+  std::vector<int> owner;
+  read_config_fold(xyz, c.cell, dom, owner);
+  gpu.dev_load(xyz, in.has("vel") ? in.d("vel") : std::vector<double>(), in.i("ltg"), in.i("lsite"));
   const int nsteps = in.i1("nsteps");
   const double dt = in.d1("timestep");
   std::vector<double> sums((size_t)16 * (nsteps + 1), 0.0);

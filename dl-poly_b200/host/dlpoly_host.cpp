@@ -375,6 +375,33 @@ void vdw_lrc(const std::vector<double>& num_type, const std::vector<double>& num
   v.vlrc = plrc * (-3.0 * volm);
 }
 
+// configuration.F90:1183-1205
+void read_config_fold(std::vector<double>& xyz, const double cell[9], const domains_type& dom, std::vector<int>& owner) {
+  double rc[9], det;
+  invert(cell, rc, det);
+  const size_t n = xyz.size() / 3;
+  owner.assign(n, 0);
+  const double hm = half_minus();
+  auto fold = [hm](double s) {
+    // Anint: round half away from zero
+    const double t = std::trunc(s);
+    const double a = std::fabs(s - t) >= 0.5 ? t + (s < 0.0 ? -1.0 : 1.0) : t;
+    s = s - a;
+    return s >= hm ? -s : s;
+  };
+  auto ip = [](double s, int nd) { return std::min(std::max((int)((s + 0.5) * (double)nd), 0), nd - 1); };
+  for (size_t i = 0; i < n; ++i) {
+    const double ax = xyz[3 * i], ay = xyz[3 * i + 1], az = xyz[3 * i + 2];
+    const double sx = fold(rc[0] * ax + rc[3] * ay + rc[6] * az);
+    const double sy = fold(rc[1] * ax + rc[4] * ay + rc[7] * az);
+    const double sz = fold(rc[2] * ax + rc[5] * ay + rc[8] * az);
+    xyz[3 * i] = cell[0] * sx + cell[3] * sy + cell[6] * sz;
+    xyz[3 * i + 1] = cell[1] * sx + cell[4] * sy + cell[7] * sz;
+    xyz[3 * i + 2] = cell[2] * sx + cell[5] * sy + cell[8] * sz;
+    owner[i] = ip(sx, dom.nx) + dom.nx * (ip(sy, dom.ny) + dom.ny * ip(sz, dom.nz));
+  }
+}
+
 // two_body.F90:672-790
 void two_body_totals(stats_type& st, const vdw_type& v, const electrostatic_type& el, const ewald_type& ew, const configuration_type& c,
                      int mxnode, double engvdw, double virvdw, double engcpe_rc, double vircpe_rc, double engcpe_rl, double vircpe_rl,

@@ -140,6 +140,11 @@ struct configuration_type {
   std::vector<int> ltg, lsite, ltype, lfrzn;
 };
 
+// configuration.F90:1183-1205 (read_config): fold every atom into the reduced cell [-0.5, 0.5), recompute its Cartesian position
+// from cell . s (so positions carry the bits a DL_POLY run starts from) and assign it to its domain
+// idm = ipx + nx (ipy + ny ipz), ip = Int((s + 0.5) n).  xyz(3, n) in / out; owner(n) out (0-based rank).
+void read_config_fold(std::vector<double>& xyz, const double cell[9], const domains_type& domain, std::vector<int>& owner);
+
 // The end of two_body_forces (two_body.F90:672-790) for the terms of this path, AFTER the caller's gsum of the six partial sums
 // (:729): Fuchs' net-charge correction (SPME only), stats%engcpe / vircpe / engsrp / virsrp incl. the long-range corrections,
 // and the per-rank share of the corrections on the stress diagonal.  engcpe_rc / vircpe_rc: the caller's reciprocal-space sums.

@@ -156,6 +156,20 @@ def test_cpp_dcell_invert_map_domains_equal_the_oracle(oracle, tmp_path):
                 k += 1
 
 
+def test_cpp_read_config_fold_equals_the_oracle_load(oracle, tmp_path):
+    """configuration.F90:1183-1205: folded positions (same bits) and domain assignment as the oracle's read_config restatement."""
+    for s, P in ((systems.argon(6), 1), (systems.nacl((4, 2, 2), rcut=5.0, padding=0.2), 4), (systems.spce_water(512, rcut=8.0, padding=0.2), 8)):
+        shifted = s.xyz + np.array([3.0, -2.0, 1.0]) * np.array([s.cell[0], s.cell[4], s.cell[8]])   # images far outside the cell
+        w = oracle.World(P, s.cell, s.imcon)
+        w.set_cutoffs(s.rcut, s.padding, s.pdplnc)
+        w.set_sites(s.type_site, s.charge_site, s.freeze_site)
+        w.load(shifted, None, s.lsite)
+        out = run_check("host", dict(cell=s.cell, imcon=[s.imcon], mxnode=[P], fold_xyz=shifted), tmp_path)
+        assert np.array_equal(out["folded_xyz"].reshape(-1, 3), w.gather_positions())
+        for r in range(P):
+            assert np.array_equal(np.sort(w.ints(r)["ltg"][:w.counts(r)["natms"]]), np.nonzero(out["owner"] == r)[0] + 1)
+
+
 def test_cpp_map_domains_slab_limits(tmp_path):
     """imcon 0 (no periodicity) limits every axis to two domains, imcon 6 (slab) the z axis (domains.F90:103-105); where no
     factorisation fits, error 520."""
@@ -385,9 +399,7 @@ def test_cpp_host_native_md_against_oracle(tmp_path):
                 timestep=[dt], force_mode=[1])
     from oracle import oracle as ora
     w = ora.World.from_system(s, P=1)
-    # the device engine starts from the folded CONFIG positions, like the oracle's load
-    from dl_poly_b200 import dd
-    recs["xyz"] = dd.read_config_fold(s.xyz, s.cell, (1, 1, 1))[0]
+    # the C++ driver folds the CONFIG positions itself (read_config_fold), like the oracle's load
     out = run_check("md", recs, tmp_path)
     sums = out["sums"].reshape(nsteps + 1, 16)
     w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
