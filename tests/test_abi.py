@@ -88,3 +88,46 @@ def test_cpp_host_fails_loudly_without_gpu(tmp_path):
     fin.write_bytes(b"".join(recs))
     r = subprocess.run([exe, "md", str(fin), str(tmp_path / "out.bundle")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_fortran_binding_agrees_with_the_header():
+    """fortran/dlp_gpu_binding.F90 cannot be compiled in this image, so hold its Bind(C) interfaces against include/dlpgpu.h
+    textually: every bound name is declared in the header with the same number of arguments, value / reference passing
+    matches (scalars by Value, arrays and out-arguments by reference), and the drop-in entry points are all bound."""
+    hdr = open(os.path.join(ROOT, "include", "dlpgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*|long long|void\*)\s+(dlpgpu_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if args == ["void"] else args
+    src = open(os.path.join(ROOT, "fortran", "dlp_gpu_binding.F90")).read()
+    joined = re.sub(r"&\s*\n\s*", " ", src)                                   # continuation lines
+    bound = {}
+    for m in re.finditer(r"Function\s+(\w+)\s*\(([^)]*)\)\s*Bind\(C,\s*name='(\w+)'\)(.*?)End Function", joined, flags=re.S):
+        fname, fargs, cname, body = m.group(1), [a.strip() for a in m.group(2).split(",") if a.strip()], m.group(3), m.group(4)
+        assert fname == cname
+        bound[cname] = (fargs, body)
+    for must in ("dlpgpu_create", "dlpgpu_destroy", "dlpgpu_set_domain", "dlpgpu_set_cell", "dlpgpu_set_cutoffs", "dlpgpu_set_vdw",
+                 "dlpgpu_set_ewald", "dlpgpu_set_coulomb", "dlpgpu_link_cell_pairs", "dlpgpu_two_body_forces", "dlpgpu_vnl_check",
+                 "dlpgpu_rdf_collect", "dlpgpu_parts_unchanged_since_list"):
+        assert must in bound, must
+    for cname, (fargs, body) in bound.items():
+        assert cname in protos, "%s is not declared in dlpgpu.h" % cname
+        cargs = protos[cname]
+        assert len(fargs) == len(cargs), (cname, fargs, cargs)
+        for fa, ca in zip(fargs, cargs):
+            decl = [ln for ln in body.split("\n") if re.search(r"::.*\b%s\b" % re.escape(fa), ln)]
+            assert decl, (cname, fa)
+            by_value = "Value" in decl[0]
+            c_is_pointer = "*" in ca or "[" in ca
+            if "dlpgpu_ctx**" in ca.replace(" ", ""):
+                assert not by_value                                            # Type(c_ptr), Intent(Out)
+            elif "dlpgpu_ctx*" in ca.replace(" ", ""):
+                assert by_value and "c_ptr" in decl[0], (cname, fa, decl[0])   # the handle itself
+            elif c_is_pointer:
+                # arrays / out-arguments by reference, or a C pointer passed as Type(c_ptr), Value (c_loc of a Fortran array)
+                assert (not by_value) or "c_ptr" in decl[0], (cname, fa, decl[0])
+            else:
+                assert by_value, (cname, fa, decl[0])                          # C scalars
+                want = "c_double" if ca.split()[0] == "double" else "c_int"
+                assert want in decl[0], (cname, fa, decl[0])
