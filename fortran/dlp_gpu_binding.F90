@@ -266,8 +266,11 @@ Contains
     Real(Kind=wp), Allocatable, Save, Target :: shifted(:, :)
     Integer, Save                            :: used = 0
 
+    If (Allocated(shifted)) Then
+      If (Ubound(shifted, 1) /= Size(table)) Deallocate (shifted)
+    End If
     If (.not. Allocated(shifted)) Allocate (shifted(0:Size(table), 2))
-    used = used + 1
+    used = Mod(used, 2) + 1     ! two tables per call of dlp_gpu_set_forcefield; the library copies them before returning
     shifted(0, used) = 0.0_wp
     shifted(1:Size(table), used) = table(:)
     p = c_loc(shifted(0, used))
