@@ -89,12 +89,39 @@ def face_neighbours(rank, nx, ny, nz):
             idcube(idx, idy, (idz - 1) % nz, nx, ny), idcube(idx, idy, (idz + 1) % nz, nx, ny)]
 
 
+def dcell(cell):
+    """numerics.F90:1344-1446: lengths, cosines, perpendicular widths and volume of the cell (bbb(1:10)), with the
+    reference's operation order (so that Int(width / cutoff) decisions agree bit for bit with the other hosts)."""
+    a = [float(v) for v in np.asarray(cell, dtype=np.float64).reshape(9)]
+    sq = lambda x, y, z: float(np.sqrt(x * x + y * y + z * z))
+    b = [0.0] * 10
+    b[0], b[1], b[2] = sq(a[0], a[1], a[2]), sq(a[3], a[4], a[5]), sq(a[6], a[7], a[8])
+    b[3] = (a[0] * a[3] + a[1] * a[4] + a[2] * a[5]) / (b[0] * b[1])
+    b[4] = (a[0] * a[6] + a[1] * a[7] + a[2] * a[8]) / (b[0] * b[2])
+    b[5] = (a[3] * a[6] + a[4] * a[7] + a[5] * a[8]) / (b[1] * b[2])
+    axb = (a[1] * a[5] - a[2] * a[4], a[2] * a[3] - a[0] * a[5], a[0] * a[4] - a[1] * a[3])
+    bxc = (a[4] * a[8] - a[5] * a[7], a[5] * a[6] - a[3] * a[8], a[3] * a[7] - a[4] * a[6])
+    cxa = (a[7] * a[2] - a[8] * a[1], a[8] * a[0] - a[6] * a[2], a[6] * a[1] - a[7] * a[0])
+    b[9] = abs(a[0] * bxc[0] + a[1] * bxc[1] + a[2] * bxc[2])
+    d = (b[9] / sq(*bxc), b[9] / sq(*cxa), b[9] / sq(*axb))
+    x = [abs(a[3 * v]) / b[v] for v in range(3)]
+    y = [abs(a[3 * v + 1]) / b[v] for v in range(3)]
+    if x[0] >= x[1] and x[0] >= x[2]:
+        first = 0
+    elif x[1] >= x[0] and x[1] >= x[2]:
+        first = 1
+    else:
+        first = 2
+    p, q = (1 if first == 0 else 0), (1 if first == 2 else 2)
+    b[6] = d[first]
+    b[7], b[8] = (d[p], d[q]) if y[p] >= y[q] else (d[q], d[p])
+    return b
+
+
 def cell_widths(cell):
     """celprp(7:9) of numerics.F90::dcell for the lattice vectors in ``cell`` (rows)."""
-    a = np.asarray(cell, dtype=np.float64).reshape(3, 3)
-    vol = abs(np.linalg.det(a))
-    bxc, cxa, axb = np.cross(a[1], a[2]), np.cross(a[2], a[0]), np.cross(a[0], a[1])
-    return vol / np.linalg.norm(bxc), vol / np.linalg.norm(cxa), vol / np.linalg.norm(axb)
+    b = dcell(cell)
+    return b[6], b[7], b[8]
 
 
 def invert(cell):
@@ -263,10 +290,9 @@ def exchange_capacities(sysm, dims, safety=2.0):
     the widest face (link-cell width w = domain width / Int(domain width / cutoff_extended), halo.F90:219-239, grown by the
     halo layers already received in the earlier directions) at the mean density, times ``safety``; migration: a layer of
     one padding thickness across that face (an atom moves less than padding / 2 between rebuilds, neighbours.F90:182)."""
-    cell = np.asarray(sysm.cell, dtype=np.float64).reshape(3, 3)
-    vol = abs(np.linalg.det(cell))
-    rho = sysm.megatm / vol
-    wid = [w / d for w, d in zip(cell_widths(cell), dims)]
+    b = dcell(sysm.cell)
+    rho = sysm.megatm / b[9]
+    wid = [w / d for w, d in zip(b[6:9], dims)]
     rx = sysm.rcut + sysm.padding
     lw = [wd / max(int(wd / (rx + 1.0e-6)), 1) for wd in wid]
     full = [wd + 2.0 * l for wd, l in zip(wid, lw)]

@@ -201,6 +201,22 @@ int mode_host(const Bundle& in, Bundle& out) {
     const double a = ewald_alpha_from_precision(in.has("ew_precision") ? in.d1("ew_precision") : 1.0e-6, in.d1("rcut"));
     out.put("alpha_from_precision", 'd', &a, 1);
   }
+  if (in.has("cap_cases")) {   // exchange_capacities: (mxnode, megatm) pairs with (rcut, padding) pairs
+    const std::vector<int> cs = in.i("cap_cases");
+    const std::vector<double> cp2 = in.d("cap_cutoffs");
+    std::vector<int> res;
+    double w[10];
+    dcell(cell.data(), w);
+    for (size_t k = 0; k < cs.size() / 2; ++k) {
+      domains_type dom;
+      map_domains(in.i1("imcon"), w[6], w[7], w[8], 0, cs[2 * k], dom);
+      int cr = 0, ch = 0;
+      exchange_capacities(cell.data(), cs[2 * k + 1], dom, cp2[2 * k], cp2[2 * k + 1], 2.0, cr, ch);
+      res.push_back(cr);
+      res.push_back(ch);
+    }
+    out.put("cap_results", res);
+  }
   if (in.has("fold_xyz")) {   // read_config: fold + domain assignment
     std::vector<double> xyz = in.d("fold_xyz");
     std::vector<int> owner;

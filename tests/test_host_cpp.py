@@ -141,6 +141,8 @@ def test_cpp_dcell_invert_map_domains_equal_the_oracle(oracle, tmp_path):
                 wid += list(widths)
         out = run_check("host", dict(cell=cell, dd_cases=np.array(cases, dtype=np.int32), dd_widths=np.array(wid)), tmp_path)
         assert np.array_equal(out["celprp"], oracle.dcell(cell))
+        from dl_poly_b200 import dd
+        assert np.array_equal(np.array(dd.dcell(cell)), oracle.dcell(cell))          # the Python host's dcell: same bits
         inv, det = oracle.invert(cell)
         assert np.array_equal(out["rcell"], inv) and out["det"][0] == det
         res = out["dd_results"].reshape(-1, 58)
@@ -168,6 +170,19 @@ def test_cpp_read_config_fold_equals_the_oracle_load(oracle, tmp_path):
         assert np.array_equal(out["folded_xyz"].reshape(-1, 3), w.gather_positions())
         for r in range(P):
             assert np.array_equal(np.sort(w.ints(r)["ltg"][:w.counts(r)["natms"]]), np.nonzero(out["owner"] == r)[0] + 1)
+
+
+def test_cpp_exchange_capacities_equal_the_python_engine(tmp_path):
+    """Stage-buffer capacities of the device-side exchange must be identical on every rank and in both hosts."""
+    from dl_poly_b200 import dd
+    cases = [(systems.nacl((8, 8, 8), rcut=8.0, padding=0.3), 8), (systems.nacl((6, 4, 4), rcut=6.0, padding=0.2), 4),
+             (systems.argon(8), 2), (systems.argon(6), 1), (systems.spce_water(512, rcut=8.0, padding=0.2), 1)]
+    for s, P in cases:
+        dims = dd.map_domains(P, dd.cell_widths(s.cell), s.imcon)
+        want = dd.exchange_capacities(s, dims, safety=2.0)
+        out = run_check("host", dict(cell=s.cell, imcon=[s.imcon], cap_cases=np.array([P, s.megatm], dtype=np.int32),
+                                     cap_cutoffs=np.array([s.rcut, s.padding])), tmp_path)
+        assert tuple(out["cap_results"]) == tuple(want), (s.name, P)
 
 
 def test_cpp_map_domains_slab_limits(tmp_path):
