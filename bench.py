@@ -428,7 +428,7 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)   # >= 200 steps, so rebuilds are amortised at their natural frequency
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ionic", choices=["ionic", "table", "lj", "c1", "c2", "c3"])
