@@ -536,3 +536,39 @@ def test_vdw_lrc_and_two_body_totals(oracle, tmp_path, name):
     assert np.array_equal(np.array(py[:4]), tot_o) and np.array_equal(py[4], st_o)
     if name == "buck":
         assert tot_o[0] != sums8[6] + sums8[2] + sums8[4]         # the net-charge term is in
+
+
+def test_cpp_host_logic_fuzz_against_the_oracle(oracle, tmp_path):
+    """Random cells, decompositions, cutoffs and displacement sequences: map_domains and every branch of the vnl_check
+    decision logic (incl. the error-307 exits) give the oracle's answers bit for bit."""
+    rng = np.random.default_rng(2026)
+    seen_kodes, seen_retune = set(), 0
+    for case in range(60):
+        if case % 3 == 0:
+            cellm = np.diag(rng.uniform(14.0, 120.0, 3)).reshape(9)
+        elif case % 3 == 1:
+            L = rng.uniform(14.0, 120.0)
+            cellm = np.diag([L, L, L]).reshape(9)
+        else:
+            cellm = (np.diag(rng.uniform(20.0, 90.0, 3)) + rng.uniform(-3.0, 3.0, (3, 3))).reshape(9)
+        P = int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 24, 27, 32, 64]))
+        rcut = float(rng.uniform(5.0, 14.0))
+        padding = float(rng.choice([0.05, 0.1, 0.2, 0.35, 0.6, 1.0]))
+        l_str, bspline = bool(rng.integers(0, 2)), int(rng.integers(0, 2)) * 8
+        tols = list(rng.uniform(0.0, 0.6 * padding + 0.05, 12))
+        w = oracle.World(P, cellm, 1)
+        dd6, map26 = w.dd(P - 1)
+        recs = dict(cell=cellm, imcon=[1], megatm=[1000], rcut=[rcut], padding=[padding], mxnode=[P], idnode=[0],
+                    vnl_tols=np.array(tols), l_str=[int(l_str)], bspline=[bspline],
+                    dd_cases=np.array([1, P, P - 1], dtype=np.int32), dd_widths=oracle.dcell(cellm)[6:9])
+        out = run_check("host", recs, tmp_path)
+        res = out["dd_results"]
+        assert np.array_equal(res[:6], dd6) and np.array_equal(res[6:32], map26), (case, P)
+        rows, kodes = _ora_vnl_trace(oracle, l_str, bspline, rcut, padding, cellm, dd6[:3], tols)
+        assert list(out["vnl_kode"]) == kodes, (case, kodes)
+        got = out["vnl_trace"].reshape(-1, 10)
+        if kodes[-1] == 0:
+            assert np.array_equal(got, rows), case
+            seen_retune += int(len(set(rows[:, 1])) > 1 or rows[0, 1] != padding)
+        seen_kodes.add(kodes[-1])
+    assert seen_kodes == {0, 307} and seen_retune >= 5
