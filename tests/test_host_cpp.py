@@ -572,3 +572,40 @@ def test_cpp_host_logic_fuzz_against_the_oracle(oracle, tmp_path):
             seen_retune += int(len(set(rows[:, 1])) > 1 or rows[0, 1] != padding)
         seen_kodes.add(kodes[-1])
     assert seen_kodes == {0, 307} and seen_retune >= 5
+
+
+def test_cpp_tables_fuzz_against_the_oracle(oracle, tmp_path):
+    """Random parameters for the four analytic forms, random cutoffs (table sizes), force-shift constants, random Ewald
+    alpha: vdw_generate / vdw_direct_fs_generate / erfcgen of the C++ host equal the oracle's bit for bit."""
+    rng = np.random.default_rng(77)
+    forms = {"12-6": lambda: [rng.uniform(1e5, 1e8), rng.uniform(1e2, 1e4)], "lj": lambda: [rng.uniform(10, 500), rng.uniform(2.0, 4.0)],
+             "buck": lambda: [rng.uniform(1e4, 1e6), rng.uniform(0.2, 0.4), rng.uniform(10, 5e3)],
+             "bhm": lambda: [rng.uniform(1e3, 5e3), rng.uniform(2.5, 3.5), rng.uniform(2.0, 3.5), rng.uniform(1e4, 1e6), rng.uniform(1e3, 1e6)]}
+    for case in range(12):
+        rvdw = float(rng.uniform(6.0, 14.0))
+        rcut = rvdw + float(rng.choice([0.0, 0.5, 1.5]))
+        alpha = float(rng.uniform(0.15, 0.45))
+        names = list(forms)
+        spec = []
+        for k, (ai, aj) in enumerate([(1, 1), (1, 2), (2, 2)]):
+            f = names[int(rng.integers(0, 4))]
+            spec.append((ai, aj, f, forms[f]()))
+        pairs, prm = [], []
+        for ai, aj, f, p in spec:
+            pairs += [ai, aj, tables.KEYPOT[f]]
+            q = np.zeros(7); q[:len(p)] = p
+            prm.append(q)
+        recs = dict(cell=np.diag([60.0, 60.0, 60.0]).reshape(9), ntypes=[2], rvdw=[rvdw], rcut=[rcut], padding=[0.2], force_shift=[1], direct=[1],
+                    pot_pairs=np.array(pairs, dtype=np.int32), pot_param=np.array(prm).reshape(-1), electro_key=[1], eps=[1.0],
+                    damping=[0.0], fdens=[0.03], ew_alpha=[alpha])
+        out = run_check("host", recs, tmp_path)
+        g = oracle.lib().ora_max_grid(rvdw)
+        assert tuple(out["vdw_sizes"]) == (3, 3, g)
+        for k, (ai, aj, f, p) in enumerate(spec):
+            tp, tf = oracle.vdw_generate(tables.KEYPOT[f], p, rvdw, g)
+            assert np.array_equal(out["tab_potential"].reshape(-1, g + 1)[k], tp), (case, f)
+            assert np.array_equal(out["tab_force"].reshape(-1, g + 1)[k], tf), (case, f)
+            assert (out["afs"][k], out["bfs"][k]) == oracle.vdw_direct_fs(tables.KEYPOT[f], p, rvdw), (case, f)
+        n = oracle.lib().ora_max_grid(rcut)
+        e, d, rs = oracle.erfcgen(rcut, alpha, n)
+        assert np.array_equal(out["erfc"], e) and np.array_equal(out["erfc_deriv"], d) and out["electro"][1] == rs
