@@ -18,14 +18,40 @@ COREPART = np.dtype([("xxx", "f8"), ("yyy", "f8"), ("zzz", "f8"), ("fxx", "f8"),
 assert COREPART.itemsize == 64
 
 
+def _host_fingerprint():
+    """Identifies the CPU the perf variant (-march=native) was built for: it must never run on another machine's cores (the
+    built file travels with the repo snapshot to the GPU box)."""
+    import hashlib
+    import platform
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        flags = [ln.split(":", 1)[1] for ln in txt.split("\n") if ln.startswith(("flags", "model name"))][:2]
+    except OSError:
+        flags = []
+    return hashlib.sha1((platform.machine() + "|" + "|".join(flags)).encode()).hexdigest()
+
+
 def build(perf=False, quiet=True):
     target = "perf" if perf else "all"
     src = os.path.join(HERE, "dlp_oracle.cpp")
     out = PERF_PATH if perf else LIB_PATH
-    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+    stamp = out + ".host"
+    fresh = os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src)
+    if perf and fresh:
+        try:
+            fresh = open(stamp).read().strip() == _host_fingerprint()
+        except OSError:
+            fresh = False
+    if fresh:
         return out
+    if perf and os.path.exists(out):
+        os.remove(out)                      # make would consider it up to date
     subprocess.run(["make", "-C", HERE, target], check=True,
                    stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.STDOUT if quiet else None)
+    if perf:
+        with open(stamp, "w") as f:
+            f.write(_host_fingerprint())
     return out
 
 
