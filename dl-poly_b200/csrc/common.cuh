@@ -125,7 +125,7 @@ struct dlpgpu_ctx {
   int tpr_override = 0;
   int tx_override = -1;    // DLPGPU_TX: which table reads of k_pair_v2 go through the texture pipe (tuning knob)
   int variant = 0;         // DLPGPU_VARIANT: timing experiments of the pair kernel (development only)
-  bool no_fast = false;    // DLPGPU_NO_FAST=1: always use the general pair kernel
+  bool no_fast = false;    // dlpgpu_set_pair_kernel: always use the general pair kernel
 
   // sites (native mode)
   int nsites = 0;

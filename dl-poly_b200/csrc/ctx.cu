@@ -148,7 +148,6 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   if (const char* e = getenv("DLPGPU_TPR")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) ctx->tpr_override = v; }   // tuning knob
   if (const char* e = getenv("DLPGPU_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("DLPGPU_TX")) ctx->tx_override = atoi(e);
-  if (const char* e = getenv("DLPGPU_NO_FAST")) ctx->no_fast = atoi(e) != 0;
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
   *out = ctx;
@@ -333,6 +332,12 @@ int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 1) return DLPGPU_ERR_ARG;
   if (mode != ctx->force_mode) ctx->list_valid = false;
   ctx->force_mode = mode;
+  return 0;
+}
+
+int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int general_only) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  ctx->no_fast = general_only != 0;
   return 0;
 }
 

@@ -97,6 +97,10 @@ class ShortRange:
         self._ck(self.L.dlpgpu_set_force_mode(self.h, int(mode)))
         self.force_mode = int(mode)
 
+    def set_pair_kernel(self, general_only=False):
+        """Diagnostic: always use the general pair kernel (the reference's operation order statement by statement)."""
+        self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(bool(general_only))))
+
     # ---- drop-in entry points (host buffers, Fortran index conventions) ------------------------------------------
     def link_cell_pairs(self, natms, nlast, parts, ltype, ltg, lfrzn=None, lbook=False, megfrz=0, list_excl=None,
                         max_list=None, want_list=True):

@@ -82,6 +82,7 @@ SIGNATURES = {
     "dlpgpu_fp64_peak": (ci, [vp, cd, pd_]),
     "dlpgpu_last_timings": (ci, [vp, vp]),
     "dlpgpu_set_force_mode": (ci, [vp, ci]),
+    "dlpgpu_set_pair_kernel": (ci, [vp, ci]),
 }
 
 _lib = None

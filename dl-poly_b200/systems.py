@@ -16,7 +16,9 @@ class System:
                  freeze_site=None, excl=None, temperature=0.0, seed=0):
         self.name = name
         self.cell = np.ascontiguousarray(cell, dtype=np.float64).reshape(9)
-        self.imcon = 1 if (self.cell[0] == self.cell[4] == self.cell[8]) else 2
+        offdiag = np.abs(self.cell[[1, 2, 3, 5, 6, 7]]).max()
+        # imcon of the CONFIG header: 1 cubic, 2 orthorhombic, 3 parallelepiped
+        self.imcon = 3 if offdiag > 0.0 else (1 if (self.cell[0] == self.cell[4] == self.cell[8]) else 2)
         self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self.megatm = self.xyz.shape[0]
         self.lsite = np.ascontiguousarray(lsite, dtype=np.int32)            # 1-based site index per atom
@@ -92,6 +94,26 @@ def argon(ncell=20, seed=1001, rcut=8.5, padding=0.3, form="12-6", direct=False,
     ff.finalize()
     cell = np.diag(L)
     return System("C1-argon-%d" % n, cell, xyz, np.ones(n, dtype=np.int32), [1], [0.0], [39.948], ff, rcut, padding,
+                  temperature=temperature, seed=seed)
+
+
+def argon_triclinic(ncell=6, seed=1011, rcut=8.5, padding=0.3, shear=(0.20, 0.10, 0.15), jitter=0.25, temperature=85.0):
+    """The C1 fluid in a parallelepiped cell (imcon = 3): the cubic lattice sheared by b += shear[0] a, c += shear[1] a +
+    shear[2] b.  Positions are cell . s with s the reduced coordinates of the jittered fcc sites."""
+    nc = np.array(_n3(ncell), dtype=np.float64)
+    n = int(4 * nc.prod())
+    a = (4.0 / 0.02138) ** (1.0 / 3.0)
+    L = nc * a
+    rng = np.random.default_rng(seed)
+    xyz = _fcc(ncell, a) - 0.5 * L + 0.25 * a
+    sred = _wrap(xyz + rng.uniform(-jitter, jitter, xyz.shape), L) / L            # reduced coordinates in [-0.5, 0.5)
+    cell = np.array([[L[0], 0.0, 0.0], [shear[0] * L[0], L[1], 0.0], [shear[1] * L[0], shear[2] * L[1], L[2]]])
+    xyz = sred @ cell                                                             # r = s_a a + s_b b + s_c c  (rows = lattice vectors)
+    eps, sig = 99.61, 3.405
+    ff = tables.ForceField(1, rcut, rcut)
+    ff.add(1, 1, "12-6", [4 * eps * sig ** 12, 4 * eps * sig ** 6])
+    ff.finalize()
+    return System("argon-triclinic-%d" % n, cell.reshape(9), xyz, np.ones(n, dtype=np.int32), [1], [0.0], [39.948], ff, rcut, padding,
                   temperature=temperature, seed=seed)
 
 
@@ -178,7 +200,7 @@ def ionic_mixture(ncell=4, ntypes=4, seed=1010, rcut=8.0, padding=0.2, jitter=0.
 
 
 def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0e-6, temperature=0.0, coulomb=None, eps=1.0,
-               damping=0.0):
+               damping=0.0, rvdw=None):
     """C3: SPC/E water, 3*nmol atoms, rigid geometry 1.0 A / 109.47 deg, random orientations, O-O LJ, exclusions =
     the two other atoms of the molecule."""
     L = (nmol / 0.0334) ** (1.0 / 3.0)
@@ -200,7 +222,7 @@ def spce_water(nmol=72000, seed=1003, rcut=9.0, padding=0.18, spme_precision=1.0
     xyz = _wrap(xyz, L)
     n = 3 * nmol
     lsite = np.tile(np.array([1, 2, 3], dtype=np.int32), nmol)
-    ff = tables.ForceField(2, rcut, rcut)
+    ff = tables.ForceField(2, rcut if rvdw is None else rvdw, rcut)      # rvdw < rcut: control.F90:1499-1543
     ff.add(1, 1, "lj", [65.0, 3.166])
     if coulomb is not None:
         ff.set_coulomb(coulomb, eps=eps, damping=damping)

@@ -221,8 +221,13 @@ int dlpgpu_fp64_peak(dlpgpu_ctx* ctx, double seconds, double* tflops);
 /* device time (ms, CUDA events on the context's stream) of the last list build and the last force evaluation,
  * and of their dominant kernels: t[0]=list total, t[1]=force total, t[2]=pair-force kernel, t[3]=full-list kernel */
 int dlpgpu_last_timings(dlpgpu_ctx* ctx, double t[4]);
-/* 0: full list, no atomics (default).  1: half list + fp64 RED atomics (Newton's third law). */
+/* 1 (default, common.cuh force_mode): half list + fp64 RED atomics (Newton's third law) -- the reference's own pair count.
+ * 0: full list without atomics (every local-local pair evaluated from both ends; bitwise reproducible forces). */
 int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
+/* Diagnostic: general_only != 0 makes two_body_forces always use the general pair kernel (k_pair_forces: the reference's
+ * operation order statement by statement, vdw.F90:1790-2024 / ewald_spole.F90:58-242) instead of the fast tabulated kernel.
+ * The parity tests hold the two against each other; results agree within the north-star bars either way. */
+int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int general_only);
 
 #ifdef __cplusplus
 }

@@ -2253,13 +2253,26 @@ void ora_world_vv(void* h, int stage, double dt, const double* weight_by_type /*
 // Returns number of pairs; pairs_out may be null to query size.  band_out counts pairs within rel 1e-12 of rx^2.
 long ora_brute_pairs(int n, const double* xyz, const double* cell9, double rx, int* pairs_out, long cap, long* band_out) {
   long np = 0, band = 0;
-  long double Lx = cell9[0], Ly = cell9[4], Lz = cell9[8];
+  long double c[10], rc[10];   // general cell: minimum image in reduced coordinates (see ora_world_brute_forces)
+  for (int k = 1; k <= 9; ++k) c[k] = cell9[k - 1];
+  rc[1] = c[5] * c[9] - c[6] * c[8]; rc[2] = c[3] * c[8] - c[2] * c[9]; rc[3] = c[2] * c[6] - c[3] * c[5];
+  rc[4] = c[6] * c[7] - c[4] * c[9]; rc[5] = c[1] * c[9] - c[3] * c[7]; rc[6] = c[3] * c[4] - c[1] * c[6];
+  rc[7] = c[4] * c[8] - c[5] * c[7]; rc[8] = c[2] * c[7] - c[1] * c[8]; rc[9] = c[1] * c[5] - c[2] * c[4];
+  {
+    long double det = c[1] * rc[1] + c[4] * rc[2] + c[7] * rc[3];
+    for (int k = 1; k <= 9; ++k) rc[k] /= det;
+  }
   long double rc2 = (long double)rx * rx;
   for (int i = 0; i < n; ++i)
     for (int j = i + 1; j < n; ++j) {
       long double dx = (long double)xyz[3 * i] - xyz[3 * j], dy = (long double)xyz[3 * i + 1] - xyz[3 * j + 1],
                   dz = (long double)xyz[3 * i + 2] - xyz[3 * j + 2];
-      dx -= Lx * roundl(dx / Lx); dy -= Ly * roundl(dy / Ly); dz -= Lz * roundl(dz / Lz);
+      {
+        long double sx = rc[1] * dx + rc[4] * dy + rc[7] * dz, sy = rc[2] * dx + rc[5] * dy + rc[8] * dz,
+                    sz = rc[3] * dx + rc[6] * dy + rc[9] * dz;
+        long double nx = roundl(sx), ny = roundl(sy), nz = roundl(sz);
+        dx -= c[1] * nx + c[4] * ny + c[7] * nz; dy -= c[2] * nx + c[5] * ny + c[8] * nz; dz -= c[3] * nx + c[6] * ny + c[9] * nz;
+      }
       long double r2 = dx * dx + dy * dy + dz * dz;
       if (fabsl(r2 - rc2) <= 1e-12L * rc2) band++;
       if (r2 <= rc2) {
@@ -2275,14 +2288,29 @@ long ora_brute_pairs(int n, const double* xyz, const double* cell9, double rx, i
 void ora_world_brute_forces(void* h, int n, const double* xyz, const int* lsite, double* f_out /*3n*/, double* out6) {
   World* w = (World*)h;
   Vdw& v = w->vdw; Ewald& e = w->ew;
-  long double Lx = w->cell[1], Ly = w->cell[5], Lz = w->cell[9];
+  // minimum image in reduced coordinates of the general (parallelepiped) cell, in long double: exact for every pair closer
+  // than half the smallest perpendicular width, which cutoff_extended always is (neighbours.F90:409-412)
+  long double c[10], rc[10];
+  for (int k = 1; k <= 9; ++k) c[k] = w->cell[k];
+  {
+    rc[1] = c[5] * c[9] - c[6] * c[8]; rc[2] = c[3] * c[8] - c[2] * c[9]; rc[3] = c[2] * c[6] - c[3] * c[5];
+    rc[4] = c[6] * c[7] - c[4] * c[9]; rc[5] = c[1] * c[9] - c[3] * c[7]; rc[6] = c[3] * c[4] - c[1] * c[6];
+    rc[7] = c[4] * c[8] - c[5] * c[7]; rc[8] = c[2] * c[7] - c[1] * c[8]; rc[9] = c[1] * c[5] - c[2] * c[4];
+    long double det = c[1] * rc[1] + c[4] * rc[2] + c[7] * rc[3];
+    for (int k = 1; k <= 9; ++k) rc[k] /= det;
+  }
   std::vector<long double> F(3 * (size_t)n, 0.0L);
   long double ev = 0, vv = 0, ec = 0, vc = 0, ex = 0, vx = 0;
   for (int i = 0; i < n; ++i)
     for (int j = i + 1; j < n; ++j) {
       long double dxl = (long double)xyz[3 * i] - xyz[3 * j], dyl = (long double)xyz[3 * i + 1] - xyz[3 * j + 1],
                   dzl = (long double)xyz[3 * i + 2] - xyz[3 * j + 2];
-      dxl -= Lx * roundl(dxl / Lx); dyl -= Ly * roundl(dyl / Ly); dzl -= Lz * roundl(dzl / Lz);
+      {
+        long double sx = rc[1] * dxl + rc[4] * dyl + rc[7] * dzl, sy = rc[2] * dxl + rc[5] * dyl + rc[8] * dzl,
+                    sz = rc[3] * dxl + rc[6] * dyl + rc[9] * dzl;
+        long double nx = roundl(sx), ny = roundl(sy), nz = roundl(sz);
+        dxl -= c[1] * nx + c[4] * ny + c[7] * nz; dyl -= c[2] * nx + c[5] * ny + c[8] * nz; dzl -= c[3] * nx + c[6] * ny + c[9] * nz;
+      }
       long double r2 = dxl * dxl + dyl * dyl + dzl * dzl;
       if (r2 > (long double)w->rx * w->rx) continue;
       double dx = (double)dxl, dy = (double)dyl, dz = (double)dzl;

@@ -14,7 +14,7 @@ import pytest
 from dl_poly_b200 import build as dlp_build
 from dl_poly_b200 import systems, tables
 from dl_poly_b200.lib import COREPART
-from util import domain_inputs, force_errors, parts_forces, world_for
+from util import domain_inputs, force_errors, parts_forces, world_for, per_atom_force_error
 
 FORCE_TOL = 1.0e-9      # north star: per-atom forces, relative to the largest force
 ENERGY_TOL = 1.0e-10    # north star: energies / virials, relative
@@ -390,6 +390,7 @@ def test_cpp_host_dropin_against_oracle(tmp_path, name):
     parts = np.frombuffer(out["parts"], dtype=COREPART)
     a, b = force_errors(parts_forces(parts, d["natms"]), parts_forces(d["parts"], d["natms"]))
     assert a <= FORCE_TOL and b <= 1.0e-7
+    assert per_atom_force_error(parts_forces(parts, d["natms"]), parts_forces(d["parts"], d["natms"]))["per_atom_significant"] <= FORCE_TOL
     oo = w.results(rank)
     scale = max(abs(oo[:6]).max(), 1.0)
     for k in range(6):

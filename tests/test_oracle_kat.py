@@ -120,7 +120,45 @@ CASES = {
     "argon_864": lambda: systems.argon(6),
     "nacl_512": lambda: systems.nacl(4, rcut=8.0, padding=0.2),
     "water_1536": lambda: systems.spce_water(512, rcut=8.0, padding=0.2),
+    "argon_triclinic_864": lambda: systems.argon_triclinic(6),                       # imcon = 3, parallelepiped cell
+    "water_rvdw_below_rcut": lambda: systems.spce_water(512, rcut=8.0, padding=0.2, rvdw=6.5),
 }
+
+
+def _with_pdplnc(s, v):
+    s.pdplnc = v
+    return s
+
+
+@pytest.mark.parametrize("pdplnc,nlp", [(2.0, 3), (0.5, 4)])
+def test_oracle_nlp3_shortcut_over_admits_but_forces_agree(oracle, pdplnc, nlp):
+    """neighbours.F90:537: for nlp >= 3 the cells within (nlp-1)^2 of the primary cell skip the distance test, so the list
+    is a SUPERSET of the pairs within cutoff_extended; the force loops test r < rcut themselves, so forces
+    and energies still equal the brute force."""
+    s = _with_pdplnc(systems.argon(6), pdplnc)
+    w = world_for(s, P=1)
+    c = w.counts(0)
+    assert c["nlp"] == nlp
+    out = w.two_body()
+    x = w.gather_positions()
+    bp, band = oracle.brute_pairs(x, s.cell, s.rx)
+    got = set()
+    lst, ints = w.list(0), w.ints(0)
+    for i in range(c["natms"]):
+        for k in range(1, lst[i, 1] + 1):
+            j = lst[i, 3 + k] - 1
+            gi, gj = ints["ltg"][i], ints["ltg"][j]
+            if j < c["natms"] or gi < gj:
+                got.add((min(gi, gj), max(gi, gj)))
+    want = set(map(tuple, bp))
+    assert want <= got
+    if nlp == 3:
+        assert len(got) > len(want)                          # over-admission is real at this cell size
+    fb, ob = w.brute_forces(x, s.lsite)
+    f = w.gather_forces()
+    assert np.abs(f - fb).max() <= 1e-12 * np.abs(fb).max()
+    for k in range(2):
+        assert abs(out[k] - ob[k]) <= 1e-12 * max(abs(ob[k]), 1.0)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
