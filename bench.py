@@ -93,7 +93,8 @@ def flop_per_atom_step(sysm, listed_pairs_per_atom):
         for a in range(ff.ntypes):
             for b in range(ff.ntypes):
                 hi, lo = max(a, b) + 1, min(a, b) + 1
-                if ff.vdw_list_c[hi * (hi - 1) // 2 + lo - 1] > 0:
+                k = int(ff.vdw_list_c[hi * (hi - 1) // 2 + lo - 1])      # undefined pairs point at n_vdw + 1 with ltp = VDW_NULL
+                if 1 <= k <= ff.n_vdw and int(ff.ltp[k - 1]) != -1:
                     frac += cnt[a] * cnt[b]
         per_pair += FLOP_VDW * frac
     if ff.ew_active:
@@ -167,6 +168,7 @@ def cpu_trajectory(sample, nthreads_hint, steps, warmup, dt, budget_s=None):
     while P * 2 <= min(cores, nthreads_hint or cores, 64):
         P *= 2
     w = ora.World.from_system(sample, P=P, perf=True)
+    w.set_threads(P)          # every phase runs one domain per host thread (halo, migration, vnl_check, integrator too)
     w.relocate(); w.set_halo()
     rc = w.link_cell_pairs(P)
     assert rc == 0, "oracle link_cell_pairs rc=%d" % rc
@@ -240,6 +242,134 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def timed_trajectory(torch, dom, transport, dt, steps, warmup, sampler_rank0=None):
+    """W untimed + K timed MD steps of the device-resident engine.  Returns the device time (CUDA events on the library's
+    stream, max over ranks) and the accounting of the timed region.  The step is dlpgpu_dev_md_step: velocity-Verlet stage 1,
+    vnl_check + gmax AND the gsum of the previous step's 16 sums (both ride on one peer-memory mailbox message), rebuild
+    (migration + halo + list) or halo refresh, two_body_forces, velocity-Verlet stage 2."""
+    sr = dom.sr
+    for _ in range(warmup):
+        dom.step(dt, lazy=True)
+    dom.collect()
+    dom.rebuilds = 0
+    acc0 = dict(dom.acc)
+    stream = dom.stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if transport is not None:
+        transport.barrier()
+    torch.cuda.synchronize()
+    l0 = sr.launch_count()
+    ev0.record(stream)
+    for _ in range(steps):
+        dom.step(dt, lazy=True)          # the sums of step n arrive, already reduced over the ranks, with the gmax of step n+1
+    out = dom.collect()                  # ... and the last step's here, inside the timed region,
+    out = dom.gsum(out)                  # with the classic collective for its reduction (two_body.F90:729)
+    ev1.record(stream)
+    if transport is not None:
+        transport.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    assert dom.acc["force_calls"] - acc0["force_calls"] == steps and np.all(np.isfinite(out))
+    res = {"ms": ms, "launches": sr.launch_count() - l0, "out": out,
+           "pair_ms": dom.acc["pair_ms"] - acc0["pair_ms"], "force_ms": dom.acc["force_ms"] - acc0["force_ms"],
+           "list_ms": dom.acc["list_ms"] - acc0["list_ms"], "list_builds": dom.acc["list_builds"] - acc0["list_builds"],
+           "rebuilds": dom.rebuilds}
+    natms, nlast = sr.dev_counts()
+    res["natms"], res["nlast"], res["pairs"] = natms, nlast, sr.dev_list_pairs()
+    world = 1 if transport is None else transport.world
+    if transport is not None:
+        res["ms"] = transport.allreduce_max(ms)
+        tot = transport.allreduce_sum([natms, res["launches"], res["pairs"], res["pair_ms"], res["rebuilds"], res["list_ms"], res["force_ms"]])
+        res["natoms_total"], res["launches"], res["pairs"] = int(round(tot[0])), int(round(tot[1])), tot[2]
+        res["pair_ms_avg"] = tot[3] / world / steps
+        res["rebuilds"] = int(round(tot[4] / world))
+        res["list_ms"], res["force_ms"] = tot[5] / world, tot[6] / world
+    else:
+        res["natoms_total"] = natms
+        res["pair_ms_avg"] = res["pair_ms"] / steps
+    res["value"] = res["natoms_total"] * steps / (res["ms"] * 1e-3)
+    return res
+
+
+def roofline_of(sysm, res, world, fp64_peak, workload):
+    n_l = res["pairs"] / res["natoms_total"]                 # listed half pairs per atom, measured from the list
+    flop_as = flop_per_atom_step(sysm, n_l)
+    byte_as = bytes_per_atom_step(sysm, n_l)
+    atoms_per_launch = res["natoms_total"] / world
+    ach_tf = flop_as * atoms_per_launch / (res["pair_ms_avg"] * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach_gbs = byte_as * atoms_per_launch / (res["pair_ms_avg"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+    except Exception:
+        pass
+    whole = flop_as * res["value"] / world / 1e12
+    return {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+            "traffic": traffic, "kernel": "pair kernel of two_body_forces (vdW + real-space Ewald, half list, fp64)",
+            "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written by one launch)" if traffic else None,
+            "kernel_ms_avg": res["pair_ms_avg"], "flop_per_atom_step": flop_as, "listed_pairs_per_atom": n_l,
+            "peak_source": "DFMA micro-benchmark run in this process (dlpgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+            "whole_step": {"achieved": whole, "frac": whole / fp64_peak},
+            "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                    "bytes_per_atom_step": byte_as,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}, byte_as * atoms_per_launch
+
+
+def sub_run(torch, dd, transport, local, world, workload, strong, dt, steps, warmup, fp64_peak, cells=None, rebuild_every=0):
+    """A second, separately timed workload on the same N GPUs (BASELINE configs[4]: the fixed 8M-atom box = strong scaling,
+    and the LJ system): same step, same timing rules, reported as a sub-object of the JSON line."""
+    dims = DIMS[world]
+    sysm = make_system(workload, dims, cells, strong=strong)
+    dom = dd.Domain(sysm, device=local, transport=transport)
+    if rebuild_every:
+        dom.sr.dev_set_rebuild_every(rebuild_every)
+    dom.rebuild(); dom.forces()
+    res = timed_trajectory(torch, dom, transport, dt, steps, warmup)
+    roof, _ = roofline_of(sysm, res, world, fp64_peak, workload)
+    dom.close()
+    return {"workload": workload_name(workload, sysm, world).replace("weak scaling", "strong scaling (fixed 8M-atom box)" if strong else "weak scaling"),
+            "atoms": res["natoms_total"], "scaling": "strong" if strong else "weak", "steps": steps, "warmup": warmup,
+            "ms_per_step": res["ms"] / steps, "value": res["value"], "unit": UNIT, "rebuilds_in_timed_region": res["rebuilds"],
+            "pair_kernel_ms_avg": res["pair_ms_avg"], "roofline_frac": roof["frac"], "whole_step_frac": roof["whole_step"]["frac"],
+            "flop_per_atom_step": roof["flop_per_atom_step"], "gpu_launches": res["launches"]}
+
+
+def parity_report(torch, dd, transport, local, world, rank):
+    """Always-on pre-flight: the CUDA path against the oracle's P-domain world BEFORE anything is timed (the oracle is the
+    checker here, never the thing measured).  N > 1: tests/dd_common.check_rank on a small NaCl melt and an SPC/E box through
+    dd.Domain with the same exchange the timed run uses (resident atoms bit-equal after migration + halo, per-atom forces 1e-9,
+    gsum'med sums 1e-10, rebuilds with atoms migrating, the mailbox gsum of dlpgpu_dev_md_step).  N = 1: the same check with one
+    domain."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dd_common
+    t = transport if transport is not None else dd.SelfTransport()
+    t0 = time.perf_counter()
+    reps = []
+    try:
+        for which in ("nacl", "water"):
+            reps.append(dd_common.check_rank(t, local, which))
+        ok = True
+        err = None
+    except AssertionError as e:
+        ok, err = False, repr(e)[:300]
+    if transport is not None:
+        ok = transport.allreduce_max(0.0 if ok else 1.0) == 0.0
+    out = {"ranks": world, "ok": bool(ok), "seconds": time.perf_counter() - t0,
+           "checks": "resident atoms bit-equal to the oracle's domains after migration + halo build; per-atom forces <= 1e-9 (atoms "
+                     "with |F| >= 1e-3 max|F|); energy / virial sums after gsum <= 1e-10; stress <= 1e-10; rebuild decisions and atom "
+                     "counts along a trajectory with migration; sums of dlpgpu_dev_md_step reduced over the ranks by the gmax mailbox",
+           "cases": reps}
+    if err:
+        out["error"] = err
+    return out
+
+
 def run_gpu(args):
     import torch
     import _pkg
@@ -260,115 +390,77 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         transport = dd.TorchTransport(torch.device("cuda", local))
+    preflight = None if args.no_preflight else parity_report(torch, dd, transport, local, world, rank)
+    if preflight is not None and not preflight["ok"]:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity_preflight": preflight,
+                              "error": "parity pre-flight failed: nothing is timed on a path whose results differ from the oracle's"}))
+        raise SystemExit(3)
     dims = DIMS[world]
     sysm = make_system(args.workload, dims, args.cells_per_gpu, strong=args.strong)
     dom = dd.Domain(sysm, device=local, transport=transport)
     sr = dom.sr
     if args.force_mode is not None:
         sr.set_force_mode(args.force_mode)
+    if args.rebuild_every:
+        sr.dev_set_rebuild_every(args.rebuild_every)
     dt = args.dt
     fp64_peak = sr.fp64_peak(0.3)               # DFMA micro-benchmark on this GPU, TFLOP/s
     # first build + forces (untimed)
     dom.rebuild()
     dom.forces()
     sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~100 ms to deliver its first sample
-    for _ in range(args.warmup):
-        dom.step(dt, lazy=True)
-    dom.collect()
-    dom.rebuilds = 0
-    acc0 = dict(dom.acc)
-    stream = dom.stream
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if transport is not None:
-        transport.barrier()
-    torch.cuda.synchronize()
-    l0 = sr.launch_count()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        dom.step(dt, lazy=True)          # energies of step n are read behind the gmax synchronisation of step n+1
-    out = dom.collect()                  # ... and the last step's here, inside the timed region
-    ev1.record(stream)
-    pair_ms = dom.acc["pair_ms"] - acc0["pair_ms"]; force_ms = dom.acc["force_ms"] - acc0["force_ms"]
-    list_ms = dom.acc["list_ms"] - acc0["list_ms"]; nlist = dom.acc["list_builds"] - acc0["list_builds"]
-    assert dom.acc["force_calls"] - acc0["force_calls"] == args.steps and np.all(np.isfinite(out))
-    if transport is not None:
-        transport.barrier()
-    torch.cuda.synchronize()
+    res = timed_trajectory(torch, dom, transport, dt, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    ms = ev0.elapsed_time(ev1)
-    launches = sr.launch_count() - l0
-    natms, nlast = sr.dev_counts()
-    pairs = sr.dev_list_pairs()
-    if transport is not None:
-        ms = transport.allreduce_max(ms)
-        tot = transport.allreduce_sum([natms, launches, pairs, pair_ms, dom.rebuilds, list_ms, force_ms])
-        natoms_total, launches, pairs = int(round(tot[0])), int(round(tot[1])), tot[2]
-        pair_ms_avg = tot[3] / world / args.steps
-        list_ms_tot, force_ms_tot = tot[5] / world, tot[6] / world
-    else:
-        natoms_total = natms
-        pair_ms_avg = pair_ms / args.steps
-        list_ms_tot, force_ms_tot = list_ms, force_ms
-    value = natoms_total * args.steps / (ms * 1e-3)
-    n_l = pairs / natoms_total                              # listed half pairs per atom, measured from the list
-    flop_as = flop_per_atom_step(sysm, n_l)
-    byte_as = bytes_per_atom_step(sysm, n_l)
-    atoms_per_launch = natoms_total / world
-    ach_tf = flop_as * atoms_per_launch / (pair_ms_avg * 1e-3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach_gbs = byte_as * atoms_per_launch / (pair_ms_avg * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-    except Exception:
-        pass
-    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                "traffic": traffic, "kernel": "k_pair_v2 (two_body_forces pair loop: vdW + real-space Ewald, half list, fp64)",
-                "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written by one launch)" if traffic else None,
-                "kernel_ms_avg": pair_ms_avg, "flop_per_atom_step": flop_as, "listed_pairs_per_atom": n_l,
-                "peak_source": "DFMA micro-benchmark run in this process (dlpgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
-                "whole_step": {"achieved": flop_as * value / world / 1e12, "frac": flop_as * value / world / 1e12 / fp64_peak},
-                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                        "bytes_per_atom_step": byte_as,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}
+    natoms_total = res["natoms_total"]
+    roofline, bytes_per_launch = roofline_of(sysm, res, world, fp64_peak, args.workload)
 
     # ---- end-to-end through the drop-in C ABI with HOST buffers (what the ISO_C_BINDING shim calls)
-    e2e = run_e2e(args, torch, dom, transport, world, natoms_total, max(1, args.steps // max(dom.rebuilds, 1)))
+    e2e = run_e2e(args, torch, dom, transport, world, natoms_total, max(1, args.steps // max(res["rebuilds"], 1)))
+    if dom.profile is not None:
+        sys.stderr.write("rank %d phase profile (ms per step, synchronised phases): %s\n" % (rank,
+                         {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()}))
+    dom.close()
+
+    # ---- the other BASELINE configs[4] systems on the same N GPUs, separately timed (sub-objects of the line)
+    extra = {}
+    if args.workload == "ionic" and not args.strong and not args.no_extra:
+        ksteps = max(10, min(args.steps, 40))
+        extra["strong"] = sub_run(torch, dd, transport, local, world, "ionic", True, dt, ksteps, 3, fp64_peak)
+        extra["lj"] = sub_run(torch, dd, transport, local, world, "lj", False, dt, max(20, min(args.steps, 100)), 3, fp64_peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample, what = sample_system(args.workload)
         v, info = cpu_trajectory(sample, None, 40, 2, dt, budget_s=25.0)
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
-               "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread; restatement "
-                         "of the reference algorithm (oracle/), not the reference binary" % (what, info["steps"], info["rebuilds"], info["cores"])}
+               "sample": "%s; %d MD steps (%d rebuilds) on %d host threads, one reference domain per thread in every phase, built "
+                         "-O3 -ffast-math -march=native like the reference's Release flags; restatement of the reference algorithm "
+                         "(oracle/), not the reference binary: ratios against it are upper estimates" % (what, info["steps"], info["rebuilds"], info["cores"])}
         vs, infos = cpu_trajectory(sample, 1, 6, 1, dt, budget_s=8.0)     # the serial path: one domain on one core
         cpu["serial"] = {"value": vs, "unit": UNIT, "cores": 1, "steps": infos["steps"]}
-    if dom.profile is not None:
-        sys.stderr.write("rank %d phase profile (ms per step, synchronised phases): %s\n" % (rank,
-                         {k: round(1e3 * v / (args.steps + args.warmup), 4) for k, v in dom.profile.items()}))
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_label(args, sysm, world), "domains": list(dims), "atoms": natoms_total,
                        "rcut": sysm.rcut, "padding": sysm.padding, "timestep_ps": dt,
-                       "rebuilds_in_timed_region": dom.rebuilds if transport is None else int(round(tot[4] / world)),
-                       "list_build_ms_total": list_ms_tot, "force_call_ms_total": force_ms_tot,
-                       "l2": "inputs larger than L2: positions+list of one step are %.0f MB per GPU" % (byte_as * atoms_per_launch / 1e6),
+                       "rebuilds_in_timed_region": res["rebuilds"],
+                       "forced_rebuild_every": args.rebuild_every or None,
+                       "list_build_ms_total": res["list_ms"], "force_call_ms_total": res["force_ms"],
+                       "reduction": "gsum of the 16 energy / virial / stress sums inside every timed step: the partial sums ride on the "
+                                    "gmax mailbox message of the next step (peer memory, rank-ordered sum); the last step's by all-reduce",
+                       "l2": "inputs larger than L2: positions+list of one step are %.0f MB per GPU" % (bytes_per_launch / 1e6),
                        "force_mode": "half list + fp64 RED (Newton 3)" if sr.force_mode == 1 else "full list, no atomics"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": res["launches"], "clocks": clocks,
         }
+        if preflight is not None:
+            line["parity_preflight"] = preflight
+        line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    dom.close()
     if transport is not None:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -437,6 +529,9 @@ def main():
     ap.add_argument("--force-mode", type=int, default=None, choices=[0, 1])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the fixed 8M-atom box of BASELINE configs[4] on N GPUs")
+    ap.add_argument("--no-preflight", action="store_true", help="skip the parity pre-flight against the oracle")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and LJ sub-runs of the default workload")
+    ap.add_argument("--rebuild-every", type=int, default=0, help="force a rebuild at least every N steps (0: padding-driven only)")
     args = ap.parse_args()
     if args.gpus not in DIMS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
@@ -445,9 +540,12 @@ def main():
     if args.workload == "c3" and args.dt == 0.001:
         # SHAKE stays on the reference CPU path, so the rigid SPC/E molecules are free atoms in this driver and the bare
         # hydrogens collapse onto neighbouring oxygens within ~50 fs.  The configuration is therefore held near its start
-        # (1e-3 fs steps): the line measures the force evaluation (exclusion rows included) on the C3 geometry; list rebuilds
-        # are timed separately (scripts/quick_bench.py c3).
+        # (1e-3 fs steps) and the list is REBUILT AT A FORCED CADENCE instead (relocate + halo + list every 3rd step, about
+        # what the padding-driven test gives 300 K water with 0.18 A padding and 1 fs steps: the fastest of 144,000 hydrogens
+        # needs ~3 fs for 0.09 A), so the line is "list + forces" like the others.
         args.dt = 1.0e-6
+        if not args.rebuild_every:
+            args.rebuild_every = 3
     if args.impl == "reference":
         run_reference(args)
     else:

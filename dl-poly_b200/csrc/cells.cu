@@ -876,3 +876,14 @@ extern "C" int dlpgpu_dev_link_cell_pairs(dlpgpu_ctx* ctx, int want_ref_list, in
   CK(cudaSetDevice(ctx->device));
   return dlp_build_lists(ctx, want_ref_list, ibig);
 }
+
+int dlp_preload_cells() {   // see dlp_preload_halo
+  const void* ks[] = {(const void*)k_cell_index, (const void*)k_cell_scatter, (const void*)k_cell0_flag, (const void*)k_cell0_place,
+                      (const void*)k_cell_order, (const void*)k_sorted_static, (const void*)k_loc_slot, (const void*)k_gather_posq,
+                      (const void*)k_list_ref, (const void*)k_row_partition, (const void*)k_list_dev<false>, (const void*)k_list_dev<true>,
+                      (const void*)k_list_cell<0>, (const void*)k_list_cell<1>, (const void*)k_list_cell<2>, (const void*)k_bg_copy,
+                      (const void*)k_count_pairs};
+  cudaFuncAttributes a;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+  return 0;
+}

@@ -29,19 +29,21 @@ template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t cap = 0;
-  // grow to at least n elements; keep=true preserves the first `keep_n` elements
+  // grow to at least n elements; keep=true preserves the first `keep_n` elements.  Stream-ordered allocation (cudaMallocAsync /
+  // cudaFreeAsync on the context's stream): growing a buffer never synchronises the DEVICE, which matters when several ranks
+  // drive one GPU from threads of one process -- a peer's receive kernel may be spinning on this rank's next message, and a
+  // device-wide implicit synchronisation (cudaFree) would wait for it for ever.
   cudaError_t ensure(size_t n, cudaStream_t s = 0, bool keep = false, size_t keep_n = 0) {
     if (n <= cap) return cudaSuccess;
     size_t ncap = n + n / 8 + 64;
     T* q = nullptr;
-    cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)&q, ncap * sizeof(T), s);
     if (e != cudaSuccess) return e;
     if (keep && p && keep_n) {
       e = cudaMemcpyAsync(q, p, std::min(keep_n, cap) * sizeof(T), cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) return e;
-      cudaStreamSynchronize(s);
     }
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
     p = q;
     cap = ncap;
     return cudaSuccess;
@@ -118,13 +120,17 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
+  DBuf<double> tab3a;                 // k_pair_v3: plane A {g0_force, g0_energy} per unit, completions in the 12 low bits
+  DBuf<float> tab3b;                  // k_pair_v3: plane B fp32 {c1_force, c1_energy, h_force, h_energy} per unit
+  bool tab3_valid = false;
+  int tab3_llo = 1;                   // grid intervals below this one keep fp64 coefficients (side path of k_pair_v3)
+  double tab3_err = 0.0;              // worst deviation of the packed polynomial from the fp64 one, relative to the local table magnitude
+  int last_pair_kernel = 0;           // 1 k_pair_forces, 2 k_pair_v2, 3 k_pair_v3 (dlpgpu_pair_kernel_used)
+  int pair_layout = 0;                // dlpgpu_set_pair_kernel: 0 automatic, 2 keep the k_pair_v2 layouts
   cudaTextureObject_t tab2_tex = 0;   // the same buffer as 16-byte texels: table reads through the texture pipe (see pair2)
   int ew_off = 0;
   bool tab4_valid = false;
   std::vector<double> h_vdw_f, h_vdw_e, h_ew_d, h_ew_e;   // host copies the tab4 build reads
-  int tpr_override = 0;
-  int tx_override = -1;    // DLPGPU_TX: which table reads of k_pair_v2 go through the texture pipe (tuning knob)
-  int variant = 0;         // DLPGPU_VARIANT: timing experiments of the pair kernel (development only)
   bool no_fast = false;    // dlpgpu_set_pair_kernel: always use the general pair kernel
 
   // sites (native mode)
@@ -153,6 +159,7 @@ struct dlpgpu_ctx {
   bool p2p_ready = false, pub_valid = false;
   bool tol_fresh = false, pub_fresh = false;   // left behind by the fused velocity-Verlet stage 1 (dlp_vv1_fused)
   std::vector<double4*> peer_pub;   // [2 * nranks]
+  std::vector<char> peer_pub_local, peer_xr_local;   // [nranks] 1: the peer lives in this process (plain pointer, nothing to close)
   DBuf<unsigned long long> peer_pub_dev;   // the same table on the device
   // fused device-side exchange (dlpgpu_dev_xchg_*): one CUDA-IPC exported region with the gmax mailboxes and the per-stage
   // receive buffers of migration and halo build, the peers' regions, and the device-resident atom counts
@@ -162,7 +169,10 @@ struct dlpgpu_ctx {
   std::vector<char*> peer_xr;
   DBuf<unsigned long long> peer_xr_dev;
   DBuf<int> dcnt;
-  DBuf<unsigned long long> gmax_out;
+  DBuf<unsigned long long> gmax_out;   // [1 + 16]: gmax bits, then the gsum of the previous force call's 16 sums
+  unsigned long long* gm_pinned = nullptr;
+  double gsum_prev[16] = {0};
+  int rebuild_every = 0, steps_since_rebuild = 0;   // dlpgpu_dev_set_rebuild_every: forced cadence on top of the padding test
   DBuf<double> xbg, ybg, zbg;
   bool have_bg = false;
 
@@ -243,6 +253,11 @@ int dlp_fail(dlpgpu_ctx* ctx, int code, const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// every translation unit loads its kernels up front (see dlp_preload_halo)
+int dlp_preload_halo();
+int dlp_preload_cells();
+int dlp_preload_forces();
+int dlp_preload_ctx();
 // util.cu
 int dlp_exclusive_scan(dlpgpu_ctx* ctx, const int* in_dev, int* out_dev, int n, int* total_host /*nullable*/);
 int dlp_ensure_atoms(dlpgpu_ctx* ctx, int n);

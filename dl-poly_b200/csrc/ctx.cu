@@ -145,9 +145,10 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaEventCreate(&ctx->ev_res);
-  if (const char* e = getenv("DLPGPU_TPR")) { int v = atoi(e); if (v == 8 || v == 16 || v == 32) ctx->tpr_override = v; }   // tuning knob
-  if (const char* e = getenv("DLPGPU_VARIANT")) ctx->variant = atoi(e);
-  if (const char* e = getenv("DLPGPU_TX")) ctx->tx_override = atoi(e);
+  {   // once per device and process
+    static bool loaded[64] = {false};
+    if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); loaded[device] = true; }
+  }
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
   *out = ctx;
@@ -172,23 +173,25 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
-  ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
+  ctx->tab2h.release(); ctx->tab2s.release(); ctx->tab3a.release(); ctx->tab3b.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
   for (int r = 0; r < ctx->p2p_nranks; ++r)
-    if (r != ctx->p2p_rank)
+    if (r != ctx->p2p_rank && !(ctx->peer_pub_local.size() > (size_t)r && ctx->peer_pub_local[r]))
       for (int b = 0; b < 2; ++b)
         if (ctx->peer_pub.size() > (size_t)(2 * r + b) && ctx->peer_pub[2 * r + b]) cudaIpcCloseMemHandle(ctx->peer_pub[2 * r + b]);
   for (int b = 0; b < 2; ++b) if (ctx->pub[b]) cudaFree(ctx->pub[b]);
   ctx->peer_pub_dev.release();
   for (int r = 0; r < ctx->xr_nranks; ++r)
-    if (r != ctx->xr_rank && ctx->peer_xr.size() > (size_t)r && ctx->peer_xr[r]) cudaIpcCloseMemHandle(ctx->peer_xr[r]);
+    if (r != ctx->xr_rank && ctx->peer_xr.size() > (size_t)r && ctx->peer_xr[r] &&
+        !(ctx->peer_xr_local.size() > (size_t)r && ctx->peer_xr_local[r])) cudaIpcCloseMemHandle(ctx->peer_xr[r]);
   if (ctx->xr) cudaFree(ctx->xr);
   ctx->peer_xr_dev.release(); ctx->dcnt.release(); ctx->gmax_out.release();
   if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
   if (ctx->out_pinned) cudaFreeHost(ctx->out_pinned);
+  if (ctx->gm_pinned) cudaFreeHost(ctx->gm_pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -335,9 +338,10 @@ int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode) {
   return 0;
 }
 
-int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int general_only) {
-  if (!ctx) return DLPGPU_ERR_ARG;
-  ctx->no_fast = general_only != 0;
+int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 2) return DLPGPU_ERR_ARG;
+  ctx->no_fast = which == 1;
+  ctx->pair_layout = which == 2 ? 2 : 0;
   return 0;
 }
 
@@ -675,3 +679,11 @@ int dlpgpu_dev_get_full_row(dlpgpu_ctx* ctx, int i, int* n_main, int* main_out, 
 }
 
 }  // extern "C"
+
+int dlp_preload_ctx() {   // see dlp_preload_halo
+  const void* ks[] = {(const void*)k_scan_block, (const void*)k_scan_add, (const void*)k_unpack_parts, (const void*)k_pack_parts,
+                      (const void*)k_add_forces, (const void*)k_load_atoms, (const void*)k_zero3};
+  cudaFuncAttributes a;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+  return 0;
+}

@@ -10,6 +10,8 @@
 // atom's origin for the one-kernel refresh below --, 3 doubles on a staged refresh, the sender applies the periodic shift); selection, ordering (ascending local index, appended in stage order -x,+x,-y,+y,-z,+z) and the
 // restack of staying atoms after migration reproduce the reference so local indices agree with a DL_POLY run.
 // Compiled with -fmad=false: thresholds and shifts decide set membership.
+#include <unistd.h>
+
 #include "common.cuh"
 
 namespace {
@@ -399,11 +401,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// true when the header carries `seq`; gives up after a few seconds and raises DCNT_ERR bit 2 (a peer died / lost lock-step)
+// true when the header carries `seq`; gives up after g_wait_ns nanoseconds (default 60 s, dlpgpu_dev_xchg_set_timeout) and raises
+// DC_ERR bit 2 (a peer died / lost lock-step) -- long enough for a peer that is still in a first-touch list build
+__device__ unsigned long long g_wait_ns = 60ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long x_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ bool x_wait(const unsigned long long* seq_word, unsigned long long seq, int* err) {
-  for (long long it = 0; it < 20000000LL; ++it) {   // several seconds
+  const unsigned long long t0 = x_now_ns(), limit = g_wait_ns;
+  for (long long it = 0;; ++it) {
     if (ld_acquire_sys(seq_word) == seq) return true;
-    if ((it & 1023) == 1023 && (*(volatile int*)err & 4)) return false;   // somebody already gave up: do not wait again
+    if ((it & 1023) == 1023) {
+      if (*(volatile int*)err & 4) return false;   // somebody already gave up: do not wait again
+      if (x_now_ns() - t0 > limit) break;
+    }
     __nanosleep(200);
   }
   atomicOr(err, 4);
@@ -655,23 +668,39 @@ __global__ void k_x_halo_end(const int* __restrict__ dc, const int* __restrict__
 }
 // gmax of vnl_check (neighbours.F90:176) through the peers' mailboxes: lane r writes this rank's value into rank r's slot
 // and waits for rank r's value in its own.  Slots alternate with the parity of the sequence number.
+// The same message carries the 16 partial sums (energies, virials, stress) of the force call that completed before it on this
+// stream, i.e. of the PREVIOUS step, and every rank adds the ranks' values in rank order: the gsum of two_body.F90:729 and
+// drivers.F90:795 without an extra launch, collective or host round trip (deterministic: fixed summation order).
+struct XGm { unsigned long long seq; unsigned long long tol; double sums[16]; };
 __global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const unsigned long long* __restrict__ tol_bits,
-                         const unsigned long long* __restrict__ peers, size_t off_gm, unsigned long long* __restrict__ out, int* __restrict__ dc) {
+                         const double* __restrict__ my_sums, const unsigned long long* __restrict__ peers, size_t off_gm,
+                         unsigned long long* __restrict__ out /*[1 + 16]*/, int* __restrict__ dc) {
   const int r = threadIdx.x;
   unsigned long long v = 0;
+  const size_t slot = ((seq & 1) * (size_t)nranks);
   if (r < nranks) {
     const unsigned long long mine = *tol_bits;
-    const size_t slot = ((seq & 1) * (size_t)nranks);
-    XHdr* dst = reinterpret_cast<XHdr*>(peers[r] + off_gm) + slot + rank;
-    dst->count = (long long)mine;
+    XGm* dst = reinterpret_cast<XGm*>(peers[r] + off_gm) + slot + rank;
+    dst->tol = mine;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dst->sums[k] = my_sums[k];
     __threadfence_system();
     st_release_sys(&dst->seq, seq);
-    const XHdr* src = reinterpret_cast<const XHdr*>(peers[rank] + off_gm) + slot + r;
-    if (x_wait(&src->seq, seq, &dc[DC_ERR])) v = (unsigned long long)src->count;
+    const XGm* src = reinterpret_cast<const XGm*>(peers[rank] + off_gm) + slot + r;
+    if (x_wait(&src->seq, seq, &dc[DC_ERR])) v = ld_acquire_sys(&src->tol);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(DLP_FULL, v, d); v = o > v ? o : v; }   // non-negative doubles order like their bits
-  if (r == 0) *out = v;
+  if (r == 0) out[0] = v;
+  __syncwarp();   // every peer's message has been acquired by the lane that waited for it
+  if (r < 16) {
+    double t = 0.0;
+    for (int q = 0; q < nranks; ++q) {
+      const XGm* src = reinterpret_cast<const XGm*>(peers[rank] + off_gm) + slot + q;
+      t += __longlong_as_double((long long)ld_acquire_sys(reinterpret_cast<const unsigned long long*>(&src->sums[r])));
+    }
+    out[1 + r] = (unsigned long long)__double_as_longlong(t);
+  }
 }
 
 static size_t x_align(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -679,7 +708,7 @@ struct XLayout { size_t off_gm, off_hdr, off_rbuf, off_hbuf, bytes; };
 static XLayout x_layout(int nranks, int cap_r, int cap_h) {
   XLayout L;
   L.off_gm = 0;
-  L.off_hdr = x_align((size_t)2 * nranks * sizeof(XHdr));
+  L.off_hdr = x_align((size_t)2 * nranks * sizeof(XGm));
   L.off_rbuf = x_align(L.off_hdr + 12 * sizeof(XHdr));
   L.off_hbuf = x_align(L.off_rbuf + (size_t)6 * cap_r * 12 * sizeof(double));
   L.bytes = x_align(L.off_hbuf + (size_t)6 * cap_h * DLP_HALO_W * sizeof(double));
@@ -688,6 +717,18 @@ static XLayout x_layout(int nranks, int cap_r, int cap_h) {
 
 
 }  // namespace
+
+// a peer rank that lives in this process on ANOTHER device: enable direct access once (no-op for the same device)
+static int x_enable_peer(dlpgpu_ctx* ctx, int dev) {
+  if (dev == ctx->device) return 0;
+  int can = 0;
+  CK(cudaDeviceCanAccessPeer(&can, ctx->device, dev));
+  if (!can) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "device %d cannot access the memory of device %d", ctx->device, dev);
+  cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+  cudaGetLastError();
+  return 0;
+}
 
 int dlp_vnl_check(dlpgpu_ctx* ctx, double* tol) {
   cudaStream_t s = ctx->stream;
@@ -852,12 +893,12 @@ int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_d
 }
 
 // ---- peer-memory refresh
-int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[128]) {
+int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[DLPGPU_P2P_BLOB]) {
   if (!ctx || rank < 0 || nranks < 1 || rank >= nranks || capacity_atoms < 1 || !handles_out) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "p2p_init: already initialised");
   ctx->p2p_rank = rank; ctx->p2p_nranks = nranks; ctx->pub_cap = capacity_atoms;
-  std::memset(handles_out, 0, 128);
+  std::memset(handles_out, 0, DLPGPU_P2P_BLOB);
   for (int b = 0; b < 2; ++b) {
     CK(cudaMalloc((void**)&ctx->pub[b], (size_t)capacity_atoms * sizeof(double4)));
     if (nranks > 1) {
@@ -866,6 +907,12 @@ int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atom
       static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
       std::memcpy(handles_out + 64 * b, &h, 64);
     }
+  }
+  {   // ranks that live in the SAME process (one host thread per rank) reach each other's buffers by plain pointers
+    const long long pid = (long long)getpid(), dev = ctx->device;
+    const unsigned long long p0 = (unsigned long long)(size_t)ctx->pub[0], p1 = (unsigned long long)(size_t)ctx->pub[1];
+    std::memcpy(handles_out + 128, &pid, 8); std::memcpy(handles_out + 136, &p0, 8); std::memcpy(handles_out + 144, &p1, 8);
+    std::memcpy(handles_out + 152, &dev, 8);
   }
   ctx->peer_pub.assign((size_t)2 * nranks, nullptr);
   ctx->peer_pub[2 * rank] = ctx->pub[0]; ctx->peer_pub[2 * rank + 1] = ctx->pub[1];
@@ -877,15 +924,28 @@ int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atom
   return 0;
 }
 
-int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x 128 bytes, rank-major */) {
+int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x DLPGPU_P2P_BLOB bytes, rank-major */) {
   if (!ctx || !all_handles) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->pub[0]) return dlp_fail(ctx, DLPGPU_ERR_STATE, "p2p_open: call p2p_init first");
   for (int r = 0; r < ctx->p2p_nranks; ++r) {
     if (r == ctx->p2p_rank) continue;
+    const unsigned char* blob = all_handles + (size_t)DLPGPU_P2P_BLOB * r;
+    long long pid = 0, dev = 0;
+    std::memcpy(&pid, blob + 128, 8); std::memcpy(&dev, blob + 152, 8);
+    if (pid == (long long)getpid()) {   // same process: the pointer itself (peer access between two devices enabled on demand)
+      CKRC(x_enable_peer(ctx, (int)dev));
+      for (int b = 0; b < 2; ++b) {
+        unsigned long long q = 0;
+        std::memcpy(&q, blob + 136 + 8 * b, 8);
+        ctx->peer_pub[2 * r + b] = (double4*)(size_t)q;
+      }
+      ctx->peer_pub_local.resize((size_t)ctx->p2p_nranks, 0); ctx->peer_pub_local[r] = 1;
+      continue;
+    }
     for (int b = 0; b < 2; ++b) {
       cudaIpcMemHandle_t h;
-      std::memcpy(&h, all_handles + (size_t)128 * r + 64 * b, 64);
+      std::memcpy(&h, blob + 64 * b, 64);
       void* p = nullptr;
       CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
       ctx->peer_pub[2 * r + b] = (double4*)p;
@@ -1031,7 +1091,7 @@ int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now) {
 
 extern "C" {
 
-int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[64]) {
+int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[DLPGPU_XCHG_BLOB]) {
   if (!ctx || rank < 0 || nranks < 1 || nranks > 32 || rank >= nranks || cap_reloc_atoms < 1 || cap_halo_atoms < 1 || !handle_out) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->xr) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_init: already initialised");
@@ -1040,17 +1100,22 @@ int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_at
   CK(cudaMemset(ctx->xr, 0, L.bytes));
   CK(cudaDeviceSynchronize());
   ctx->xr_rank = rank; ctx->xr_nranks = nranks; ctx->xr_cap_r = cap_reloc_atoms; ctx->xr_cap_h = cap_halo_atoms;
-  std::memset(handle_out, 0, 64);
+  std::memset(handle_out, 0, DLPGPU_XCHG_BLOB);
   if (nranks > 1) {
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->xr));
     std::memcpy(handle_out, &h, 64);
   }
+  {
+    const long long pid = (long long)getpid(), dev = ctx->device;
+    const unsigned long long p0 = (unsigned long long)(size_t)ctx->xr;
+    std::memcpy(handle_out + 64, &pid, 8); std::memcpy(handle_out + 72, &p0, 8); std::memcpy(handle_out + 80, &dev, 8);
+  }
   ctx->peer_xr.assign(nranks, nullptr);
   ctx->peer_xr[rank] = ctx->xr;
   CK(ctx->dcnt.ensure(DC_WORDS, ctx->stream));
   CK(cudaMemset(ctx->dcnt.p, 0, DC_WORDS * sizeof(int)));
-  CK(ctx->gmax_out.ensure(2, ctx->stream));
+  CK(ctx->gmax_out.ensure(32, ctx->stream));
   ctx->xr_ready = false;
   if (nranks == 1) {
     CK(ctx->peer_xr_dev.ensure(1, ctx->stream));
@@ -1060,14 +1125,39 @@ int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_at
   return 0;
 }
 
-int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x 64 bytes */) {
+int dlpgpu_dev_set_rebuild_every(dlpgpu_ctx* ctx, int every) {
+  if (!ctx || every < 0) return DLPGPU_ERR_ARG;
+  ctx->rebuild_every = every; ctx->steps_since_rebuild = 0;
+  return 0;
+}
+
+int dlpgpu_dev_xchg_set_timeout(dlpgpu_ctx* ctx, double seconds) {
+  if (!ctx || !(seconds > 0.0)) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const unsigned long long ns = (unsigned long long)(seconds * 1.0e9);
+  CK(cudaMemcpyToSymbol(g_wait_ns, &ns, sizeof ns));
+  return 0;
+}
+
+int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles /* nranks x DLPGPU_XCHG_BLOB bytes */) {
   if (!ctx || !all_handles) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->xr) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_open: call xchg_init first");
   for (int r = 0; r < ctx->xr_nranks; ++r) {
     if (r == ctx->xr_rank) continue;
+    const unsigned char* blob = all_handles + (size_t)DLPGPU_XCHG_BLOB * r;
+    long long pid = 0, dev = 0;
+    std::memcpy(&pid, blob + 64, 8); std::memcpy(&dev, blob + 80, 8);
+    if (pid == (long long)getpid()) {
+      CKRC(x_enable_peer(ctx, (int)dev));
+      unsigned long long q = 0;
+      std::memcpy(&q, blob + 72, 8);
+      ctx->peer_xr[r] = (char*)(size_t)q;
+      ctx->peer_xr_local.resize((size_t)ctx->xr_nranks, 0); ctx->peer_xr_local[r] = 1;
+      continue;
+    }
     cudaIpcMemHandle_t h;
-    std::memcpy(&h, all_handles + (size_t)64 * r, 64);
+    std::memcpy(&h, blob, 64);
     void* p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_xr[r] = (char*)p;
@@ -1095,16 +1185,19 @@ int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol) {
   }
   ctx->tol_fresh = false;
   const XLayout L = x_layout(ctx->xr_nranks, ctx->xr_cap_r, ctx->xr_cap_h);
-  LAUNCH(ctx, k_x_gmax, 1, 32, 0, ctx->xr_rank, ctx->xr_nranks, seq, ctx->tol_bits.p, ctx->peer_xr_dev.p, L.off_gm, ctx->gmax_out.p, ctx->dcnt.p);
-  unsigned long long bits = 0;
-  int err = 0;
-  CK(cudaMemcpyAsync(&bits, ctx->gmax_out.p, sizeof bits, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&err, ctx->dcnt.p + DC_ERR, sizeof err, cudaMemcpyDeviceToHost, s));
+  LAUNCH(ctx, k_x_gmax, 1, 32, 0, ctx->xr_rank, ctx->xr_nranks, seq, ctx->tol_bits.p, ctx->out_dev.p, ctx->peer_xr_dev.p, L.off_gm,
+         ctx->gmax_out.p, ctx->dcnt.p);
+  if (!ctx->gm_pinned) CK(cudaMallocHost((void**)&ctx->gm_pinned, 32 * sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(ctx->gm_pinned, ctx->gmax_out.p, 17 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->gm_pinned + 17, ctx->dcnt.p + DC_ERR, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  int err = 0;
+  std::memcpy(&err, ctx->gm_pinned + 17, sizeof err);
   if (err & 4) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_gmax: timed out waiting for a peer (ranks out of lock-step)");
   double r;
-  std::memcpy(&r, &bits, sizeof r);
+  std::memcpy(&r, ctx->gm_pinned, sizeof r);
   *tol = r;
+  std::memcpy(ctx->gsum_prev, ctx->gm_pinned + 1, 16 * sizeof(double));   // all-reduced sums of the previous force call
   return 0;
 }
 
@@ -1212,7 +1305,13 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   ctx->natms = h_dc[DC_NATMS]; ctx->nlast = h_dc[DC_NLAST];
   if (natms_out) *natms_out = ctx->natms;
   if (nlast_out) *nlast_out = ctx->nlast;
-  if (h_dc[DC_ERR] & 4) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: timed out waiting for a peer (ranks out of lock-step)");
+  if (h_dc[DC_ERR] & 4)
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: timed out waiting for a peer (ranks out of lock-step); rank %d seq %llu, migration "
+                    "stages sent %d %d %d %d %d %d received %d %d %d %d %d %d, halo stages sent %d %d %d %d %d %d received %d %d %d %d %d %d",
+                    me, seq, h_dc[DC_RSENT], h_dc[DC_RSENT + 1], h_dc[DC_RSENT + 2], h_dc[DC_RSENT + 3], h_dc[DC_RSENT + 4], h_dc[DC_RSENT + 5],
+                    h_dc[DC_RRECV], h_dc[DC_RRECV + 1], h_dc[DC_RRECV + 2], h_dc[DC_RRECV + 3], h_dc[DC_RRECV + 4], h_dc[DC_RRECV + 5],
+                    h_dc[DC_HSENT], h_dc[DC_HSENT + 1], h_dc[DC_HSENT + 2], h_dc[DC_HSENT + 3], h_dc[DC_HSENT + 4], h_dc[DC_HSENT + 5],
+                    h_dc[DC_HRECV], h_dc[DC_HRECV + 1], h_dc[DC_HRECV + 2], h_dc[DC_HRECV + 3], h_dc[DC_HRECV + 4], h_dc[DC_HRECV + 5]);
   if (h_dc[DC_ERR] & 1) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 43: outgoing migration buffer too small (capacity %d atoms per stage)", cap_r);
   if (h_dc[DC_ERR] & 2) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "error 54: outgoing halo buffer too small (capacity %d atoms per stage)", cap_h);
   if (h_dc[DC_ERR] & 8) return dlp_fail(ctx, DLPGPU_ERR_BUFFER, "xchg_rebuild: atom arrays full (%d)", capacity);
@@ -1261,9 +1360,15 @@ int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned 
   double tol = 0.0;
   CKRC(dlpgpu_dev_xchg_gmax(ctx, gseq, &tol));
   *have_prev = 0;
-  if (ctx->res_pending) { CKRC(dlpgpu_dev_fetch_results(ctx, out_prev)); *have_prev = 1; }
+  if (ctx->res_pending) {
+    CKRC(dlpgpu_dev_fetch_results(ctx, out_prev));       // this rank's partial sums (and the timing bookkeeping) ...
+    std::memcpy(out_prev, ctx->gsum_prev, 16 * sizeof(double));   // ... replaced by the gsum over the ranks that rode on the gmax message
+    *have_prev = 1;
+  }
   const double half_minus = 0.499999999999999944488848768742172978818416595458984375;
   *rebuilt = (tol >= half_minus * ctx->padding) ? 1 : 0;                       // neighbours.F90:182
+  if (ctx->rebuild_every > 0 && ++ctx->steps_since_rebuild >= ctx->rebuild_every) *rebuilt = 1;   // dlpgpu_dev_set_rebuild_every
+  if (*rebuilt) ctx->steps_since_rebuild = 0;
   if (list_ms) *list_ms = 0.0;
   if (*rebuilt) {
     CKRC(dlpgpu_dev_xchg_rebuild(ctx, neigh, rseq, nullptr, nullptr));
@@ -1280,3 +1385,21 @@ int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned 
 }
 
 }  // extern "C"
+
+// Function-level lazy loading (the CUDA 12 default) loads a kernel at its first launch, and that load can synchronise the
+// whole context.  When several ranks drive ONE GPU from threads of one process, a peer's receive / gmax kernel may be
+// spinning on the device at that moment, waiting for a message this rank can only send after the load: a deadlock (seen on
+// B200; CUDA_MODULE_LOADING=EAGER cures it).  dlpgpu_create therefore loads every kernel of the library up front.
+int dlp_preload_halo() {
+  const void* ks[] = {(const void*)k_vnl_tol, (const void*)k_vv1_fused, (const void*)k_halo_tag, (const void*)k_halo_flag, (const void*)k_halo_pack,
+                      (const void*)k_halo_unpack, (const void*)k_assign_sites, (const void*)k_refresh_pack, (const void*)k_refresh_unpack,
+                      (const void*)k_publish, (const void*)k_refresh_pull, (const void*)k_pbcshift, (const void*)k_reloc_tag,
+                      (const void*)k_reloc_flag, (const void*)k_reloc_pack, (const void*)k_reloc_restack, (const void*)k_reloc_unpack,
+                      (const void*)k_count_nonzero, (const void*)k_x_reloc_tag, (const void*)k_x_count<0>, (const void*)k_x_count<1>,
+                      (const void*)k_x_pack<0>, (const void*)k_x_pack<1>, (const void*)k_x_reloc_restack, (const void*)k_x_recv<0>,
+                      (const void*)k_x_recv<1>, (const void*)k_x_reloc_end, (const void*)k_x_halo_tag, (const void*)k_x_halo_end,
+                      (const void*)k_x_gmax};
+  cudaFuncAttributes a;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+  return 0;
+}

@@ -189,8 +189,71 @@ class SelfTransport:
     def allreduce_sum(self, arr):
         return arr
 
+    def allgather_bytes(self, blob):
+        return np.ascontiguousarray(blob, dtype=np.uint8).copy()
+
     def barrier(self):
         pass
+
+
+class ThreadGroup:
+    """Shared state of ranks that are THREADS of one process (several domains on one GPU, or one thread per GPU): the host
+    side of the collectives is a barrier and a shared table.  The data plane is the library's own peer-memory exchange
+    (handle blobs carry plain pointers for same-process peers); ctypes releases the GIL inside every library call, so a rank
+    waiting in a stream synchronisation does not stop the others from enqueueing."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.bar = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def transport(self, rank, device=None):
+        return ThreadTransport(self, rank, device)
+
+
+class ThreadTransport:
+    def __init__(self, group, rank, device=None):
+        self.g, self.rank, self.world, self.device = group, rank, group.world, device
+
+    def _all(self, v):
+        self.g.slots[self.rank] = v
+        self.g.bar.wait()
+        out = list(self.g.slots)
+        self.g.bar.wait()
+        return out
+
+    def allreduce_max(self, v):
+        return max(float(x) for x in self._all(float(v)))
+
+    def allreduce_sum(self, arr):
+        parts = self._all(np.asarray(arr, dtype=np.float64).copy())
+        tot = np.zeros_like(parts[0])
+        for p in parts:                      # rank order: every rank forms the same bits
+            tot = tot + p
+        return tot
+
+    def allgather_bytes(self, blob):
+        return np.concatenate([np.ascontiguousarray(b, dtype=np.uint8) for b in self._all(np.array(blob, dtype=np.uint8))])
+
+    def barrier(self):
+        self.g.bar.wait()
+
+    def exchange_counts(self, n_send, dst, src):
+        """deport_data.F90:1888-1893 between threads: every rank posts (dst, count); the receiver picks the one addressed to it."""
+        posts = self._all((int(dst), int(n_send)))
+        return posts[src][1]
+
+    def exchange(self, sendbuf, n_send, recvbuf, n_recv, dst, src):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        posts = self._all((sendbuf, int(n_send)))
+        sb, ns = posts[src]
+        assert ns == n_recv
+        if n_recv > 0:
+            recvbuf[:n_recv].copy_(sb[:n_recv])
+        torch.cuda.current_stream().synchronize()
+        self.g.bar.wait()                    # nobody reuses its send buffer before every receiver has copied
 
 
 class TorchTransport:
@@ -239,6 +302,12 @@ class TorchTransport:
         t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+    def allgather_bytes(self, blob):
+        t_blob = self.torch.from_numpy(np.ascontiguousarray(blob, dtype=np.uint8).copy()).to(self.device)
+        allb = [self.torch.empty_like(t_blob) for _ in range(self.world)]
+        self.dist.all_gather(allb, t_blob, group=self.group)
+        return self.torch.cat(allb).cpu().numpy()
 
     def barrier(self):
         self.dist.barrier(group=self.group)
@@ -342,11 +411,7 @@ class Domain:
             """True only if the step succeeded on every rank (peer memory is all-or-nothing across the ranks)."""
             return ok if self.world == 1 else self.t.allreduce_max(0.0 if ok else 1.0) == 0.0
 
-        def gather_blobs(blob):
-            t_blob = torch.from_numpy(blob.copy()).to(self.device)
-            allb = [torch.empty_like(t_blob) for _ in range(self.world)]
-            self.t.dist.all_gather(allb, t_blob, group=self.t.group)
-            return torch.cat(allb).cpu().numpy()
+        gather_blobs = self.t.allgather_bytes
 
         from .lib import DlpError
         if self.p2p:

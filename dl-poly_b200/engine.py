@@ -97,9 +97,16 @@ class ShortRange:
         self._ck(self.L.dlpgpu_set_force_mode(self.h, int(mode)))
         self.force_mode = int(mode)
 
-    def set_pair_kernel(self, general_only=False):
-        """Diagnostic: always use the general pair kernel (the reference's operation order statement by statement)."""
-        self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(bool(general_only))))
+    def set_pair_kernel(self, general_only=False, which=None):
+        """Diagnostic: 0 automatic, 1 always the general pair kernel (the reference's operation order statement by statement),
+        2 never the packed-unit kernel k_pair_v3."""
+        self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(which) if which is not None else int(bool(general_only))))
+
+    def pair_kernel_used(self):
+        """(kernel of the last two_body_forces call: 1 general, 2 k_pair_v2, 3 k_pair_v3; worst packed-table deviation)."""
+        w, e = C.c_int(0), C.c_double(0.0)
+        self._ck(self.L.dlpgpu_pair_kernel_used(self.h, C.byref(w), C.byref(e)))
+        return w.value, e.value
 
     # ---- drop-in entry points (host buffers, Fortran index conventions) ------------------------------------------
     def link_cell_pairs(self, natms, nlast, parts, ltype, ltg, lfrzn=None, lbook=False, megfrz=0, list_excl=None,
@@ -224,8 +231,8 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_halo_end(self.h))
 
     def dev_p2p_init(self, rank, nranks, capacity_atoms):
-        """Returns the 128-byte IPC handle blob of this rank's two peer-visible coordinate buffers."""
-        h = np.zeros(128, dtype=np.uint8)
+        """Returns the handle blob (DLPGPU_P2P_BLOB bytes) of this rank's two peer-visible coordinate buffers."""
+        h = np.zeros(192, dtype=np.uint8)
         self._ck(self.L.dlpgpu_dev_p2p_init(self.h, int(rank), int(nranks), int(capacity_atoms), ptr(h)))
         return h
 
@@ -240,8 +247,9 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_refresh_pull(self.h))
 
     def dev_xchg_init(self, rank, nranks, cap_reloc_atoms, cap_halo_atoms):
-        """Allocates the peer-visible exchange region (gmax mailboxes + per-stage receive buffers); returns its 64-byte IPC handle."""
-        h = np.zeros(64, dtype=np.uint8)
+        """Allocates the peer-visible exchange region (gmax mailboxes + per-stage receive buffers); returns its handle blob
+        (DLPGPU_XCHG_BLOB bytes)."""
+        h = np.zeros(128, dtype=np.uint8)
         self._ck(self.L.dlpgpu_dev_xchg_init(self.h, int(rank), int(nranks), int(cap_reloc_atoms), int(cap_halo_atoms), ptr(h)))
         return h
 
@@ -261,6 +269,12 @@ class ShortRange:
         tol = C.c_double(0.0)
         self._ck(self.L.dlpgpu_dev_xchg_gmax(self.h, C.c_ulonglong(int(seq)), C.byref(tol)))
         return tol.value
+
+    def dev_set_rebuild_every(self, every):
+        self._ck(self.L.dlpgpu_dev_set_rebuild_every(self.h, int(every)))
+
+    def dev_xchg_set_timeout(self, seconds):
+        self._ck(self.L.dlpgpu_dev_xchg_set_timeout(self.h, float(seconds)))
 
     def dev_md_step(self, neigh, dt, gseq, rseq):
         """One MD step enqueued from C (see dlpgpu_dev_md_step); returns (rebuilt, previous step's sums or None, list_ms)."""

@@ -661,7 +661,7 @@ void gpu_short_range::dev_setup(const configuration_type& c, const neighbours_ty
   ck(dlpgpu_dev_set_list_capacity(ctx_, n.max_list, c.megfrz));
   int cap_r = 0, cap_h = 0;
   exchange_capacities(cell_, c.megatm, dom_, rcut_, padding_, 2.0, cap_r, cap_h);
-  unsigned char handle[64];
+  unsigned char handle[DLPGPU_XCHG_BLOB];
   ck(dlpgpu_dev_xchg_init(ctx_, dom_.idnode, dom_.mxnode, cap_r, cap_h, handle));   // one domain: no IPC involved
 }
 

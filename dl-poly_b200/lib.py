@@ -58,6 +58,8 @@ SIGNATURES = {
     "dlpgpu_dev_refresh_pull": (ci, [vp]),
     "dlpgpu_dev_xchg_init": (ci, [vp, ci, ci, ci, ci, vp]),
     "dlpgpu_dev_xchg_open": (ci, [vp, vp]),
+    "dlpgpu_dev_xchg_set_timeout": (ci, [vp, cd]),
+    "dlpgpu_dev_set_rebuild_every": (ci, [vp, ci]),
     "dlpgpu_dev_xchg_rebuild": (ci, [vp, vp, C.c_ulonglong, pi_, pi_]),
     "dlpgpu_dev_xchg_gmax": (ci, [vp, C.c_ulonglong, pd_]),
     "dlpgpu_dev_md_step": (ci, [vp, vp, cd, C.c_ulonglong, C.c_ulonglong, pi_, vp, pi_, pd_]),
@@ -83,6 +85,7 @@ SIGNATURES = {
     "dlpgpu_last_timings": (ci, [vp, vp]),
     "dlpgpu_set_force_mode": (ci, [vp, ci]),
     "dlpgpu_set_pair_kernel": (ci, [vp, ci]),
+    "dlpgpu_pair_kernel_used": (ci, [vp, pi_, pd_]),
 }
 
 _lib = None

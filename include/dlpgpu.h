@@ -155,34 +155,44 @@ int dlpgpu_dev_refresh_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int*
 int dlpgpu_dev_refresh_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count);
 /* refresh_halo_positions (halo.F90:47-113) as ONE kernel over NVLink peer memory instead of six staged messages: every
  * rank keeps a double-buffered, CUDA-IPC exported copy of its local coordinates; p2p_init allocates it and returns the two
- * IPC handles (2 x 64 bytes), p2p_open maps the buffers of all ranks (handles gathered rank-major, 128 bytes each).  Per
+ * IPC handles (a DLPGPU_P2P_BLOB), p2p_open maps the buffers of all ranks (blobs gathered rank-major).  Per
  * step: dlpgpu_dev_publish after the positions moved, a collective on the same streams (the gmax of vnl_check), then
  * dlpgpu_dev_refresh_pull fills the whole halo from the owners' buffers, replaying the periodic shifts in stage order
  * (same bits as the staged exchange).  With nranks == 1 no IPC is involved. */
-int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[128]);
+#define DLPGPU_P2P_BLOB 192   /* two CUDA-IPC handles (2 x 64 B) + {pid, pointer 0, pointer 1, device}: ranks that are threads of one
+                               * process reach each other's buffers by the plain pointers, processes by the IPC handles */
+#define DLPGPU_XCHG_BLOB 128  /* one CUDA-IPC handle + {pid, pointer, device} */
+int dlpgpu_dev_p2p_init(dlpgpu_ctx* ctx, int rank, int nranks, int capacity_atoms, unsigned char handles_out[DLPGPU_P2P_BLOB]);
 int dlpgpu_dev_p2p_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
 int dlpgpu_dev_publish(dlpgpu_ctx* ctx);
 int dlpgpu_dev_refresh_pull(dlpgpu_ctx* ctx);
 /* relocate_particles + set_halo_particles (+ vnl_set_check) and the gmax of vnl_check as device-side exchanges over NVLink
  * peer memory: no NCCL, no host synchronisation between the twelve dependent stages of a rebuild.  xchg_init allocates this
  * rank's CUDA-IPC exported region (gmax mailboxes + one fixed-capacity receive buffer and {sequence, count} header per
- * stage; capacities in atoms per stage, identical on every rank) and returns its 64-byte handle; xchg_open maps the regions
+ * stage; capacities in atoms per stage, identical on every rank) and returns its handle (a DLPGPU_XCHG_BLOB); xchg_open maps the regions
  * of all ranks (handles gathered rank-major).  xchg_rebuild enqueues everything and synchronises ONCE at the end (natms /
  * nlast live on the device meanwhile); neigh = map(1:6) of domains.F90:206-211 (0-based ranks; the rank itself where the
  * decomposition has one domain in that direction).  seq must be a fresh, rank-uniform sequence number per call (ranks run
  * in lock-step: every rank calls xchg_rebuild / xchg_gmax in the same order).  Errors: 43 / 54 (a stage exceeded its
- * capacity), 58 (lost atoms), 9002 on a peer time-out.  With nranks == 1 no IPC is involved. */
-int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[64]);
+ * capacity), 58 (lost atoms), DLPGPU_ERR_STATE on a peer time-out.  With nranks == 1 no IPC is involved. */
+int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[DLPGPU_XCHG_BLOB]);
 int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
+/* how long a receive / gmax kernel waits for its peer before the call fails with DLPGPU_ERR_STATE (default 60 s; per device) */
+int dlpgpu_dev_xchg_set_timeout(dlpgpu_ctx* ctx, double seconds);
 int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long long seq, int* natms, int* nlast);
 int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol);
 /* One MD step of the native driver around the path (md_vv, drivers.F90:1910-2290), enqueued from C: dev_vv(1) + publish,
  * xchg_gmax (the only host synchronisation), then xchg_rebuild + link_cell_pairs when tol >= half_minus * padding
  * (neighbours.F90:182; *rebuilt = 1, *list_ms = time of the list build) or the one-kernel halo refresh, two_body_forces
  * without waiting for its sums, dev_vv(2).  out_prev / *have_prev: the sums of the previous step's force call, if one was
- * pending; collect the last step's with dlpgpu_dev_fetch_results.  gseq / rseq: as for xchg_gmax / xchg_rebuild. */
+ * pending, ALREADY SUMMED OVER ALL RANKS: the 16 partial sums ride on the gmax message and every rank adds them in rank
+ * order (the gsum of two_body.F90:729 and drivers.F90:795, deterministic).  The last step's sums come from
+ * dlpgpu_dev_fetch_results as this rank's partial sums.  gseq / rseq: as for xchg_gmax / xchg_rebuild. */
 int dlpgpu_dev_md_step(dlpgpu_ctx* ctx, const int neigh[6], double dt, unsigned long long gseq, unsigned long long rseq,
                        int* rebuilt, double out_prev[16], int* have_prev, double* list_ms);
+/* dlpgpu_dev_md_step rebuilds at least every `every` steps in addition to the padding-driven test of neighbours.F90:182
+ * (0 = off, the default; must be the same on every rank).  For trajectories that are held still on purpose (measurement). */
+int dlpgpu_dev_set_rebuild_every(dlpgpu_ctx* ctx, int every);
 /* atoms sent / received in each of the six stages of the last halo build (order -x,+x,-y,+y,-z,+z) */
 int dlpgpu_dev_halo_stage_counts(dlpgpu_ctx* ctx, int sent[6], int received[6]);
 /* single-domain shortcuts (mxnode == 1: the neighbour is the rank itself, deport_data.F90:1884-1886) */
@@ -224,10 +234,16 @@ int dlpgpu_last_timings(dlpgpu_ctx* ctx, double t[4]);
 /* 1 (default, common.cuh force_mode): half list + fp64 RED atomics (Newton's third law) -- the reference's own pair count.
  * 0: full list without atomics (every local-local pair evaluated from both ends; bitwise reproducible forces). */
 int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
-/* Diagnostic: general_only != 0 makes two_body_forces always use the general pair kernel (k_pair_forces: the reference's
- * operation order statement by statement, vdw.F90:1790-2024 / ewald_spole.F90:58-242) instead of the fast tabulated kernel.
- * The parity tests hold the two against each other; results agree within the north-star bars either way. */
-int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int general_only);
+/* Diagnostic: which pair kernel two_body_forces uses.  0 (default): automatic -- the fast tabulated kernels where they apply
+ * (k_pair_v3 with packed table units when the tables pass its build-time verification, else k_pair_v2), the general kernel
+ * otherwise.  1: always the general kernel (k_pair_forces: the reference's operation order statement by statement,
+ * vdw.F90:1790-2024 / ewald_spole.F90:58-242).  2: never k_pair_v3.  The parity tests hold the three against the oracle and
+ * against each other; results agree within the north-star bars whichever runs. */
+int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which);
+/* which kernel the last two_body_forces call ran (1 general, 2 k_pair_v2, 3 k_pair_v3; 0 none) and the worst deviation of the
+ * packed table units from the fp64 interpolation polynomial found by the build-time verification (relative to the local table
+ * magnitude; the packed layout is used only below 2e-11) */
+int dlpgpu_pair_kernel_used(dlpgpu_ctx* ctx, int* which, double* packed_table_error);
 
 #ifdef __cplusplus
 }

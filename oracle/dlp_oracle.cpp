@@ -614,6 +614,7 @@ struct Dom {
 
 struct World {
   int P = 1, imcon = 1;
+  int nthreads = 1;   // host threads the world-level loops over domains may use (one domain = one would-be MPI rank)
   double cell[10] = {0};
   int megatm = 0, megfrz = 0;
   bool lbook = false;
@@ -812,7 +813,9 @@ DirSet dir_settings(const World& w, const Dom& dom, int mdir) {
 // deport_data.F90:1673-1951 export_atomic_data, all ranks of the world "simultaneously"
 void export_atomic_data(World& w, int mdir) {
   const int iadd = 6;
-  for (Dom& dom : w.d) {   // pack phase (every rank packs before anybody unpacks = MPI semantics)
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {   // pack phase (every rank packs before anybody unpacks = MPI semantics)
+    Dom& dom = w.d[rr];
     DirSet s = dir_settings(w, dom, mdir);
     dom.sendbuf.clear();
     for (int i = 1; i <= dom.nlast; ++i) {
@@ -835,7 +838,9 @@ void export_atomic_data(World& w, int mdir) {
       }
     }
   }
-  for (Dom& dom : w.d) {   // unpack phase: receive from kdnode
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {   // unpack phase: receive from kdnode
+    Dom& dom = w.d[rr];
     DirSet s = dir_settings(w, dom, mdir);
     const std::vector<double>& buf = w.d[s.kd].sendbuf;
     int jmove = (int)buf.size();
@@ -864,11 +869,14 @@ void vnl_set_check(Dom& dom) {
 
 // halo.F90:153-355 set_halo_particles (world-wide)
 void set_halo_particles(World& w) {
-  for (Dom& dom : w.d) halo_tag(w, dom);
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) halo_tag(w, w.d[rr]);
   export_atomic_data(w, -1); export_atomic_data(w, 1);
   export_atomic_data(w, -2); export_atomic_data(w, 2);
   export_atomic_data(w, -3); export_atomic_data(w, 3);
-  for (Dom& dom : w.d) {
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {
+    Dom& dom = w.d[rr];
     for (int i = dom.natms + 1; i <= dom.nlast; ++i) {          // halo.F90:296-302
       dom.ltype[i] = w.sites.type_site[dom.lsite[i]];
       dom.parts[i].chge = w.sites.charge_site[dom.lsite[i]];
@@ -881,7 +889,8 @@ void set_halo_particles(World& w) {
 // deport_data.F90:2301-2553 export_atomic_positions (world-wide); mlast per domain
 void export_atomic_positions(World& w, int mdir, std::vector<int>& mlast) {
   const int iadd = 3;
-  for (size_t r = 0; r < w.d.size(); ++r) {
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int r = 0; r < (int)w.d.size(); ++r) {
     Dom& dom = w.d[r];
     DirSet s = dir_settings(w, dom, mdir);
     dom.sendbuf.clear();
@@ -902,7 +911,8 @@ void export_atomic_positions(World& w, int mdir, std::vector<int>& mlast) {
       }
     }
   }
-  for (size_t r = 0; r < w.d.size(); ++r) {
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int r = 0; r < (int)w.d.size(); ++r) {
     Dom& dom = w.d[r];
     DirSet s = dir_settings(w, dom, mdir);
     const std::vector<double>& buf = w.d[s.kd].sendbuf;
@@ -1006,7 +1016,9 @@ bool vnl_check(World& w, double* tol_out) {
     return true;
   }
   double tol = 0.0;
-  for (Dom& dom : w.d) {
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1) reduction(max : tol)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {
+    Dom& dom = w.d[rr];
     int n = dom.natms;
     std::vector<double> x(n + 1), y(n + 1), z(n + 1);
     for (int i = 1; i <= n; ++i) {
@@ -1683,7 +1695,9 @@ int relocate_particles(World& w) {
   }
   double rcell[10], det;
   invert(w.cell, rcell, det);
-  for (Dom& dom : w.d) {   // :2981-3025
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {   // :2981-3025
+    Dom& dom = w.d[rr];
     for (int i = 1; i <= dom.natms; ++i) {
       dom.ixyz[i] = 0;
       const CorePart& p = dom.parts[i];
@@ -1704,7 +1718,8 @@ int relocate_particles(World& w) {
   for (int q = 0; q < 6; ++q) {
     int mdir = mdirs[q];
     std::vector<std::vector<int>> excl_rows(w.d.size());
-    for (size_t r = 0; r < w.d.size(); ++r) {
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+    for (int r = 0; r < (int)w.d.size(); ++r) {
       Dom& dom = w.d[r];
       DirSet s = dir_settings(w, dom, mdir);
       dom.sendbuf.clear();
@@ -1746,7 +1761,8 @@ int relocate_particles(World& w) {
       }
       dom.natms = k;   // keep
     }
-    for (size_t r = 0; r < w.d.size(); ++r) {   // receive
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+    for (int r = 0; r < (int)w.d.size(); ++r) {   // receive
       Dom& dom = w.d[r];
       DirSet s = dir_settings(w, dom, mdir);
       const std::vector<double>& buf = w.d[s.kd].sendbuf;
@@ -2136,13 +2152,12 @@ void ora_world_neighskip(void* h, double* out5) { for (int i = 0; i < 5; ++i) ou
 
 static void par_for_domains(World* w, int nthreads, void (*fn)(World*, int)) {
   int P = (int)w->d.size();
-  if (nthreads <= 1 || P == 1) { for (int r = 0; r < P; ++r) fn(w, r); return; }
-  std::vector<std::thread> th;
-  int nt = std::min(nthreads, P);
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([=]() { for (int r = t; r < P; r += nt) fn(w, r); });
-  for (auto& t : th) t.join();
+  int nt = std::max(1, std::min(nthreads, P));
+#pragma omp parallel for schedule(static, 1) num_threads(nt) if (nt > 1)
+  for (int r = 0; r < P; ++r) fn(w, r);
 }
+// host threads for the world-level loops over domains of every other phase (halo, migration, vnl_check, integrator)
+void ora_world_set_threads(void* h, int nthreads) { ((World*)h)->nthreads = std::max(1, nthreads); }
 static int g_rc[4096];
 int ora_world_link_cell_pairs(void* h, int nthreads) {
   World* w = (World*)h;
@@ -2159,9 +2174,14 @@ int ora_world_link_cell_pairs(void* h, int nthreads) {
 // engcpe_ex,vircpe_ex] + stress(9) (the gsum of two_body.F90:729 / drivers.F90:795)
 int ora_world_two_body(void* h, int nthreads, int zero_forces, double* out15) {
   World* w = (World*)h;
-  if (zero_forces)
-    for (Dom& d : w->d)
+  if (zero_forces) {
+    const int nt0 = std::max(1, std::min(nthreads, (int)w->d.size()));
+#pragma omp parallel for schedule(static, 1) num_threads(nt0) if (nt0 > 1)
+    for (int rr = 0; rr < (int)w->d.size(); ++rr) {
+      Dom& d = w->d[rr];
       for (int i = 1; i <= d.nlast; ++i) { d.parts[i].fxx = 0; d.parts[i].fyy = 0; d.parts[i].fzz = 0; }
+    }
+  }
   par_for_domains(w, nthreads, [](World* ww, int r) { two_body_forces(*ww, ww->d[r]); });
   if (out15) {
     for (int i = 0; i < 15; ++i) out15[i] = 0.0;
@@ -2237,8 +2257,10 @@ void ora_dom_get_bg(void* h, int rank, double* xbg, double* ybg, double* zbg) {
 // simple NVE velocity-Verlet stages (nve.F90:163-173, :198-217) so the CPU baseline can advance a trajectory:
 // stage 1: v += (dt/2m) f ; x += dt v      stage 2: v += (dt/2m) f       (weight per type)
 void ora_world_vv(void* h, int stage, double dt, const double* weight_by_type /*1-based via type-1*/) {
-  World* w = (World*)h;
-  for (Dom& d : w->d)
+  World& w = *(World*)h;
+#pragma omp parallel for schedule(static, 1) num_threads(w.nthreads) if (w.nthreads > 1)
+  for (int rr = 0; rr < (int)w.d.size(); ++rr) {
+    Dom& d = w.d[rr];
     for (int i = 1; i <= d.natms; ++i) {
       double hstep = 0.5 * dt, rm = 1.0 / weight_by_type[d.ltype[i] - 1];
       CorePart& p = d.parts[i];
@@ -2246,6 +2268,7 @@ void ora_world_vv(void* h, int stage, double dt, const double* weight_by_type /*
       d.vxx[i] = d.vxx[i] + tmp * p.fxx; d.vyy[i] = d.vyy[i] + tmp * p.fyy; d.vzz[i] = d.vzz[i] + tmp * p.fzz;
       if (stage == 1) { p.xxx = p.xxx + dt * d.vxx[i]; p.yyy = p.yyy + dt * d.vyy[i]; p.zzz = p.zzz + dt * d.vzz[i]; }
     }
+  }
 }
 
 // ---- independent second opinion: O(N^2) minimum-image brute force ---------------------------------------------

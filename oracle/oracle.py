@@ -262,6 +262,10 @@ class World:
         return self.L.ora_world_load(self.h, C.c_int(x.shape[0]), _vp(x), _vp(v) if v is not None else None,
                                      _vp(s), C.c_int(int(fold)))
 
+    def set_threads(self, n):
+        """Host threads for the world-level loops over domains (halo, migration, vnl_check, integrator)."""
+        self.L.ora_world_set_threads(self.h, C.c_int(int(n)))
+
     def relocate(self):
         return self.L.ora_world_relocate(self.h)
 

@@ -1,104 +1,25 @@
-"""Multi-GPU parity check (run under torch.distributed.run, one rank per GPU): the dd.Domain engine against the CPU oracle's
-P-domain world on the same seeded system -- resident atoms after relocation + halo build (same atoms, order and bits),
-forces, energies, and a short trajectory with rebuild / refresh decisions."""
+"""Multi-GPU parity check (run under torch.distributed.run, one rank per GPU): see tests/dd_common.py."""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import torch.distributed as dist
 
 import _pkg
 
 _pkg.load()
-from dl_poly_b200 import dd, systems
-from oracle import oracle as ora
+from dl_poly_b200 import dd
+import dd_common
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 t = dd.TorchTransport(torch.device("cuda", local))
 which = sys.argv[1] if len(sys.argv) > 1 else "nacl"
-if which == "nacl":
-    s = systems.nacl((8, 8, 8), rcut=8.0, padding=0.3, temperature=1200.0)
-elif which == "water":
-    s = systems.spce_water(4096, rcut=8.0, padding=0.3, temperature=300.0)
-else:
-    s = systems.argon(12, temperature=200.0)
-ora.build()
-w = ora.World.from_system(s, P=world)
-dom = dd.Domain(s, device=local, transport=t)
-assert tuple(w.dd(rank)[0][:3]) == dom.dims
-w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
-oo = w.two_body()
-dom.rebuild()
-out = dom.forces()
-natms, nlast = dom.sr.dev_counts()
-c = w.counts(rank)
-assert (natms, nlast) == (c["natms"], c["nlast"]), ((natms, nlast), (c["natms"], c["nlast"]))
-po, pg = w.parts(rank), dom.sr.dev_get_parts()
-io, ig = w.ints(rank), dom.sr.dev_get_ints()
-for k in ("xxx", "yyy", "zzz", "chge"):
-    assert np.array_equal(po[k], pg[k]), k
-for k in ("ltg", "lsite", "ltype", "ixyz"):
-    assert np.array_equal(io[k], ig[k]), k
-fo = np.stack([po["fxx"], po["fyy"], po["fzz"]], 1)[:natms]
-fg = np.stack([pg["fxx"], pg["fyy"], pg["fzz"]], 1)[:natms]
-ferr = np.abs(fg - fo).max() / np.abs(fo).max()
-assert ferr < 1e-9, ferr
-tot = dom.gsum(out)
-for k in range(6):
-    assert abs(tot[k] - oo[k]) <= 1e-10 * max(abs(oo[k]), 1e-6 * np.abs(oo[:6]).max()), (k, tot[k], oo[k])
-# the one-kernel peer-memory refresh must reproduce the staged exchange bit for bit
-if dom.p2p:
-    with torch.cuda.stream(dom.stream):
-        dom.sr.dev_vv(1, 0.001)              # move the atoms a little (forces are in place)
-    dom.publish()
-    t.barrier()
-    dom.refresh_halo(staged=True)
-    p_staged = dom.sr.dev_get_parts()
-    torch.cuda.synchronize(); t.barrier()
-    dom.refresh_halo()
-    p_pull = dom.sr.dev_get_parts()
-    for k in ("xxx", "yyy", "zzz", "chge"):
-        assert np.array_equal(p_staged[k], p_pull[k]), ("pull vs staged", k)
-    w.vv(1, 0.001, s.weight_by_type); assert w.refresh_halo() == 0
-    po2 = w.parts(rank)
-    for k in ("xxx", "yyy", "zzz"):      # the two engines' forces differ in the last bits, so do the moved coordinates
-        assert np.abs(po2[k] - p_pull[k]).max() < 1e-9, ("pull vs oracle", k)
-    # put both engines back in step: finish this step like any other
-    oo = w.two_body(); w.vv(2, 0.001, s.weight_by_type)
-    dom.forces()
-    with torch.cuda.stream(dom.stream):
-        dom.sr.dev_vv(2, 0.001)
-# trajectory
-# rigid SPC/E has no constraint solver in this harness (SHAKE stays on the CPU path), so its trajectory is only followed for a
-# few small steps before the unconstrained molecules fall apart and the dynamics turn chaotic
-dt, nsteps = (0.0005, 8) if which == "water" else (0.002, 25)
-reb = 0
-for step in range(nsteps):
-    w.vv(1, dt, s.weight_by_type)
-    upd, tol = w.vnl_check()
-    if upd:
-        w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
-    else:
-        assert w.refresh_halo() == 0
-    oo = w.two_body()
-    w.vv(2, dt, s.weight_by_type)
-    r0 = dom.rebuilds
-    out = dom.step(dt)
-    assert (dom.rebuilds != r0) == upd, (step, upd)
-    reb += int(upd)
-    tot = dom.gsum(out)
-    assert abs(tot[0] + tot[2] - oo[0] - oo[2]) <= 1e-8 * abs(oo[0] + oo[2]), (step, tot[:4], oo[:4])
-    n2, l2 = dom.sr.dev_counts()
-    c = w.counts(rank)
-    assert (n2, l2) == (c["natms"], c["nlast"]), (step, (n2, l2), (c["natms"], c["nlast"]))
-assert reb >= 1 or which == "water"
-t.barrier()
+rep = dd_common.check_rank(t, local, which)
 if rank == 0:
-    print("dd_check %s world=%d dims=%s natms(rank0)=%d nlast=%d max|dF|/max|F|=%.2e rebuilds=%d OK" % (which, world, dom.dims, natms, nlast, ferr, reb))
-dom.close()
+    print("dd_check %s world=%d %s OK" % (which, world, rep))
 dist.destroy_process_group()

@@ -1,0 +1,48 @@
+"""Multi-rank parity on ONE GPU: the ranks of the domain decomposition run as threads of this process, one CUDA stream and
+one library context each, and exchange migrating atoms, halo atoms, refreshed positions, the gmax and the gsum through the
+library's peer-memory kernels exactly as they do between GPUs (the peers' buffers are plain device pointers instead of
+CUDA-IPC mappings).  Checked against the oracle's P-domain world: see tests/dd_common.py.  This is what puts the N > 1 path
+on the record of a 1-GPU box; tests/test_gpu_multi.py runs the same check with one process per GPU when there are several."""
+import threading
+
+import pytest
+
+from dl_poly_b200 import dd
+import dd_common
+
+pytestmark = pytest.mark.gpu
+
+
+def run_threads(world, which):
+    grp = dd.ThreadGroup(world)
+    reps, errs = [None] * world, [None] * world
+
+    def body(rank):
+        import torch
+        try:
+            torch.cuda.set_device(0)
+            reps[rank] = dd_common.check_rank(grp.transport(rank), 0, which)
+        except BaseException as e:          # a failing rank must not leave the others waiting at a barrier for ever
+            errs[rank] = e
+            grp.bar.abort()
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(timeout=900)
+    real = [e for e in errs if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+    if real:
+        raise real[0]
+    assert all(e is None for e in errs), errs
+    assert all(r is not None and r["ok"] for r in reps)
+    return reps[0]
+
+
+@pytest.mark.parametrize("world,which", [(2, "nacl"), (4, "nacl"), (8, "nacl"), (2, "water"), (8, "argon")])
+def test_domains_as_threads_against_oracle(world, which):
+    rep = run_threads(world, which)
+    print("THREAD-RANKS %s" % rep)
+    assert rep["ranks"] == world and rep["rebuilds"] >= (0 if which == "water" else 1)
+    if which != "water":
+        assert rep["migrated_atoms"] > 0 and rep["mailbox_gsum_steps"] > 0
