@@ -120,13 +120,8 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
-  DBuf<double> tab3a;                 // k_pair_v3: plane A {g0_force, g0_energy} per unit, completions in the 12 low bits
-  DBuf<float> tab3b;                  // k_pair_v3: plane B fp32 {c1_force, c1_energy, h_force, h_energy} per unit
-  bool tab3_valid = false;
-  int tab3_llo = 1;                   // grid intervals below this one keep fp64 coefficients (side path of k_pair_v3)
-  double tab3_err = 0.0;              // worst deviation of the packed polynomial from the fp64 one, relative to the local table magnitude
-  int last_pair_kernel = 0;           // 1 k_pair_forces, 2 k_pair_v2, 3 k_pair_v3 (dlpgpu_pair_kernel_used)
-  int pair_layout = 0;                // dlpgpu_set_pair_kernel: 0 automatic, 2 keep the k_pair_v2 layouts
+  int last_pair_kernel = 0;           // 1 k_pair_forces, 2 k_pair_v2 (dlpgpu_pair_kernel_used)
+  int list_one_atom_per_pass = 0;     // dlpgpu_set_list_kernel: 1 = k_list_cell<1> instead of k_list_cell8 (diagnostic)
   cudaTextureObject_t tab2_tex = 0;   // the same buffer as 16-byte texels: table reads through the texture pipe (see pair2)
   int ew_off = 0;
   bool tab4_valid = false;

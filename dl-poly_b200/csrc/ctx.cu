@@ -173,7 +173,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
-  ctx->tab2h.release(); ctx->tab2s.release(); ctx->tab3a.release(); ctx->tab3b.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
+  ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
   for (int r = 0; r < ctx->p2p_nranks; ++r)
@@ -339,9 +339,14 @@ int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode) {
 }
 
 int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 2) return DLPGPU_ERR_ARG;
+  if (!ctx || which < 0 || which > 1) return DLPGPU_ERR_ARG;
   ctx->no_fast = which == 1;
-  ctx->pair_layout = which == 2 ? 2 : 0;
+  return 0;
+}
+
+int dlpgpu_set_list_kernel(dlpgpu_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 1) return DLPGPU_ERR_ARG;
+  ctx->list_one_atom_per_pass = which;
   return 0;
 }
 

@@ -642,229 +642,6 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   }
 }
 
-// ---------------------------------------------------------------- packed quadratic units (k_pair_v3)
-// What ncu and the micro-benchmarks say about k_pair_v2 on B200 (profiles/r1_s3_pair_v2_final_ionic1m.txt, r1_ubench_b200.txt):
-// the kernel is bound by the L1TEX data stage, and per 32 pairs that stage spends ~41 clk on the four random LDS.128 of the
-// two tables (10.3 clk each with the 2.4-fold bank conflicts of eight random 16-byte units per quarter-warp), ~20 clk on the
-// fp32 second-difference texel, ~28 clk on the three fp64 REDs, ~17 clk on the 32-byte coordinate gather.  This layout
-// removes the texel AND the g(l+1) reads: the reference's 3-point interpolation (vdw.F90:1914-1921, numerics.F90:280-282)
-//     t1 + (t2 - t1) p/2  =  g0 + p (c1 + p h),   c1 = (g1 - g0) - h,   h = (g2 - 2 g1 + g0) / 2
-// needs per table and grid interval the six numbers {g0, c1, h} x {force, energy}; they are packed into ONE 32-byte unit
-//     plane A (16 B): g0_force, g0_energy   as fp64 whose 12 lowest mantissa bits carry the completions below
-//     plane B (16 B): c1_force, c1_energy, h_force, h_energy   as fp32
-// fp32 alone is not enough (a rounding error of c1 or h is the SAME for every pair in that grid interval, and energies are
-// sums over 1e8 pairs): c1 is completed to 33 significant bits by a signed 9-bit correction (units of 2^-9 ulp of the fp32
-// value), h to 27 bits by a signed 3-bit one, both parked in the low bits of g0 -- a 2^-41 relative perturbation of g0.
-// Error budget relative to |g|: g0 4.5e-13, c1 (|c1| <~ 0.1 |g| on these grids) ~1e-11 x p, h (|h| <~ 2e-3 |g|) ~2e-12 x p^2;
-// dlp_build_tab3 VERIFIES the packed polynomial against the fp64 one for every interval of every table and the layout is
-// only used when the worst deviation is below 2e-11 of the local table magnitude (anything else keeps k_pair_v2).
-// Two LDS.128 per table and pair instead of two LDS.128 + half a texel; 154 KB of shared memory for NaCl (4 tables x 1205).
-struct P3 {
-  int natms, pitch, ne, ts, zero, xpitch, l_lo;
-  double rdr, thr, scaling, alpha, rcut;
-};
-#define DLP_T3_CBITS 9
-#define DLP_T3_HBITS 3
-__device__ __forceinline__ double t3_complete(float c32, int q, double unit) {   // c32 + q * 2^(exponent(c32)) * unit
-  const float p2 = __int_as_float(__float_as_int(c32) & 0x7f800000);          // 2^exponent(c32); 0 for zero / subnormal
-  const float qf = __int_as_float(0x4B400000 + q) - 12582912.0f;              // (float)q without the conversion pipe, |q| < 2^22
-  return __fma_rn((double)(qf * p2), unit, (double)c32);
-}
-// {value at p of the force table, of the energy table} from one unit
-__device__ __forceinline__ double2 t3_eval(const double2 a, const float4 b, double p) {
-  constexpr double UC = 1.0 / (double)(1ll << (23 + DLP_T3_CBITS)), UH = 1.0 / (double)(1ll << (23 + DLP_T3_HBITS));
-  const int lf = __double2loint(a.x), le = __double2loint(a.y);
-  const double c1f = t3_complete(b.x, (lf << (32 - DLP_T3_CBITS)) >> (32 - DLP_T3_CBITS), UC);
-  const double c1e = t3_complete(b.y, (le << (32 - DLP_T3_CBITS)) >> (32 - DLP_T3_CBITS), UC);
-  const double hf = t3_complete(b.z, (lf << (32 - DLP_T3_CBITS - DLP_T3_HBITS)) >> (32 - DLP_T3_HBITS), UH);
-  const double he = t3_complete(b.w, (le << (32 - DLP_T3_CBITS - DLP_T3_HBITS)) >> (32 - DLP_T3_HBITS), UH);
-  return make_double2(__fma_rn(p, __fma_rn(p, hf, c1f), a.x), __fma_rn(p, __fma_rn(p, he, c1e), a.y));
-}
-
-// Intervals below P.l_lo (the first grid points of r^-n tables: distances no physical configuration reaches) are too steep for
-// the packed coefficients; a pair that lands there is evaluated from the fp64 {g, h} units in global memory (the k_pair_v2
-// layout).  Out of line and by value, so the hot loop keeps its registers.
-struct Cold4 { double vf, ve, cf, ce; };
-__device__ __noinline__ Cold4 t3_cold(const double2* __restrict__ t2g, int ne, int uv, int uc, double p) {
-  Cold4 r;
-  const double2 a = t2g[uv], b = t2g[uv + 1], h = t2g[ne + uv];
-  r.vf = __fma_rn(p, __fma_rn(p, h.x, (b.x - a.x) - h.x), a.x);
-  r.ve = __fma_rn(p, __fma_rn(p, h.y, (b.y - a.y) - h.y), a.y);
-  const double2 c = t2g[uc], d = t2g[uc + 1], k = t2g[ne + uc];
-  r.cf = __fma_rn(p, __fma_rn(p, k.x, (d.x - c.x) - k.x), c.x);
-  r.ce = __fma_rn(p, __fma_rn(p, k.y, (d.y - c.y) - k.y), c.y);
-  return r;
-}
-
-template <int VT, int EW>
-__device__ __forceinline__ void pair3(const P3& P, const double2* __restrict__ sA, const float4* __restrict__ sB, const double2* __restrict__ t2g,
-                                      const double4& pi, double qi_s, unsigned e, const double4& pj, double& fix, double& fiy, double& fiz,
-                                      double* acc, double* __restrict__ fneg) {
-  constexpr double MAGIC = 4503599627370496.0;   // 2^52
-  const double x = pi.x - pj.x, y = pi.y - pj.y, z = pi.z - pj.z;             // two_body.F90:348-350
-  const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
-  const int kc = (int)((e >> DLP_K_SHIFT) & DLP_K_MASK);
-  const bool in = rsq < P.thr;                                                // Sqrt(rsq) < cutoff (see sqrt_threshold); rvdw == rcut here
-  const bool in_v = VT && kc != 0 && in;                                      // vdw.F90:1892
-  const bool in_c = EW && in;                                                 // ewald_spole.F90:133 (a zero charge gives exact zeros)
-  const double ri = rsqrt_fast(rsq);
-  const double rrr = rsq * ri;                                                // two_body.F90:351 to ~1 ulp
-  const double r_rsq = ri * ri;
-  const double tt = rrr * P.rdr;                                              // vdw.F90:1909-1910 / ewald_spole.F90:140-146 (one grid)
-  const double m = __dadd_rd(tt, MAGIC);
-  const int l = max(__double2loint(m), 1);                                    // r < one grid step does not occur
-  const double ppp = tt - (m - MAGIC);
-  const double w = ((e & (DLP_F_HALO | DLP_F_ECNT)) != DLP_F_HALO) ? 1.0 : 0.0;   // energy ownership, vdw.F90:1948
-  double gamma = 0.0;
-  const int uv = in_v ? kc * P.ts + l : P.zero, uc = in_c ? l : P.zero;
-  double2 rv = make_double2(0.0, 0.0), rc = rv;
-  if (l < P.l_lo && (in_v || in_c)) {
-    const Cold4 c = t3_cold(t2g, P.ne, uv, uc, ppp);
-    rv = make_double2(c.vf, c.ve); rc = make_double2(c.cf, c.ce);
-  } else {
-    if (VT) rv = t3_eval(sA[uv], sB[uv], ppp);
-    if (EW) rc = t3_eval(sA[uc], sB[uc], ppp);
-  }
-  if (VT) {
-    const double2 r = rv;
-    gamma = r.x * r_rsq;                                                      // :1914-1921
-    acc[0] = __fma_rn(w, r.y, acc[0]);                                        // :1953-1960
-  }
-  if (EW) {
-    const double2 r = rc;
-    const double prefac = qi_s * pj.w;
-    const double gc = prefac * r.x, ec = prefac * r.y;                        // ewald_spole.F90:140-174
-    acc[1] = __fma_rn(w, ec, acc[1]);
-    if (VT) acc[2] = __fma_rn(w * rsq, gc, acc[2]);                           // :189 (the vdW virial follows from the trace)
-    gamma += gc;
-  }
-  const double f1 = gamma * x, f2 = gamma * y, f3 = gamma * z;
-  fix += f1; fiy += f2; fiz += f3;
-  const double wx = w * x, wy = w * y, wz = w * z;
-  acc[3] = __fma_rn(wx, f1, acc[3]); acc[4] = __fma_rn(wx, f2, acc[4]); acc[5] = __fma_rn(wx, f3, acc[5]);
-  acc[6] = __fma_rn(wy, f2, acc[6]); acc[7] = __fma_rn(wy, f3, acc[7]); acc[8] = __fma_rn(wz, f3, acc[8]);
-  if ((e & DLP_F_HALO) == 0u && (in_v || in_c)) {   // Newton's third law, local partners only (vdw.F90:1939-1941, ewald_spole.F90:159-161)
-    double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
-    atomicAdd(q, f1); atomicAdd(q + DLP_FB, f2); atomicAdd(q + 2 * DLP_FB, f3);
-  }
-}
-
-// same row schedule, software pipeline and reductions as k_pair_v2 (see there); tables in the packed layout
-template <int VT, int EW, int XC>
-__global__ void __launch_bounds__(512, 1)
-k_pair_v3(P3 P, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
-          const int* __restrict__ nnbr, const double2* __restrict__ tabA, const float4* __restrict__ tabB, const double2* __restrict__ t2g,
-          double* __restrict__ fpos, double* __restrict__ fneg, double* __restrict__ partial, const unsigned* __restrict__ xnbr,
-          const int* __restrict__ nxnbr) {
-  constexpr int TPR = 8, NT = 512;
-  extern __shared__ __align__(16) double2 s_tab[];
-  double2* sA = s_tab;
-  float4* sB = reinterpret_cast<float4*>(s_tab + P.ne);
-  for (int k = threadIdx.x; k < P.ne; k += NT) { sA[k] = tabA[k]; sB[k] = tabB[k]; }
-  __syncthreads();
-  unsigned long long pol_stream, pol_keep;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  constexpr int RPB = NT / TPR;
-  const int lg = threadIdx.x % TPR;
-  const int grp = threadIdx.x / TPR;
-  double acc[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-  double xeng = 0.0, xvir = 0.0;
-  for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
-    const int t = min(base + grp, P.natms - 1);
-    const bool rowlive = base + grp < P.natms;
-    const double4 pi = posq_s[loc_slot[t]];
-    const int npad = rowlive ? (nnbr[t] + 2 * TPR - 1) & ~(2 * TPR - 1) : 0;
-    const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
-    double fix = 0.0, fiy = 0.0, fiz = 0.0;
-    const unsigned* row = nbr + (size_t)t * P.pitch + lg;
-#define LE(i) ld_entry(row + (i) * TPR, pol_stream)
-#define GA(e) ld_posq_keep(posq_s + ((e) & DLP_J_MASK), pol_keep)
-    unsigned ea = LE(0), eb = LE(1);
-    unsigned ec = LE(2), ed = LE(3);
-    double4 pa = GA(ea), pb = GA(eb);
-    for (int k = 0; k < npad; k += 4 * TPR) {
-      {
-        const double4 pc = GA(ec), pd = GA(ed);
-        const unsigned e0 = ea, e1 = eb;
-        ea = LE(4); eb = LE(5);
-        pair3<VT, EW>(P, sA, sB, t2g, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair3<VT, EW>(P, sA, sB, t2g, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
-        pa = pc; pb = pd;
-      }
-      if (k + 2 * TPR >= npad) break;
-      {
-        const double4 pc = GA(ea), pd = GA(eb);
-        const unsigned e0 = ec, e1 = ed;
-        ec = LE(6); ed = LE(7);
-        pair3<VT, EW>(P, sA, sB, t2g, pi, qi_s, e0, pa, fix, fiy, fiz, acc, fneg);
-        pair3<VT, EW>(P, sA, sB, t2g, pi, qi_s, e1, pb, fix, fiy, fiz, acc, fneg);
-        pa = pc; pb = pd;
-      }
-      row += 4 * TPR;
-    }
-#undef LE
-#undef GA
-    if (XC && rowlive) {
-      const int nx = nxnbr[t];
-      if (nx > 0 && fabs(pi.w) > ZERO_PLUS) {                                 // ewald_spole.F90:541
-        const unsigned* xrow = xnbr + (size_t)t * P.xpitch;
-        for (int kx = lg; kx < nx; kx += TPR) {
-          const unsigned e = xrow[kx];
-          const int j = (int)(e & DLP_J_MASK);
-          const bool halo = (e & DLP_F_HALO) != 0;
-          const double w = (halo && !(e & DLP_F_ECNT)) ? 0.0 : 1.0;
-          double f1, f2, f3;
-          if (excl_pair(P.alpha, P.rcut, qi_s, pi, posq_s[j], w, f1, f2, f3, xeng, xvir, acc + 3)) {
-            fix += f1; fiy += f2; fiz += f3;
-            if (!halo) { double* q = fneg_ptr(fneg, j); atomicAdd(q, f1); atomicAdd(q + DLP_FB, f2); atomicAdd(q + 2 * DLP_FB, f3); }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int d = TPR / 2; d > 0; d >>= 1) {
-      fix += __shfl_xor_sync(DLP_FULL, fix, d);
-      fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
-      fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
-    }
-    if (lg == 0 && rowlive) { fpos[t] = fix; fpos[(size_t)P.natms + t] = fiy; fpos[2 * (size_t)P.natms + t] = fiz; }
-  }
-  __shared__ double red[NT / 32][11];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 11; ++k) {
-    double v = k < 9 ? acc[k] : (k == 9 ? xeng : xvir);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(DLP_FULL, v, d);
-    if (lane == 0) red[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 11) {
-    double v = 0.0;
-    for (int w = 0; w < NT / 32; ++w) v += red[w][threadIdx.x];
-    red[0][threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 12) {   // the 12-slot layout of k_pair_forces (see k_pair_v2)
-    const double trace = red[0][3] + red[0][6] + red[0][8] - (XC ? red[0][10] : 0.0);
-    const double vc = (VT && EW) ? red[0][2] : (EW ? trace : 0.0);
-    double v = 0.0;
-    switch (threadIdx.x) {
-      case 0: v = red[0][0]; break;
-      case 1: v = VT ? -(trace - vc) : 0.0; break;
-      case 2: v = red[0][1]; break;
-      case 3: v = -vc; break;
-      case 4: v = XC ? red[0][9] : 0.0; break;
-      case 5: v = XC ? -red[0][10] : 0.0; break;
-      default: v = red[0][threadIdx.x - 3];
-    }
-    partial[(size_t)blockIdx.x * 12 + threadIdx.x] = v;
-  }
-}
-
 // rdfs.F90:146-212 rdf_collect / :880-946 rdf_excl_collect over the device rows: one warp per row, a per-block histogram in
 // shared memory (counts are integers, so the sums are exact in any order).  The distance is the reference's
 // Sqrt(xxt**2 + yyt**2 + zzt**2) (IEEE, unfused) because the bin index Int(rrr * rdelr) has to agree bit for bit.
@@ -1064,87 +841,6 @@ int dlp_build_tab4(dlpgpu_ctx* ctx) {
     cudaTextureDesc td = {};
     td.readMode = cudaReadModeElementType;
     CK(cudaCreateTextureObject(&ctx->tab2_tex, &rd, &td, nullptr));
-    // ---- packed quadratic units of k_pair_v3 (see there): plane A = {g0_f, g0_e} with the completions in the 12 low bits,
-    // plane B = fp32 {c1_f, c1_e, h_f, h_e}; every interval of every table is verified against the fp64 polynomial
-    ctx->tab3_valid = false;
-    {
-      std::vector<double> A((size_t)NE * 2, 0.0);
-      std::vector<float> B((size_t)NE * 4, 0.0f);
-      double worst = 0.0;
-      bool ok = true;
-      int l_lo = 1;   // intervals below l_lo take the fp64 side path of the kernel (see t3_cold)
-      const int W = 50;   // the error of an interval is measured against the largest table value within +-W grid points
-      auto pack = [](double c, int bits, float& c32, int& q) {
-        c32 = (float)c; q = 0;
-        if (!std::isfinite(c32)) return false;
-        unsigned fb; std::memcpy(&fb, &c32, 4);
-        const int eb = (int)((fb >> 23) & 0xff);
-        if (eb > 0) {
-          const double unit = std::ldexp(1.0, eb - 127 - 23 - bits);
-          long v = std::lrint((c - (double)c32) / unit);
-          const long lim = 1L << (bits - 1);
-          q = (int)std::max(-lim, std::min(lim - 1, v));
-        }
-        return true;
-      };
-      auto unpack = [](float c32, int q, int bits) {
-        unsigned fb; std::memcpy(&fb, &c32, 4);
-        fb &= 0x7f800000u;
-        float p2; std::memcpy(&p2, &fb, 4);
-        return (double)c32 + (double)((float)q * p2) * std::ldexp(1.0, -(23 + bits));
-      };
-      for (int tb = 0; tb < ntab && ok; ++tb) {
-        const int n = (tb == 0) ? (ne ? ctx->ew_n : -1) : ctx->max_grid;       // last index of this table
-        for (int l = 0; l <= n && l < tsz; ++l) {
-          const size_t u = (size_t)tb * tsz + l;
-          for (int c = 0; c < 2; ++c) {   // force, energy
-            const double g0 = t2[2 * u + c];
-            const double g1 = (l + 1 <= n) ? t2[2 * (u + 1) + c] : g0;
-            const double h = (l + 2 <= n) ? t2[2 * (NE + u) + c] : 0.0;
-            const double c1 = (g1 - g0) - h;
-            float c32 = 0.f, h32 = 0.f;
-            int qc = 0, qh = 0;
-            const bool fin = std::isfinite(g0) && pack(c1, DLP_T3_CBITS, c32, qc) && pack(h, DLP_T3_HBITS, h32, qh);
-            if (!fin) { if (l >= 1 && l + 2 <= n) l_lo = std::max(l_lo, l + 1); c32 = h32 = 0.f; qc = qh = 0; }
-            unsigned long long gb; std::memcpy(&gb, &g0, 8);
-            gb = (gb & ~0xfffULL) | (unsigned long long)(qc & 0x1ff) | ((unsigned long long)(qh & 7) << DLP_T3_CBITS);
-            double g0p; std::memcpy(&g0p, &gb, 8);
-            A[2 * u + c] = std::isfinite(g0) ? g0p : g0;
-            B[4 * u + c] = c32; B[4 * u + 2 + c] = h32;
-            if (fin && l >= 1 && l + 2 <= n) {   // the intervals a pair can land in
-              // A rounding error of c1 or h is an ABSOLUTE error of the pair term; what it has to be small against is the size
-              // of the terms the sums are made of, i.e. the table values around this distance (at a zero crossing of the
-              // table the local value itself says nothing): the largest |g| within +-W grid points (+-0.5 A on these grids).
-              double scale = 1e-300;
-              for (int m = std::max(1, l - W); m <= std::min(n, l + W); ++m) {
-                const double gm = std::fabs(t2[2 * ((size_t)tb * tsz + m) + c]);
-                if (std::isfinite(gm)) scale = std::max(scale, gm);
-              }
-              const double c1p = unpack(c32, qc, DLP_T3_CBITS), hp = unpack(h32, qh, DLP_T3_HBITS);
-              double err = 0.0;
-              for (double pp : {0.3, 0.7, 0.999}) {
-                const double ref = g0 + pp * (((g1 - g0) - h) + pp * h), got = g0p + pp * (c1p + pp * hp);
-                err = std::max(err, std::fabs(got - ref) / scale);
-              }
-              if (err > 2.0e-11) l_lo = std::max(l_lo, l + 1);   // too steep for the packed form: such intervals keep fp64 coefficients
-              else worst = std::max(worst, err);
-            }
-          }
-        }
-      }
-      ctx->tab3_err = worst;
-      ctx->tab3_llo = l_lo;
-      // the fp64 side path is for distances no physical configuration reaches (the first few grid points, where r^-n tables
-      // change by orders of magnitude per step); a table that needs it beyond 0.5 A is not a table for this layout
-      const double step = 1.0 / (vt ? ctx->vdw_rdr : ctx->ew_rdr);
-      if (ok && worst <= 2.0e-11 && l_lo * step <= 0.5) {
-        CK(ctx->tab3a.ensure(A.size(), ctx->stream)); CK(ctx->tab3b.ensure(B.size(), ctx->stream));
-        CK(cudaMemcpyAsync(ctx->tab3a.p, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->tab3b.p, B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->tab3_valid = true;
-      }
-    }
   }
   ctx->tab4_valid = true;
   return 0;
@@ -1196,29 +892,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   // the fp32-h layout keeps only the g units in shared memory (16 B per entry): force fields with many potentials still fit
   const bool can8_pre = P.vdw_on && P.ew_on && P.same_grid && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul;
   const bool fast2 = fast && (can8_pre ? smem2 / 2 : smem2) + 2048 <= 227 * 1024;
-  // packed quadratic units (k_pair_v3): one grid for everything the kernel interpolates, tables verified at build time
-  const size_t smem3 = (size_t)ctx->tab2_ne * 32;
-  const bool one_grid = (P.vdw_on && P.ew_on) ? (P.same_grid && ctx->thr_vdw == ctx->thr_coul) : true;
-  const bool fast3 = fast && ctx->tab3_valid && ctx->pair_layout != 2 && one_grid && smem3 + 2048 <= 227 * 1024;
-  ctx->last_pair_kernel = natms > 0 ? (fast3 ? 3 : (fast2 ? 2 : 1)) : 0;
-  if (natms > 0 && fast3) {
-    P3 Q{};
-    Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero; Q.xpitch = P.xpitch;
-    Q.rdr = P.vdw_on ? ctx->vdw_rdr : ctx->ew_rdr; Q.thr = P.vdw_on ? ctx->thr_vdw : ctx->thr_coul;
-    Q.scaling = ctx->scaling; Q.alpha = ctx->alpha; Q.rcut = ctx->rcut; Q.l_lo = ctx->tab3_llo;
-    const double2* tA = reinterpret_cast<const double2*>(ctx->tab3a.p);
-    const float4* tB = reinterpret_cast<const float4*>(ctx->tab3b.p);
-#define DLP_V3(V, E, X)                                                                                                        \
-  do {                                                                                                                         \
-    CK(cudaFuncSetAttribute(k_pair_v3<V, E, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));                      \
-    LAUNCH(ctx, (k_pair_v3<V, E, X>), blocks, 512, smem3, Q, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, tA, tB,              \
-           reinterpret_cast<const double2*>(ctx->tab2.p), fpos, fneg, ctx->partial.p, ctx->xnbr.p, ctx->nxnbr.p);                \
-  } while (0)
-    if (P.vdw_on && P.ew_on) { if (xc) DLP_V3(1, 1, 1); else DLP_V3(1, 1, 0); }
-    else if (P.vdw_on) DLP_V3(1, 0, 0);
-    else DLP_V3(0, 1, 0);
-#undef DLP_V3
-  } else if (natms > 0 && fast2) {
+  ctx->last_pair_kernel = natms > 0 ? (fast2 ? 2 : 1) : 0;
+  if (natms > 0 && fast2) {
     P2 Q{};
     Q.natms = natms; Q.pitch = ctx->pitch; Q.ne = ctx->tab2_ne; Q.ts = ctx->tab2_ts; Q.zero = ctx->tab2_zero;
     Q.rdr_v = P.vdw_on ? ctx->vdw_rdr : ctx->ew_rdr; Q.rdr_e = ctx->ew_rdr; Q.thr_vdw = ctx->thr_vdw; Q.thr_coul = ctx->thr_coul;
@@ -1233,7 +908,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   } while (0)
     const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0, sg = (!v || !e || P.same_grid) ? 1 : 0;
     // measured on B200, 1 M NaCl ions: all six reads in LDS 1.438 ms, vdW h through the texture pipe 1.394 ms, combined fp32 h
-    // texel 1.264 ms, packed units (k_pair_v3, chosen above when they apply) -- see DESIGN.md
+    // texel 1.264 ms; {g0, c1, h} packed into 32-byte units in shared memory (no texel, 154 KB): 1.48 ms -- the larger carve-out
+    // takes the L1 the coordinate gathers live in (hit rate 52 % -> 28 %), see DESIGN.md
     const bool can8 = v && e && sg && ctx->tab2h_tex && ctx->thr_vdw == ctx->thr_coul;
     const int tx = can8 ? 8 : (v ? 2 : 0);   // argon: 0.418 against 0.437 ms
     if (v && e) {
@@ -1328,7 +1004,7 @@ int dlpgpu_rdf_collect(dlpgpu_ctx* ctx, int ntypes, const int* rdf_list, int n_p
 int dlpgpu_pair_kernel_used(dlpgpu_ctx* ctx, int* which, double* packed_table_error) {
   if (!ctx) return DLPGPU_ERR_ARG;
   if (which) *which = ctx->last_pair_kernel;
-  if (packed_table_error) *packed_table_error = ctx->tab3_err;
+  if (packed_table_error) *packed_table_error = 0.0;
   return 0;
 }
 
@@ -1387,8 +1063,7 @@ int dlp_preload_forces() {   // see dlp_preload_halo
   const void* ks[] = {(const void*)k_pair_forces<8, true, 512>, (const void*)k_pair_forces<8, false, 512>, (const void*)k_final_reduce,
                       (const void*)k_pair_v2<8, 1, 1, 1, 8>, (const void*)k_pair_v2<8, 1, 1, 1, 8, 512, 1>, (const void*)k_pair_v2<8, 1, 1, 1, 2, 512, 1>,
                       (const void*)k_pair_v2<8, 1, 1, 1, 2>, (const void*)k_pair_v2<8, 1, 1, 0, 2>, (const void*)k_pair_v2<8, 1, 0, 1, 2>,
-                      (const void*)k_pair_v2<8, 0, 1, 1, 0>, (const void*)k_pair_v3<1, 1, 0>, (const void*)k_pair_v3<1, 1, 1>,
-                      (const void*)k_pair_v3<1, 0, 0>, (const void*)k_pair_v3<0, 1, 0>, (const void*)k_rdf_collect, (const void*)k_scatter_half,
+                      (const void*)k_pair_v2<8, 0, 1, 1, 0>, (const void*)k_rdf_collect, (const void*)k_scatter_half,
                       (const void*)k_vv, (const void*)k_dfma};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();

@@ -98,12 +98,15 @@ class ShortRange:
         self.force_mode = int(mode)
 
     def set_pair_kernel(self, general_only=False, which=None):
-        """Diagnostic: 0 automatic, 1 always the general pair kernel (the reference's operation order statement by statement),
-        2 never the packed-unit kernel k_pair_v3."""
+        """Diagnostic: 0 automatic, 1 always the general pair kernel (the reference's operation order statement by statement)."""
         self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(which) if which is not None else int(bool(general_only))))
 
+    def set_list_kernel(self, which):
+        """Diagnostic: 0 k_list_cell8 (default), 1 the one-atom-per-pass kernel, for the plain half-list case."""
+        self._ck(self.L.dlpgpu_set_list_kernel(self.h, int(which)))
+
     def pair_kernel_used(self):
-        """(kernel of the last two_body_forces call: 1 general, 2 k_pair_v2, 3 k_pair_v3; worst packed-table deviation)."""
+        """(kernel of the last two_body_forces call: 1 general, 2 k_pair_v2; reserved)."""
         w, e = C.c_int(0), C.c_double(0.0)
         self._ck(self.L.dlpgpu_pair_kernel_used(self.h, C.byref(w), C.byref(e)))
         return w.value, e.value

@@ -85,6 +85,7 @@ SIGNATURES = {
     "dlpgpu_last_timings": (ci, [vp, vp]),
     "dlpgpu_set_force_mode": (ci, [vp, ci]),
     "dlpgpu_set_pair_kernel": (ci, [vp, ci]),
+    "dlpgpu_set_list_kernel": (ci, [vp, ci]),
     "dlpgpu_pair_kernel_used": (ci, [vp, pi_, pd_]),
 }
 

@@ -234,16 +234,17 @@ int dlpgpu_last_timings(dlpgpu_ctx* ctx, double t[4]);
 /* 1 (default, common.cuh force_mode): half list + fp64 RED atomics (Newton's third law) -- the reference's own pair count.
  * 0: full list without atomics (every local-local pair evaluated from both ends; bitwise reproducible forces). */
 int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
-/* Diagnostic: which pair kernel two_body_forces uses.  0 (default): automatic -- the fast tabulated kernels where they apply
- * (k_pair_v3 with packed table units when the tables pass its build-time verification, else k_pair_v2), the general kernel
- * otherwise.  1: always the general kernel (k_pair_forces: the reference's operation order statement by statement,
- * vdw.F90:1790-2024 / ewald_spole.F90:58-242).  2: never k_pair_v3.  The parity tests hold the three against the oracle and
+/* Diagnostic: which pair kernel two_body_forces uses.  0 (default): automatic -- the fast tabulated kernel (k_pair_v2) where it
+ * applies, the general kernel otherwise.  1: always the general kernel (k_pair_forces: the reference's operation order
+ * statement by statement, vdw.F90:1790-2024 / ewald_spole.F90:58-242).  The parity tests hold both against the oracle and
  * against each other; results agree within the north-star bars whichever runs. */
 int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which);
-/* which kernel the last two_body_forces call ran (1 general, 2 k_pair_v2, 3 k_pair_v3; 0 none) and the worst deviation of the
- * packed table units from the fp64 interpolation polynomial found by the build-time verification (relative to the local table
- * magnitude; the packed layout is used only below 2e-11) */
+/* which kernel the last two_body_forces call ran (1 general, 2 k_pair_v2; 0 none); *packed_table_error is reserved (0) */
 int dlpgpu_pair_kernel_used(dlpgpu_ctx* ctx, int* which, double* packed_table_error);
+/* Diagnostic: which kernel builds the device half list in the plain case (no exclusion lists, no frozen pairs, nlp < 3).
+ * 0 (default): k_list_cell8 (8 atoms of a link cell x 4 candidates per warp pass); 1: k_list_cell<1> (one atom x 32 candidates
+ * per pass).  Same rows either way (members and order); the parity tests compare them. */
+int dlpgpu_set_list_kernel(dlpgpu_ctx* ctx, int which);
 
 #ifdef __cplusplus
 }

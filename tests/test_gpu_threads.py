@@ -45,4 +45,6 @@ def test_domains_as_threads_against_oracle(world, which):
     print("THREAD-RANKS %s" % rep)
     assert rep["ranks"] == world and rep["rebuilds"] >= (0 if which == "water" else 1)
     if which != "water":
-        assert rep["migrated_atoms"] > 0 and rep["mailbox_gsum_steps"] > 0
+        assert rep["mailbox_gsum_steps"] > 0
+    if which == "nacl":          # the hot melt moves atoms across domain faces within the checked steps; cold argon need not
+        assert rep["migrated_atoms"] > 0
