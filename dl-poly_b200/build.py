@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libdlpgpu.so")
 SOURCES = ["ctx.cu", "cells.cu", "forces.cu", "halo.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
-         "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]   # host pass un-fused too (aarch64 hosts would contract h_dcell / h_geometry)
 # -fmad=false where a floating-point expression decides an integer (cell index, list membership, halo / migration
 # thresholds): those follow the reference's un-fused IEEE arithmetic bit for bit.  forces.cu contracts to FMA (the pair
 # terms only need the 1e-9 / 1e-10 bars); its cutoff tests use explicit _rn intrinsics.

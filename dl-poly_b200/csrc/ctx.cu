@@ -240,6 +240,10 @@ int dlpgpu_set_vdw(dlpgpu_ctx* ctx, int ntypes, const int* vdw_list, int max_vdw
   if (ntypes < 1 || !vdw_list || !ltp || max_vdw < n_vdw) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: bad arguments");
   if (!direct && (!tab_potential || !tab_force || max_grid < 8)) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: tables missing");
   if (direct && !param) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: direct evaluation needs param");
+  if (direct)   // vdw_forces_direct evaluates analytic forms only: keys 1..24 of vdw.F90:71-113 (a TABLE-file potential has none)
+    for (int k = 0; k < n_vdw; ++k)
+      if (ltp[k] != -1 && (ltp[k] < 1 || ltp[k] > 24))
+        return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_vdw: potential %d has key %d, which vdw_method direct cannot evaluate", k + 1, ltp[k]);
   ctx->ntypes = ntypes; ctx->n_vdw = n_vdw; ctx->max_vdw = max_vdw; ctx->max_grid = max_grid;
   ctx->rvdw = rvdw; ctx->vdw_fshift = force_shift != 0; ctx->vdw_direct = direct != 0;
   if (max_grid > 4) {   // vdw.F90:1836-1837
@@ -583,7 +587,9 @@ int dlpgpu_vnl_set_check(dlpgpu_ctx* ctx, int nlast, const dlpgpu_corepart* part
   CKRC(dlp_ensure_atoms(ctx, nlast + 16));
   CKRC(upload_parts(ctx, nlast, parts));
   if (ctx->nlast < nlast) ctx->nlast = nlast;
-  return dlp_vnl_set_check(ctx);
+  CKRC(dlp_vnl_set_check(ctx));
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's array is page-locked, so the upload is a real DMA: it has to be over before the caller may touch parts again
+  return 0;
 }
 
 int dlpgpu_vnl_check(dlpgpu_ctx* ctx, int natms, const dlpgpu_corepart* parts, double* tol) {

@@ -4,9 +4,11 @@
 //   vdw.F90:1578-1788      vdw_forces_direct                   ewald_spole.F90:58-242   ewald_real_forces_coul
 //   two_body.F90:552-606 + ewald_spole.F90:479-679  excluded-pair Ewald correction
 //
-// One warp per local atom (lanes = neighbours), warps persistent over atoms.  Per-pair arithmetic keeps the reference's
-// operation order (this file is compiled with -fmad=false), so a pair term computed here has the same bits as the
-// reference's; only the order in which pair terms are summed differs (the 1e-9 / 1e-10 allowance of the north star).
+// Groups of 8 lanes per local atom (lanes = neighbours), blocks persistent over rows.  The general kernel keeps the reference's
+// statement order per pair; the file is compiled WITH FMA contraction (build.py: pair terms only need the 1e-9 / 1e-10 bars of
+// the north star), so a pair term agrees with the reference's to a few ulp, not bit for bit.  What decides an integer -- the
+// cutoff tests and, in k_rdf_collect, the bin index -- is formed with explicit _rn intrinsics in the reference's association
+// order and is exact.
 // FULL mode: each local-local pair is evaluated from both ends and weighted 1/2 in energy / virial / stress (exact:
 // the two evaluations are bitwise mirror images), local-halo pairs once with the reference's global-id ownership rule.
 // HALF mode: Newton's third law with fp64 RED atomics on the partner.
@@ -25,8 +27,170 @@ struct FParams {
 constexpr double ZERO_PLUS = 2.2250738585072014e-308;   // Tiny(1.0_wp), constants.F90:189
 
 __device__ __forceinline__ double powi6(double x) { double x2 = x * x; double x4 = x2 * x2; return x2 * x4; }   // __powidf2(x,6)
+// x**n for an integer n the way gfortran's __powidf2 forms it (binary powering; 1 / x**|n| for n < 0)
+__device__ __forceinline__ double powin(double x, int n) {
+  unsigned m = n < 0 ? (unsigned)(-n) : (unsigned)n;
+  double y = (m & 1u) ? x : 1.0;
+  while (m >>= 1) { x = x * x; if (m & 1u) y = y * x; }
+  return n < 0 ? 1.0 / y : y;
+}
 
-// two_body_potentials.F90 analytic forms used by vdw_forces_direct; p = param(1:7) of potential k
+// two_body_potentials.F90: {energy, gamma = -r dU/dr} of the analytic forms vdw_forces_direct evaluates per pair
+// (vdw.F90:1690-1692); q = param(1:7) of the potential, 0-based here.  Building blocks first (the ZBL-switched and MDF-tapered
+// forms are products of these), then the dispatcher over vdws%ltp (keys: vdw.F90:67-113).
+struct EG { double e, g; };
+__device__ __forceinline__ EG pot_lj126(double a, double b, double r) {             // :307-317  u = a/r^12 - b/r^6
+  const double r_6 = powi6(1.0 / r);
+  return {(a * r_6 - b) * r_6, 6.0 * r_6 * (2.0 * a * r_6 - b)};
+}
+__device__ __forceinline__ EG pot_lj(double eps, double sig, double coh, double r) {  // :260-270 (coh = 1) / :283-293
+  const double s6 = powi6(sig / r);
+  return {4.0 * eps * s6 * (s6 - coh), 24.0 * eps * s6 * (2.0 * s6 - coh)};
+}
+__device__ __forceinline__ EG pot_buck(double A, double rho, double C, double r) {  // :471-485  u = A exp(-r/rho) - C/r^6
+  const double b = r / rho;
+  const double t1 = A * exp(-b), t2 = -C / powi6(r);
+  return {t1 + t2, t1 * b + 6.0 * t2};
+}
+__device__ __forceinline__ EG pot_morse(double e0, double r0, double k, double r) {  // :416-428
+  const double t = exp(-k * (r - r0));
+  return {e0 * ((1.0 - t) * (1.0 - t) - 1.0), -2.0 * r * e0 * k * (1.0 - t) * t};
+}
+__device__ __forceinline__ EG pot_zbl(double z1, double z2, double r) {             // :718-743
+  const double zb[4] = {0.18175, 0.50986, 0.28022, 0.02817}, zc[4] = {3.1998, 0.94229, 0.40290, 0.20162};
+  const double ainv = (pow(z1, 0.23) + pow(z2, 0.23)) / (0.52917721067 * 0.88534);   // "this is in fact inverse a"
+  const double kk = z1 * z2 * 138935.4835;                                         // r4pie0, constants.F90:100
+  const double x = r * ainv;
+  double e = 0.0, g = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const double t1 = zb[i] * exp(-x * zc[i]); e = e + t1; g = g - zc[i] * t1; }
+  e = kk * e * (1.0 / r);
+  return {e, e - ainv * kk * g};
+}
+__device__ __forceinline__ EG pot_fm(double rm, double ic, double r) {              // :754-775  Fermi-like switch
+  const double c = 1.0 / ic;
+  const double t = 0.5 * exp(-(r < rm ? rm - r : r - rm) * c);
+  return {r < rm ? 1.0 - t : t, r * c * t};
+}
+__device__ __forceinline__ EG pot_mdf(double ri, double rc, double r) {             // MDF taper
+  if (r < ri) return {1.0, 0.0};
+  if (r > rc) return {0.0, 0.0};
+  const double d = rc - ri, d2 = d * d, rci = d2 * d2 * d;
+  const double u = rc - r;
+  const double e = (u * u * u) * (10.0 * ri * ri - 5.0 * rc * ri - 15.0 * r * ri + rc * rc + 3.0 * r * rc + 6.0 * r * r) / rci;
+  return {e, 30.0 * r * ((r - rc) * (r - rc)) * ((r - ri) * (r - ri)) / rci};
+}
+__device__ __forceinline__ EG eg_switch(const EG& f, const EG& z, const EG& m) {     // zbls / zblb: f z + (1 - f) m
+  return {f.e * z.e + (1.0 - f.e) * m.e, f.e * z.g + f.g * z.e + (1.0 - f.e) * m.g - f.g * m.e};
+}
+__device__ __forceinline__ EG eg_taper(const EG& l, const EG& m) { return {l.e * m.e, l.g * m.e + m.g * l.e}; }   // mlj / mbuck / mlj126
+
+// returns false for a key that has no analytic form (VDW_TAB, VDW_NULL, unknown)
+__device__ __noinline__ bool pot_direct_any(int key, const double* __restrict__ q, double r, double& e, double& g) {
+  EG v = {0.0, 0.0};
+  switch (key) {
+    case 3: {   // n-m  :330-345  e0, n, m, r0
+      const double a = q[3] / r, b = 1.0 / (q[1] - q[2]);
+      const double r_n = powin(a, (int)q[1]), r_m = powin(a, (int)q[2]);
+      v = {q[0] * (q[2] * r_n - q[1] * r_m) * b, q[0] * q[2] * q[1] * (r_n - r_m) * b};
+      break;
+    }
+    case 6: {   // hydrogen bond 12-10  :530-546
+      const double ri2 = 1.0 / (r * r);
+      const double fac12 = q[0] * powin(ri2, 6), fac10 = -q[1] * powin(ri2, 5);
+      v = {fac12 + fac10, 12.0 * fac12 + 10.0 * fac10};
+      break;
+    }
+    case 7: {   // shifted, force-corrected n-m  :360-400  e0, n, m, r0, r_trunc
+      const double n = q[1], m = q[2], r0 = q[3], rt = q[4];
+      if (r <= rt) {
+        const int ni = (int)rint(n), mi = (int)rint(m);
+        const double t = n - m, b = 1.0 / t, c = rt / r0, ci = r0 / rt;
+        const double beta = c * pow((powin(c, mi + 1) - 1.0) / (powin(c, ni + 1) - 1.0), b);
+        const double bn = powin(beta, ni), bm = powin(beta, mi), cn = powin(ci, ni), cm = powin(ci, mi);
+        const double alpha = -t / (m * bn * (1.0 + (n * ci - n - 1.0) * cn) - n * bm * (1.0 + (m * ci - m - 1.0) * cm));
+        const double e1 = q[0] * alpha, a = r0 / r;
+        const double an = powin(a, ni), am = powin(a, mi), bcn = powin(beta * ci, ni), bcm = powin(beta * ci, mi);
+        v = {e1 * (m * bn * (an - cn) - n * bm * (am - cm) + n * m * ((r / rt - 1.0) * (bcn - bcm))) * b,
+             e1 * m * n * (bn * an - bm * am - r / rt * (bcn - bcm)) * b};
+      }
+      break;
+    }
+    case 8: v = pot_morse(q[0], q[1], q[2], r); break;
+    case 9: {   // WCA  :559-576  eps, sig, d, cut
+      if (r < q[3] || fabs(r - q[2]) < 1.0e-10) {
+        const double s6 = powi6(q[1] / (r - q[2]));
+        v = {4.0 * q[0] * s6 * (s6 - 1.0) + q[0], 24.0 * q[0] * s6 * (2.0 * s6 - 1.0) * r / (r - q[2])};
+      }
+      break;
+    }
+    case 10: {  // DPD  :591-610  a, rc
+      if (r < q[1]) { const double t2 = r / q[1], t1 = 0.5 * q[0] * q[1] * (1.0 - t2); v = {t1 * (1.0 - t2), 2.0 * t1 * t2}; }
+      break;
+    }
+    case 11: {  // AMOEBA 14-7  :657-676  eps, sig
+      const double rho = r / q[1];
+      const double t1 = 1.0 / (0.07 + rho), t2 = 1.0 / (0.12 + powin(rho, 7));
+      const double t3 = q[0] * powin(1.07 * t1, 7);
+      const double t = t3 * (1.12 * t2 - 2.0);
+      v = {t, 7.0 * (t1 * t + 1.12 * t3 * (t2 * t2) * powi6(rho)) * rho};
+      break;
+    }
+    case 13: {  // Morse + c/r^12  :442-456  e0, r0, kk, c
+      const double t1 = exp(-q[2] * (r - q[1])), t2 = q[3] * powin(r, -12);
+      v = {q[0] * t1 * (t1 - 2.0) + t2, -2.0 * r * q[0] * q[2] * (1.0 - t1) * t1 + 12.0 * t2};
+      break;
+    }
+    case 14: {  // Rydberg  a, b, c
+      const double kk = r / q[2], t1 = exp(-kk);
+      v = {(q[0] + q[1] * r) * t1, kk * t1 * (q[0] - q[1] * q[2] + q[1] * r)};
+      break;
+    }
+    case 15: v = pot_zbl(q[0], q[1], r); break;
+    case 16: v = eg_switch(pot_fm(q[2], q[3], r), pot_zbl(q[0], q[1], r), pot_morse(q[4], q[5], q[6], r)); break;
+    case 17: v = eg_switch(pot_fm(q[2], q[3], r), pot_zbl(q[0], q[1], r), pot_buck(q[4], q[5], q[6], r)); break;
+    case 18: v = eg_taper(pot_lj(q[0], q[1], 1.0, r), pot_mdf(q[2], q[3], r)); break;
+    case 19: v = eg_taper(pot_buck(q[0], q[1], q[2], r), pot_mdf(q[3], q[4], r)); break;
+    case 20: v = eg_taper(pot_lj126(q[0], q[1], r), pot_mdf(q[2], q[3], r)); break;
+    case 21: {  // LJ-Frenkel  ea, sig2, rc2
+      const double r2 = r * r;
+      if (!(r2 > q[2])) {
+        const double ir = 1.0 / r2, st = q[1] * ir, rct = q[2] * ir;
+        const double x = q[0] * ((rct - 1.0) * (rct - 1.0));
+        v = {x * (st - 1.0), 4.0 * q[0] * rct * (rct - 1.0) * (st - 1.0) + 2.0 * x * st};
+      }
+      break;
+    }
+    case 22: {  // Sanderson  A, L, d
+      const double u = (r - q[1]) / q[2];
+      const double t = q[0] * exp(-(u * u));
+      v = {-t, -2.0 * (r - q[1]) * r * t / (q[2] * q[2])};
+      break;
+    }
+    case 23: {  // nDPD  :623-642  a, b, n, rc
+      if (r < q[3]) {
+        const double t2 = r / q[3], t1 = q[0] * q[3] * (1.0 - t2), t0 = q[1] * pow(1.0 - t2, q[2] - 1.0);
+        v = {t1 * (1.0 - t2) * (t0 / (q[2] + 1.0) - 0.5), t1 * t2 * (t0 - 1.0)};
+      }
+      break;
+    }
+    case 24: {  // Stillinger-Weber two-body part  eps, A, B, sig, p, q, aa
+      const double cut = q[6] * q[3];
+      if (r < cut) {
+        const double ee = q[3] / (r - cut), p_r = q[3] / r;
+        const double c = q[2] * pow(p_r, q[4]), pq = pow(p_r, q[5]), ex = exp(ee);
+        const double t = q[1] * q[0] * (c - pq) * ex;
+        v = {t, q[1] * q[0] * (q[4] * c - q[5] * pq) * ex + t * r * ee / (r - cut)};
+      }
+      break;
+    }
+    default: return false;
+  }
+  e = v.e; g = v.g;
+  return true;
+}
+
+// the forms of the BASELINE force fields inline, everything else through pot_direct_any
 __device__ __forceinline__ void pot_direct(int key, const double* __restrict__ p, double r, double& e, double& g) {
   switch (key) {
     case 1: {   // 12-6  :307-317
@@ -65,7 +229,7 @@ __device__ __forceinline__ void pot_direct(int key, const double* __restrict__ p
       g = 24.0 * p[0] * s6 * (2.0 * s6 - p[2]);
       break;
     }
-    default: e = 0.0; g = 0.0;
+    default: if (!pot_direct_any(key, p, r, e, g)) { e = 0.0; g = 0.0; }   // dlpgpu_set_vdw refuses such keys for vdw_method direct
   }
 }
 

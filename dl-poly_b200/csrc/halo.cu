@@ -83,7 +83,7 @@ __device__ __forceinline__ double vnl_displacement(int imcon, const Mat9& cell, 
     if (imcon == 1) {                                              // numerics.F90:1553-1563
       double aaa = 1.0 / cell.m[0];
       x = x - cell.m[0] * round(aaa * x) ; y = y - cell.m[0] * round(aaa * y); z = z - cell.m[0] * round(aaa * z);
-    } else if (imcon == 2 || imcon == 0) {
+    } else if (imcon == 2 || imcon == 0) {                         // :1563 (IMCON_ORTHORHOMBIC .or. IMCON_NOPBC: the reference folds both)
       double aaa = 1.0 / cell.m[0], bbb = 1.0 / cell.m[4], ccc = 1.0 / cell.m[8];
       x = x - cell.m[0] * round(aaa * x); y = y - cell.m[4] * round(bbb * y); z = z - cell.m[8] * round(ccc * z);
     } else if (imcon == 3) {

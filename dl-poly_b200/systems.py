@@ -97,6 +97,34 @@ def argon(ncell=20, seed=1001, rcut=8.5, padding=0.3, form="12-6", direct=False,
                   temperature=temperature, seed=seed)
 
 
+# One sane parameter set per analytic form of two_body_potentials.F90 (keys: vdw.F90:71-113) for an argon-like fluid whose
+# nearest neighbours sit at ~3.3 A and whose cutoff is 8.5 A: used by the parity tests of vdw_method direct.
+_S12, _S6 = 3.4 ** 12, 3.4 ** 6
+VDW_DIRECT_PARAMS = {
+    1: [4.0 * _S12, 4.0 * _S6], 2: [1.0, 3.4], 3: [1.0, 12.0, 6.0, 3.8], 4: [1.0e5, 0.3, 1.0e3], 5: [1.0e3, 3.0, 3.0, 5.0e2, 1.0e3],
+    6: [1.0e6, 1.0e5], 7: [1.0, 12.0, 6.0, 3.8, 8.0], 8: [1.0, 3.8, 1.5], 9: [1.0, 3.4, 0.5, 2.0 ** (1.0 / 6.0) * 3.4 + 0.5],
+    10: [25.0, 6.0], 11: [1.0, 3.8], 12: [1.0, 3.4, 0.8], 13: [1.0, 3.8, 1.5, 1.0e5], 14: [100.0, -20.0, 1.2], 15: [18.0, 18.0],
+    16: [18.0, 18.0, 3.5, 0.25, 1.0, 3.8, 1.5], 17: [18.0, 18.0, 3.5, 0.25, 1.0e5, 0.3, 1.0e3], 18: [1.0, 3.4, 6.0, 8.0],
+    19: [1.0e5, 0.3, 1.0e3, 6.0, 8.0], 20: [4.0 * _S12, 4.0 * _S6, 6.0, 8.0], 21: [1.0, 3.4 ** 2, 64.0], 22: [1.0, 4.0, 1.5],
+    23: [25.0, 2.0, 3.0, 6.0], 24: [1.0, 7.05, 0.602, 3.4, 4.0, 0.0, 1.8],
+}
+
+
+def vdw_direct_fluid(keypot, ncell=6, seed=1012, rcut=8.5, padding=0.3, jitter=0.25, temperature=85.0):
+    """An argon-density fluid whose single vdW potential is analytic form `keypot` (1..24) evaluated with vdw_method direct."""
+    nc = np.array(_n3(ncell), dtype=np.float64)
+    n = int(4 * nc.prod())
+    a = (4.0 / 0.02138) ** (1.0 / 3.0)
+    L = nc * a
+    rng = np.random.default_rng(seed)
+    xyz = _wrap(_fcc(ncell, a) - 0.5 * L + 0.25 * a + rng.uniform(-jitter, jitter, (n, 3)), L)
+    ff = tables.ForceField(1, rcut, rcut, direct=True)
+    ff.add(1, 1, int(keypot), VDW_DIRECT_PARAMS[int(keypot)])
+    ff.finalize()
+    return System("direct-key%d-%d" % (keypot, n), np.diag(L), xyz, np.ones(n, dtype=np.int32), [1], [0.0], [39.948], ff, rcut,
+                  padding, temperature=temperature, seed=seed)
+
+
 def argon_triclinic(ncell=6, seed=1011, rcut=8.5, padding=0.3, shear=(0.20, 0.10, 0.15), jitter=0.25, temperature=85.0):
     """The C1 fluid in a parallelepiped cell (imcon = 3): the cubic lattice sheared by b += shear[0] a, c += shear[1] a +
     shear[2] b.  Positions are cell . s with s the reduced coordinates of the jittered fcc sites."""

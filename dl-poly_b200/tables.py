@@ -372,6 +372,13 @@ class ForceField:
                     tp = tp.copy(); tf = tf.copy()
                     tp[g - 3] = tp[g - 2] = 0.0
                     tf[g - 3] = tf[g - 2] = 0.0
+            elif self.direct and keypot not in (VDW_12_6, VDW_LJ, VDW_BUCK, VDW_BHM):
+                # vdw_method direct never reads the tables; the forms this host generator does not tabulate are evaluated
+                # per pair on the device (forces.cu::pot_direct_any)
+                if self.force_shift:
+                    raise ValueError("force-shifted direct evaluation of form %d is not available in the native host" % keypot)
+                tp, tf = np.zeros(g + 1), np.zeros(g + 1)
+                tp[0] = tf[0] = HUGE
             else:
                 tp, tf = vdw_generate(keypot, p, self.rvdw, g)
                 if self.force_shift and self.direct:

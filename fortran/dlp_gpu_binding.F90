@@ -308,8 +308,12 @@ Contains
     Type(configuration_type), Intent(InOut), Target :: config
     Type(stats_type),         Intent(InOut)         :: stats
     Real(Kind=wp),            Intent(InOut)         :: engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex
-    Logical, Optional,        Intent(In   )         :: list_just_built   !! = neigh%update: link_cell_pairs_gpu ran in this
-                                                                         !! calculate_forces and parts is untouched since
+    Logical, Optional,        Intent(In   )         :: list_just_built   !! link_cell_pairs_gpu ran in this calculate_forces
+                                                                         !! AND nothing has written config%parts since --
+                                                                         !! forces included: pass neigh%update only when no
+                                                                         !! tersoff / three-body / four-body provider is
+                                                                         !! active (they add into parts%f between the two
+                                                                         !! calls, drivers.F90:675-700); otherwise .false.
 
     Real(c_double) :: out(16)
 

@@ -107,10 +107,13 @@ int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_c
  * of parts(1:natms) are incremented.  out[0..5] = engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex;
  * out[6..14] = this rank's contribution to stats%stress(1:9); out[15] = 0. */
 int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepart* parts, double out[16]);
-/* The caller asserts that parts(1:nlast) has not been written since the last dlpgpu_link_cell_pairs (calculate_forces calls
- * link_cell_pairs and two_body_forces back to back, drivers.F90:675-679 then two_body_forces): the next
- * dlpgpu_two_body_forces then works on the copy that call left on the device and skips its own 64 nlast-byte upload.
- * One-shot: the assertion is consumed by the next dlpgpu_two_body_forces. */
+/* The caller asserts that NO FIELD of parts(1:nlast) -- positions, charges AND forces -- has been written since the last
+ * dlpgpu_link_cell_pairs: the next dlpgpu_two_body_forces then works on the copy that call left on the device, skips its own
+ * 64 nlast-byte upload, and returns parts(1:natms) = that copy + the pair forces.  calculate_forces runs tersoff_forces,
+ * three_body_forces and four_body_forces between the two calls when the FIELD defines such terms (drivers.F90:675-700), and
+ * they add into parts%f: with any of them active the assertion is FALSE and must not be made (their contributions would be
+ * overwritten by the stale copy).  It holds for force fields whose only providers before two_body_forces are the pair terms
+ * themselves (every BASELINE configuration).  One-shot: consumed by the next dlpgpu_two_body_forces. */
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
 /* rdfs.F90:146-212 rdf_collect and :880-946 rdf_excl_collect for the atoms and list of the last dlpgpu_two_body_forces /
  * dlpgpu_dev_two_body_forces call (two_body_forces calls them inside its loops, two_body.F90:523, :581):

@@ -664,3 +664,26 @@ def test_md_step_enqueued_from_c_follows_the_python_driver():
     for k, (x, y) in enumerate(zip(eager, lazy)):
         assert np.allclose(x[:6], y[:6], rtol=1e-9, atol=1e-9 * np.abs(x[:6]).max()), (k, x[:6], y[:6])
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("key", range(1, 25))
+def test_vdw_direct_all_analytic_forms_against_oracle(key):
+    """vdw_method direct with each of the 24 analytic forms of two_body_potentials.F90 (the keys of the reference's own
+    known-answer list, unit_tests/test_vdw.F90:46-59, which pins the oracle's forms in tests/test_oracle_kat.py): per-atom
+    forces, energy / virial and stress of an 864-atom fluid against the oracle."""
+    s = systems.vdw_direct_fluid(key)
+    rep = _native_against_oracle(s, check_list=False)
+    assert rep["significant_atoms"] > 0
+
+
+def test_vdw_direct_refuses_keys_without_an_analytic_form():
+    """A TABLE-file potential (key 0) or an unknown key has nothing vdw_forces_direct could evaluate: dlpgpu_set_vdw says so
+    instead of returning zero forces."""
+    from dl_poly_b200.lib import DlpError
+    s = systems.vdw_direct_fluid(2)
+    for bad in (0, 25):
+        s.ff.ltp[0] = bad
+        sr = engine.ShortRange(0)
+        with pytest.raises(DlpError):
+            sr.dev_setup_system(s)
+        sr.close()
