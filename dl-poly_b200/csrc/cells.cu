@@ -535,7 +535,8 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             const int* __restrict__ cell_s, const int* __restrict__ slot_rank, const double4* __restrict__ posq_s,
             const int2* __restrict__ info_s, const int* __restrict__ pair_k, int ntypes, const int* __restrict__ excl,
             unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
-            int* __restrict__ status, unsigned long long* __restrict__ cnt64, unsigned sentinel, int prune) {
+            int* __restrict__ status, unsigned long long* __restrict__ cnt64, unsigned sentinel, int prune,
+            unsigned* __restrict__ fnbr, int* __restrict__ nfnbr, int fpitch) {
   __shared__ double4 s_pi[LC_WARPS][32];
   __shared__ double4 s_pj[LC_WARPS][SIMPLE ? 64 : 1];   // ring of staged candidates (lean loops): {x, y, z, squared acceptance radius}
   __shared__ int4 s_cj[LC_WARPS][SIMPLE ? 64 : 1];      // ... {slot | halo bit, packed vdW indices, global id, ordering threshold}
@@ -569,7 +570,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   int ovf = 0;   // longest row that did not fit (error 106), reported once per warp
   for (int a0 = s_own0; a0 < s_own1; a0 += 32) {   // atoms of the cell, 32 at a time (one pass unless the cell is crowded)
     const int na = min(32, s_own1 - a0);
-    int cnt = 0, xcnt = 0;
+    int cnt = 0, xcnt = 0, fcnt = 0;
     int nex_l = 0;
     const int* ex_l = nullptr;
     __syncwarp();
@@ -722,7 +723,21 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
         const int2 infi = s_info[wid][a];
         const int ii = a0 + a;
         bool acc = valid && (jj > ii || jj < s_own0) && (nir || pair_rsq(pj, pi.x, pi.y, pi.z) <= g.rcsq);
-        if (acc && megfrz > 1 && ((infi.y >> 16) & 1) && ((infj.y >> 16) & 1)) acc = false;   // frozen-frozen (:1198-1225)
+        // frozen-frozen pairs never reach the force loops (:1198-1225); they are kept in rows of their own for rdf_frzn_collect
+        const bool isf = acc && megfrz > 1 && ((infi.y >> 16) & 1) && ((infj.y >> 16) & 1);
+        if (isf) acc = false;
+        if (megfrz > 1 && fnbr != nullptr) {
+          const unsigned mf = __ballot_sync(DLP_FULL, isf);
+          if (mf) {
+            const int cfa = __shfl_sync(DLP_FULL, fcnt, a);
+            if (isf) {
+              const unsigned entry = (unsigned)jj | (halo_j ? DLP_F_HALO : 0u) | ((halo_j && infi.x < infj.x) ? DLP_F_ECNT : 0u);
+              const int ll = cfa + __popc(mf & ((1u << lane) - 1));
+              if (ll < fpitch) fnbr[(size_t)(t0 + a) * fpitch + ll] = entry; else atomicOr(&status[0], 1);
+            }
+            if (lane == a) fcnt += __popc(mf);
+          }
+        }
         bool isx = false;
         if (lbook) {
           const int nex = __shfl_sync(DLP_FULL, nex_l, a);
@@ -753,7 +768,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
       }
     }
     }
-    if (lane < na) { nnbr[t0 + lane] = cnt; nxnbr[t0 + lane] = xcnt; written += cnt; }
+    if (lane < na) { nnbr[t0 + lane] = cnt; nxnbr[t0 + lane] = xcnt; written += cnt; if (nfnbr != nullptr) nfnbr[t0 + lane] = fcnt; }
     for (int a = 0; a < na; ++a)   // sentinel padding the pair kernel relies on
       dlp_pad_row(nbr + (size_t)(t0 + a) * pitch, min(__shfl_sync(DLP_FULL, cnt, a), pitch - DLP_ROW_PAD), sentinel, lane, 32);
   }
@@ -834,6 +849,10 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   if (natms > 0) {
     CK(ctx->nnbr.ensure(natms + 1, s)); CK(ctx->nxnbr.ensure(natms + 1, s));
     CK(ctx->xnbr.ensure((size_t)natms * std::max(ctx->xpitch, 1) + 1, s));
+    // frozen-frozen pairs (rdf_frzn_collect): rows of their own, only when the system has frozen atoms
+    ctx->fpitch = ctx->megfrz > 1 ? ctx->pitch - DLP_ROW_PAD : 0;
+    ctx->frz_rows_valid = false;
+    if (ctx->fpitch > 0) { CK(ctx->fnbr.ensure((size_t)natms * ctx->fpitch + 1, s)); CK(ctx->nfnbr.ensure(natms + 1, s)); }
     cudaEventRecord(ctx->ev[2], s);
     if (ctx->force_mode == 0) {
       CK(ctx->nbr.ensure((size_t)natms * ctx->pitch + 256, s));
@@ -862,10 +881,11 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
-               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel, ctx->list_one_atom_per_pass ? 0 : 1
+               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel, ctx->list_one_atom_per_pass ? 0 : 1, \
+               ctx->fnbr.p, ctx->nfnbr.p, ctx->fpitch
         if (simple) LAUNCH(ctx, k_list_cell<1>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
         else if (lean) LAUNCH(ctx, k_list_cell<2>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else LAUNCH(ctx, k_list_cell<0>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else { LAUNCH(ctx, k_list_cell<0>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS); ctx->frz_rows_valid = ctx->fpitch > 0; }
 #undef DLP_LC_ARGS
       } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,

@@ -120,6 +120,13 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
+  DBuf<unsigned> fnbr;                // frozen-frozen partners per row (kept for rdf_frzn_collect only), pitch fpitch
+  DBuf<int> nfnbr;
+  int fpitch = 0;
+  bool frz_rows_valid = false;
+  bool collect_pp = false;            // dlpgpu_set_collect_pp: stats%collect_pp
+  int pp_natms = -1;
+  DBuf<double> pp_pos, pp_neg, pp_energy, pp_stress;   // per-particle sums of the last force call (see k_pair_forces<.., PP>)
   int last_pair_kernel = 0;           // 1 k_pair_forces, 2 k_pair_v2 (dlpgpu_pair_kernel_used)
   int list_one_atom_per_pass = 0;     // dlpgpu_set_list_kernel: 1 = k_list_cell<1> instead of k_list_cell8 (diagnostic)
   cudaTextureObject_t tab2_tex = 0;   // the same buffer as 16-byte texels: table reads through the texture pipe (see pair2)

@@ -173,6 +173,8 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
+  ctx->fnbr.release(); ctx->nfnbr.release();
+  ctx->pp_pos.release(); ctx->pp_neg.release(); ctx->pp_energy.release(); ctx->pp_stress.release();
   ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
   for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();

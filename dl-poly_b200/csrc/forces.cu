@@ -261,14 +261,18 @@ struct Tab4 { double2 lo, hi; };   // lo = {g_force, g_energy}, hi = {h_force, h
 #define DLP_FB (1 << DLP_FB_SH)
 __device__ __forceinline__ double* fneg_ptr(double* base, int j) { return base + (size_t)(j >> DLP_FB_SH) * (3 * DLP_FB) + (j & (DLP_FB - 1)); }
 
-template <int TPR, bool SMEM, int NT>
+// PP: stats%collect_pp -- every pair also books half of its energy and half of its stress tensor r (x) f on each LOCAL partner
+// (vdw.F90:1741-1755, :1987-2001, ewald_spole.F90:205-215): seven sums per atom {e, xx, xy, xz, yy, yz, zz} (f is parallel to r, so
+// the nine components of calculate_stress, statistics.F90:2616-2625, are six), row sums in pp_pos, partner sums by RED in pp_neg.
+template <int TPR, bool SMEM, int NT, bool PP = false>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict__ at_list, const double4* __restrict__ posq_s,
               const unsigned* __restrict__ nbr, const int* __restrict__ nnbr, const unsigned* __restrict__ xnbr,
               const int* __restrict__ nxnbr, const int* __restrict__ ltp, const Tab4* __restrict__ tab4_g,
               const double2* __restrict__ vdw_raw, const double* __restrict__ vdw_par, const double2* __restrict__ ew_raw,
               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz, double* __restrict__ fpos,
-              double* __restrict__ fneg, double* __restrict__ partial) {
+              double* __restrict__ fneg, double* __restrict__ partial, double* __restrict__ pp_pos = nullptr,
+              double* __restrict__ pp_neg = nullptr, int pp_slots = 0) {
   extern __shared__ __align__(16) double2 s_tab[];   // Tab4 entries as pairs of double2: [2e] = lo, [2e+1] = hi
   if (SMEM) {
     const double2* gv = reinterpret_cast<const double2*>(tab4_g);
@@ -293,6 +297,9 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
     const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
     const bool coul_i = (P.ew_on || P.coul_kind) && !(fabs(qi_s) < ZERO_PLUS);  // :117 / coul_spole.F90:218
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    double ppi[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) ppi[q] = 0.0;
     const unsigned* row = nbr + (size_t)t * P.pitch;
     // software pipeline: list entries are fetched two passes ahead, partner coordinates one pass ahead
     int k = lg;
@@ -319,6 +326,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
       const double rrr = rsq * r_rrr;                                         // two_body.F90:351 to ~1 ulp
       const double r_rsq = r_rrr * r_rrr;
       double gamma = 0.0;
+      double pp_e = 0.0;   // PP: the pair energy as the reference's per-particle bookkeeping sees it
       int l = 0;
       double ppp = 0.0;
       if (in_v) {
@@ -355,6 +363,9 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
         gamma = gam;
         acc[0] += w * eng;
         acc[1] -= w * (gam * rsq);
+        // vdw_forces_tab resets eng to 0 for every pair (vdw.F90:1905) and evaluates it only where this rank owns the pair's
+        // energy; vdw_forces_direct keeps it for every pair when collect_pp is set (:1707)
+        if (PP) pp_e = P.vdw_direct ? eng : w * eng;
       }
       if (in_c && P.coul_kind && !P.coul_tab) {   // coul_spole.F90: undamped direct-space variants, analytic
         const double chgprd = qi_s * pj.w;
@@ -405,6 +416,7 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
         gamma += erf_gamma;
         acc[2] += w * e_comp;
         acc[3] -= w * (erf_gamma * rsq);                                      // :189
+        if (PP) pp_e += e_comp;                                               // :155: with collect_pp e_comp is formed for every pair
       }
       const double f1 = gamma * xxt, f2 = gamma * yyt, f3 = gamma * zzt;
       fix += f1; fiy += f2; fiz += f3;
@@ -414,6 +426,17 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
       if (P.half && !halo) {   // Newton's third law: parts(jatm)%f -= f  (vdw.F90:1939-1941, ewald_spole.F90:159-161)
         double* q = fneg_ptr(fneg, (int)(e & DLP_J_MASK));
         atomicAdd(q, f1); atomicAdd(q + DLP_FB, f2); atomicAdd(q + 2 * DLP_FB, f3);
+      }
+      if (PP) {
+        const double hx = 0.5 * xxt, hy = 0.5 * yyt, hz = 0.5 * zzt;
+        const double v[7] = {0.5 * pp_e, hx * f1, hx * f2, hx * f3, hy * f2, hy * f3, hz * f3};
+#pragma unroll
+        for (int q = 0; q < 7; ++q) ppi[q] += v[q];
+        if (!halo) {
+          double* q = pp_neg + (e & DLP_J_MASK);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) atomicAdd(q + (size_t)c * pp_slots, v[c]);
+        }
       }
     }
     // excluded pairs (two_body.F90:555-606 -> ewald_excl_forces)
@@ -470,6 +493,14 @@ k_pair_forces(FParams P, const int* __restrict__ loc_slot, const int* __restrict
       fix += __shfl_xor_sync(DLP_FULL, fix, d);
       fiy += __shfl_xor_sync(DLP_FULL, fiy, d);
       fiz += __shfl_xor_sync(DLP_FULL, fiz, d);
+    }
+    if (PP) {
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int d = TPR / 2; d > 0; d >>= 1) ppi[q] += __shfl_xor_sync(DLP_FULL, ppi[q], d);
+        if (lg == 0 && live) pp_pos[(size_t)q * P.natms + t] = ppi[q];
+      }
     }
     if (lg == 0 && live) {
       if (P.half) {
@@ -806,14 +837,15 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   }
 }
 
-// rdfs.F90:146-212 rdf_collect / :880-946 rdf_excl_collect over the device rows: one warp per row, a per-block histogram in
+// rdfs.F90:146-212 rdf_collect / :880-946 rdf_excl_collect / :948-1018 rdf_frzn_collect over the device rows: one warp per row, a per-block histogram in
 // shared memory (counts are integers, so the sums are exact in any order).  The distance is the reference's
 // Sqrt(xxt**2 + yyt**2 + zzt**2) (IEEE, unfused) because the bin index Int(rrr * rdelr) has to agree bit for bit.
 __global__ void k_rdf_collect(int natms, int pitch, int xpitch, int lbook, int ntypes, int n_pairs, int max_grid, double rcut,
                               double rdelr, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s,
                               const int2* __restrict__ info_s, const unsigned* __restrict__ nbr, const int* __restrict__ nnbr,
                               const unsigned* __restrict__ xnbr, const int* __restrict__ nxnbr, const int* __restrict__ rdf_list,
-                              unsigned long long* __restrict__ hist) {
+                              unsigned long long* __restrict__ hist, const unsigned* __restrict__ fnbr, const int* __restrict__ nfnbr,
+                              int fpitch) {
   extern __shared__ unsigned s_hist[];
   const int nbin = n_pairs * max_grid;
   for (int k = threadIdx.x; k < nbin; k += blockDim.x) s_hist[k] = 0u;
@@ -824,9 +856,10 @@ __global__ void k_rdf_collect(int natms, int pitch, int xpitch, int lbook, int n
     const int ii = loc_slot[t];
     const double4 pi = posq_s[ii];
     const int ai = info_s[ii].y & 0xffff;
-    for (int pass = 0; pass < (lbook ? 2 : 1); ++pass) {
-      const unsigned* row = pass ? xnbr + (size_t)t * xpitch : nbr + (size_t)t * pitch;
-      const int n = pass ? nxnbr[t] : nnbr[t];
+    for (int pass = 0; pass < 3; ++pass) {   // main rows, excluded partners, frozen-frozen partners (two_body.F90:523, :581, :649)
+      if ((pass == 1 && !lbook) || (pass == 2 && fnbr == nullptr)) continue;
+      const unsigned* row = pass == 0 ? nbr + (size_t)t * pitch : (pass == 1 ? xnbr + (size_t)t * xpitch : fnbr + (size_t)t * fpitch);
+      const int n = pass == 0 ? nnbr[t] : (pass == 1 ? nxnbr[t] : nfnbr[t]);
       for (int k = lane; k < n; k += 32) {
         const unsigned e = row[k];
         if ((e & (DLP_F_HALO | DLP_F_ECNT)) == DLP_F_HALO) continue;          // jatm <= natms .or. idi < ltg(jatm)
@@ -863,6 +896,22 @@ __global__ void k_scatter_half(int natms, int zero_forces, const int* __restrict
   else { fx[i] += a; fy[i] += b; fz[i] += c; }
 }
 
+// per-particle sums into local-atom order: pp_energy(i), pp_stress(1:9, i) = row sums + what the partners' rows booked
+__global__ void k_scatter_pp(int natms, int pp_slots, const int* __restrict__ loc_slot, const int* __restrict__ at_list,
+                             const double* __restrict__ pp_pos, const double* __restrict__ pp_neg, double* __restrict__ pp_energy,
+                             double* __restrict__ pp_stress) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= natms) return;
+  const int ii = loc_slot[t];
+  const int i = at_list[ii];
+  double v[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) v[q] = pp_pos[(size_t)q * natms + t] + pp_neg[(size_t)q * pp_slots + ii];
+  pp_energy[i] = v[0];
+  double* st = pp_stress + (size_t)i * 9;   // calculate_stress order: xx xy xz / yx yy yz / zx zy zz
+  st[0] = v[1]; st[1] = v[2]; st[2] = v[3]; st[3] = v[2]; st[4] = v[4]; st[5] = v[5]; st[6] = v[3]; st[7] = v[5]; st[8] = v[6];
+}
+
 // nve.F90:163-173, :198-217
 __global__ void k_vv(int natms, int stage, double dt, const int* __restrict__ lsite, const double* __restrict__ weight_site,
                      double4* __restrict__ posq, double* vx, double* vy, double* vz, const double* __restrict__ fx,
@@ -894,6 +943,29 @@ __global__ void k_dfma(int iters, double* out) {
 }
 
 }  // namespace
+
+// collect_pp: the general kernel with the per-particle sums, 256 threads (the extra accumulators want registers)
+static int launch_pair_pp(dlpgpu_ctx* ctx, const FParams& P, bool use_smem, size_t smem, int blocks, double* fpos, double* fneg) {
+  const Tab4* t4 = reinterpret_cast<const Tab4*>(ctx->tab4.p);
+  const int slots = ctx->nlast + 1;
+  CK(ctx->pp_pos.ensure((size_t)7 * std::max(P.natms, 1), ctx->stream)); CK(ctx->pp_neg.ensure((size_t)7 * slots, ctx->stream));
+  CK(cudaMemsetAsync(ctx->pp_neg.p, 0, (size_t)7 * slots * sizeof(double), ctx->stream));
+  if (use_smem) {
+    CK(cudaFuncSetAttribute(k_pair_forces<8, true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, (k_pair_forces<8, true, 256, true>), blocks, 256, smem, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fpos,
+           fneg, ctx->partial.p, ctx->pp_pos.p, ctx->pp_neg.p, slots);
+  } else {
+    LAUNCH(ctx, (k_pair_forces<8, false, 256, true>), blocks, 256, 0, P, ctx->loc_slot.p, ctx->at_list.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->ltp.p, t4, ctx->vdw_tab.p, ctx->vdw_par.p, ctx->ew_tab.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, fpos,
+           fneg, ctx->partial.p, ctx->pp_pos.p, ctx->pp_neg.p, slots);
+  }
+  CK(ctx->pp_energy.ensure((size_t)std::max(P.natms, 1), ctx->stream)); CK(ctx->pp_stress.ensure((size_t)9 * std::max(P.natms, 1), ctx->stream));
+  LAUNCH(ctx, k_scatter_pp, cdiv(std::max(P.natms, 1), 256), 256, 0, P.natms, slots, ctx->loc_slot.p, ctx->at_list.p, ctx->pp_pos.p, ctx->pp_neg.p,
+         ctx->pp_energy.p, ctx->pp_stress.p);
+  ctx->pp_natms = P.natms;
+  return 0;
+}
 
 template <int TPR, int NT>
 static int launch_pair(dlpgpu_ctx* ctx, const FParams& P, bool use_smem, size_t smem, int blocks, double* fpos, double* fneg) {
@@ -1050,7 +1122,11 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   }
   cudaEventRecord(ctx->ev[6], s);
   const bool xc = P.lbook && P.ew_on;   // rows carry excluded partners: the fast kernel has them for the vdW + Ewald, one-grid case
-  const bool fast = P.half && !ctx->no_fast && !P.coul_kind && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
+  const bool pp = ctx->collect_pp;
+  if (pp && (!P.half || P.coul_kind))
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "two_body_forces: collect_pp needs the half-list mode and vdW / Ewald real-space terms "
+                                           "(the direct-space Coulomb variants of coul_spole.F90 are not booked per particle here)");
+  const bool fast = !pp && P.half && !ctx->no_fast && !P.coul_kind && !P.vdw_fshift && !(P.vdw_on && P.vdw_direct) && (P.vdw_on || P.ew_on) &&
                     tpr == 8 && (!xc || (P.vdw_on && P.ew_on && P.same_grid));
   const size_t smem2 = (size_t)ctx->tab2_ne * 32;
   // the fp32-h layout keeps only the g units in shared memory (16 B per entry): force fields with many potentials still fit
@@ -1101,6 +1177,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
       DLP_V2(0, 1, 1, 0);
     }
 #undef DLP_V2
+  } else if (natms > 0 && pp) {
+    CKRC(launch_pair_pp(ctx, P, use_smem, smem, blocks, fpos, fneg));
   } else if (natms > 0) {
     if (tpr == 32) CKRC((launch_pair<32, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
     else if (tpr == 16) CKRC((launch_pair<16, 512>(ctx, P, use_smem, smem, blocks, fpos, fneg)));
@@ -1150,18 +1228,42 @@ int dlpgpu_rdf_collect(dlpgpu_ctx* ctx, int ntypes, const int* rdf_list, int n_p
   CK(cudaMemcpyAsync(ctx->rdf_list.p, rdf_list, nkey * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ctx->rdf_hist.p, 0, nbin * sizeof(unsigned long long), s));
   const int natms = ctx->list_natms;
+  if (ctx->megfrz > 1 && !ctx->frz_rows_valid)
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "rdf_collect: the list kernel that ran does not keep the frozen-frozen pairs rdf_frzn_collect needs");
   if (natms > 0) {
     const int threads = 256, blocks = std::min(cdiv(natms, threads / 32), ctx->sm_count * 4);
     CK(cudaFuncSetAttribute(k_rdf_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbin * sizeof(unsigned))));
     LAUNCH(ctx, k_rdf_collect, blocks, threads, nbin * sizeof(unsigned), natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->lbook, ntypes, n_pairs,
            max_grid, ctx->rcut, (double)max_grid / ctx->rcut, ctx->loc_slot.p, ctx->posq_s.p, ctx->info_s.p, ctx->nbr.p, ctx->nnbr.p,
-           ctx->xnbr.p, ctx->nxnbr.p, ctx->rdf_list.p, ctx->rdf_hist.p);
+           ctx->xnbr.p, ctx->nxnbr.p, ctx->rdf_list.p, ctx->rdf_hist.p, ctx->frz_rows_valid ? ctx->fnbr.p : nullptr, ctx->nfnbr.p, ctx->fpitch);
   }
   std::vector<unsigned long long> h(nbin);
   CK(cudaMemcpyAsync(h.data(), ctx->rdf_hist.p, nbin * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   for (size_t k = 0; k < nbin; ++k) rdf[k] += (double)h[k];
+  return 0;
+}
+
+int dlpgpu_set_collect_pp(dlpgpu_ctx* ctx, int on) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  ctx->collect_pp = on != 0;
+  if (!on) ctx->pp_natms = -1;
+  return 0;
+}
+
+int dlpgpu_get_pp(dlpgpu_ctx* ctx, int natms, double* pp_energy, double* pp_stress) {
+  if (!ctx || !pp_energy || !pp_stress || natms < 0) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pp_natms < 0) return dlp_fail(ctx, DLPGPU_ERR_STATE, "get_pp: no two_body_forces call has run with collect_pp set");
+  if (natms != ctx->pp_natms) return dlp_fail(ctx, DLPGPU_ERR_ARG, "get_pp: natms (%d) differs from the force call's (%d)", natms, ctx->pp_natms);
+  if (natms == 0) return 0;
+  std::vector<double> e(natms), st((size_t)9 * natms);
+  CK(cudaMemcpyAsync(e.data(), ctx->pp_energy.p, (size_t)natms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(st.data(), ctx->pp_stress.p, (size_t)9 * natms * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < natms; ++i) pp_energy[i] += e[i];                       // every provider ADDS (stats%pp_energy is zeroed by the caller)
+  for (size_t i = 0; i < (size_t)9 * natms; ++i) pp_stress[i] += st[i];
   return 0;
 }
 

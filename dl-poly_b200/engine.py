@@ -105,6 +105,17 @@ class ShortRange:
         """Diagnostic: 0 k_list_cell8 (default), 1 the one-atom-per-pass kernel, for the plain half-list case."""
         self._ck(self.L.dlpgpu_set_list_kernel(self.h, int(which)))
 
+    def set_collect_pp(self, on=True):
+        """stats%collect_pp: force calls also book per-particle energy / stress (see include/dlpgpu.h)."""
+        self._ck(self.L.dlpgpu_set_collect_pp(self.h, int(on)))
+
+    def get_pp(self, natms, pp_energy=None, pp_stress=None):
+        """ADDS the per-particle sums of the last force call into (pp_energy(natms), pp_stress(natms, 9)); returns them."""
+        e = np.zeros(natms) if pp_energy is None else pp_energy
+        st = np.zeros((natms, 9)) if pp_stress is None else pp_stress
+        self._ck(self.L.dlpgpu_get_pp(self.h, int(natms), ptr(e), ptr(st)))
+        return e, st
+
     def pair_kernel_used(self):
         """(kernel of the last two_body_forces call: 1 general, 2 k_pair_v2; reserved)."""
         w, e = C.c_int(0), C.c_double(0.0)

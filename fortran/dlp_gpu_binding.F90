@@ -131,6 +131,19 @@ Module dlp_gpu_binding
       Type(c_ptr), Value    :: rdf_list, rdf
       Integer(c_int)        :: rc
     End Function
+    Function dlpgpu_set_collect_pp(ctx, on) Bind(C, name='dlpgpu_set_collect_pp') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int), Value :: on
+      Integer(c_int)        :: rc
+    End Function
+    Function dlpgpu_get_pp(ctx, natms, pp_energy, pp_stress) Bind(C, name='dlpgpu_get_pp') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int), Value :: natms
+      Type(c_ptr), Value    :: pp_energy, pp_stress
+      Integer(c_int)        :: rc
+    End Function
     Function dlpgpu_parts_unchanged_since_list(ctx) Bind(C, name='dlpgpu_parts_unchanged_since_list') Result(rc)
       Import :: c_ptr, c_int
       Type(c_ptr), Value :: ctx
@@ -317,6 +330,9 @@ Contains
 
     Real(c_double) :: out(16)
 
+    ! per-particle energy / stress (statistics.F90:227): the library books them inside the same pair loop
+    Call check(dlpgpu_set_collect_pp(ctx, Merge(1_c_int, 0_c_int, stats%collect_pp)), 'set_collect_pp')
+
     If (Present(list_just_built)) Then
       If (list_just_built) Call check(dlpgpu_parts_unchanged_since_list(ctx), 'parts_unchanged_since_list')
     End If
@@ -327,6 +343,9 @@ Contains
     engcpe_rl = engcpe_rl + out(3); vircpe_rl = vircpe_rl + out(4)
     engcpe_ex = engcpe_ex + out(5); vircpe_ex = vircpe_ex + out(6)
     stats%stress(1:9) = stats%stress(1:9) + out(7:15)
+    If (stats%collect_pp) Then   ! vdw.F90:1741-1755, :1987-2001, ewald_spole.F90:205-215: added to what other providers booked
+      Call check(dlpgpu_get_pp(ctx, Int(config%natms, c_int), c_loc(stats%pp_energy), c_loc(stats%pp_stress)), 'get_pp')
+    End If
   End Subroutine two_body_pairs_gpu
 
   Subroutine rdf_collect_gpu(ntpatm, rdf)

@@ -115,11 +115,21 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
  * overwritten by the stale copy).  It holds for force fields whose only providers before two_body_forces are the pair terms
  * themselves (every BASELINE configuration).  One-shot: consumed by the next dlpgpu_two_body_forces. */
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
-/* rdfs.F90:146-212 rdf_collect and :880-946 rdf_excl_collect for the atoms and list of the last dlpgpu_two_body_forces /
- * dlpgpu_dev_two_body_forces call (two_body_forces calls them inside its loops, two_body.F90:523, :581):
+/* stats%collect_pp (statistics.F90:227, set by the per-particle / heat-flux options): while on, two_body_forces (drop-in and
+ * dev_) also books, for every pair, half of its energy and half of its stress tensor r (x) f on each LOCAL partner, following
+ * the reference path by path -- vdw_forces_direct (vdw.F90:1707, :1741-1755: the pair energy for every pair),
+ * vdw_forces_tab (:1905, :1987-2001: the energy only where this rank owns it, i.e. a local partner or idi < ltg(jatm)),
+ * ewald_real_forces_coul (ewald_spole.F90:155, :205-215: every pair); ewald_excl_forces books nothing per particle.  The general pair
+ * kernel runs (not the fast one).  Needs the half-list force mode; not available with the coul_spole.F90 variants
+ * (DLPGPU_ERR_STATE).  dlpgpu_get_pp ADDS the sums of the last force call into pp_energy(1:natms) and pp_stress(1:9,1:natms)
+ * (column-major: nine per atom, calculate_stress order, statistics.F90:2616-2625). */
+int dlpgpu_set_collect_pp(dlpgpu_ctx* ctx, int on);
+int dlpgpu_get_pp(dlpgpu_ctx* ctx, int natms, double* pp_energy, double* pp_stress);
+/* rdfs.F90:146-212 rdf_collect, :880-946 rdf_excl_collect and :948-1018 rdf_frzn_collect for the atoms and list of the last
+ * dlpgpu_two_body_forces / dlpgpu_dev_two_body_forces call (two_body_forces calls them at two_body.F90:523, :581, :649):
  * rdf_list(1:ntypes(ntypes+1)/2) = rdf%list (0 or > n_pairs: pair not collected), rdf = rdf%rdf(1:max_grid,1:n_pairs)
- * column-major on the host, INCREMENTED by this rank's counts.  Frozen-frozen pairs (rdf_frzn_collect) are not kept on the
- * device and stay with the caller. */
+ * column-major on the host, INCREMENTED by this rank's counts.  Frozen-frozen pairs never reach the force loops
+ * (neighbours.F90:1198-1225) but are kept in device rows of their own for this call when megfrz > 1. */
 int dlpgpu_rdf_collect(dlpgpu_ctx* ctx, int ntypes, const int* rdf_list, int n_pairs, int max_grid, double* rdf);
 /* neighbours.F90:157-171: tol = max_i |r_i - r_bg,i| (minimum image) over parts(1:natms); caller does gmax + test */
 int dlpgpu_vnl_check(dlpgpu_ctx* ctx, int natms, const dlpgpu_corepart* parts, double* tol);

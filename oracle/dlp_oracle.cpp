@@ -599,6 +599,13 @@ struct Dom {
   // results of the last two_body call
   double stress[10] = {0};
   double engvdw = 0, virvdw = 0, engcpe_rl = 0, vircpe_rl = 0, engcpe_ex = 0, vircpe_ex = 0;
+  // stats%pp_energy(1:natms), stats%pp_stress(1:9, 1:natms) of the last two_body call (World::collect_pp), 1-based atoms
+  std::vector<double> pp_energy, pp_stress;
+  inline void pp_add(int atom, double e_half, const double* x, const double* f) {   // statistics.F90:2616-2625 calculate_stress, * 0.5
+    pp_energy[atom] += e_half;
+    double* t = &pp_stress[(size_t)atom * 9];
+    for (int c = 0; c < 3; ++c) { t[c] += x[0] * f[c] * 0.5; t[3 + c] += x[1] * f[c] * 0.5; t[6 + c] += x[2] * f[c] * 0.5; }
+  }
   // halo exchange scratch
   std::vector<double> sendbuf;
   inline int& L(int k, int i) { return list[(size_t)(i - 1) * (max_list + 4) + (k + 3)]; }
@@ -627,6 +634,7 @@ struct World {
   int max_exclude = 0;
   std::vector<int> excl_global;          // (0:max_exclude, 1:megatm) by global id
   std::vector<Dom> d;
+  bool collect_pp = false;               // stats%collect_pp (statistics.F90:227): per-particle energy / stress
   bool update = true;                    // neigh%update
   double neighskip[6] = {0, 0, 0, 0, 999999999.0, 0};   // statistics.F90:185-186 (index 0 unused)
   bool newstart = true;
@@ -1339,6 +1347,7 @@ Acc vdw_forces_tab(World& w, Dom& dom, int iatm, const double* xxt, const double
       double t2 = gk1 + (gk2 - gk1) * (ppp - 1.0);
       double gamma = (t1 + (t2 - t1) * ppp * 0.5) * r_rsq;
       if (v.l_force_shift) gamma = gamma - v.tf(v.max_grid - 4, k) * r_rrv;
+      double eng_pp = 0.0;   // vdw.F90:1905: eng = 0 at the top of every pair; it stays 0 for a halo partner this rank does not own
       double fx = gamma * xxt[mm], fy = gamma * yyt[mm], fz = gamma * zzt[mm];
       fix = fix + fx; fiy = fiy + fy; fiz = fiz + fz;
       if (jatm <= dom.natms) {
@@ -1353,9 +1362,15 @@ Acc vdw_forces_tab(World& w, Dom& dom, int iatm, const double* xxt, const double
         double eng = t1 + (t2 - t1) * ppp * 0.5;
         if (v.l_force_shift) eng = eng + v.tf(v.max_grid - 4, k) * (rscl - 1.0) - v.tp(v.max_grid - 4, k);
         engvdw = engvdw + eng;
+        eng_pp = eng;
         virvdw = virvdw - gamma * rsq;
         strs1 = strs1 + xxt[mm] * fx; strs2 = strs2 + xxt[mm] * fy; strs3 = strs3 + xxt[mm] * fz;
         strs5 = strs5 + yyt[mm] * fy; strs6 = strs6 + yyt[mm] * fz; strs9 = strs9 + zzt[mm] * fz;
+      }
+      if (w.collect_pp) {   // vdw.F90:1987-2001
+        const double x3[3] = {xxt[mm], yyt[mm], zzt[mm]}, f3[3] = {fx, fy, fz};
+        dom.pp_add(iatm, eng_pp * 0.5, x3, f3);
+        if (jatm <= dom.natms) dom.pp_add(jatm, eng_pp * 0.5, x3, f3);
       }
     }
   }
@@ -1389,7 +1404,7 @@ Acc vdw_forces_direct(World& w, Dom& dom, int iatm, const double* xxt, const dou
       double gamma = eg.gamma * r_rsq - v.afs[k] * r_rrr;
       double fx = gamma * xxt[mm], fy = gamma * yyt[mm], fz = gamma * zzt[mm];
       fix = fix + fx; fiy = fiy + fy; fiz = fiz + fz;
-      if (jatm > dom.natms && idi >= dom.ltg[jatm]) eng = 0.0;
+      if (jatm > dom.natms && idi >= dom.ltg[jatm] && !w.collect_pp) eng = 0.0;   // vdw.F90:1707
       if (jatm <= dom.natms) {
         parts[jatm].fxx = parts[jatm].fxx - fx;
         parts[jatm].fyy = parts[jatm].fyy - fy;
@@ -1400,6 +1415,11 @@ Acc vdw_forces_direct(World& w, Dom& dom, int iatm, const double* xxt, const dou
         virvdw = virvdw - gamma * rsq;
         strs1 = strs1 + xxt[mm] * fx; strs2 = strs2 + xxt[mm] * fy; strs3 = strs3 + xxt[mm] * fz;
         strs5 = strs5 + yyt[mm] * fy; strs6 = strs6 + yyt[mm] * fz; strs9 = strs9 + zzt[mm] * fz;
+      }
+      if (w.collect_pp) {   // vdw.F90:1741-1755
+        const double x3[3] = {xxt[mm], yyt[mm], zzt[mm]}, f3[3] = {fx, fy, fz};
+        dom.pp_add(iatm, eng * 0.5, x3, f3);
+        if (jatm <= dom.natms) dom.pp_add(jatm, eng * 0.5, x3, f3);
       }
     }
   }
@@ -1439,7 +1459,7 @@ Acc ewald_real_forces_coul(World& w, Dom& dom, int iatm, const double* x_pos, co
       double fcx = erf_gamma * px, fcy = erf_gamma * py, fcz = erf_gamma * pz;
       ft[1] = ft[1] + fcx; ft[2] = ft[2] + fcy; ft[3] = ft[3] + fcz;
       double e_comp = 0.0;
-      if (jatm <= dom.natms || global_id_i < global_id_j) {
+      if (jatm <= dom.natms || global_id_i < global_id_j || w.collect_pp) {   // ewald_spole.F90:155
         if (jatm <= dom.natms) {
           parts[jatm].fxx = parts[jatm].fxx - fcx;
           parts[jatm].fyy = parts[jatm].fyy - fcy;
@@ -1458,6 +1478,11 @@ Acc ewald_real_forces_coul(World& w, Dom& dom, int iatm, const double* x_pos, co
         vircpe_rl = vircpe_rl - erf_gamma * (mod_r_ij * mod_r_ij);
         st[1] = st[1] + px * fcx; st[2] = st[2] + px * fcy; st[3] = st[3] + px * fcz;
         st[4] = st[4] + py * fcy; st[5] = st[5] + py * fcz; st[6] = st[6] + pz * fcz;
+      }
+      if (w.collect_pp) {   // ewald_spole.F90:205-215
+        const double x3[3] = {px, py, pz}, f3[3] = {fcx, fcy, fcz};
+        dom.pp_add(iatm, e_comp * 0.5, x3, f3);
+        if (jatm <= dom.natms) dom.pp_add(jatm, e_comp * 0.5, x3, f3);
       }
     }
   }
@@ -1634,6 +1659,7 @@ void rdf_collect_domain(World& w, Dom& dom, const int* rdf_list /*1-based keys*/
   for (int i = 1; i <= dom.natms; ++i) {
     collect(i, 0, dom.L(0, i));                                         // rdf_collect
     if (w.lbook) collect(i, dom.L(0, i), dom.L(-1, i) - dom.L(0, i));   // rdf_excl_collect
+    if (w.megfrz != 0) collect(i, dom.L(-1, i), dom.L(-2, i) - dom.L(-1, i));   // rdf_frzn_collect (two_body.F90:615-652, rdfs.F90:948-1018)
   }
 }
 
@@ -1642,6 +1668,7 @@ void two_body_forces(World& w, Dom& dom) {
   const int ml = dom.max_list;
   std::vector<double> xxt(ml + 1), yyt(ml + 1), zzt(ml + 1), rrt(ml + 1);
   for (int k = 1; k <= 9; ++k) dom.stress[k] = 0.0;
+  if (w.collect_pp) { dom.pp_energy.assign((size_t)dom.natms + 1, 0.0); dom.pp_stress.assign(((size_t)dom.natms + 1) * 9, 0.0); }
   double engvdw = 0, virvdw = 0, engcpe_rl = 0, vircpe_rl = 0, engcpe_ex = 0, vircpe_ex = 0;
   CorePart* parts = dom.parts.data();
   for (int i = 1; i <= dom.natms; ++i) {
@@ -2172,6 +2199,18 @@ int ora_world_link_cell_pairs(void* h, int nthreads) {
 }
 // zero_forces!=0: parts(:)%f = 0 first (drivers.F90:655-660).  out: per-world sums [engvdw,virvdw,engcpe_rl,vircpe_rl,
 // engcpe_ex,vircpe_ex] + stress(9) (the gsum of two_body.F90:729 / drivers.F90:795)
+int ora_world_set_collect_pp(void* h, int on) { ((World*)h)->collect_pp = on != 0; return 0; }
+// pp_energy(1:natms) and pp_stress(1:9, 1:natms) (column-major, 9 per atom) of domain `rank` after the last two_body call
+int ora_dom_get_pp(void* h, int rank, double* pp_energy, double* pp_stress) {
+  World* w = (World*)h;
+  Dom& d = w->d[rank];
+  if ((int)d.pp_energy.size() < d.natms + 1) return 1;
+  for (int i = 1; i <= d.natms; ++i) {
+    pp_energy[i - 1] = d.pp_energy[i];
+    for (int c = 0; c < 9; ++c) pp_stress[(size_t)(i - 1) * 9 + c] = d.pp_stress[(size_t)i * 9 + c];
+  }
+  return 0;
+}
 int ora_world_two_body(void* h, int nthreads, int zero_forces, double* out15) {
   World* w = (World*)h;
   if (zero_forces) {

@@ -353,6 +353,18 @@ class World:
         self.L.ora_dom_get_cells(self.h, C.c_int(rank), _vp(wc), _vp(al), _vp(ls))
         return wc, al, ls
 
+    def set_collect_pp(self, on=True):
+        """stats%collect_pp: the next two_body calls also fill pp_energy / pp_stress (vdw.F90:1741-1755, :1987-2001,
+        ewald_spole.F90:205-215)."""
+        self.L.ora_world_set_collect_pp(self.h, C.c_int(int(on)))
+
+    def pp(self, rank=0):
+        """(pp_energy(natms), pp_stress(natms, 9)) of the last two_body call."""
+        n = self.counts(rank)["natms"]
+        e, st = np.zeros(n), np.zeros((n, 9))
+        assert self.L.ora_dom_get_pp(self.h, C.c_int(rank), _vp(e), _vp(st)) == 0
+        return e, st
+
     def results(self, rank=0):
         out = np.zeros(15)
         self.L.ora_dom_get_results(self.h, C.c_int(rank), _vp(out))

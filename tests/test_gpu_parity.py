@@ -617,11 +617,16 @@ def test_list_kernels_build_the_same_rows(name):
             assert np.array_equal(np.asarray(xa), np.asarray(xb))
 
 
-@pytest.mark.parametrize("which,P", [("nacl", 1), ("nacl", 8), ("water", 1)])
+@pytest.mark.parametrize("which,P", [("nacl", 1), ("nacl", 8), ("water", 1), ("nacl_frozen", 1), ("nacl_frozen", 8)])
 def test_rdf_collect_counts_are_exact(which, P):
-    """rdf_collect / rdf_excl_collect (rdfs.F90:146-212, :880-946) on the device list: integer pair counts per (bin, type
-    pair), summed over the domains, equal the oracle's exactly (bin index from the reference's IEEE distance)."""
-    s = systems.nacl(8 if P > 1 else 4, rcut=8.0, padding=0.2) if which == "nacl" else systems.spce_water(512, rcut=8.0, padding=0.2)
+    """rdf_collect / rdf_excl_collect / rdf_frzn_collect (rdfs.F90:146-212, :880-946, :948-1018) on the device list: integer pair
+    counts per (bin, type pair), summed over the domains, equal the oracle's exactly (bin index from the reference's IEEE
+    distance).  nacl_frozen: every Na+ frozen, so the Na-Na pairs sit in the frozen-frozen rows and reach the histogram only
+    through rdf_frzn_collect."""
+    s = systems.nacl(8 if P > 1 else 4, rcut=8.0, padding=0.2) if which.startswith("nacl") else systems.spce_water(512, rcut=8.0, padding=0.2)
+    if which == "nacl_frozen":
+        s.freeze_site[:] = [1, 0]
+        s.megfrz = int((s.freeze_site[s.lsite - 1] > 0).sum())
     w = world_for(s, P=P)
     nt = s.ff.ntypes
     nkey = nt * (nt + 1) // 2
@@ -643,6 +648,8 @@ def test_rdf_collect_counts_are_exact(which, P):
         sr.close()
     assert ref.sum() > 1000
     assert np.array_equal(got, ref)
+    if which == "nacl_frozen":
+        assert ref[0].sum() > 100          # key 1 = Na-Na: collected although no force row holds such a pair
 
 
 def test_md_step_enqueued_from_c_follows_the_python_driver():
@@ -687,3 +694,37 @@ def test_vdw_direct_refuses_keys_without_an_analytic_form():
         with pytest.raises(DlpError):
             sr.dev_setup_system(s)
         sr.close()
+
+
+@pytest.mark.parametrize("name", ["argon_direct", "nacl", "water", "morse_direct"])
+def test_collect_pp_per_particle_energy_and_stress(name):
+    """stats%collect_pp (f3): per-particle energy and stress of the pair terms against the oracle, which restates the reference path
+    by path (vdw_forces_direct books the pair energy for every pair, vdw_forces_tab only where the rank owns it, ewald_real for
+    every pair; vdw.F90:1707, :1741-1755, :1905, :1987-2001, ewald_spole.F90:155, :205-215).  Also the sum rule: the per-particle
+    stresses add up to the stress tensor of the call plus the unowned halo halves."""
+    s = {"argon_direct": lambda: systems.argon(6, direct=True), "nacl": lambda: systems.nacl(4, rcut=8.0, padding=0.2),
+         "water": lambda: systems.spce_water(512, rcut=8.0, padding=0.2),
+         "morse_direct": lambda: systems.vdw_direct_fluid(8)}[name]()
+    w = world_for(s, P=1, with_halo=False, with_list=False)
+    w.set_collect_pp(True)
+    w.relocate(); w.set_halo(); assert w.link_cell_pairs() == 0
+    oo = w.two_body()
+    eo, so = w.pp(0)
+    sr = native_serial(s)
+    sr.set_collect_pp(True)
+    sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs()
+    out = sr.dev_two_body_forces()
+    assert sr.pair_kernel_used()[0] == 1
+    natms, _ = sr.dev_counts()
+    eg, sg = sr.get_pp(natms)
+    for k in range(6):
+        assert abs(out[k] - oo[k]) <= ENERGY_TOL * max(abs(oo[k]), 1e-6 * np.abs(oo[:6]).max())
+    assert np.abs(eg - eo).max() <= 1e-10 * np.abs(eo).max()
+    assert np.abs(sg - so).max() <= 1e-10 * np.abs(so).max()
+    # the direct and Ewald paths give every local atom half of each of its pairs: the halves add up to the totals
+    if name.endswith("direct"):
+        assert abs(eg.sum() - (oo[0] + oo[2])) <= 1e-10 * abs(oo[0] + oo[2])
+    # ... and get_pp ADDS into the caller's arrays
+    e2, s2 = sr.get_pp(natms, eg.copy(), sg.copy())
+    assert np.allclose(e2, 2.0 * eg, rtol=1e-15, atol=0.0) and np.allclose(s2, 2.0 * sg, rtol=1e-15, atol=0.0)
+    sr.close()
