@@ -124,6 +124,10 @@ struct dlpgpu_ctx {
   DBuf<int> nfnbr;
   int fpitch = 0;
   bool frz_rows_valid = false;
+  // SPME reciprocal space (spme.cu)
+  int spme_k[3] = {0, 0, 0}, spme_n = 0, spme_kmax = 0, spme_plan = 0;
+  bool spme_plan_valid = false;
+  DBuf<double> spme_grid, spme_norm2, spme_fraw, spme_tot;
   bool collect_pp = false;            // dlpgpu_set_collect_pp: stats%collect_pp
   int pp_natms = -1;
   DBuf<double> pp_pos, pp_neg, pp_energy, pp_stress;   // per-particle sums of the last force call (see k_pair_forces<.., PP>)
@@ -260,6 +264,8 @@ int dlp_preload_halo();
 int dlp_preload_cells();
 int dlp_preload_forces();
 int dlp_preload_ctx();
+int dlp_preload_spme();
+void dlp_spme_release(dlpgpu_ctx* ctx);
 // util.cu
 int dlp_exclusive_scan(dlpgpu_ctx* ctx, const int* in_dev, int* out_dev, int n, int* total_host /*nullable*/);
 int dlp_ensure_atoms(dlpgpu_ctx* ctx, int n);

@@ -147,7 +147,7 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   cudaEventCreate(&ctx->ev_res);
   {   // once per device and process
     static bool loaded[64] = {false};
-    if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); loaded[device] = true; }
+    if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); dlp_preload_spme(); loaded[device] = true; }
   }
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
@@ -173,6 +173,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
+  dlp_spme_release(ctx);
   ctx->fnbr.release(); ctx->nfnbr.release();
   ctx->pp_pos.release(); ctx->pp_neg.release(); ctx->pp_energy.release(); ctx->pp_stress.release();
   ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();

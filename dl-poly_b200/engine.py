@@ -105,6 +105,17 @@ class ShortRange:
         """Diagnostic: 0 k_list_cell8 (default), 1 the one-atom-per-pass kernel, for the plain half-list case."""
         self._ck(self.L.dlpgpu_set_list_kernel(self.h, int(which)))
 
+    def set_spme(self, kdim, nsplines=8):
+        """SPME grid (k_vec_dim after adjust_kmax) and B-spline order; see include/dlpgpu.h."""
+        k = np.ascontiguousarray(kdim, dtype=np.int32)
+        self._ck(self.L.dlpgpu_set_spme(self.h, ptr(k), int(nsplines)))
+
+    def dev_spme_forces(self, megatm):
+        """ewald_spme_forces_coul on the device-resident atoms: adds the reciprocal forces, returns out[16]."""
+        out = np.zeros(16)
+        self._ck(self.L.dlpgpu_dev_spme_forces(self.h, int(megatm), ptr(out)))
+        return out
+
     def set_collect_pp(self, on=True):
         """stats%collect_pp: force calls also book per-particle energy / stress (see include/dlpgpu.h)."""
         self._ck(self.L.dlpgpu_set_collect_pp(self.h, int(on)))

@@ -115,6 +115,18 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
  * overwritten by the stale copy).  It holds for force fields whose only providers before two_body_forces are the pair terms
  * themselves (every BASELINE configuration).  One-shot: consumed by the next dlpgpu_two_body_forces. */
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
+/* SPME reciprocal-space Coulomb term, ewald_spme_forces_coul (ewald_spole.F90:244-477; SURVEY section 8f row 4, beyond the hot path
+ * of the north star): B-spline charge spreading (ewald_general.F90:517-576), forward transform, the reference's influence
+ * function inside its spherical k cutoff with the stress kernel (ewald_spole.F90:1257-1386), backward transform, force / energy
+ * gather with the net force removed (ewald_general.F90:717-869), self interaction (spme.F90:159-231).  First version: the whole
+ * grid lives on one domain (mxnode = 1; DLPGPU_ERR_STATE otherwise); the 3-D transforms are cuFFT's, loaded on first use.
+ * set_spme: kdim = ewld%kspace%k_vec_dim (after adjust_kmax), nsplines = bspline%num_splines (3..12); alpha, the Coulomb
+ * scaling and the cell come from dlpgpu_set_ewald / dlpgpu_set_cell.
+ * dev_spme_forces works on the device-resident atoms (1:natms), ADDS the reciprocal forces to the device force arrays and
+ * returns out[0] = engcpe_rc (reciprocal energy + self interaction), out[1] = vircpe_rc, out[2..10] = what the routine adds to
+ * stats%stress(1:9), out[11] = the reciprocal energy alone, out[12] = the self interaction.  megatm = atoms in the system. */
+int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines);
+int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]);
 /* stats%collect_pp (statistics.F90:227, set by the per-particle / heat-flux options): while on, two_body_forces (drop-in and
  * dev_) also books, for every pair, half of its energy and half of its stress tensor r (x) f on each LOCAL partner, following
  * the reference path by path -- vdw_forces_direct (vdw.F90:1707, :1741-1755: the pair energy for every pair),

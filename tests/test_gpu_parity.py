@@ -728,3 +728,34 @@ def test_collect_pp_per_particle_energy_and_stress(name):
     e2, s2 = sr.get_pp(natms, eg.copy(), sg.copy())
     assert np.allclose(e2, 2.0 * eg, rtol=1e-15, atol=0.0) and np.allclose(s2, 2.0 * sg, rtol=1e-15, atol=0.0)
     sr.close()
+
+
+@pytest.mark.parametrize("name,nspl", [("nacl", 8), ("nacl", 6), ("water", 8), ("ionic_mixture", 10), ("nacl_orthorhombic", 8)])
+def test_spme_reciprocal_space_against_oracle(name, nspl):
+    """f4, first version: ewald_spme_forces_coul on one domain (B-spline spreading, cuFFT, the reference's influence function
+    inside its spherical k cutoff, gather with the net force removed, self interaction) against oracle/spme_oracle.py -- the
+    numpy restatement that tests/test_spme_oracle.py pins to the exact Ewald reciprocal sum.  Grid and alpha as control.F90:1707-1713
+    derives them from spme_precision 1e-6."""
+    from oracle import spme_oracle as so
+    s = {"nacl": lambda: systems.nacl(4, rcut=8.0, padding=0.2), "water": lambda: systems.spce_water(512, rcut=8.0, padding=0.2),
+         "ionic_mixture": lambda: systems.ionic_mixture(5), "nacl_orthorhombic": lambda: systems.nacl((5, 4, 3), rcut=8.0, padding=0.2)}[name]()
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]
+    q = s.charge_site[s.lsite - 1]
+    _, kdim = so.spme_grid(1.0e-6, s.rcut, s.cell)
+    ref = so.ewald_spme_forces_coul(s.cell, xyz, q, s.ff.alpha, kdim, nspl, s.ff.scaling)
+    sr = native_serial(s)
+    sr.set_spme(kdim, nspl)
+    out = sr.dev_spme_forces(s.megatm)
+    f = parts_forces(sr.dev_get_parts(), s.megatm)
+    assert abs(out[11] - ref["eng_recip"]) <= 1e-10 * abs(ref["eng_recip"]), (out[11], ref["eng_recip"])
+    assert abs(out[0] - ref["engcpe_rc"]) <= 1e-10 * abs(ref["engcpe_rc"])
+    assert abs(out[1] - ref["vircpe_rc"]) <= 1e-10 * abs(ref["vircpe_rc"])
+    assert np.abs(out[2:11] - ref["stress"]).max() <= 1e-10 * np.abs(ref["stress"]).max()
+    rep = per_atom_force_error(f, ref["forces"])
+    print("SPME %s order %d grid %s: %s" % (s.name, nspl, kdim, rep))
+    assert rep["max_normalised"] <= FORCE_TOL and rep["per_atom_significant"] <= FORCE_TOL, rep
+    # a second call ADDS the same forces again (every provider adds, drivers.F90:655-660)
+    sr.dev_spme_forces(s.megatm)
+    f2 = parts_forces(sr.dev_get_parts(), s.megatm)
+    assert np.abs(f2 - 2.0 * f).max() <= 1e-12 * np.abs(f).max()
+    sr.close()
