@@ -127,7 +127,7 @@ struct dlpgpu_ctx {
   // SPME reciprocal space (spme.cu)
   int spme_k[3] = {0, 0, 0}, spme_n = 0, spme_kmax = 0, spme_plan = 0;
   bool spme_plan_valid = false;
-  DBuf<double> spme_grid, spme_norm2, spme_fraw, spme_tot;
+  DBuf<double> spme_grid, spme_rgrid, spme_norm2, spme_fraw, spme_tot;
   bool collect_pp = false;            // dlpgpu_set_collect_pp: stats%collect_pp
   int pp_natms = -1;
   DBuf<double> pp_pos, pp_neg, pp_energy, pp_stress;   // per-particle sums of the last force call (see k_pair_forces<.., PP>)

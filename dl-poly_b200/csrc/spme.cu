@@ -60,38 +60,52 @@ __device__ __forceinline__ void atom_splines(const SpmeP& P, const double4& p, i
 __device__ __forceinline__ int wrapk(int i, int K) { i %= K; return i < 0 ? i + K : i; }
 
 constexpr int SPME_GROUP = 64;      // threads per atom: an n x n face of its footprint (n <= 8), looped for larger orders
-constexpr int SPME_APB = 4;         // atoms per block pass
+constexpr int SPME_NG = 4;          // groups per block
+constexpr int SPME_AGP = 8;         // atoms a group takes per block pass: the spline sets of all SPME_NG * SPME_AGP atoms of a pass are
+constexpr int SPME_APB = SPME_NG * SPME_AGP;   // ... filled together (one thread per atom and dimension), then each group walks its atoms
 
-// spme_construct_charge_array: Q(j,k,l) += q vx vy vz over the n^3 footprint; also sum q^2 (self interaction)
-__global__ void __launch_bounds__(SPME_GROUP * SPME_APB)
-k_spme_spread(SpmeP P, const double4* __restrict__ posq, double2* __restrict__ grid, double* __restrict__ totals) {
+// spme_construct_charge_array: Q(j,k,l) += q vx vy vz over the n^3 footprint (real grid, z fastest); also sum q^2 (self interaction)
+__global__ void __launch_bounds__(SPME_GROUP * SPME_NG)
+k_spme_spread(SpmeP P, const double4* __restrict__ posq, double* __restrict__ rgrid, double* __restrict__ totals) {
   __shared__ AtomSpl s_a[SPME_APB];
   const int g = threadIdx.x / SPME_GROUP, t = threadIdx.x % SPME_GROUP;
   double q2 = 0.0;
   for (int base = blockIdx.x * SPME_APB; base < P.natms; base += gridDim.x * SPME_APB) {
-    const int a = base + g;
     __syncthreads();
-    if (a < P.natms && t < 3) atom_splines(P, posq[a], t, s_a[g]);
+    if (threadIdx.x < 3 * SPME_APB) {
+      const int a = base + threadIdx.x / 3;
+      if (a < P.natms) atom_splines(P, posq[a], threadIdx.x % 3, s_a[threadIdx.x / 3]);
+    }
     __syncthreads();
-    if (a >= P.natms) continue;
-    const AtomSpl& s = s_a[g];
-    if (t == 0) q2 += s.q * s.q;
-    if (!(fabs(s.q) > ZERO_PLUS)) continue;                                    // ewald_general.F90:536
-    for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
-      const int py = f / P.n, pz = f % P.n;
-      const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
-      const double fyz = s.q * s.v[2][pz] * s.v[1][py];
-      for (int px = 0; px < P.n; ++px) {
-        const int ix = wrapk(s.idx[0] - px, P.K[0]);
-        atomicAdd(&grid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz].x, fyz * s.v[0][px]);
+    for (int w = 0; w < SPME_AGP; ++w) {
+      const int sl = g * SPME_AGP + w, a = base + sl;
+      if (a >= P.natms) break;
+      const AtomSpl& s = s_a[sl];
+      if (t == 0) q2 += s.q * s.q;
+      if (!(fabs(s.q) > ZERO_PLUS)) continue;                                  // ewald_general.F90:536
+      for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
+        const int py = f / P.n, pz = f % P.n;
+        const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
+        const double fyz = s.q * s.v[2][pz] * s.v[1][py];
+        for (int px = 0; px < P.n; ++px) {
+          const int ix = wrapk(s.idx[0] - px, P.K[0]);
+          atomicAdd(&rgrid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz], fyz * s.v[0][px]);
+        }
       }
     }
   }
   // sum of q^2: one add per block
-  __shared__ double s_q2[SPME_APB];
+  __shared__ double s_q2[SPME_NG];
   if (t == 0) s_q2[g] = q2;
   __syncthreads();
-  if (threadIdx.x == 0) { double v = 0.0; for (int k = 0; k < SPME_APB; ++k) v += s_q2[k]; atomicAdd(&totals[10], v); }
+  if (threadIdx.x == 0) { double v = 0.0; for (int k = 0; k < SPME_NG; ++k) v += s_q2[k]; atomicAdd(&totals[10], v); }
+}
+
+__global__ void k_spme_real_to_complex(size_t n, const double* __restrict__ r, double2* __restrict__ c) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) c[e] = make_double2(r[e], 0.0);
+}
+__global__ void k_spme_complex_to_real(size_t n, const double2* __restrict__ c, double* __restrict__ r) {   // extended_potential_grid is Real
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) r[e] = c[e].x;
 }
 
 // spme_construct_potential_grid_coul between the two transforms: potential_component = B(m) S(m) exp(-x^2) / (sqrt(pi) x^2) inside
@@ -136,50 +150,56 @@ __global__ void k_spme_influence(SpmeP P, double conv, double test_fac, double c
 }
 
 // spme_calc_force_energy: per atom, energy and the three force sums over its footprint of the (real) potential grid
-__global__ void __launch_bounds__(SPME_GROUP * SPME_APB)
-k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __restrict__ posq, const double2* __restrict__ grid,
+__global__ void __launch_bounds__(SPME_GROUP * SPME_NG)
+k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __restrict__ posq, const double* __restrict__ rgrid,
               double* __restrict__ fraw, double* __restrict__ totals) {
   __shared__ AtomSpl s_a[SPME_APB];
-  __shared__ double s_red[SPME_APB][SPME_GROUP / 32][4];
+  __shared__ double s_red[SPME_NG][SPME_GROUP / 32][4];
   const int g = threadIdx.x / SPME_GROUP, t = threadIdx.x % SPME_GROUP;
   double te = 0.0, tf0 = 0.0, tf1 = 0.0, tf2 = 0.0;   // block totals, kept by thread 0 of each group
   for (int base = blockIdx.x * SPME_APB; base < P.natms; base += gridDim.x * SPME_APB) {
-    const int a = base + g;
     __syncthreads();
-    if (a < P.natms && t < 3) atom_splines(P, posq[a], t, s_a[g]);
+    if (threadIdx.x < 3 * SPME_APB) {
+      const int a = base + threadIdx.x / 3;
+      if (a < P.natms) atom_splines(P, posq[a], threadIdx.x % 3, s_a[threadIdx.x / 3]);
+    }
     __syncthreads();
-    const AtomSpl& s = s_a[g];
-    const bool live = a < P.natms && fabs(s.q) > ZERO_PLUS;                    // ewald_general.F90:779
-    double e = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    if (live) {
-      for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
-        const int py = f / P.n, pz = f % P.n;
-        const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
-        const double y0 = s.v[1][py], z0 = s.v[2][pz], y1 = s.d[1][py], z1 = s.d[2][pz];
-        double sx0 = 0.0, sx1 = 0.0;                                           // sum over x of phi vx, phi vx'
-        for (int px = 0; px < P.n; ++px) {
-          const int ix = wrapk(s.idx[0] - px, P.K[0]);
-          const double phi = grid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz].x;
-          sx0 += phi * s.v[0][px]; sx1 += phi * s.d[0][px];
+    for (int w = 0; w < SPME_AGP; ++w) {   // the two warps of a group stay together through the named barrier below
+      const int sl = g * SPME_AGP + w, a = base + sl;
+      const AtomSpl& s = s_a[sl];
+      const bool live = a < P.natms && fabs(s.q) > ZERO_PLUS;                  // ewald_general.F90:779
+      double e = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
+      if (live) {
+        for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
+          const int py = f / P.n, pz = f % P.n;
+          const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
+          const double y0 = s.v[1][py], z0 = s.v[2][pz], y1 = s.d[1][py], z1 = s.d[2][pz];
+          double sx0 = 0.0, sx1 = 0.0;                                         // sum over x of phi vx, phi vx'
+          for (int px = 0; px < P.n; ++px) {
+            const int ix = wrapk(s.idx[0] - px, P.K[0]);
+            const double phi = rgrid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz];
+            sx0 += phi * s.v[0][px]; sx1 += phi * s.d[0][px];
+          }
+          e += y0 * z0 * sx0;
+          f0 += y0 * z0 * sx1; f1 += y1 * z0 * sx0; f2 += y0 * z1 * sx0;
         }
-        e += y0 * z0 * sx0;
-        f0 += y0 * z0 * sx1; f1 += y1 * z0 * sx0; f2 += y0 * z1 * sx0;
       }
-    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      e += __shfl_xor_sync(DLP_FULL, e, d); f0 += __shfl_xor_sync(DLP_FULL, f0, d);
-      f1 += __shfl_xor_sync(DLP_FULL, f1, d); f2 += __shfl_xor_sync(DLP_FULL, f2, d);
-    }
-    if ((t & 31) == 0) { double* r = s_red[g][t >> 5]; r[0] = e; r[1] = f0; r[2] = f1; r[3] = f2; }
-    __syncthreads();
-    if (t == 0 && a < P.natms) {
-      double r[4] = {0, 0, 0, 0};
-      for (int w = 0; w < SPME_GROUP / 32; ++w) for (int c = 0; c < 4; ++c) r[c] += s_red[g][w][c];
-      // curr_force_temp = q (sum) recip_kmax; forces(:, i) = -curr_force_temp; force_total -= curr_force_temp
-      const double c0 = s.q * r[1] * kmx, c1 = s.q * r[2] * kmy, c2 = s.q * r[3] * kmz;
-      fraw[a] = live ? -c0 : 0.0; fraw[(size_t)P.natms + a] = live ? -c1 : 0.0; fraw[2 * (size_t)P.natms + a] = live ? -c2 : 0.0;
-      if (live) { te += s.q * r[0]; tf0 -= c0; tf1 -= c1; tf2 -= c2; }
+      for (int d = 16; d > 0; d >>= 1) {
+        e += __shfl_xor_sync(DLP_FULL, e, d); f0 += __shfl_xor_sync(DLP_FULL, f0, d);
+        f1 += __shfl_xor_sync(DLP_FULL, f1, d); f2 += __shfl_xor_sync(DLP_FULL, f2, d);
+      }
+      if ((t & 31) == 0) { double* r = s_red[g][t >> 5]; r[0] = e; r[1] = f0; r[2] = f1; r[3] = f2; }
+      asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(SPME_GROUP) : "memory");
+      if (t == 0 && a < P.natms) {
+        double r[4] = {0, 0, 0, 0};
+        for (int ww = 0; ww < SPME_GROUP / 32; ++ww) for (int c = 0; c < 4; ++c) r[c] += s_red[g][ww][c];
+        // curr_force_temp = q (sum) recip_kmax; forces(:, i) = -curr_force_temp; force_total -= curr_force_temp
+        const double c0 = s.q * r[1] * kmx, c1 = s.q * r[2] * kmy, c2 = s.q * r[3] * kmz;
+        fraw[a] = live ? -c0 : 0.0; fraw[(size_t)P.natms + a] = live ? -c1 : 0.0; fraw[2 * (size_t)P.natms + a] = live ? -c2 : 0.0;
+        if (live) { te += s.q * r[0]; tf0 -= c0; tf1 -= c1; tf2 -= c2; }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(SPME_GROUP) : "memory");
     }
   }
   __syncthreads();
@@ -187,7 +207,7 @@ k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __rest
   __syncthreads();
   if (threadIdx.x < 4) {
     double v = 0.0;
-    for (int k = 0; k < SPME_APB; ++k) v += s_red[k][0][threadIdx.x];
+    for (int k = 0; k < SPME_NG; ++k) v += s_red[k][0][threadIdx.x];
     atomicAdd(&totals[threadIdx.x], v);
   }
 }
@@ -241,7 +261,7 @@ bool load_cufft() {
 void dlp_spme_release(dlpgpu_ctx* ctx) {
   if (ctx->spme_plan_valid && g_fft.destroy) g_fft.destroy(ctx->spme_plan);
   ctx->spme_plan_valid = false;
-  ctx->spme_grid.release(); ctx->spme_norm2.release(); ctx->spme_fraw.release(); ctx->spme_tot.release();
+  ctx->spme_grid.release(); ctx->spme_rgrid.release(); ctx->spme_norm2.release(); ctx->spme_fraw.release(); ctx->spme_tot.release();
 }
 
 extern "C" {
@@ -281,6 +301,7 @@ int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines) {
   ctx->spme_kmax = kmax;
   const size_t ntot = (size_t)kdim[0] * kdim[1] * kdim[2];
   CK(ctx->spme_grid.ensure(2 * ntot, ctx->stream));
+  CK(ctx->spme_rgrid.ensure(ntot, ctx->stream));
   CK(ctx->spme_tot.ensure(16, ctx->stream));
   int plan = 0;
   if (g_fft.plan3d(&plan, kdim[0], kdim[1], kdim[2], CUFFT_Z2Z_TYPE) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "set_spme: cufftPlan3d failed");
@@ -309,11 +330,14 @@ int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
   for (int k = 0; k < 9; ++k) P.rc[k] = inv[k];
   const size_t ntot = (size_t)P.K[0] * P.K[1] * P.K[2];
   double2* grid = reinterpret_cast<double2*>(ctx->spme_grid.p);
-  CK(cudaMemsetAsync(grid, 0, ntot * sizeof(double2), s));
+  double* rgrid = ctx->spme_rgrid.p;   // the charge grid, later the real potential grid
+  CK(cudaMemsetAsync(rgrid, 0, ntot * sizeof(double), s));
   CK(cudaMemsetAsync(ctx->spme_tot.p, 0, 16 * sizeof(double), s));
   CK(ctx->spme_fraw.ensure((size_t)3 * std::max(natms, 1), s));
   const int blocks_a = std::max(1, std::min(cdiv(std::max(natms, 1), SPME_APB), ctx->sm_count * 8));
-  if (natms > 0) LAUNCH(ctx, k_spme_spread, blocks_a, SPME_GROUP * SPME_APB, 0, P, ctx->posq.p, grid, ctx->spme_tot.p);
+  const int blocks_g = std::max(1, std::min(cdiv((long long)ntot, 256), ctx->sm_count * 16));
+  if (natms > 0) LAUNCH(ctx, k_spme_spread, blocks_a, SPME_GROUP * SPME_NG, 0, P, ctx->posq.p, rgrid, ctx->spme_tot.p);
+  LAUNCH(ctx, k_spme_real_to_complex, blocks_g, 256, 0, ntot, rgrid, grid);
   if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_FWD) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme_forces: forward FFT failed");
   // the spherical cutoff of the reference: 0.525 min_d(K_d * width_d of the reciprocal cell), ewald_spole.F90:1287-1291
   double w[3];
@@ -329,16 +353,17 @@ int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
   const double cut = 0.5 * 1.05 * std::min(P.K[0] * w[0], std::min(P.K[1] * w[1], P.K[2] * w[2]));
   const double pi = 3.14159265358979323846264338327950288;
   const double conv = pi / ctx->alpha, test_fac = (1.0e-6 / conv) * (1.0e-6 / conv);
-  LAUNCH(ctx, k_spme_influence, std::min(cdiv((long long)ntot, 256), ctx->sm_count * 16), 256, 0, P, conv, test_fac, cut * cut, ctx->spme_norm2.p,
+  LAUNCH(ctx, k_spme_influence, blocks_g, 256, 0, P, conv, test_fac, cut * cut, ctx->spme_norm2.p,
          ctx->spme_kmax, grid, ctx->spme_tot.p);
   if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_INV) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme_forces: backward FFT failed");
+  LAUNCH(ctx, k_spme_complex_to_real, blocks_g, 256, 0, ntot, grid, rgrid);
   // recip_kmax = Matmul(Reshape(rcell, [3, 3]), k_vec_dim_real): component a = sum_b rcell(a + 3 (b - 1)) K_b  (ewald_general.F90:755-756)
   const double kmx = inv[0] * P.K[0] + inv[3] * P.K[1] + inv[6] * P.K[2], kmy = inv[1] * P.K[0] + inv[4] * P.K[1] + inv[7] * P.K[2],
                kmz = inv[2] * P.K[0] + inv[5] * P.K[1] + inv[8] * P.K[2];
   const double volm = std::fabs(det);
   const double scale = pi * SQRPI * (1.0 / (ctx->alpha * ctx->alpha)) * (0.5 / volm) * ctx->scaling;   // ewald_spole.F90:299, pot_order 1
   if (natms > 0) {
-    LAUNCH(ctx, k_spme_gather, blocks_a, SPME_GROUP * SPME_APB, 0, P, kmx, kmy, kmz, ctx->posq.p, grid, ctx->spme_fraw.p, ctx->spme_tot.p);
+    LAUNCH(ctx, k_spme_gather, blocks_a, SPME_GROUP * SPME_NG, 0, P, kmx, kmy, kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
     LAUNCH(ctx, k_spme_finish, cdiv(natms, 256), 256, 0, natms, 1.0 / (double)megatm, scale * 2.0, ctx->spme_fraw.p, ctx->spme_tot.p, ctx->fx.p,
            ctx->fy.p, ctx->fz.p);
   }
@@ -361,7 +386,8 @@ int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
 }  // extern "C"
 
 int dlp_preload_spme() {
-  const void* ks[] = {(const void*)k_spme_spread, (const void*)k_spme_influence, (const void*)k_spme_gather, (const void*)k_spme_finish};
+  const void* ks[] = {(const void*)k_spme_spread, (const void*)k_spme_influence, (const void*)k_spme_gather, (const void*)k_spme_finish, (const void*)k_spme_real_to_complex,
+                      (const void*)k_spme_complex_to_real};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
   return 0;

@@ -49,6 +49,34 @@ def ewald_alpha(precision, rcut):
     return math.sqrt(abs(math.log(precision * rcut * tol))) / rcut
 
 
+def adjust_kmax(kmax, nproc=1):
+    """parallel_fft.F90:1999-2054: the next multiple of nproc whose per-domain length is 2^a 3^b 5^c."""
+    def ok(n):
+        for p in (2, 3, 5):
+            while n > 1 and n % p == 0:
+                n //= p
+        return n == 1
+    if kmax % nproc:
+        kmax = (kmax // nproc + 1) * nproc
+    while not ok(kmax // nproc):
+        kmax += nproc
+    return kmax
+
+
+def spme_grid(precision, rcut, cell, dims=(1, 1, 1)):
+    """control.F90:1707-1713 + ewald.F90:1210-1212: (alpha, k_vec_dim) the reference derives from spme_precision; cell = 9
+    doubles, rows = lattice vectors; dims = domains per direction."""
+    a, b, c = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    vol = abs(float(np.dot(a, np.cross(b, c))))
+    widths = [vol / float(np.linalg.norm(np.cross(b, c))), vol / float(np.linalg.norm(np.cross(c, a))),
+              vol / float(np.linalg.norm(np.cross(a, b)))]                      # dcell(7:9)
+    tol = math.sqrt(abs(math.log(precision * rcut)))
+    alpha = math.sqrt(abs(math.log(precision * rcut * tol))) / rcut
+    tol1 = math.sqrt(-math.log(precision * rcut * (2.0 * tol * alpha) ** 2))
+    k = [2 * f_nint(0.25 + w * alpha * tol1 / math.pi) for w in widths]
+    return alpha, tuple(adjust_kmax(int(k[d]), int(dims[d])) for d in range(3))
+
+
 def _powi(x, n):
     """libgcc __powidf2 ordering (what real**integer compiles to)."""
     m = abs(n)

@@ -74,3 +74,15 @@ def test_spme_stress_against_the_volume_derivative():
     em = so.ewald_spme_forces_coul(cell * (1 - h), xyz * (1 - h), q, alpha, kdim, 8, s.ff.scaling)["eng_recip"]
     dE_dlnL = (ep - em) / (2 * h)
     assert abs(dE_dlnL + r["stress"][0::4].sum()) <= 5e-5 * abs(r["stress"][0::4].sum()), (dE_dlnL, r["stress"][0::4].sum())
+
+
+def test_host_grid_selection_agrees_with_the_oracle():
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        L = rng.uniform(20.0, 400.0, 3)
+        cell = np.diag(L).reshape(9)
+        if rng.random() < 0.3:
+            cell[3] = 0.2 * L[0]; cell[7] = 0.1 * L[1]
+        prec = 10.0 ** rng.uniform(-8, -4); rcut = rng.uniform(6.0, 14.0)
+        dims = tuple(int(x) for x in rng.choice([1, 2, 3, 4], 3))
+        assert tables.spme_grid(prec, rcut, cell, dims) == so.spme_grid(prec, rcut, cell, dims)
