@@ -214,6 +214,19 @@ def sample_system(workload):
     return systems.by_name(workload, temperature={"c1": 85.0, "c2": 1200.0, "c3": 300.0}[workload]), "the full configuration"
 
 
+def workload_atoms(args, dims):
+    """Atoms of the configuration the GPU arm runs (make_system) without building it."""
+    dx, dy, dz = dims
+    w = args.workload
+    if args.strong:
+        return 8 * (args.cells_per_gpu or 100) ** 3 if w in ("ionic", "table") else 4 * (args.cells_per_gpu or 126) ** 3
+    if w in ("ionic", "table"):
+        return 8 * (args.cells_per_gpu or 50) ** 3 * dx * dy * dz
+    if w == "lj":
+        return 4 * (args.cells_per_gpu or 63) ** 3 * dx * dy * dz
+    return {"c1": 32000, "c2": 27000, "c3": 216000}[w]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,12 +236,19 @@ def run_reference(args):
     # the reference's serial path (one domain, one core) next to the MPI-equivalent one, on a few steps of the same sample
     vs, infos = cpu_trajectory(sample, 1, min(args.steps, 6), 1, args.dt, budget_s=20.0)
     dims = DIMS[args.gpus]
+    # the arm's config is the GPU arm's (same workload label, decomposition, atoms, cutoffs, timestep): each step of this arm is a
+    # bounded sample of that workload (cpu_baseline.sample), and the metric is per atom
+    natoms = workload_atoms(args, dims)
+
+    class _Sz:
+        megatm = natoms
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps"],
         "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * info["seconds"] / info["steps"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "CPU path of " + args.workload + " (bounded sample)", "sample": what,
-                   "domains_per_gpu_run": list(dims)},
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_label(args, _Sz, args.gpus), "domains": list(dims), "atoms": natoms,
+                   "rcut": sample.rcut, "padding": sample.padding, "timestep_ps": args.dt,
+                   "sample": "each step of this arm runs " + what + " on the host cores"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                          "sample": "%s; %d MD steps on %d host threads (one reference domain per thread), %d rebuilds; "
                                    "oracle/dlp_oracle.cpp is a restatement of the reference algorithm, not the reference "

@@ -176,7 +176,8 @@ struct dlpgpu_ctx {
   DBuf<unsigned long long> peer_xr_dev;
   DBuf<int> dcnt;
   DBuf<unsigned long long> gmax_out;   // [1 + 16]: gmax bits, then the gsum of the previous force call's 16 sums
-  unsigned long long* gm_pinned = nullptr;
+  unsigned long long* gm_pinned = nullptr;       // mapped pinned memory k_x_gmax reports into (the host polls its flag)
+  unsigned long long* gm_pinned_dev = nullptr;
   double gsum_prev[16] = {0};
   int rebuild_every = 0, steps_since_rebuild = 0;   // dlpgpu_dev_set_rebuild_every: forced cadence on top of the padding test
   DBuf<double> xbg, ybg, zbg;

@@ -14,6 +14,9 @@
 
 #include "common.cuh"
 
+#include <atomic>
+#include <chrono>
+
 namespace {
 
 struct Dir { int kx, ky, kz, jxyz, kxyz; double xadd, yadd, zadd; int lwrap; };
@@ -674,7 +677,8 @@ __global__ void k_x_halo_end(const int* __restrict__ dc, const int* __restrict__
 struct XGm { unsigned long long seq; unsigned long long tol; double sums[16]; };
 __global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const unsigned long long* __restrict__ tol_bits,
                          const double* __restrict__ my_sums, const unsigned long long* __restrict__ peers, size_t off_gm,
-                         unsigned long long* __restrict__ out /*[1 + 16]*/, int* __restrict__ dc) {
+                         unsigned long long* __restrict__ out /*[1 + 16]*/, int* __restrict__ dc,
+                         unsigned long long* __restrict__ host_out /* pinned, mapped: [0..16] values, [17] error bits, [18] seq */) {
   const int r = threadIdx.x;
   unsigned long long v = 0;
   const size_t slot = ((seq & 1) * (size_t)nranks);
@@ -691,7 +695,7 @@ __global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const uns
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(DLP_FULL, v, d); v = o > v ? o : v; }   // non-negative doubles order like their bits
-  if (r == 0) out[0] = v;
+  if (r == 0) { out[0] = v; host_out[0] = v; }
   __syncwarp();   // every peer's message has been acquired by the lane that waited for it
   if (r < 16) {
     double t = 0.0;
@@ -700,6 +704,16 @@ __global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const uns
       t += __longlong_as_double((long long)ld_acquire_sys(reinterpret_cast<const unsigned long long*>(&src->sums[r])));
     }
     out[1 + r] = (unsigned long long)__double_as_longlong(t);
+    host_out[1 + r] = (unsigned long long)__double_as_longlong(t);
+  }
+  // the host polls host_out[18] for this sequence number instead of synchronising the stream (no DMA, no wake-up): the values
+  // above are written straight into its pinned memory and fenced before the flag
+  __threadfence_system();
+  __syncwarp();
+  if (r == 0) {
+    host_out[17] = (unsigned long long)(unsigned)dc[DC_ERR];
+    __threadfence_system();
+    st_release_sys(&host_out[18], seq);
   }
 }
 
@@ -1185,12 +1199,30 @@ int dlpgpu_dev_xchg_gmax(dlpgpu_ctx* ctx, unsigned long long seq, double* tol) {
   }
   ctx->tol_fresh = false;
   const XLayout L = x_layout(ctx->xr_nranks, ctx->xr_cap_r, ctx->xr_cap_h);
+  if (!ctx->gm_pinned) {
+    CK(cudaHostAlloc((void**)&ctx->gm_pinned, 32 * sizeof(unsigned long long), cudaHostAllocMapped));
+    std::memset(ctx->gm_pinned, 0xff, 32 * sizeof(unsigned long long));
+    CK(cudaHostGetDevicePointer((void**)&ctx->gm_pinned_dev, ctx->gm_pinned, 0));
+  }
   LAUNCH(ctx, k_x_gmax, 1, 32, 0, ctx->xr_rank, ctx->xr_nranks, seq, ctx->tol_bits.p, ctx->out_dev.p, ctx->peer_xr_dev.p, L.off_gm,
-         ctx->gmax_out.p, ctx->dcnt.p);
-  if (!ctx->gm_pinned) CK(cudaMallocHost((void**)&ctx->gm_pinned, 32 * sizeof(unsigned long long)));
-  CK(cudaMemcpyAsync(ctx->gm_pinned, ctx->gmax_out.p, 17 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(ctx->gm_pinned + 17, ctx->dcnt.p + DC_ERR, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+         ctx->gmax_out.p, ctx->dcnt.p, ctx->gm_pinned_dev);
+  {   // wait for the kernel's flag in pinned memory; fall back to the stream if it does not show up (a failed launch)
+    volatile unsigned long long* flag = ctx->gm_pinned + 18;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*flag != seq) {
+      if ((++spins & 0xfff) == 0) {
+        if (cudaStreamQuery(s) != cudaErrorNotReady) break;          // the stream drained (or failed): the flag is final
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 600.0) break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (*flag != seq) { CK(cudaStreamSynchronize(s)); CK(cudaGetLastError()); }
+    if (*flag != seq) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_gmax: the gmax kernel did not report (sequence %llu)", seq);
+  }
   int err = 0;
   std::memcpy(&err, ctx->gm_pinned + 17, sizeof err);
   if (err & 4) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_gmax: timed out waiting for a peer (ranks out of lock-step)");
