@@ -479,12 +479,42 @@ __global__ void k_list_dev(LCGeom g, int natms, int pitch, int xpitch, int megfr
 #define LC_MAXRUN 96
 struct LCRow { int dy, dz, b; };
 
+// Bounding box of the atoms of every link cell (halo cells included), single precision, rounded outward: what the run table of
+// k_list_cell trims its x-runs against.  An empty cell gets an inverted box (never within reach of anything).
+__global__ void k_cell_boxes(int ncells, const int* __restrict__ lct_start, const double4* __restrict__ posq_s,
+                             float4* __restrict__ box /* [2 * (ncells + 1)]: lo, hi */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  float lx = 3.0e38f, ly = 3.0e38f, lz = 3.0e38f, hx = -3.0e38f, hy = -3.0e38f, hz = -3.0e38f;
+  if (c >= 1) {
+    for (int s = lct_start[c]; s < lct_start[c + 1]; ++s) {
+      const double4 p = posq_s[s];
+      lx = fminf(lx, __double2float_rd(p.x)); ly = fminf(ly, __double2float_rd(p.y)); lz = fminf(lz, __double2float_rd(p.z));
+      hx = fmaxf(hx, __double2float_ru(p.x)); hy = fmaxf(hy, __double2float_ru(p.y)); hz = fmaxf(hz, __double2float_ru(p.z));
+    }
+  }
+  box[2 * c] = make_float4(lx, ly, lz, 0.f);
+  box[2 * c + 1] = make_float4(hx, hy, hz, 0.f);
+}
+// squared distance between two boxes (0 when they overlap; huge when one is inverted)
+__device__ __forceinline__ float box_dist2(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi) {
+  const float dx = fmaxf(fmaxf(blo.x - ahi.x, alo.x - bhi.x), 0.f), dy = fmaxf(fmaxf(blo.y - ahi.y, alo.y - bhi.y), 0.f),
+              dz = fmaxf(fmaxf(blo.z - ahi.z, alo.z - bhi.z), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
 // Run table of a cell's candidate slots: potential run p < nrows: positive row p; p >= nrows: negative row (p-nrows)/2, low /
 // high x part (halo cells only, neighbours.F90:1033-1184).  run0[r] = first slot of run r, pre[r] = candidates before run r;
 // returns the number of candidates.  One warp; run0 / pre are that warp's shared arrays.
+// box != nullptr: every run is trimmed to the cells whose atoms' bounding box lies within the Verlet radius of the bounding box of
+// this cell's atoms (single precision, boxes rounded outward, radius widened: conservative, membership stays exact).  The
+// stencil's semi-volume is 62.5 cells; about a third of its candidates sit in cells out of reach.
 __device__ __forceinline__ int lc_run_table(const LCGeom& g, int nrows, const LCRow* __restrict__ rows, const int* __restrict__ lct_start,
-                                            int cx, int cy, int cz, int* run0, int* pre, int lane) {
+                                            int cx, int cy, int cz, int* run0, int* pre, int lane, const float4* __restrict__ box = nullptr,
+                                            float rc2_trim = 0.f) {
   const int nlp = g.nlp;
+  float4 mylo = make_float4(0, 0, 0, 0), myhi = mylo;
+  if (box) { const int ic = 1 + cx + g.sx * (cy + g.sy * cz); mylo = box[2 * ic]; myhi = box[2 * ic + 1]; }
   const int lo_x = nlp - 1, hi_x = g.nlx + nlp, lo_y = nlp - 1, hi_y = g.nly + nlp, lo_z = nlp - 1, hi_z = g.nlz + nlp;
   const bool border = (cx - lo_x <= nlp) || (hi_x - cx <= nlp) || (cy - lo_y <= nlp) || (hi_y - cy <= nlp) || (cz - lo_z <= nlp) || (hi_z - cz <= nlp);
   // ---- run table: potential run p < nrows: positive row p; p >= nrows: negative row (p-nrows)/2, low / high x part
@@ -510,6 +540,11 @@ __device__ __forceinline__ int lc_run_table(const LCGeom& g, int nrows, const LC
         else if (side == 0) xbb = min(xbb, lo_x);                // low-x halo cells
         else xa = max(xa, hi_x);                                 // high-x halo cells
       }
+      if (box) {   // cells are convex in x: the reachable ones of a row are contiguous
+        const int rowbase = 1 + g.sx * (jy + g.sy * jz);
+        while (xa <= xbb && box_dist2(mylo, myhi, box[2 * (rowbase + xa)], box[2 * (rowbase + xa) + 1]) > rc2_trim) ++xa;
+        while (xa <= xbb && box_dist2(mylo, myhi, box[2 * (rowbase + xbb)], box[2 * (rowbase + xbb) + 1]) > rc2_trim) --xbb;
+      }
       if (xa <= xbb) {
         const int c0 = 1 + xa + g.sx * (jy + g.sy * jz), c1 = 1 + xbb + g.sx * (jy + g.sy * jz);
         start = lct_start[c0];
@@ -528,7 +563,10 @@ __device__ __forceinline__ int lc_run_table(const LCGeom& g, int nrows, const LC
   return pre[LC_MAXRUN];
 }
 
-template <int SIMPLE>   // 1: no exclusion lists, no frozen pairs, nlp < 3 -- the lean inner loop; 2: the lean loop with exclusion lists
+// SIMPLE 1: no exclusion lists, no frozen pairs, nlp < 3 -- the lean inner loop; 2: the lean loop with exclusion lists.
+// RING (lean loops): candidates are additionally pruned one by one against the box of the pass's atoms and compacted into a
+// shared-memory ring (fewer passes, dearer staging); without it they are staged 32 at a time as they come.
+template <int SIMPLE, int RING = 0>
 __global__ void __launch_bounds__(LC_WARPS * 32)
 k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, int max_exclude, int excl_by_gid, int nrows,
             const LCRow* __restrict__ rows, const int* __restrict__ at_list, const int* __restrict__ lct_start,
@@ -536,10 +574,10 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             const int2* __restrict__ info_s, const int* __restrict__ pair_k, int ntypes, const int* __restrict__ excl,
             unsigned* __restrict__ nbr, int* __restrict__ nnbr, unsigned* __restrict__ xnbr, int* __restrict__ nxnbr,
             int* __restrict__ status, unsigned long long* __restrict__ cnt64, unsigned sentinel, int prune,
-            unsigned* __restrict__ fnbr, int* __restrict__ nfnbr, int fpitch) {
+            unsigned* __restrict__ fnbr, int* __restrict__ nfnbr, int fpitch, const float4* __restrict__ box, float rc2_trim) {
   __shared__ double4 s_pi[LC_WARPS][32];
-  __shared__ double4 s_pj[LC_WARPS][SIMPLE ? 64 : 1];   // ring of staged candidates (lean loops): {x, y, z, squared acceptance radius}
-  __shared__ int4 s_cj[LC_WARPS][SIMPLE ? 64 : 1];      // ... {slot | halo bit, packed vdW indices, global id, ordering threshold}
+  __shared__ double4 s_pj[LC_WARPS][(SIMPLE && RING) ? 64 : 1];   // ring of staged candidates (lean loops): {x, y, z, squared acceptance radius}
+  __shared__ int4 s_cj[LC_WARPS][(SIMPLE && RING) ? 64 : 1];      // ... {slot | halo bit, packed vdW indices, global id, ordering threshold}
   __shared__ int2 s_info[LC_WARPS][32];
   __shared__ int s_run0[LC_WARPS][LC_MAXRUN];      // first slot of run r
   __shared__ int s_pre[LC_WARPS][LC_MAXRUN + 1];   // candidates before run r
@@ -565,7 +603,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   const int ic = 1 + cx + g.sx * (cy + g.sy * cz);
   const int s_own0 = lct_start[ic], s_own1 = lct_start[ic + 1];
   if (s_own1 == s_own0) return;
-  const int total = lc_run_table(g, nrows, rows, lct_start, cx, cy, cz, s_run0[wid], s_pre[wid], lane);
+  const int total = lc_run_table(g, nrows, rows, lct_start, cx, cy, cz, s_run0[wid], s_pre[wid], lane, box, rc2_trim);
   long long written = 0;
   int ovf = 0;   // longest row that did not fit (error 106), reported once per warp
   for (int a0 = s_own0; a0 < s_own1; a0 += 32) {   // atoms of the cell, 32 at a time (one pass unless the cell is crowded)
@@ -597,76 +635,9 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
       const unsigned ltmask = (1u << lane) - 1u;
       const int cap = pitch - DLP_ROW_PAD;
       unsigned* const row0 = nbr + (size_t)t0 * pitch;
-      // Candidates are pruned while they are staged: a slot farther than the Verlet radius from the bounding box of the pass's
-      // atoms cannot be anybody's partner (the stencil's semi-volume is 62.5 cells, the semi-ball around a cell's atoms about
-      // half of that), and the survivors are compacted into a 64-entry ring in shared memory, from which the atoms take 32 at
-      // a time.  The test runs in single precision relative to the box centre with the box and the radius widened by far more
-      // than its rounding (coordinates within ~2 rx of the centre carry < 1e-5 A of fp32 error), so it never drops a slot whose
-      // squared distance to some atom is <= rcsq; order is kept, so the rows are the same rows.
-      const double4 pref = s_pi[wid][0];   // reference point of the single-precision box arithmetic
-      float bx0, bx1, by0, by1, bz0, bz1;
-      {
-        const double4 pb = s_pi[wid][min(lane, na - 1)];
-        bx0 = bx1 = (float)(pb.x - pref.x); by0 = by1 = (float)(pb.y - pref.y); bz0 = bz1 = (float)(pb.z - pref.z);
-      }
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        bx0 = fminf(bx0, __shfl_xor_sync(DLP_FULL, bx0, d)); bx1 = fmaxf(bx1, __shfl_xor_sync(DLP_FULL, bx1, d));
-        by0 = fminf(by0, __shfl_xor_sync(DLP_FULL, by0, d)); by1 = fmaxf(by1, __shfl_xor_sync(DLP_FULL, by1, d));
-        bz0 = fminf(bz0, __shfl_xor_sync(DLP_FULL, bz0, d)); bz1 = fmaxf(bz1, __shfl_xor_sync(DLP_FULL, bz1, d));
-      }
-      const float bcx = 0.5f * (bx0 + bx1), bcy = 0.5f * (by0 + by1), bcz = 0.5f * (bz0 + bz1);
-      const float bhx = 0.5f * (bx1 - bx0) + 1.0e-4f, bhy = 0.5f * (by1 - by0) + 1.0e-4f, bhz = 0.5f * (bz1 - bz0) + 1.0e-4f;
-      const float rc_prune = prune ? (float)(g.rcsq * (1.0 + 1.0e-4) + 1.0e-3) : 3.0e38f;
-      double4* const ring_p = s_pj[wid];
-      int4* const ring_c = s_cj[wid];
-      int run = 0, head = 0, fill = 0;   // ring: `fill` staged candidates from `head`
-      for (int c0 = 0; c0 < total || fill > 0; c0 += 32) {
-        if (c0 < total) {   // stage up to 32 more candidates; a lane's candidates only move forward, so its run index does too
-          const int c = c0 + lane;
-          int jj = -1;
-          double4 pj = make_double4(0.0, 0.0, 0.0, g.rcsq);
-          int2 infj = make_int2(0, 0);
-          bool keep = false;
-          if (c < total) {
-            while (s_pre[wid][run + 1] <= c) ++run;          // pre[LC_MAXRUN] = total > c ends the walk
-            jj = s_run0[wid][run] + (c - s_pre[wid][run]);
-            pj = posq_s[jj]; infj = info_s[jj];
-            // nlp == 2: the only stencil entry with the "no distance check" flag is the cell itself (neighbours.F90:537, :922-943)
-            const bool own = jj >= s_own0 && jj < s_own1;
-            pj.w = (g.nir_r2 > 0 && own) ? 1e301 : g.rcsq;
-            const float dx = fmaxf(fabsf((float)(pj.x - pref.x) - bcx) - bhx, 0.0f), dy = fmaxf(fabsf((float)(pj.y - pref.y) - bcy) - bhy, 0.0f),
-                        dz = fmaxf(fabsf((float)(pj.z - pref.z) - bcz) - bhz, 0.0f);
-            keep = own || (dx * dx + dy * dy + dz * dz <= rc_prune);
-          }
-          const unsigned mk = __ballot_sync(DLP_FULL, keep);
-          if (keep) {
-            int4 cj;
-            cj.x = (int)((unsigned)jj | (((infj.y >> 17) & 1) ? DLP_F_HALO : 0u));
-            cj.y = (int)s_kcp[((infj.y & 0xffff) - 1) & 7];   // lean loops: ntypes <= 5
-            cj.z = infj.x;
-            // (jj > ii || jj < s_own0) with ii = a0 + a  <=>  jrel > a
-            cj.w = jj < s_own0 ? 0x7fffffff : jj - a0;
-            const int q = (head + fill + __popc(mk & ltmask)) & 63;
-            ring_p[q] = pj; ring_c[q] = cj;
-          }
-          fill += __popc(mk);
-          __syncwarp();
-          if (fill < 32 && c0 + 32 < total) continue;          // wait for a full batch while there are candidates left
-        }
-        const int nb = min(32, fill);
-        double4 pj = make_double4(1e300, 1e300, 1e300, g.rcsq);   // lanes without a candidate sit at 1e300: never within the cutoff
-        int4 cj = make_int4(-1, 0, 0, -1);
-        if (lane < nb) { const int q = (head + lane) & 63; pj = ring_p[q]; cj = ring_c[q]; }
-        head = (head + nb) & 63; fill -= nb;
-        if (c0 >= total) c0 -= 32;                                // draining the ring: no new candidates
-        __syncwarp();
-        const unsigned jbits = (unsigned)cj.x;
-        const int2 infj = make_int2(cj.z, 0);
-        const int gid_j = (jbits & DLP_F_HALO) ? cj.z : 0;       // energy ownership: halo partner and idi < ltg(jatm); gids are >= 1
-        const unsigned kcp = (unsigned)cj.y;
-        const int jrel = cj.w;
-        const double rc_eff = pj.w;
+      // the passes of one staged batch: every atom of the cell against the lanes' candidates
+      auto passes = [&](const double4& pj, const unsigned jbits, const int2 infj, const int gid_j, const unsigned kcp, const int jrel,
+                        const double rc_eff) {
         for (int a = 0; a < na; ++a) {
           const double4 pi = s_pi[wid][a];
           const bool acc = pair_rsq(pj, pi.x, pi.y, pi.z) <= rc_eff && jrel > a;
@@ -699,6 +670,103 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
             else ovf = max(ovf, ll + 1);
           }
           if (lane == a) cnt += __popc(m);
+        }
+      };
+      if (RING) {
+        // Candidates are pruned while they are staged: a slot farther than the Verlet radius from the bounding box of the pass's
+        // atoms cannot be anybody's partner (the stencil's semi-volume is 62.5 cells, the semi-ball around a cell's atoms about
+        // half of that), and the survivors are compacted into a 64-entry ring in shared memory, from which the atoms take 32 at
+        // a time.  The test runs in single precision relative to the box centre with the box and the radius widened by far more
+        // than its rounding (coordinates within ~2 rx of the centre carry < 1e-5 A of fp32 error), so it never drops a slot whose
+        // squared distance to some atom is <= rcsq; order is kept, so the rows are the same rows.
+        const double4 pref = s_pi[wid][0];   // reference point of the single-precision box arithmetic
+        float bx0, bx1, by0, by1, bz0, bz1;
+        {
+          const double4 pb = s_pi[wid][min(lane, na - 1)];
+          bx0 = bx1 = (float)(pb.x - pref.x); by0 = by1 = (float)(pb.y - pref.y); bz0 = bz1 = (float)(pb.z - pref.z);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          bx0 = fminf(bx0, __shfl_xor_sync(DLP_FULL, bx0, d)); bx1 = fmaxf(bx1, __shfl_xor_sync(DLP_FULL, bx1, d));
+          by0 = fminf(by0, __shfl_xor_sync(DLP_FULL, by0, d)); by1 = fmaxf(by1, __shfl_xor_sync(DLP_FULL, by1, d));
+          bz0 = fminf(bz0, __shfl_xor_sync(DLP_FULL, bz0, d)); bz1 = fmaxf(bz1, __shfl_xor_sync(DLP_FULL, bz1, d));
+        }
+        const float bcx = 0.5f * (bx0 + bx1), bcy = 0.5f * (by0 + by1), bcz = 0.5f * (bz0 + bz1);
+        const float bhx = 0.5f * (bx1 - bx0) + 1.0e-4f, bhy = 0.5f * (by1 - by0) + 1.0e-4f, bhz = 0.5f * (bz1 - bz0) + 1.0e-4f;
+        const float rc_prune = prune ? (float)(g.rcsq * (1.0 + 1.0e-4) + 1.0e-3) : 3.0e38f;
+        double4* const ring_p = s_pj[wid];
+        int4* const ring_c = s_cj[wid];
+        int run = 0, head = 0, fill = 0;   // ring: `fill` staged candidates from `head`
+        for (int c0 = 0; c0 < total || fill > 0; c0 += 32) {
+          if (c0 < total) {   // stage up to 32 more candidates; a lane's candidates only move forward, so its run index does too
+            const int c = c0 + lane;
+            int jj = -1;
+            double4 pj = make_double4(0.0, 0.0, 0.0, g.rcsq);
+            int2 infj = make_int2(0, 0);
+            bool keep = false;
+            if (c < total) {
+              while (s_pre[wid][run + 1] <= c) ++run;          // pre[LC_MAXRUN] = total > c ends the walk
+              jj = s_run0[wid][run] + (c - s_pre[wid][run]);
+              pj = posq_s[jj]; infj = info_s[jj];
+              // nlp == 2: the only stencil entry with the "no distance check" flag is the cell itself (neighbours.F90:537, :922-943)
+              const bool own = jj >= s_own0 && jj < s_own1;
+              pj.w = (g.nir_r2 > 0 && own) ? 1e301 : g.rcsq;
+              const float dx = fmaxf(fabsf((float)(pj.x - pref.x) - bcx) - bhx, 0.0f), dy = fmaxf(fabsf((float)(pj.y - pref.y) - bcy) - bhy, 0.0f),
+                          dz = fmaxf(fabsf((float)(pj.z - pref.z) - bcz) - bhz, 0.0f);
+              keep = own || (dx * dx + dy * dy + dz * dz <= rc_prune);
+            }
+            const unsigned mk = __ballot_sync(DLP_FULL, keep);
+            if (keep) {
+              int4 cj;
+              cj.x = (int)((unsigned)jj | (((infj.y >> 17) & 1) ? DLP_F_HALO : 0u));
+              cj.y = (int)s_kcp[((infj.y & 0xffff) - 1) & 7];   // lean loops: ntypes <= 5
+              cj.z = infj.x;
+              // (jj > ii || jj < s_own0) with ii = a0 + a  <=>  jrel > a
+              cj.w = jj < s_own0 ? 0x7fffffff : jj - a0;
+              const int q = (head + fill + __popc(mk & ltmask)) & 63;
+              ring_p[q] = pj; ring_c[q] = cj;
+            }
+            fill += __popc(mk);
+            __syncwarp();
+            if (fill < 32 && c0 + 32 < total) continue;          // wait for a full batch while there are candidates left
+          }
+          const int nb = min(32, fill);
+          double4 pj = make_double4(1e300, 1e300, 1e300, g.rcsq);   // lanes without a candidate sit at 1e300: never within the cutoff
+          int4 cj = make_int4(-1, 0, 0, -1);
+          if (lane < nb) { const int q = (head + lane) & 63; pj = ring_p[q]; cj = ring_c[q]; }
+          head = (head + nb) & 63; fill -= nb;
+          if (c0 >= total) c0 -= 32;                                // draining the ring: no new candidates
+          __syncwarp();
+          const unsigned jbits = (unsigned)cj.x;
+          const int2 infj = make_int2(cj.z, 0);
+          const int gid_j = (jbits & DLP_F_HALO) ? cj.z : 0;       // energy ownership: halo partner and idi < ltg(jatm); gids are >= 1
+          const unsigned kcp = (unsigned)cj.y;
+          const int jrel = cj.w;
+          const double rc_eff = pj.w;
+          passes(pj, jbits, infj, gid_j, kcp, jrel, rc_eff);
+        }
+      } else {
+        // plain staging: 32 candidates at a time as the (trimmed) runs deliver them
+        int run = 0;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+          const int c = c0 + lane;
+          int jj = -1;
+          double4 pj = make_double4(1e300, 1e300, 1e300, 0);   // lanes without a candidate sit at 1e300: never within the cutoff
+          int2 infj = make_int2(0, 0);
+          if (c < total) {   // run of candidate c: the lane's candidates only move forward, so its run index does too
+            while (s_pre[wid][run + 1] <= c) ++run;          // pre[LC_MAXRUN] = total > c ends the walk
+            jj = s_run0[wid][run] + (c - s_pre[wid][run]);
+            pj = posq_s[jj]; infj = info_s[jj];
+          }
+          const bool halo_j = (infj.y >> 17) & 1;
+          const unsigned jbits = (unsigned)jj | (halo_j ? DLP_F_HALO : 0u);
+          const int gid_j = halo_j ? infj.x : 0;               // energy ownership: halo partner and idi < ltg(jatm); gids are >= 1
+          const unsigned kcp = jj >= 0 ? s_kcp[((infj.y & 0xffff) - 1) & 7] : 0u;
+          // (jj > ii || jj < s_own0) with ii = a0 + a  <=>  jrel > a
+          const int jrel = jj < 0 ? -1 : (jj < s_own0 ? 0x7fffffff : jj - a0);
+          // nlp == 2: the only stencil entry with the "no distance check" flag is the cell itself (neighbours.F90:537, :922-943)
+          const double rc_eff = (g.nir_r2 > 0 && jj >= s_own0 && jj < s_own1) ? 1e301 : g.rcsq;
+          passes(pj, jbits, infj, gid_j, kcp, jrel, rc_eff);
         }
       }
     } else
@@ -878,14 +946,25 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
         const int ncd = g.nlx * g.nly * g.nlz;
         const bool lean = ctx->megfrz <= 1 && g.nir_r2 <= 1 && ctx->ntypes <= 5;
         const bool simple = lean && !ctx->lbook;
+        // run trimming against the cells' bounding boxes; not with the nlp >= 3 shortcut (neighbours.F90:537 admits whole cells
+        // without a distance test, so a cell out of reach of the atoms' box may still have to be listed)
+        const int lk = ctx->list_one_atom_per_pass;   // dlpgpu_set_list_kernel: 0 trimmed runs (default), 1 untrimmed, 2 trimmed + per-candidate ring
+        const bool trim = lk != 1 && g.nir_r2 <= 1;
+        const float rc2_trim = (float)(g.rcsq * (1.0 + 1.0e-4) + 1.0e-3);
+        if (trim) {
+          CK(ctx->cell_box.ensure((size_t)8 * (g.ncells + 2), s));
+          LAUNCH(ctx, k_cell_boxes, cdiv(g.ncells + 1, 128), 128, 0, g.ncells, ctx->lct_start.p, ctx->posq_s.p, reinterpret_cast<float4*>(ctx->cell_box.p));
+        }
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
-               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel, ctx->list_one_atom_per_pass ? 0 : 1, \
-               ctx->fnbr.p, ctx->nfnbr.p, ctx->fpitch
-        if (simple) LAUNCH(ctx, k_list_cell<1>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else if (lean) LAUNCH(ctx, k_list_cell<2>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else { LAUNCH(ctx, k_list_cell<0>, cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS); ctx->frz_rows_valid = ctx->fpitch > 0; }
+               ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel, 1, \
+               ctx->fnbr.p, ctx->nfnbr.p, ctx->fpitch, trim ? reinterpret_cast<const float4*>(ctx->cell_box.p) : nullptr, rc2_trim
+        if (simple && lk == 2) LAUNCH(ctx, (k_list_cell<1, 1>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (simple) LAUNCH(ctx, (k_list_cell<1, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (lean && lk == 2) LAUNCH(ctx, (k_list_cell<2, 1>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (lean) LAUNCH(ctx, (k_list_cell<2, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else { LAUNCH(ctx, (k_list_cell<0, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS); ctx->frz_rows_valid = ctx->fpitch > 0; }
 #undef DLP_LC_ARGS
       } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
@@ -966,7 +1045,8 @@ int dlp_preload_cells() {   // see dlp_preload_halo
   const void* ks[] = {(const void*)k_cell_index, (const void*)k_cell_scatter, (const void*)k_cell0_flag, (const void*)k_cell0_place,
                       (const void*)k_cell_order, (const void*)k_sorted_static, (const void*)k_loc_slot, (const void*)k_gather_posq,
                       (const void*)k_list_ref, (const void*)k_row_partition, (const void*)k_list_dev<false>, (const void*)k_list_dev<true>,
-                      (const void*)k_list_cell<0>, (const void*)k_list_cell<1>, (const void*)k_list_cell<2>, (const void*)k_bg_copy,
+                      (const void*)k_list_cell<0, 0>, (const void*)k_list_cell<1, 0>, (const void*)k_list_cell<2, 0>, (const void*)k_list_cell<1, 1>,
+                      (const void*)k_list_cell<2, 1>, (const void*)k_cell_boxes, (const void*)k_bg_copy,
                       (const void*)k_count_pairs};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();

@@ -120,6 +120,7 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
+  DBuf<float> cell_box;               // {lo, hi} float4 per link cell: bounding boxes of the cells' atoms (k_cell_boxes)
   DBuf<unsigned> fnbr;                // frozen-frozen partners per row (kept for rdf_frzn_collect only), pitch fpitch
   DBuf<int> nfnbr;
   int fpitch = 0;

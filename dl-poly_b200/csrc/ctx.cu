@@ -174,7 +174,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
   dlp_spme_release(ctx);
-  ctx->fnbr.release(); ctx->nfnbr.release();
+  ctx->fnbr.release(); ctx->nfnbr.release(); ctx->cell_box.release();
   ctx->pp_pos.release(); ctx->pp_neg.release(); ctx->pp_energy.release(); ctx->pp_stress.release();
   ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
@@ -352,7 +352,7 @@ int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which) {
 }
 
 int dlpgpu_set_list_kernel(dlpgpu_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 1) return DLPGPU_ERR_ARG;
+  if (!ctx || which < 0 || which > 2) return DLPGPU_ERR_ARG;
   ctx->list_one_atom_per_pass = which;
   return 0;
 }

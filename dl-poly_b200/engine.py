@@ -102,7 +102,7 @@ class ShortRange:
         self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(which) if which is not None else int(bool(general_only))))
 
     def set_list_kernel(self, which):
-        """Diagnostic: 0 k_list_cell8 (default), 1 the one-atom-per-pass kernel, for the plain half-list case."""
+        """Diagnostic: 0 trimmed candidate runs (default), 1 untrimmed, 2 trimmed + per-candidate ring (see include/dlpgpu.h)."""
         self._ck(self.L.dlpgpu_set_list_kernel(self.h, int(which)))
 
     def set_spme(self, kdim, nsplines=8):

@@ -266,9 +266,9 @@ int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
 int dlpgpu_set_pair_kernel(dlpgpu_ctx* ctx, int which);
 /* which kernel the last two_body_forces call ran (1 general, 2 k_pair_v2; 0 none); *packed_table_error is reserved (0) */
 int dlpgpu_pair_kernel_used(dlpgpu_ctx* ctx, int* which, double* packed_table_error);
-/* Diagnostic: which kernel builds the device half list in the plain case (no exclusion lists, no frozen pairs, nlp < 3).
- * 0 (default): k_list_cell8 (8 atoms of a link cell x 4 candidates per warp pass); 1: k_list_cell<1> (one atom x 32 candidates
- * per pass).  Same rows either way (members and order); the parity tests compare them. */
+/* Diagnostic: how the warp-per-cell kernel builds the device half list.  0 (default): the x-runs of candidate cells are trimmed
+ * against the bounding boxes of the cells' atoms; 1: untrimmed runs; 2: trimmed runs plus a per-candidate prune with compaction
+ * into a shared-memory ring.  Same rows either way (members and order); the parity tests compare them. */
 int dlpgpu_set_list_kernel(dlpgpu_ctx* ctx, int which);
 
 #ifdef __cplusplus

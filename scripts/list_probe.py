@@ -11,7 +11,7 @@ sr = engine.ShortRange(0)
 sr.dev_setup_system(s)
 sr.dev_load_atoms(s.xyz, s.vel, np.arange(1, s.megatm + 1, dtype=np.int32), s.lsite)
 sr.dev_relocate_serial(); sr.dev_halo_serial()
-for which in (0, 1, 0, 1):
+for which in (0, 1, 2, 0, 1, 2):
     sr.set_list_kernel(which)
     ts, tk = [], []
     for rep in range(5):

@@ -597,24 +597,27 @@ def test_fast_pair_kernel_is_used_and_matches(name):
         assert abs(out[k] - outs[1][1][k]) <= ENERGY_TOL * max(abs(outs[1][1][k]), 1e-6 * np.abs(outs[1][1][:6]).max())
 
 
-@pytest.mark.parametrize("name", ["argon", "nacl", "ionic_mixture", "argon_triclinic"])
+@pytest.mark.parametrize("name", ["argon", "nacl", "ionic_mixture", "argon_triclinic", "water"])
 def test_list_kernels_build_the_same_rows(name):
-    """k_list_cell8 (8 atoms x 4 candidates per warp pass, the default in the plain case) against the one-atom-per-pass kernel:
-    identical device rows (length, members AND order) for every local atom."""
+    """The half-list kernel with its x-runs trimmed against the cells' bounding boxes (the default), untrimmed (1), and trimmed
+    with the per-candidate prune and the shared-memory ring on top (2): identical device rows (length, members AND order) for
+    every sampled local atom, and the same pair count."""
     s = {"argon": lambda: systems.argon(8), "nacl": lambda: systems.nacl(6, rcut=8.0, padding=0.2),
-         "ionic_mixture": lambda: systems.ionic_mixture(5), "argon_triclinic": lambda: systems.argon_triclinic(6)}[name]()
+         "ionic_mixture": lambda: systems.ionic_mixture(5), "argon_triclinic": lambda: systems.argon_triclinic(6),
+         "water": lambda: systems.spce_water(512, rcut=8.0, padding=0.2)}[name]()
     rows = []
-    for which in (0, 1):
+    for which in (0, 1, 2):
         sr = native_serial(s)
         sr.set_list_kernel(which)
         sr.dev_relocate_serial(); sr.dev_halo_serial(); sr.dev_link_cell_pairs()
         natms, _ = sr.dev_counts()
         rows.append((sr.dev_list_pairs(), [sr.dev_get_full_row(i) for i in range(1, natms + 1, max(1, natms // 300))]))
         sr.close()
-    assert rows[0][0] == rows[1][0] and rows[0][0] > 0
-    for ra, rb in zip(rows[0][1], rows[1][1]):
-        for xa, xb in zip(ra, rb):
-            assert np.array_equal(np.asarray(xa), np.asarray(xb))
+    assert rows[0][0] == rows[1][0] == rows[2][0] and rows[0][0] > 0
+    for other in (rows[1], rows[2]):
+        for ra, rb in zip(rows[0][1], other[1]):
+            for xa, xb in zip(ra, rb):
+                assert np.array_equal(np.asarray(xa), np.asarray(xb))
 
 
 @pytest.mark.parametrize("which,P", [("nacl", 1), ("nacl", 8), ("water", 1), ("nacl_frozen", 1), ("nacl_frozen", 8)])
