@@ -910,7 +910,11 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   }
   ctx->list_natms = natms; ctx->list_nlast = nlast;
   // device-internal lists
-  ctx->pitch = ((ctx->max_list + 31) / 32) * 32 + DLP_ROW_PAD;   // room for the sentinel padding (see dlp_pad_row)
+  // room for the sentinel padding (see dlp_pad_row).  Full-list mode keeps every local-local pair in BOTH rows, so a row can be
+  // twice as long as the reference's half row that neigh%max_list was sized for (error 106 stays the reference's: it is raised by
+  // the reference-format list, k_list_ref, against max_list itself)
+  const int row_cap = ctx->force_mode == 0 ? 2 * ctx->max_list : ctx->max_list;
+  ctx->pitch = ((row_cap + 31) / 32) * 32 + DLP_ROW_PAD;
   const unsigned sentinel = (unsigned)nlast | DLP_F_HALO;   // slot nlast of posq_s: a chargeless point 1e15 A away
   ctx->xpitch = ctx->lbook ? ((ctx->max_exclude + 31) / 32) * 32 : 0;
   const int wpb = 8;   // warps per block

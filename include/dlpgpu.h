@@ -256,6 +256,10 @@ int dlpgpu_fp64_peak(dlpgpu_ctx* ctx, double seconds, double* tflops);
 /* device time (ms, CUDA events on the context's stream) of the last list build and the last force evaluation,
  * and of their dominant kernels: t[0]=list total, t[1]=force total, t[2]=pair-force kernel, t[3]=full-list kernel */
 int dlpgpu_last_timings(dlpgpu_ctx* ctx, double t[4]);
+/* Two notes on the tabulated fast path (k_pair_v2): a pair closer than ONE grid step of the interpolation tables (r < rcut / (mxgrid - 4),
+ * ~0.01 A) is evaluated in the first full interval (l clamped to 1) where the reference would read its Huge(1.0) / r-scaled entry 0;
+ * no physical configuration reaches it, and the general kernel (dlpgpu_set_pair_kernel(ctx, 1)) follows the reference there.
+ * And: in full-list mode the device rows hold up to 2 max_list partners (each local-local pair sits in both rows). */
 /* 1 (default, common.cuh force_mode): half list + fp64 RED atomics (Newton's third law) -- the reference's own pair count.
  * 0: full list without atomics (every local-local pair evaluated from both ends; bitwise reproducible forces). */
 int dlpgpu_set_force_mode(dlpgpu_ctx* ctx, int mode);
