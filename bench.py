@@ -360,6 +360,38 @@ def sub_run(torch, dd, transport, local, world, workload, strong, dt, steps, war
             "flop_per_atom_step": roof["flop_per_atom_step"], "gpu_launches": res["launches"]}
 
 
+def spme_sub_run(torch, local, workload, cells, calls=10, warmup=3):
+    """SURVEY section 8f row 4 (beyond the north star's path, first version): the SPME reciprocal-space call of the same melt on ONE
+    domain, timed with CUDA events on the library's stream next to the short-range numbers.  Grid and alpha as control.F90:1707-1713
+    derives them from spme_precision 1e-6, B-spline order 8."""
+    import _pkg
+    _pkg.load()
+    from dl_poly_b200 import engine, tables
+    sysm = make_system(workload, (1, 1, 1), cells)
+    if not sysm.ff.ew_active:
+        return None
+    _, kdim = tables.spme_grid(1.0e-6, sysm.rcut, sysm.cell)
+    sr = engine.ShortRange(local)
+    sr.dev_setup_system(sysm)
+    sr.dev_load_atoms(sysm.xyz, sysm.vel, np.arange(1, sysm.megatm + 1, dtype=np.int32), sysm.lsite)
+    sr.set_spme(kdim, 8)
+    for _ in range(warmup):
+        out = sr.dev_spme_forces(sysm.megatm)
+    stream = torch.cuda.ExternalStream(sr.stream(), device=torch.device("cuda", local))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(calls):
+        out = sr.dev_spme_forces(sysm.megatm)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / calls
+    sr.close()
+    return {"what": "ewald_spme_forces_coul on one domain (spread, cuFFT Z2Z, influence function + stress, gather); not part of `value`",
+            "atoms": sysm.megatm, "grid": list(kdim), "bspline_order": 8, "ms_per_call": ms, "calls": calls,
+            "engcpe_rc": float(out[0]), "vircpe_rc": float(out[1])}
+
+
 def parity_report(torch, dd, transport, local, world, rank):
     """Always-on pre-flight: the CUDA path against the oracle's P-domain world BEFORE anything is timed (the oracle is the
     checker here, never the thing measured).  N > 1: tests/dd_common.check_rank on a small NaCl melt and an SPC/E box through
@@ -475,6 +507,13 @@ def run_gpu(args):
         ksteps = max(10, min(args.steps, 40))
         extra["strong"] = sub_run(torch, dd, transport, local, world, "ionic", True, dt, ksteps, 3, fp64_peak)
         extra["lj"] = sub_run(torch, dd, transport, local, world, "lj", False, dt, max(20, min(args.steps, 100)), 3, fp64_peak)
+        if world == 1:
+            try:
+                spme = spme_sub_run(torch, local, args.workload, args.cells_per_gpu)
+                if spme is not None:
+                    extra["spme"] = spme
+            except Exception as e:          # cuFFT missing on the box: the short-range line stands on its own
+                extra["spme"] = {"unavailable": repr(e)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -576,6 +576,28 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
   return 0;
 }
 
+// ewald_spme_forces_coul with the caller's corePart array (one domain): parts(1:natms) go up, the reciprocal forces are ADDED
+// to parts%f on the device and the records come back; out as for dlpgpu_dev_spme_forces
+int dlpgpu_spme_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts, int megatm, double out[16]) {
+  if (!ctx || !parts || !out || natms < 0 || megatm < 1) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CKRC(dlp_ensure_atoms(ctx, natms + 16));
+  CKRC(upload_parts(ctx, natms, parts));
+  const int keep_n = ctx->natms, keep_l = ctx->nlast;
+  ctx->natms = natms;
+  if (natms > 0) LAUNCH(ctx, k_zero3, cdiv(natms, 256), 256, 0, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
+  const int rc = dlpgpu_dev_spme_forces(ctx, megatm, out);
+  ctx->natms = keep_n; ctx->nlast = keep_l;
+  if (rc) return rc;
+  if (natms > 0) {
+    LAUNCH(ctx, k_add_forces, cdiv(natms, 256), 256, 0, ctx->parts_dev.p, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
+    CK(cudaMemcpyAsync(parts, ctx->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->list_valid = false;   // the device force / position arrays were reused: the next short-range call starts from link_cell_pairs
+  return 0;
+}
+
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx) {
   if (!ctx) return DLPGPU_ERR_ARG;
   if (!ctx->list_valid || ctx->parts_resident < ctx->list_nlast)

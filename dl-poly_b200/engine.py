@@ -116,6 +116,13 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_spme_forces(self.h, int(megatm), ptr(out)))
         return out
 
+    def spme_forces(self, natms, parts, megatm):
+        """Drop-in form: parts (host corePart array) up, reciprocal forces added to parts%f, records back; returns out[16]."""
+        assert parts.dtype == COREPART and parts.flags.c_contiguous
+        out = np.zeros(16)
+        self._ck(self.L.dlpgpu_spme_forces(self.h, int(natms), ptr(parts), int(megatm), ptr(out)))
+        return out
+
     def set_collect_pp(self, on=True):
         """stats%collect_pp: force calls also book per-particle energy / stress (see include/dlpgpu.h)."""
         self._ck(self.L.dlpgpu_set_collect_pp(self.h, int(on)))

@@ -88,6 +88,7 @@ SIGNATURES = {
     "dlpgpu_set_list_kernel": (ci, [vp, ci]),
     "dlpgpu_set_spme": (ci, [vp, vp, ci]),
     "dlpgpu_dev_spme_forces": (ci, [vp, ci, vp]),
+    "dlpgpu_spme_forces": (ci, [vp, ci, vp, ci, vp]),
     "dlpgpu_set_collect_pp": (ci, [vp, ci]),
     "dlpgpu_get_pp": (ci, [vp, ci, vp, vp]),
     "dlpgpu_pair_kernel_used": (ci, [vp, pi_, pd_]),

@@ -131,6 +131,21 @@ Module dlp_gpu_binding
       Type(c_ptr), Value    :: rdf_list, rdf
       Integer(c_int)        :: rc
     End Function
+    Function dlpgpu_set_spme(ctx, kdim, nsplines) Bind(C, name='dlpgpu_set_spme') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int)        :: kdim(3)
+      Integer(c_int), Value :: nsplines
+      Integer(c_int)        :: rc
+    End Function
+    Function dlpgpu_spme_forces(ctx, natms, parts, megatm, out) Bind(C, name='dlpgpu_spme_forces') Result(rc)
+      Import :: c_ptr, c_int, c_double
+      Type(c_ptr), Value          :: ctx
+      Integer(c_int), Value       :: natms, megatm
+      Type(c_ptr), Value          :: parts
+      Real(c_double), Intent(Out) :: out(16)
+      Integer(c_int)              :: rc
+    End Function
     Function dlpgpu_set_collect_pp(ctx, on) Bind(C, name='dlpgpu_set_collect_pp') Result(rc)
       Import :: c_ptr, c_int
       Type(c_ptr), Value    :: ctx
@@ -347,6 +362,29 @@ Contains
       Call check(dlpgpu_get_pp(ctx, Int(config%natms, c_int), c_loc(stats%pp_energy), c_loc(stats%pp_stress)), 'get_pp')
     End If
   End Subroutine two_body_pairs_gpu
+
+  Subroutine ewald_spme_forces_gpu(ewld, config, stats, engcpe_rc, vircpe_rc)
+    !! one-domain counterpart of ewald_spme_forces_coul (ewald_spole.F90:244-477; call site two_body.F90:298-302): reciprocal forces
+    !! are ADDED into config%parts(1:natms)%f, the stress contributions into stats%stress.  comm%mxnode == 1 only; call it before
+    !! link_cell_pairs_gpu of the step (it reuses the device atom arrays).
+    Type(ewald_type),         Intent(In   )         :: ewld
+    Type(configuration_type), Intent(InOut), Target :: config
+    Type(stats_type),         Intent(InOut)         :: stats
+    Real(Kind=wp),            Intent(  Out)         :: engcpe_rc, vircpe_rc
+
+    Real(c_double), Save :: out(16)
+    Logical,        Save :: grid_set = .false.
+    Integer(c_int)       :: kdim(3)
+
+    If (.not. grid_set) Then
+      kdim = Int(ewld%kspace%k_vec_dim, c_int)
+      Call check(dlpgpu_set_spme(ctx, kdim, Int(ewld%bspline%num_splines, c_int)), 'set_spme')
+      grid_set = .true.
+    End If
+    Call check(dlpgpu_spme_forces(ctx, Int(config%natms, c_int), c_loc(config%parts), Int(config%megatm, c_int), out), 'spme_forces')
+    engcpe_rc = out(1); vircpe_rc = out(2)
+    stats%stress(1:9) = stats%stress(1:9) + out(3:11)
+  End Subroutine ewald_spme_forces_gpu
 
   Subroutine rdf_collect_gpu(ntpatm, rdf)
     !! replaces the per-atom Call rdf_collect / rdf_excl_collect inside two_body_forces (two_body.F90:523, :581) on steps with

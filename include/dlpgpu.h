@@ -127,6 +127,10 @@ int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
  * stats%stress(1:9), out[11] = the reciprocal energy alone, out[12] = the self interaction.  megatm = atoms in the system. */
 int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines);
 int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]);
+/* the same with the caller's corePart array (drop-in for the call at two_body.F90:298-302 when comm%mxnode == 1): parts(1:natms) are
+ * uploaded, the reciprocal forces ADDED to parts(1:natms)%f, the records copied back.  It reuses the device atom arrays, so the
+ * neighbour list held by the context is invalidated: call it BEFORE dlpgpu_link_cell_pairs of the step, or from a context of its own. */
+int dlpgpu_spme_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts, int megatm, double out[16]);
 /* stats%collect_pp (statistics.F90:227, set by the per-particle / heat-flux options): while on, two_body_forces (drop-in and
  * dev_) also books, for every pair, half of its energy and half of its stress tensor r (x) f on each LOCAL partner, following
  * the reference path by path -- vdw_forces_direct (vdw.F90:1707, :1741-1755: the pair energy for every pair),

@@ -762,3 +762,29 @@ def test_spme_reciprocal_space_against_oracle(name, nspl):
     f2 = parts_forces(sr.dev_get_parts(), s.megatm)
     assert np.abs(f2 - 2.0 * f).max() <= 1e-12 * np.abs(f).max()
     sr.close()
+
+
+def test_spme_dropin_adds_into_the_callers_records():
+    """dlpgpu_spme_forces (host corePart array): the reciprocal forces are ADDED to what parts%f holds, positions and charges
+    come back untouched, the sums equal the device-resident call's."""
+    from oracle import spme_oracle as so
+    s = systems.nacl(4, rcut=8.0, padding=0.2)
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]
+    q = s.charge_site[s.lsite - 1]
+    _, kdim = so.spme_grid(1.0e-6, s.rcut, s.cell)
+    ref = so.ewald_spme_forces_coul(s.cell, xyz, q, s.ff.alpha, kdim, 8, s.ff.scaling)
+    parts = np.zeros(s.megatm, dtype=COREPART)
+    parts["xxx"], parts["yyy"], parts["zzz"], parts["chge"] = xyz[:, 0], xyz[:, 1], xyz[:, 2], q
+    rng = np.random.default_rng(2)
+    f0 = rng.standard_normal((s.megatm, 3)) * 1.0e3
+    parts["fxx"], parts["fyy"], parts["fzz"] = f0[:, 0], f0[:, 1], f0[:, 2]
+    before = parts.copy()
+    sr = make_sr(s)
+    sr.set_spme(kdim, 8)
+    out = sr.spme_forces(s.megatm, parts, s.megatm)
+    f = parts_forces(parts, s.megatm) - f0
+    assert per_atom_force_error(f, ref["forces"])["max_normalised"] <= FORCE_TOL
+    assert abs(out[0] - ref["engcpe_rc"]) <= 1e-10 * abs(ref["engcpe_rc"]) and abs(out[1] - ref["vircpe_rc"]) <= 1e-10 * abs(ref["vircpe_rc"])
+    for k in ("xxx", "yyy", "zzz", "chge"):
+        assert np.array_equal(parts[k], before[k])
+    sr.close()
