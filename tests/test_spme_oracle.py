@@ -86,3 +86,23 @@ def test_host_grid_selection_agrees_with_the_oracle():
         prec = 10.0 ** rng.uniform(-8, -4); rcut = rng.uniform(6.0, 14.0)
         dims = tuple(int(x) for x in rng.choice([1, 2, 3, 4], 3))
         assert tables.spme_grid(prec, rcut, cell, dims) == so.spme_grid(prec, rcut, cell, dims)
+
+
+@pytest.mark.parametrize("name", ["spme_nacl_512_order8", "spme_water_1536_order6"])
+def test_golden_spme_fixture(name):
+    """tests/golden/spme_*.json (tests/golden/make_golden_spme.py) freeze the restatement's answers."""
+    import json, os
+    from dl_poly_b200 import dd
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
+    s = getattr(systems, g["generator"])(**g["kwargs"])
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]
+    q = s.charge_site[s.lsite - 1]
+    alpha, kdim = so.spme_grid(1.0e-6, s.rcut, s.cell)
+    assert alpha == g["alpha"] and list(kdim) == g["kdim"]
+    r = so.ewald_spme_forces_coul(s.cell, xyz, q, alpha, kdim, g["nspl"], s.ff.scaling)
+    for k in ("engcpe_rc", "vircpe_rc", "eng_recip"):
+        assert abs(r[k] - g[k]) <= 1e-12 * abs(g[k]), k
+    assert np.abs(r["stress"] - np.array(g["stress"])).max() <= 1e-12 * np.abs(g["stress"]).max()
+    assert abs(np.abs(r["forces"]).sum() - g["force_l1"]) <= 1e-11 * g["force_l1"]
+    assert np.abs(r["forces"][0] - np.array(g["force_first"])).max() <= 1e-10 * np.abs(r["forces"]).max()
+    assert np.abs(r["forces"][-1] - np.array(g["force_last"])).max() <= 1e-10 * np.abs(r["forces"]).max()
