@@ -505,48 +505,65 @@ template <int HALO>
 __global__ void __launch_bounds__(XB_T)
 k_x_pack(int* __restrict__ dc, Dir d, int cap, int q, const int* __restrict__ blocksum, XAtoms A, int wrap_add, double* __restrict__ buf,
          int* __restrict__ idx_or_hole, int* __restrict__ leave, int* __restrict__ lpos, XHdr* dst_hdr, unsigned long long seq) {
-  __shared__ int s_w[XB_T / 32];
+  __shared__ int s_w[XB_T / 32], s_w2[XB_T / 32];
   __shared__ int s_last;
   const int n = HALO ? dc[DC_NLAST] : dc[DC_NATMS];
-  // atoms selected in the blocks before this one, and in all blocks
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // this thread's XB_A CONSECUTIVE atoms (one pass, one scan: the packed position of an atom = selected atoms before it --
+  // blocks before, warps before, lanes before, the thread's own earlier atoms)
+  const int i0 = blockIdx.x * XB_N + threadIdx.x * XB_A;
+  int code[XB_A];
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) {
+    const int i = i0 + j;
+    code[j] = 0;
+    if (i < n) code[j] = HALO ? halo_sel(A.ixyz[i], d) : reloc_sel(A.ixyz[i], d);
+    mine += code[j] != 0;
+  }
+  // atoms selected in the blocks before this one, and in all blocks (one pair of block reductions)
   int before = 0, all = 0;
   for (int k = threadIdx.x; k < gridDim.x; k += XB_T) { const int v = blocksum[k]; all += v; if (k < blockIdx.x) before += v; }
-  before = x_block_sum(before, s_w);
-  const int total = x_block_sum(all, s_w);
-  const int k_stay = n - total;
-  // XB_A passes over XB_T consecutive atoms each (adjacent threads = adjacent atoms = adjacent buffer records); the packed
-  // position of an atom = selected atoms before it: blocks before, passes before, warps before, lanes before
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int run = before;
-  for (int j = 0; j < XB_A; ++j) {
-    const int i = blockIdx.x * XB_N + j * XB_T + threadIdx.x;
-    int code = 0;
-    if (i < n) code = HALO ? halo_sel(A.ixyz[i], d) : reloc_sel(A.ixyz[i], d);
-    const unsigned m = __ballot_sync(DLP_FULL, code != 0);
-    __syncthreads();
-    if (lane == 0) s_w[w] = __popc(m);
-    __syncthreads();
-    int wbase = 0, tot_j = 0;
+  int incl = mine;   // inclusive scan of `mine` over the warp
 #pragma unroll
-    for (int k = 0; k < XB_T / 32; ++k) { const int v = s_w[k]; tot_j += v; if (k < w) wbase += v; }
-    const int k = run + wbase + __popc(m & ((1u << lane) - 1u));
-    run += tot_j;
-    if (i >= n) continue;
-    if (!HALO) { leave[i] = code ? 1 : 0; lpos[i] = k; }   // what the restack reads
-    if (!code || k >= cap) continue;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(DLP_FULL, incl, o); if (lane >= o) incl += v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(DLP_FULL, before, o); all += __shfl_xor_sync(DLP_FULL, all, o); }
+  if (lane == 31) s_w[w] = incl;                 // the warp's selected atoms
+  if (lane == 0) s_w2[w] = before;
+  __syncthreads();
+  int wbase = 0, before_blocks = 0;
+#pragma unroll
+  for (int k = 0; k < XB_T / 32; ++k) { if (k < w) wbase += s_w[k]; before_blocks += s_w2[k]; }
+  __syncthreads();
+  if (lane == 0) s_w[w] = all;
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < XB_T / 32; ++k) total += s_w[k];
+  const int k_stay = n - total;
+  int k = before_blocks + wbase + incl - mine;   // packed position of this thread's first selected atom
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) {
+    const int i = i0 + j;
+    if (i >= n) break;
+    const int kk = k;
+    if (code[j]) ++k;
+    if (!HALO) { leave[i] = code[j] ? 1 : 0; lpos[i] = kk; }   // what the restack reads
+    if (!code[j] || kk >= cap) continue;
     const double4 p = A.posq[i];
     if (HALO) {
-      idx_or_hole[k] = i;
-      double* b = buf + (size_t)k * DLP_HALO_W;
+      idx_or_hole[kk] = i;
+      double* b = buf + (size_t)kk * DLP_HALO_W;
       b[6] = (double)A.org_rank[i]; b[7] = (double)A.org_idx[i]; b[8] = (double)(A.org_wrap[i] + wrap_add);
       if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
       else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:1836-1844
       b[3] = (double)A.ltg[i];
       b[4] = (double)A.lsite[i];
-      b[5] = (double)(A.ixyz[i] - (code == 1 ? d.jxyz : d.kxyz));              // :1853
+      b[5] = (double)(A.ixyz[i] - (code[j] == 1 ? d.jxyz : d.kxyz));           // :1853
     } else {
-      if (i < k_stay) idx_or_hole[k] = i;       // holes below the new natms are the first ones (ascending)
-      double* b = buf + (size_t)k * 12;
+      if (i < k_stay) idx_or_hole[kk] = i;      // holes below the new natms are the first ones (ascending)
+      double* b = buf + (size_t)kk * 12;
       if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
       else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
       b[3] = A.vx[i]; b[4] = A.vy[i]; b[5] = A.vz[i];
