@@ -293,6 +293,7 @@ def timed_trajectory(torch, dom, transport, dt, steps, warmup, sampler_rank0=Non
     res = {"ms": ms, "launches": sr.launch_count() - l0, "out": out,
            "pair_ms": dom.acc["pair_ms"] - acc0["pair_ms"], "force_ms": dom.acc["force_ms"] - acc0["force_ms"],
            "list_ms": dom.acc["list_ms"] - acc0["list_ms"], "list_builds": dom.acc["list_builds"] - acc0["list_builds"],
+           "xchg_ms": dom.acc["xchg_ms"] - acc0["xchg_ms"],
            "rebuilds": dom.rebuilds}
     natms, nlast = sr.dev_counts()
     res["natms"], res["nlast"], res["pairs"] = natms, nlast, sr.dev_list_pairs()
@@ -300,6 +301,7 @@ def timed_trajectory(torch, dom, transport, dt, steps, warmup, sampler_rank0=Non
     if transport is not None:
         res["ms"] = transport.allreduce_max(ms)
         tot = transport.allreduce_sum([natms, res["launches"], res["pairs"], res["pair_ms"], res["rebuilds"], res["list_ms"], res["force_ms"]])
+        res["xchg_ms"] = transport.allreduce_max(res["xchg_ms"])
         res["natoms_total"], res["launches"], res["pairs"] = int(round(tot[0])), int(round(tot[1])), tot[2]
         res["pair_ms_avg"] = tot[3] / world / steps
         res["rebuilds"] = int(round(tot[4] / world))
@@ -535,6 +537,7 @@ def run_gpu(args):
                        "rebuilds_in_timed_region": res["rebuilds"],
                        "forced_rebuild_every": args.rebuild_every or None,
                        "list_build_ms_total": res["list_ms"], "force_call_ms_total": res["force_ms"],
+                       "exchange_ms_total": res["xchg_ms"],
                        "reduction": "gsum of the 16 energy / virial / stress sums inside every timed step: the partial sums ride on the "
                                     "gmax mailbox message of the next step (peer memory, rank-ordered sum); the last step's by all-reduce",
                        "l2": "inputs larger than L2: positions+list of one step are %.0f MB per GPU" % (bytes_per_launch / 1e6),

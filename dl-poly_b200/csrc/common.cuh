@@ -213,6 +213,10 @@ struct dlpgpu_ctx {
   DBuf<int> nhnbr;
   DBuf<double> xfer;       // internal exchange buffer of the serial halo / refresh
   DBuf<int> hole_pos;
+  cudaEvent_t ev_x[2] = {nullptr, nullptr};   // around the kernels of the last dlpgpu_dev_xchg_rebuild
+  double t_xchg = 0.0;
+  DBuf<int> movers;                   // ascending indices of the atoms with a non-zero relocation tag (k_x_reloc_stage)
+  int xchg_scan_migration = 0;        // dlpgpu_dev_xchg_set_migration: 1 = the scanning migration stages (diagnostic)
   DBuf<int> status;        // [8] device status words: 0 overflow flag, 1 ibig, 2 lost atoms, 3 spare
   DBuf<unsigned long long> cnt64;   // [4] 0: entries of the device list
   long long list_entries = 0;

@@ -174,7 +174,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
   dlp_spme_release(ctx);
-  ctx->fnbr.release(); ctx->nfnbr.release(); ctx->cell_box.release();
+  ctx->fnbr.release(); ctx->nfnbr.release(); ctx->cell_box.release(); ctx->movers.release();
   ctx->pp_pos.release(); ctx->pp_neg.release(); ctx->pp_energy.release(); ctx->pp_stress.release();
   ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
   ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
@@ -193,6 +193,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
+  for (int i = 0; i < 2; ++i) if (ctx->ev_x[i]) cudaEventDestroy(ctx->ev_x[i]);
   if (ctx->out_pinned) cudaFreeHost(ctx->out_pinned);
   if (ctx->gm_pinned) cudaFreeHost(ctx->gm_pinned);
   cudaStreamDestroy(ctx->stream);

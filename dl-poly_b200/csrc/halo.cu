@@ -734,6 +734,184 @@ __global__ void k_x_gmax(int rank, int nranks, unsigned long long seq, const uns
   }
 }
 
+// ---------------------------------------------------------------- migration over the compact list of movers
+// A rebuild moves a few hundred of a million atoms across the domain faces, and the six stages of deport_atomic_data each
+// scanned every atom for them (count + pack + restack + receive: 24 launches, ~0.2 ms of launch latency).  Here the atoms with a
+// non-zero relocation tag are compacted ONCE into an ascending index list M, and every stage is ONE single-block kernel over M:
+// select (deport_data.F90:254-274), pack in ascending order into the receiver's buffer (:290-325), restack the tail into the
+// holes (:822-925), publish, re-filter M (an atom that moved into a hole brings its tag along), wait for this rank's own
+// message, append the received atoms (:927-960) and the movers among them.  Same buffers, order, counts and error flags as the
+// scanning kernels, which is what the multi-rank parity tests hold it to.
+#define DC_NMOV 7
+#define XM_T 1024
+__device__ __forceinline__ int xm_block_excl_scan(int v, int* s_w, int* total) {   // exclusive scan over the block + block total
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(DLP_FULL, incl, o); if (lane >= o) incl += u; }
+  __syncthreads();
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < XM_T / 32; ++k) { const int u = s_w[k]; tot += u; if (k < w) base += u; }
+  *total = tot;
+  return base + incl - v;
+}
+// movers of the domain, ascending: per-block counts (k_x_mov_count), then the indices (k_x_mov_pack, the scan of k_x_pack)
+__global__ void __launch_bounds__(XB_T) k_x_mov_count(const int* __restrict__ dc, const int* __restrict__ ixyz, int* __restrict__ blocksum) {
+  __shared__ int s_w[XB_T / 32];
+  const int n = dc[DC_NATMS];
+  const int i0 = blockIdx.x * XB_N + threadIdx.x * XB_A;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) if (i0 + j < n) c += ixyz[i0 + j] != 0;
+  const int t = x_block_sum(c, s_w);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(XB_T)
+k_x_mov_pack(int* __restrict__ dc, int capM, const int* __restrict__ blocksum, const int* __restrict__ ixyz, int* __restrict__ M) {
+  __shared__ int s_w[XB_T / 32], s_w2[XB_T / 32];
+  const int n = dc[DC_NATMS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * XB_N + threadIdx.x * XB_A;
+  int f[XB_A], mine = 0;
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) { f[j] = (i0 + j < n) && ixyz[i0 + j] != 0; mine += f[j]; }
+  int before = 0, all = 0;
+  for (int k = threadIdx.x; k < gridDim.x; k += XB_T) { const int v = blocksum[k]; all += v; if (k < blockIdx.x) before += v; }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(DLP_FULL, incl, o); if (lane >= o) incl += v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(DLP_FULL, before, o); all += __shfl_xor_sync(DLP_FULL, all, o); }
+  if (lane == 31) s_w[w] = incl;
+  if (lane == 0) s_w2[w] = before;
+  __syncthreads();
+  int wbase = 0, bb = 0;
+#pragma unroll
+  for (int k = 0; k < XB_T / 32; ++k) { if (k < w) wbase += s_w[k]; bb += s_w2[k]; }
+  __syncthreads();
+  if (lane == 0) s_w[w] = all;
+  __syncthreads();
+  int k = bb + wbase + incl - mine;
+#pragma unroll
+  for (int j = 0; j < XB_A; ++j) if (f[j]) { if (k < capM) M[k] = i0 + j; ++k; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int total = 0;
+    for (int q = 0; q < XB_T / 32; ++q) total += s_w[q];
+    if (total > capM) { atomicOr(&dc[DC_ERR], 1); total = capM; }   // more movers than the migration buffers of all stages hold
+    dc[DC_NMOV] = total;
+  }
+}
+__device__ __forceinline__ void xm_move_atom(const XAtoms& A, int dst, int src) {
+  A.posq[dst] = A.posq[src];
+  A.vx[dst] = A.vx[src]; A.vy[dst] = A.vy[src]; A.vz[dst] = A.vz[src];
+  A.fx[dst] = A.fx[src]; A.fy[dst] = A.fy[src]; A.fz[dst] = A.fz[src];
+  A.ltg[dst] = A.ltg[src]; A.lsite[dst] = A.lsite[src]; A.ixyz[dst] = A.ixyz[src];
+}
+__global__ void __launch_bounds__(XM_T)
+k_x_reloc_stage(int* __restrict__ dc, Dir d, int cap, int q, int* __restrict__ M, int capM, int* __restrict__ S, XAtoms A,
+                double* __restrict__ buf_dst, XHdr* hdr_dst, const XHdr* __restrict__ hdr_me, const double* __restrict__ buf_me, int capacity,
+                unsigned long long seq) {
+  __shared__ int s_w[XM_T / 32];
+  __shared__ int s_count;
+  const int tid = threadIdx.x;
+  const int n = dc[DC_NATMS], nm = dc[DC_NMOV];
+  // ---- 1. the movers that leave in this direction, ascending: S[k]
+  int total = 0;
+  for (int base = 0; base < nm; base += XM_T) {
+    const int e = base + tid;
+    const int i = e < nm ? M[e] : -1;
+    const int sel = (i >= 0 && i < n) ? reloc_sel(A.ixyz[i], d) : 0;
+    int chunk;
+    const int pos = total + xm_block_excl_scan(sel, s_w, &chunk);
+    if (sel && pos < cap) S[pos] = i;
+    total += chunk;
+  }
+  __syncthreads();
+  const bool fits = total <= cap;
+  const int sent = fits ? total : cap;
+  const int k_stay = n - total;
+  // ---- 2. pack (the tag loses this direction, :325)
+  for (int k = tid; k < sent; k += XM_T) {
+    const int i = S[k];
+    const double4 p = A.posq[i];
+    double* b = buf_dst + (size_t)k * 12;
+    if (!d.lwrap) { b[0] = p.x; b[1] = p.y; b[2] = p.z; }
+    else { b[0] = p.x + d.xadd; b[1] = p.y + d.yadd; b[2] = p.z + d.zadd; }   // deport_data.F90:296-305
+    b[3] = A.vx[i]; b[4] = A.vy[i]; b[5] = A.vz[i];
+    b[6] = A.fx[i]; b[7] = A.fy[i]; b[8] = A.fz[i];
+    b[9] = (double)A.ltg[i]; b[10] = (double)A.lsite[i]; b[11] = (double)(A.ixyz[i] - d.jxyz);
+  }
+  __syncthreads();
+  // ---- 3. restack (:822-925): the r-th hole (ascending; holes = the leavers below the new natms = a prefix of S) takes the r-th
+  // staying atom counted from the end.  Sources sit at or above k_stay, holes below it.
+  if (fits) {
+    for (int j = k_stay + tid; j < n; j += XM_T) {
+      int lo = 0, hi = total;                     // leavers before j
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (S[mid] < j) lo = mid + 1; else hi = mid; }
+      if (lo < total && S[lo] == j) continue;     // j itself leaves
+      const int r = k_stay - 1 - (j - lo);
+      xm_move_atom(A, S[r], j);
+    }
+  }
+  __syncthreads();
+  // ---- 4. publish to the receiver, settle the local counts
+  if (tid == 0) {
+    if (!fits) atomicOr(&dc[DC_ERR], 1);
+    dc[DC_RSENT + q] = sent;
+    __threadfence_system();
+    hdr_dst->count = sent;
+    __threadfence_system();
+    st_release_sys(&hdr_dst->seq, seq);
+  }
+  const int nat1 = fits ? k_stay : n;
+  // ---- 5. the movers that are still here (a hole may have received one), ascending, compacted in place
+  int nm2 = 0;
+  for (int base = 0; base < nm; base += XM_T) {
+    const int e = base + tid;
+    const int i = e < nm ? M[e] : -1;
+    const int keep = (i >= 0 && i < nat1 && A.ixyz[i] != 0) ? 1 : 0;
+    int chunk;
+    const int pos = nm2 + xm_block_excl_scan(keep, s_w, &chunk);   // the scan's barriers separate this chunk's reads from its writes
+    if (keep) M[pos] = i;
+    nm2 += chunk;
+  }
+  __syncthreads();
+  // ---- 6. this rank's own message for the stage
+  if (tid == 0) s_count = x_wait(&hdr_me->seq, seq, &dc[DC_ERR]) ? (int)hdr_me->count : 0;
+  __syncthreads();
+  int count = s_count;
+  const bool room = nat1 + count <= capacity;
+  if (!room) count = max(capacity - nat1, 0);
+  for (int base = 0; base < count; base += XM_T) {
+    const int k = base + tid;
+    int mover = 0, i = -1;
+    if (k < count) {
+      i = nat1 + k;
+      const double* b = buf_me + (size_t)k * 12;
+      A.posq[i] = make_double4(__ldcg(b), __ldcg(b + 1), __ldcg(b + 2), 0.0);
+      A.vx[i] = __ldcg(b + 3); A.vy[i] = __ldcg(b + 4); A.vz[i] = __ldcg(b + 5);
+      A.fx[i] = __ldcg(b + 6); A.fy[i] = __ldcg(b + 7); A.fz[i] = __ldcg(b + 8);
+      const int tag = __double2int_rn(__ldcg(b + 11));
+      A.ltg[i] = __double2int_rn(__ldcg(b + 9)); A.lsite[i] = __double2int_rn(__ldcg(b + 10)); A.ixyz[i] = tag;
+      mover = tag != 0;
+    }
+    int chunk;
+    const int pos = nm2 + xm_block_excl_scan(mover, s_w, &chunk);
+    if (mover && pos < capM) M[pos] = i;
+    nm2 += chunk;
+  }
+  if (tid == 0) {
+    if (!room) atomicOr(&dc[DC_ERR], 8);
+    if (nm2 > capM) { atomicOr(&dc[DC_ERR], 1); nm2 = capM; }
+    dc[DC_RRECV + q] = count;
+    dc[DC_NATMS] = nat1 + count; dc[DC_NLAST] = nat1 + count;
+    dc[DC_NMOV] = nm2;
+  }
+}
+
 static size_t x_align(size_t v) { return (v + 255) & ~(size_t)255; }
 struct XLayout { size_t off_gm, off_hdr, off_rbuf, off_hbuf, bytes; };
 static XLayout x_layout(int nranks, int cap_r, int cap_h) {
@@ -1162,6 +1340,18 @@ int dlpgpu_dev_set_rebuild_every(dlpgpu_ctx* ctx, int every) {
   return 0;
 }
 
+int dlpgpu_dev_xchg_last_ms(dlpgpu_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return DLPGPU_ERR_ARG;
+  *ms = ctx->t_xchg;
+  return 0;
+}
+
+int dlpgpu_dev_xchg_set_migration(dlpgpu_ctx* ctx, int scan_all) {
+  if (!ctx || scan_all < 0 || scan_all > 1) return DLPGPU_ERR_ARG;
+  ctx->xchg_scan_migration = scan_all;
+  return 0;
+}
+
 int dlpgpu_dev_xchg_set_timeout(dlpgpu_ctx* ctx, double seconds) {
   if (!ctx || !(seconds > 0.0)) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -1277,6 +1467,8 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   ctx->tol_fresh = false; ctx->pub_fresh = false;
   int nub = ctx->natms;   // host-side upper bound of the live natms / nlast
   CK(ctx->scan_tmp.ensure((size_t)cdiv(ub_total, XB_N) + 64, s));   // per-block selection counts of a stage
+  if (!ctx->ev_x[0]) { cudaEventCreate(&ctx->ev_x[0]); cudaEventCreate(&ctx->ev_x[1]); }
+  cudaEventRecord(ctx->ev_x[0], s);
   XAtoms A{ctx->posq.p, ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->fx.p, ctx->fy.p, ctx->fz.p, ctx->ltg.p, ctx->lsite.p, ctx->ixyz.p,
            ctx->org_rank.p, ctx->org_idx.p, ctx->org_wrap.p};
   auto hdr_of = [&](int r, int stage) { return reinterpret_cast<XHdr*>(ctx->peer_xr[r] + L.off_hdr) + stage; };
@@ -1290,17 +1482,33 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   } else {
     DomI D{ctx->nx, ctx->ny, ctx->nz, ctx->idx, ctx->idy, ctx->idz};
     if (nub > 0) LAUNCH(ctx, k_x_reloc_tag, cdiv(nub, 256), 256, 0, dc, mat(rc), D, ctx->posq.p, ctx->ixyz.p);
-    for (int q = 0; q < 6; ++q) {
-      const Dir d = dir_settings(ctx, mdirs[q]);
-      const int dst = neigh[q];
-      if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
+    if (ctx->xchg_scan_migration) {   // dlpgpu_dev_xchg_set_migration(ctx, 1): every stage scans all atoms (the first implementation)
+      for (int q = 0; q < 6; ++q) {
+        const Dir d = dir_settings(ctx, mdirs[q]);
+        const int dst = neigh[q];
+        if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
+        const int nb = std::max(1, cdiv(nub, XB_N));
+        LAUNCH(ctx, k_x_count<0>, nb, XB_T, 0, dc, d, ctx->ixyz.p, ctx->scan_tmp.p);
+        LAUNCH(ctx, k_x_pack<0>, nb, XB_T, 0, dc, d, cap_r, q, ctx->scan_tmp.p, A, 0, rbuf_of(dst, q), ctx->hole_pos.p, ctx->flag.p, ctx->scan_out.p,
+               hdr_of(dst, q), seq);
+        LAUNCH(ctx, k_x_reloc_restack, cdiv(cap_r, 256), 256, 0, dc, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, A);
+        LAUNCH(ctx, k_x_recv<0>, cdiv(cap_r, 256), 256, 0, hdr_of(me, q), seq, rbuf_of(me, q), capacity, q, dc, A);
+        nub = std::min(nub + cap_r, capacity);
+      }
+    } else {   // the movers compacted once, one single-block kernel per stage (see k_x_reloc_stage)
+      const int capM = 6 * cap_r;
+      CK(ctx->movers.ensure((size_t)capM + 1, s)); CK(ctx->hole_pos.ensure((size_t)cap_r + 1, s));
       const int nb = std::max(1, cdiv(nub, XB_N));
-      LAUNCH(ctx, k_x_count<0>, nb, XB_T, 0, dc, d, ctx->ixyz.p, ctx->scan_tmp.p);
-      LAUNCH(ctx, k_x_pack<0>, nb, XB_T, 0, dc, d, cap_r, q, ctx->scan_tmp.p, A, 0, rbuf_of(dst, q), ctx->hole_pos.p, ctx->flag.p, ctx->scan_out.p,
-             hdr_of(dst, q), seq);
-      LAUNCH(ctx, k_x_reloc_restack, cdiv(cap_r, 256), 256, 0, dc, cap_r, ctx->flag.p, ctx->scan_out.p, ctx->hole_pos.p, A);
-      LAUNCH(ctx, k_x_recv<0>, cdiv(cap_r, 256), 256, 0, hdr_of(me, q), seq, rbuf_of(me, q), capacity, q, dc, A);
-      nub = std::min(nub + cap_r, capacity);
+      LAUNCH(ctx, k_x_mov_count, nb, XB_T, 0, dc, ctx->ixyz.p, ctx->scan_tmp.p);
+      LAUNCH(ctx, k_x_mov_pack, nb, XB_T, 0, dc, capM, ctx->scan_tmp.p, ctx->ixyz.p, ctx->movers.p);
+      for (int q = 0; q < 6; ++q) {
+        const Dir d = dir_settings(ctx, mdirs[q]);
+        const int dst = neigh[q];
+        if (dst < 0 || dst >= nr) return DLPGPU_ERR_ARG;
+        LAUNCH(ctx, k_x_reloc_stage, 1, XM_T, 0, dc, d, cap_r, q, ctx->movers.p, capM, ctx->hole_pos.p, A, rbuf_of(dst, q), hdr_of(dst, q),
+               hdr_of(me, q), rbuf_of(me, q), capacity, seq);
+        nub = std::min(nub + cap_r, capacity);
+      }
     }
     LAUNCH(ctx, k_x_reloc_end, cdiv(nub, 256), 256, 0, dc, ctx->ixyz.p, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p,
            ctx->freeze_site.p, ctx->posq.p, ctx->ltype.p, ctx->lfrzn.p);
@@ -1348,9 +1556,11 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   if (nub > 0)
     LAUNCH(ctx, k_x_halo_end, cdiv(nub, 256), 256, 0, dc, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p, ctx->freeze_site.p, ctx->posq.p,
            ctx->ltype.p, ctx->lfrzn.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p);
+  cudaEventRecord(ctx->ev_x[1], s);
   CK(cudaMemcpyAsync(h_dc, dc, sizeof h_dc, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
+  { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev_x[0], ctx->ev_x[1]) == cudaSuccess) ctx->t_xchg = ms; }
   ctx->natms = h_dc[DC_NATMS]; ctx->nlast = h_dc[DC_NLAST];
   if (natms_out) *natms_out = ctx->natms;
   if (nlast_out) *nlast_out = ctx->nlast;
@@ -1447,7 +1657,7 @@ int dlp_preload_halo() {
                       (const void*)k_count_nonzero, (const void*)k_x_reloc_tag, (const void*)k_x_count<0>, (const void*)k_x_count<1>,
                       (const void*)k_x_pack<0>, (const void*)k_x_pack<1>, (const void*)k_x_reloc_restack, (const void*)k_x_recv<0>,
                       (const void*)k_x_recv<1>, (const void*)k_x_reloc_end, (const void*)k_x_halo_tag, (const void*)k_x_halo_end,
-                      (const void*)k_x_gmax};
+                      (const void*)k_x_gmax, (const void*)k_x_mov_count, (const void*)k_x_mov_pack, (const void*)k_x_reloc_stage};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
   return 0;

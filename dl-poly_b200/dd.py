@@ -403,7 +403,7 @@ class Domain:
         self.steps = 0
         self._pending = False
         self.last_out = None
-        self.acc = {"pair_ms": 0.0, "force_ms": 0.0, "force_calls": 0, "list_ms": 0.0, "list_builds": 0}
+        self.acc = {"pair_ms": 0.0, "force_ms": 0.0, "force_calls": 0, "list_ms": 0.0, "list_builds": 0, "xchg_ms": 0.0}
         import os
         # peer-memory refresh: publish buffers sized for the local atoms with head-room for migration
         self.p2p = os.environ.get("DLP_DD_STAGED_REFRESH") is None
@@ -430,6 +430,8 @@ class Domain:
         if self.xchg:
             cap_r, cap_h = exchange_capacities(sysm, self.dims, safety=float(os.environ.get("DLP_DD_CAP_SAFETY", "2.0")))
             blob = self.sr.dev_xchg_init(self.rank, self.world, cap_r, cap_h)
+            if os.environ.get("DLP_DD_SCAN_MIGRATION") is not None:      # diagnostic: the all-atom migration stages (tests compare the two)
+                self.sr.dev_xchg_set_migration(1)
             if self.world > 1:
                 allb = gather_blobs(blob)
                 try:
@@ -566,6 +568,7 @@ class Domain:
                 self.rebuilds += 1
                 self._refresh_bufs = None
                 self.acc["list_ms"] += list_ms; self.acc["list_builds"] += 1
+                self.acc["xchg_ms"] += sr.dev_xchg_last_ms()
             self._pending = True
             self.steps += 1
             return self.last_out

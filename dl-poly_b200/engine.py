@@ -101,6 +101,15 @@ class ShortRange:
         """Diagnostic: 0 automatic, 1 always the general pair kernel (the reference's operation order statement by statement)."""
         self._ck(self.L.dlpgpu_set_pair_kernel(self.h, int(which) if which is not None else int(bool(general_only))))
 
+    def dev_xchg_last_ms(self):
+        v = C.c_double(0.0)
+        self._ck(self.L.dlpgpu_dev_xchg_last_ms(self.h, C.byref(v)))
+        return v.value
+
+    def dev_xchg_set_migration(self, scan_all):
+        """Diagnostic: 1 = the migration stages of xchg_rebuild scan all atoms (see include/dlpgpu.h)."""
+        self._ck(self.L.dlpgpu_dev_xchg_set_migration(self.h, int(scan_all)))
+
     def set_list_kernel(self, which):
         """Diagnostic: 0 trimmed candidate runs (default), 1 untrimmed, 2 trimmed + per-candidate ring (see include/dlpgpu.h)."""
         self._ck(self.L.dlpgpu_set_list_kernel(self.h, int(which)))

@@ -86,6 +86,8 @@ SIGNATURES = {
     "dlpgpu_set_force_mode": (ci, [vp, ci]),
     "dlpgpu_set_pair_kernel": (ci, [vp, ci]),
     "dlpgpu_set_list_kernel": (ci, [vp, ci]),
+    "dlpgpu_dev_xchg_set_migration": (ci, [vp, ci]),
+    "dlpgpu_dev_xchg_last_ms": (ci, [vp, vp]),
     "dlpgpu_set_spme": (ci, [vp, vp, ci]),
     "dlpgpu_dev_spme_forces": (ci, [vp, ci, vp]),
     "dlpgpu_spme_forces": (ci, [vp, ci, vp, ci, vp]),

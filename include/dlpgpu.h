@@ -206,6 +206,12 @@ int dlpgpu_dev_refresh_pull(dlpgpu_ctx* ctx);
  * capacity), 58 (lost atoms), DLPGPU_ERR_STATE on a peer time-out.  With nranks == 1 no IPC is involved. */
 int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_atoms, int cap_halo_atoms, unsigned char handle_out[DLPGPU_XCHG_BLOB]);
 int dlpgpu_dev_xchg_open(dlpgpu_ctx* ctx, const unsigned char* all_handles);
+/* Diagnostic: how the six migration stages of xchg_rebuild find their atoms.  0 (default): the atoms with a relocation tag are
+ * compacted once and every stage is one single-block kernel over that list; 1: every stage scans all atoms (count, pack,
+ * restack, receive kernels).  Same buffers, order and counts either way; must be the same on every rank. */
+int dlpgpu_dev_xchg_set_migration(dlpgpu_ctx* ctx, int scan_all);
+/* device time (CUDA events on the context's stream, ms) of the kernels of the last dlpgpu_dev_xchg_rebuild, peer waits included */
+int dlpgpu_dev_xchg_last_ms(dlpgpu_ctx* ctx, double* ms);
 /* how long a receive / gmax kernel waits for its peer before the call fails with DLPGPU_ERR_STATE (default 60 s; per device) */
 int dlpgpu_dev_xchg_set_timeout(dlpgpu_ctx* ctx, double seconds);
 int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long long seq, int* natms, int* nlast);

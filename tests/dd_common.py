@@ -24,6 +24,8 @@ FORCE_TOL, ENERGY_TOL = 1.0e-9, 1.0e-10
 def make_system(which):
     if which == "nacl":
         return systems.nacl((8, 8, 8), rcut=8.0, padding=0.3, temperature=1200.0)
+    if which == "nacl_hot":      # many atoms cross the faces between rebuilds: several holes / tail movers per migration stage
+        return systems.nacl((12, 12, 12), rcut=6.0, padding=0.5, temperature=6000.0)
     if which == "nacl_small":
         return systems.nacl((6, 6, 6), rcut=6.0, padding=0.3, temperature=1500.0)
     if which == "water":
@@ -125,6 +127,11 @@ def check_rank(t, device, which="nacl", stream_ctx=None, lazy_steps=10, log=None
     migrated = int(t.allreduce_sum([len(gid1 - gid0)])[0])
     # after the trajectory the resident atoms still are the oracle's (same set per rank; order follows the same rules)
     assert gid1 == set(w.ints(rank)["ltg"][:w.counts(rank)["natms"]].tolist())
+    # ... and in the oracle's ORDER, halo included: deport_atomic_data's restack (the r-th hole takes the r-th staying atom counted
+    # from the end, deport_data.F90:822-925) and the append order of the received atoms are reproduced, not just the sets
+    io2, ig2 = w.ints(rank), dom.sr.dev_get_ints()
+    c2 = w.counts(rank)
+    assert np.array_equal(io2["ltg"][:c2["nlast"]], ig2["ltg"][:c2["nlast"]]), "resident order after the trajectory"
     # library-enqueued steps: the sums of step n come back with step n+1, already summed over the ranks (mailbox gsum)
     lazy_checked = 0
     if dom.xchg and dom.p2p and which != "water":

@@ -39,12 +39,23 @@ def run_threads(world, which):
     return reps[0]
 
 
-@pytest.mark.parametrize("world,which", [(2, "nacl"), (4, "nacl"), (8, "nacl"), (2, "water"), (8, "argon")])
+@pytest.mark.parametrize("world,which", [(2, "nacl"), (4, "nacl"), (8, "nacl"), (2, "water"), (8, "argon"), (8, "nacl_hot"), (2, "nacl_hot")])
 def test_domains_as_threads_against_oracle(world, which):
     rep = run_threads(world, which)
     print("THREAD-RANKS %s" % rep)
     assert rep["ranks"] == world and rep["rebuilds"] >= (0 if which == "water" else 1)
     if which != "water":
         assert rep["mailbox_gsum_steps"] > 0
-    if which == "nacl":          # the hot melt moves atoms across domain faces within the checked steps; cold argon need not
+    if which in ("nacl", "nacl_hot"):          # the hot melt moves atoms across domain faces within the checked steps; cold argon need not
         assert rep["migrated_atoms"] > 0
+
+
+def test_scanning_migration_stages_against_oracle(monkeypatch):
+    """The first implementation of the migration stages (every stage scans all atoms) is kept as a diagnostic
+    (dlpgpu_dev_xchg_set_migration); the default compacts the movers once and runs one single-block kernel per stage.  Both are
+    held to the oracle's resident atoms, bit for bit and in order, by the same check."""
+    monkeypatch.setenv("DLP_DD_SCAN_MIGRATION", "1")
+    rep = run_threads(4, "nacl")
+    assert rep["ranks"] == 4 and rep["migrated_atoms"] > 0
+    rep = run_threads(8, "nacl_hot")
+    assert rep["migrated_atoms"] > 50
