@@ -872,11 +872,21 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
   size_t ns = ctx->h_nix.size();
   CK(ctx->st_nix.ensure(ns, s)); CK(ctx->st_niy.ensure(ns, s)); CK(ctx->st_niz.ensure(ns, s)); CK(ctx->st_nir.ensure(ns, s));
   CK(ctx->st_xb.ensure(ctx->h_xb.size(), s));
-  CK(cudaMemcpyAsync(ctx->st_nix.p, ctx->h_nix.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->st_niy.p, ctx->h_niy.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->st_niz.p, ctx->h_niz.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->st_nir.p, ctx->h_nir.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->st_xb.p, ctx->h_xb.data(), ctx->h_xb.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  // the stencil only changes with the link-cell geometry: upload it when it differs from what the device holds
+  std::vector<int> key;
+  key.reserve(4 * ns + ctx->h_xb.size());
+  key.insert(key.end(), ctx->h_nix.begin(), ctx->h_nix.end()); key.insert(key.end(), ctx->h_niy.begin(), ctx->h_niy.end());
+  key.insert(key.end(), ctx->h_niz.begin(), ctx->h_niz.end()); key.insert(key.end(), ctx->h_nir.begin(), ctx->h_nir.end());
+  key.insert(key.end(), ctx->h_xb.begin(), ctx->h_xb.end());
+  if (key != ctx->st_uploaded) {
+    CK(cudaMemcpyAsync(ctx->st_nix.p, ctx->h_nix.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_niy.p, ctx->h_niy.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_niz.p, ctx->h_niz.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_nir.p, ctx->h_nir.data(), ns * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_xb.p, ctx->h_xb.data(), ctx->h_xb.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));   // pageable host vectors: the copies are staged, but keep the key in step with the device
+    ctx->st_uploaded.swap(key);
+  }
   // buffers
   size_t nc = (size_t)g.ncells + 3;
   CK(ctx->which_cell.ensure(nlast + 1, s)); CK(ctx->at_list.ensure(nlast + 1, s)); CK(ctx->at_tmp.ensure(nlast + 1, s));

@@ -48,8 +48,9 @@ struct DBuf {
     cap = ncap;
     return cudaSuccess;
   }
-  void release() {
-    if (p) cudaFree(p);
+  // stream-ordered like ensure(): cudaFree would wait for every stream of the device, including a peer rank's spinning receive
+  void release(cudaStream_t s = 0) {
+    if (p) cudaFreeAsync(p, s);
     p = nullptr;
     cap = 0;
   }
@@ -120,6 +121,8 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
+  int* dc_pinned = nullptr;           // page-locked image of the exchange's device counts (dlpgpu_dev_xchg_init allocates it)
+  std::vector<int> st_uploaded;       // the stencil arrays the device currently holds (dlp_build_lists uploads on change)
   DBuf<float> cell_box;               // {lo, hi} float4 per link cell: bounding boxes of the cells' atoms (k_cell_boxes)
   DBuf<unsigned> fnbr;                // frozen-frozen partners per row (kept for rdf_frzn_collect only), pitch fpitch
   DBuf<int> nfnbr;

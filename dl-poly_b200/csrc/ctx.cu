@@ -147,6 +147,12 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
   cudaEventCreate(&ctx->ev_res);
   {   // once per device and process
     static bool loaded[64] = {false};
+    if (device < 64 && !loaded[device]) {   // keep freed DBuf memory in the stream-ordered pool instead of returning it at every synchronisation
+      cudaMemPool_t pool;
+      unsigned long long keep = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaGetLastError();
+    }
     if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); dlp_preload_spme(); loaded[device] = true; }
   }
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
@@ -165,37 +171,39 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
                      &ctx->lct_fill, &ctx->cell_s, &ctx->loc_slot, &ctx->flag, &ctx->scan_out, &ctx->scan_tmp, &ctx->type_s,
                      &ctx->gid_s, &ctx->frz_s, &ctx->st_nix, &ctx->st_niy, &ctx->st_niz, &ctx->st_nir, &ctx->st_xb, &ctx->ref_list,
                      &ctx->nnbr, &ctx->nxnbr, &ctx->nhnbr, &ctx->status};
-  for (auto* b : ib) b->release();
+  for (auto* b : ib) b->release(ctx->stream);
   DBuf<double>* db[] = {&ctx->vdw_par, &ctx->charge_site, &ctx->weight_site, &ctx->fx, &ctx->fy, &ctx->fz, &ctx->vx, &ctx->vy,
                         &ctx->vz, &ctx->xbg, &ctx->ybg, &ctx->zbg, &ctx->partial, &ctx->out_dev};
-  for (auto* b : db) b->release();
-  ctx->vdw_tab.release(); ctx->ew_tab.release(); ctx->posq.release(); ctx->posq_s.release();
-  ctx->nbr.release(); ctx->xnbr.release(); ctx->hnbr.release(); ctx->tol_bits.release(); ctx->parts_dev.release();
+  for (auto* b : db) b->release(ctx->stream);
+  ctx->vdw_tab.release(ctx->stream); ctx->ew_tab.release(ctx->stream); ctx->posq.release(ctx->stream); ctx->posq_s.release(ctx->stream);
+  ctx->nbr.release(ctx->stream); ctx->xnbr.release(ctx->stream); ctx->hnbr.release(ctx->stream); ctx->tol_bits.release(ctx->stream); ctx->parts_dev.release(ctx->stream);
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
   dlp_spme_release(ctx);
-  ctx->fnbr.release(); ctx->nfnbr.release(); ctx->cell_box.release(); ctx->movers.release();
-  ctx->pp_pos.release(); ctx->pp_neg.release(); ctx->pp_energy.release(); ctx->pp_stress.release();
-  ctx->tab2h.release(); ctx->tab2s.release(); ctx->rdf_list.release(); ctx->rdf_hist.release();
-  ctx->tab4.release(); ctx->tab2.release(); ctx->cnt64.release(); ctx->info_s.release(); ctx->st_rows.release();
-  for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release();
+  ctx->fnbr.release(ctx->stream); ctx->nfnbr.release(ctx->stream); ctx->cell_box.release(ctx->stream); ctx->movers.release(ctx->stream);
+  ctx->pp_pos.release(ctx->stream); ctx->pp_neg.release(ctx->stream); ctx->pp_energy.release(ctx->stream); ctx->pp_stress.release(ctx->stream);
+  ctx->tab2h.release(ctx->stream); ctx->tab2s.release(ctx->stream); ctx->rdf_list.release(ctx->stream); ctx->rdf_hist.release(ctx->stream);
+  ctx->tab4.release(ctx->stream); ctx->tab2.release(ctx->stream); ctx->cnt64.release(ctx->stream); ctx->info_s.release(ctx->stream); ctx->st_rows.release(ctx->stream);
+  for (int i = 0; i < 6; ++i) ctx->stage[i].idx.release(ctx->stream);
   for (int r = 0; r < ctx->p2p_nranks; ++r)
     if (r != ctx->p2p_rank && !(ctx->peer_pub_local.size() > (size_t)r && ctx->peer_pub_local[r]))
       for (int b = 0; b < 2; ++b)
         if (ctx->peer_pub.size() > (size_t)(2 * r + b) && ctx->peer_pub[2 * r + b]) cudaIpcCloseMemHandle(ctx->peer_pub[2 * r + b]);
   for (int b = 0; b < 2; ++b) if (ctx->pub[b]) cudaFree(ctx->pub[b]);
-  ctx->peer_pub_dev.release();
+  ctx->peer_pub_dev.release(ctx->stream);
   for (int r = 0; r < ctx->xr_nranks; ++r)
     if (r != ctx->xr_rank && ctx->peer_xr.size() > (size_t)r && ctx->peer_xr[r] &&
         !(ctx->peer_xr_local.size() > (size_t)r && ctx->peer_xr_local[r])) cudaIpcCloseMemHandle(ctx->peer_xr[r]);
   if (ctx->xr) cudaFree(ctx->xr);
-  ctx->peer_xr_dev.release(); ctx->dcnt.release(); ctx->gmax_out.release();
+  ctx->peer_xr_dev.release(ctx->stream); ctx->dcnt.release(ctx->stream); ctx->gmax_out.release(ctx->stream);
   if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
   for (int i = 0; i < 2; ++i) if (ctx->ev_x[i]) cudaEventDestroy(ctx->ev_x[i]);
   if (ctx->out_pinned) cudaFreeHost(ctx->out_pinned);
   if (ctx->gm_pinned) cudaFreeHost(ctx->gm_pinned);
+  if (ctx->dc_pinned) cudaFreeHost(ctx->dc_pinned);
+  cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;

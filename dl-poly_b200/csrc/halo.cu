@@ -1324,6 +1324,7 @@ int dlpgpu_dev_xchg_init(dlpgpu_ctx* ctx, int rank, int nranks, int cap_reloc_at
   ctx->peer_xr[rank] = ctx->xr;
   CK(ctx->dcnt.ensure(DC_WORDS, ctx->stream));
   CK(cudaMemset(ctx->dcnt.p, 0, DC_WORDS * sizeof(int)));
+  if (!ctx->dc_pinned) CK(cudaHostAlloc((void**)&ctx->dc_pinned, DC_WORDS * sizeof(int), cudaHostAllocDefault));
   CK(ctx->gmax_out.ensure(32, ctx->stream));
   ctx->xr_ready = false;
   if (nranks == 1) {
@@ -1459,10 +1460,14 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   double rc[9];
   h_invert(ctx->cell, rc);
   int* dc = ctx->dcnt.p;
-  int h_dc[DC_WORDS];
-  std::memset(h_dc, 0, sizeof h_dc);
+  // The counts travel through PAGE-LOCKED memory.  A cudaMemcpyAsync to or from pageable memory waits inside the driver for
+  // the stream's earlier work; when the ranks are threads of one process that wait can hold up the other threads' launches,
+  // and this stream's receive kernels are waiting for exactly those (seen on B200 as a time-out of the whole exchange).
+  int* h_dc = ctx->dc_pinned;
+  const size_t dc_bytes = DC_WORDS * sizeof(int);
+  std::memset(h_dc, 0, dc_bytes);
   h_dc[DC_NATMS] = ctx->natms; h_dc[DC_NLAST] = ctx->natms;
-  CK(cudaMemcpyAsync(dc, h_dc, sizeof h_dc, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dc, h_dc, dc_bytes, cudaMemcpyHostToDevice, s));
   ctx->halo_valid = false; ctx->list_valid = false;
   ctx->tol_fresh = false; ctx->pub_fresh = false;
   int nub = ctx->natms;   // host-side upper bound of the live natms / nlast
@@ -1557,7 +1562,7 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
     LAUNCH(ctx, k_x_halo_end, cdiv(nub, 256), 256, 0, dc, ctx->lsite.p, ctx->type_site.p, ctx->charge_site.p, ctx->freeze_site.p, ctx->posq.p,
            ctx->ltype.p, ctx->lfrzn.p, ctx->xbg.p, ctx->ybg.p, ctx->zbg.p);
   cudaEventRecord(ctx->ev_x[1], s);
-  CK(cudaMemcpyAsync(h_dc, dc, sizeof h_dc, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_dc, dc, dc_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev_x[0], ctx->ev_x[1]) == cudaSuccess) ctx->t_xchg = ms; }

@@ -261,7 +261,7 @@ bool load_cufft() {
 void dlp_spme_release(dlpgpu_ctx* ctx) {
   if (ctx->spme_plan_valid && g_fft.destroy) g_fft.destroy(ctx->spme_plan);
   ctx->spme_plan_valid = false;
-  ctx->spme_grid.release(); ctx->spme_rgrid.release(); ctx->spme_norm2.release(); ctx->spme_fraw.release(); ctx->spme_tot.release();
+  ctx->spme_grid.release(ctx->stream); ctx->spme_rgrid.release(ctx->stream); ctx->spme_norm2.release(ctx->stream); ctx->spme_fraw.release(ctx->stream); ctx->spme_tot.release(ctx->stream);
 }
 
 extern "C" {

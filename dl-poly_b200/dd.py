@@ -432,6 +432,8 @@ class Domain:
             blob = self.sr.dev_xchg_init(self.rank, self.world, cap_r, cap_h)
             if os.environ.get("DLP_DD_SCAN_MIGRATION") is not None:      # diagnostic: the all-atom migration stages (tests compare the two)
                 self.sr.dev_xchg_set_migration(1)
+            if os.environ.get("DLP_DD_XCHG_TIMEOUT") is not None:       # seconds a receive kernel waits for its peer (library default 60)
+                self.sr.dev_xchg_set_timeout(float(os.environ["DLP_DD_XCHG_TIMEOUT"]))
             if self.world > 1:
                 allb = gather_blobs(blob)
                 try:

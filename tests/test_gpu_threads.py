@@ -3,6 +3,7 @@ one library context each, and exchange migrating atoms, halo atoms, refreshed po
 library's peer-memory kernels exactly as they do between GPUs (the peers' buffers are plain device pointers instead of
 CUDA-IPC mappings).  Checked against the oracle's P-domain world: see tests/dd_common.py.  This is what puts the N > 1 path
 on the record of a 1-GPU box; tests/test_gpu_multi.py runs the same check with one process per GPU when there are several."""
+import gc
 import threading
 
 import pytest
@@ -26,14 +27,23 @@ def run_threads(world, which):
             errs[rank] = e
             grp.bar.abort()
 
-    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
-    for x in th:
-        x.start()
-    for x in th:
-        x.join(timeout=900)
+    # dlpgpu_destroy frees pinned host memory and peer regions, which waits for the whole device; a context of an EARLIER test
+    # collected by the cyclic GC from inside a rank thread would wait for a peer's spinning receive kernel, which waits for
+    # that thread's next message.  Collect before the ranks start and keep the collector quiet while they run.  (The hang this
+    # suite did hit was a different host-side wait: see the page-locked counts of dlpgpu_dev_xchg_rebuild.)
+    gc.collect()
+    gc.disable()
+    try:
+        th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join(timeout=900)
+    finally:
+        gc.enable()
     real = [e for e in errs if e is not None and not isinstance(e, threading.BrokenBarrierError)]
     if real:
-        raise real[0]
+        raise AssertionError("rank errors: " + " || ".join("rank %d: %r" % (r, e) for r, e in enumerate(errs) if e is not None)) from real[0]
     assert all(e is None for e in errs), errs
     assert all(r is not None and r["ok"] for r in reps)
     return reps[0]
