@@ -558,16 +558,17 @@ def run_gpu(args):
 
 def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     """The same metric through dlpgpu_link_cell_pairs / dlpgpu_two_body_forces with host (pinned) corePart buffers:
-    every step uploads parts(1:nlast) (64 B per atom) and reads the forces of parts(1:natms) back; every `interval`-th
-    step (the rebuild frequency observed in the device-resident run) also rebuilds the list from host arrays."""
+    every step sends parts(1:nlast) up and brings the forces of parts(1:natms) back -- whole 64-byte records by DMA, or, when
+    the rank has a dozen cores to itself, x, y, z, chge (32 B) up and the forces (24 B) down, (de)interleaved by the library's
+    host threads (csrc/hostio.cu); every `interval`-th step (the rebuild frequency observed in the device-resident run) also
+    rebuilds the list from host arrays.  The byte counts are the library's own counters."""
     from dl_poly_b200 import engine
     from dl_poly_b200.lib import COREPART
     sr = dom.sr
     natms, nlast = sr.dev_counts()
     ints = sr.dev_get_ints(nlast)
     parts_now = sr.dev_get_parts(nlast)
-    pin = torch.empty(nlast * 64, dtype=torch.uint8).pin_memory()
-    parts = pin.numpy().view(COREPART)
+    parts = np.empty(nlast, dtype=COREPART)      # the caller's config%parts: ordinary memory, the library stages through its own page-locked buffers
     parts[:] = parts_now
     sysm = dom.sys
     sr2 = engine.ShortRange(dom.device.index, sr.dd)
@@ -576,6 +577,12 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     sr2.set_forcefield(sysm.ff)
     if args.force_mode is not None:
         sr2.set_force_mode(args.force_mode)
+    # packed transfers pay from about a dozen otherwise idle cores per rank (csrc/hostio.cu); below that whole records by DMA
+    cpus_per_rank = len(os.sched_getaffinity(0)) // max(1, world)
+    host_threads = min(cpus_per_rank - 1, 32) if cpus_per_rank >= 12 else 0
+    if os.environ.get("DLPGPU_HOST_THREADS"):
+        host_threads = int(os.environ["DLPGPU_HOST_THREADS"])
+    sr2.set_host_threads(host_threads)
     excl = None
     if sysm.excl is not None:
         excl = np.ascontiguousarray(np.asarray(sysm.excl)[ints["ltg"][:natms] - 1])
@@ -586,6 +593,7 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     if transport is not None:
         transport.barrier()
     torch.cuda.synchronize()
+    sr2.transfer_bytes(reset=True)
     nb = 0
     t0 = time.perf_counter()
     for s in range(steps):
@@ -599,11 +607,12 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     t = time.perf_counter() - t0
     if transport is not None:
         t = transport.allreduce_max(t)
-    h2d = nlast * 64 + (nb / steps) * (3 * 4 * nlast)      # parts every step (once on rebuild steps too) + the three int arrays per rebuild
-    d2h = natms * 64 + 16 * 8
+    up, down = sr2.transfer_bytes()
+    h2d = up / steps                                       # x, y, z, chge of parts(1:nlast) per step + the chunks of ltype / ltg / lfrzn that changed
+    d2h = down / steps + 16 * 8                            # forces of parts(1:natms) + the 16 sums
     sr2.close()
     return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
-            "steps": steps, "rebuild_every": interval, "ms_per_step": 1e3 * t / steps,
+            "steps": steps, "rebuild_every": interval, "ms_per_step": 1e3 * t / steps, "host_threads": host_threads,
             "api": "dlpgpu_link_cell_pairs + dlpgpu_two_body_forces (include/dlpgpu.h) on host corePart arrays"}
 
 

@@ -7,14 +7,14 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdlpgpu.so")
-SOURCES = ["ctx.cu", "cells.cu", "forces.cu", "halo.cu", "spme.cu"]
+SOURCES = ["ctx.cu", "cells.cu", "forces.cu", "halo.cu", "spme.cu", "hostio.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
          "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]   # host pass un-fused too (aarch64 hosts would contract h_dcell / h_geometry)
 # -fmad=false where a floating-point expression decides an integer (cell index, list membership, halo / migration
 # thresholds): those follow the reference's un-fused IEEE arithmetic bit for bit.  forces.cu contracts to FMA (the pair
 # terms only need the 1e-9 / 1e-10 bars); its cutoff tests use explicit _rn intrinsics.
-EXTRA = {"ctx.cu": ["-fmad=false"], "cells.cu": ["-fmad=false"], "halo.cu": ["-fmad=false"], "forces.cu": [], "spme.cu": []}
+EXTRA = {"ctx.cu": ["-fmad=false"], "cells.cu": ["-fmad=false"], "halo.cu": ["-fmad=false"], "forces.cu": [], "spme.cu": [], "hostio.cu": []}
 
 
 HOST = os.path.join(HERE, "host")
@@ -76,7 +76,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    cmd = [NVCC, "-shared", "-o", OUT] + [r[1] for r in res] + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    cmd = [NVCC, "-shared", "-o", OUT] + [r[1] for r in res] + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -121,6 +121,7 @@ struct dlpgpu_ctx {
   DBuf<double> tab2s;                 // copy of tab2's g units with the 8-bit completion of the fp32 energy h parked in g_energy's low bits
   DBuf<float> tab2h;                  // float4 second differences {vdW force, vdW energy, Ewald force, Ewald energy} per (potential, l)
   cudaTextureObject_t tab2h_tex = 0;
+  void* hostio = nullptr;             // hostio.cu: worker pool, page-locked staging buffers and byte counters of the drop-in entry points
   int* dc_pinned = nullptr;           // page-locked image of the exchange's device counts (dlpgpu_dev_xchg_init allocates it)
   std::vector<int> st_uploaded;       // the stencil arrays the device currently holds (dlp_build_lists uploads on change)
   DBuf<float> cell_box;               // {lo, hi} float4 per link cell: bounding boxes of the cells' atoms (k_cell_boxes)
@@ -234,10 +235,7 @@ struct dlpgpu_ctx {
   DBuf<unsigned long long> tol_bits;
   // staging for the host-buffer entry points
   DBuf<dlpgpu_corepart> parts_dev;
-  void* pinned_ptr = nullptr;      // caller's corePart array, page-locked by us on first use
-  size_t pinned_bytes = 0;
-  bool pinned_ours = false;
-  int parts_resident = 0;          // records of the caller's parts array currently mirrored in parts_dev (set by link_cell_pairs)
+  int parts_resident = 0;          // records of the caller's parts array whose coordinates the device holds (set by link_cell_pairs)
   bool parts_current = false;      // dlpgpu_parts_unchanged_since_list: the next two_body_forces may skip its upload
   // timings
   cudaEvent_t ev[8] = {nullptr};
@@ -270,6 +268,13 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // every translation unit loads its kernels up front (see dlp_preload_halo)
 int dlp_preload_halo();
+int dlp_preload_hostio();
+// hostio.cu: the caller's corePart records <-> device arrays (packed, chunked, overlapped with the DMA engine)
+int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts);
+int dlp_upload_ints(dlpgpu_ctx* ctx, int n, const int* ltype, const int* ltg, const int* lfrzn);
+int dlp_download_add_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts);
+void dlp_hostio_ints_stale(dlpgpu_ctx* ctx);
+void dlp_hostio_release(dlpgpu_ctx* ctx);
 int dlp_preload_cells();
 int dlp_preload_forces();
 int dlp_preload_ctx();

@@ -153,7 +153,7 @@ int dlpgpu_create(dlpgpu_ctx** out, int device) {
       if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
       cudaGetLastError();
     }
-    if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); dlp_preload_spme(); loaded[device] = true; }
+    if (device < 64 && !loaded[device]) { dlp_preload_ctx(); dlp_preload_cells(); dlp_preload_forces(); dlp_preload_halo(); dlp_preload_spme(); dlp_preload_hostio(); loaded[device] = true; }
   }
   if (ctx->status.ensure(8, ctx->stream) != cudaSuccess || ctx->out_dev.ensure(16, ctx->stream) != cudaSuccess ||
       ctx->tol_bits.ensure(2, ctx->stream) != cudaSuccess || ctx->cnt64.ensure(4, ctx->stream) != cudaSuccess) { delete ctx; return DLPGPU_ERR_CUDA; }
@@ -196,7 +196,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
         !(ctx->peer_xr_local.size() > (size_t)r && ctx->peer_xr_local[r])) cudaIpcCloseMemHandle(ctx->peer_xr[r]);
   if (ctx->xr) cudaFree(ctx->xr);
   ctx->peer_xr_dev.release(ctx->stream); ctx->dcnt.release(ctx->stream); ctx->gmax_out.release(ctx->stream);
-  if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
+  dlp_hostio_release(ctx);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->ev_res) cudaEventDestroy(ctx->ev_res);
   for (int i = 0; i < 2; ++i) if (ctx->ev_x[i]) cudaEventDestroy(ctx->ev_x[i]);
@@ -428,12 +428,6 @@ int dlpgpu_dev_counts(dlpgpu_ctx* ctx, int* natms, int* nlast) {
 
 // ------------------------------------------------------------------ AoS <-> device layout kernels
 namespace {
-__global__ void k_unpack_parts(const dlpgpu_corepart* __restrict__ parts, int n, double4* __restrict__ posq) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  dlpgpu_corepart p = parts[i];
-  posq[i] = make_double4(p.xxx, p.yyy, p.zzz, p.chge);
-}
 __global__ void k_pack_parts(dlpgpu_corepart* __restrict__ parts, int n, const double4* __restrict__ posq,
                              const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,12 +436,6 @@ __global__ void k_pack_parts(dlpgpu_corepart* __restrict__ parts, int n, const d
   dlpgpu_corepart p;
   p.xxx = q.x; p.yyy = q.y; p.zzz = q.z; p.fxx = fx[i]; p.fyy = fy[i]; p.fzz = fz[i]; p.chge = q.w; p.pad1 = 0; p.pad2 = 0;
   parts[i] = p;
-}
-__global__ void k_add_forces(dlpgpu_corepart* __restrict__ parts, int n, const double* __restrict__ fx, const double* __restrict__ fy,
-                             const double* __restrict__ fz) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  parts[i].fxx += fx[i]; parts[i].fyy += fy[i]; parts[i].fzz += fz[i];
 }
 __global__ void k_load_atoms(int n, const double* __restrict__ xyz, const double* __restrict__ vel, const int* __restrict__ lsite,
                              const int* __restrict__ type_site, const double* __restrict__ charge_site,
@@ -467,28 +455,7 @@ __global__ void k_zero3(int n, double* a, double* b, double* c) {
 }
 }  // namespace
 
-// The caller's corePart array (config%parts) lives at one address for the whole run: page-lock it on first sight so the
-// per-step copies run at full PCIe rate.  Memory that is already pinned (or cannot be pinned) is used as it is.
-static void pin_host_parts(dlpgpu_ctx* ctx, const void* p, size_t bytes) {
-  if (!p || bytes == 0) return;
-  if (ctx->pinned_ptr == p && ctx->pinned_bytes >= bytes) return;
-  if (ctx->pinned_ptr && ctx->pinned_ours) cudaHostUnregister(ctx->pinned_ptr);
-  ctx->pinned_ptr = const_cast<void*>(p); ctx->pinned_bytes = bytes;
-  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
-  ctx->pinned_ours = (e == cudaSuccess);
-  if (e != cudaSuccess) cudaGetLastError();   // already registered / not registrable: plain copies still work
-}
-
-static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
-  if (n <= 0) return 0;
-  pin_host_parts(ctx, parts, (size_t)n * sizeof(dlpgpu_corepart));
-  CK(ctx->parts_dev.ensure(n, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, ctx->parts_dev.p, n, ctx->posq.p);
-  ctx->tol_fresh = false; ctx->pub_fresh = false;
-  ctx->parts_resident = 0; ctx->parts_current = false;
-  return 0;
-}
+static int upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) { return dlp_upload_parts(ctx, n, parts); }   // hostio.cu
 
 extern "C" {
 
@@ -498,6 +465,7 @@ int dlpgpu_dev_load_atoms(dlpgpu_ctx* ctx, int natms, const double* xyz, const d
   if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "load_atoms: call dlpgpu_dev_set_sites first");
   CK(cudaSetDevice(ctx->device));
   ctx->natms = 0; ctx->nlast = 0;
+  dlp_hostio_ints_stale(ctx);
   CKRC(dlp_ensure_atoms(ctx, std::max(capacity_atoms, natms + 16)));
   DBuf<double> tx, tv;
   CK(tx.ensure((size_t)3 * natms + 1, ctx->stream));
@@ -537,10 +505,7 @@ int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_c
   CKRC(dlp_ensure_atoms(ctx, nlast + 16));
   CKRC(upload_parts(ctx, nlast, parts));
   ctx->parts_resident = nlast;
-  CK(cudaMemcpyAsync(ctx->ltype.p, ltype, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->ltg.p, ltg, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  if (lfrzn) CK(cudaMemcpyAsync(ctx->lfrzn.p, lfrzn, (size_t)nlast * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  else CK(cudaMemsetAsync(ctx->lfrzn.p, 0, (size_t)nlast * sizeof(int), ctx->stream));
+  CKRC(dlp_upload_ints(ctx, nlast, ltype, ltg, lfrzn));
   ctx->lbook = lbook ? 1 : 0; ctx->megfrz = megfrz; ctx->max_exclude = lbook ? max_exclude : 0; ctx->excl_by_gid = 0;
   if (lbook && list_excl) {
     size_t n = (size_t)natms * (max_exclude + 1);
@@ -574,13 +539,12 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
     CKRC(upload_parts(ctx, nlast, parts));
   }
   ctx->parts_current = false;
-  CKRC(dlp_two_body(ctx, 1, out));
-  // every force provider ADDS (drivers.F90:655-660): the device copy of parts still holds the caller's forces, so the sum is
-  // formed there and the records of the local atoms go back in one contiguous copy (positions and charges unchanged)
-  if (natms > 0) {
-    LAUNCH(ctx, k_add_forces, cdiv(natms, 256), 256, 0, ctx->parts_dev.p, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
-    CK(cudaMemcpyAsync(parts, ctx->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  // every force provider ADDS (drivers.F90:655-660): the device computes this provider's forces from zero, they come back as
+  // {fx, fy, fz} triples behind the kernels and the host adds them into parts(1:natms)%f (hostio.cu) -- whatever other
+  // providers put there since the upload stays.  The sums are fetched last, so the copies start without a host round trip.
+  CKRC(dlp_two_body(ctx, 1, nullptr));
+  CKRC(dlp_download_add_forces(ctx, natms, parts));
+  CKRC(dlpgpu_dev_fetch_results(ctx, out));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -592,16 +556,14 @@ int dlpgpu_spme_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts, int m
   CK(cudaSetDevice(ctx->device));
   CKRC(dlp_ensure_atoms(ctx, natms + 16));
   CKRC(upload_parts(ctx, natms, parts));
+  dlp_hostio_ints_stale(ctx);
   const int keep_n = ctx->natms, keep_l = ctx->nlast;
   ctx->natms = natms;
   if (natms > 0) LAUNCH(ctx, k_zero3, cdiv(natms, 256), 256, 0, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
   const int rc = dlpgpu_dev_spme_forces(ctx, megatm, out);
   ctx->natms = keep_n; ctx->nlast = keep_l;
   if (rc) return rc;
-  if (natms > 0) {
-    LAUNCH(ctx, k_add_forces, cdiv(natms, 256), 256, 0, ctx->parts_dev.p, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
-    CK(cudaMemcpyAsync(parts, ctx->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  CKRC(dlp_download_add_forces(ctx, natms, parts));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->list_valid = false;   // the device force / position arrays were reused: the next short-range call starts from link_cell_pairs
   return 0;
@@ -726,8 +688,8 @@ int dlpgpu_dev_get_full_row(dlpgpu_ctx* ctx, int i, int* n_main, int* main_out, 
 }  // extern "C"
 
 int dlp_preload_ctx() {   // see dlp_preload_halo
-  const void* ks[] = {(const void*)k_scan_block, (const void*)k_scan_add, (const void*)k_unpack_parts, (const void*)k_pack_parts,
-                      (const void*)k_add_forces, (const void*)k_load_atoms, (const void*)k_zero3};
+  const void* ks[] = {(const void*)k_scan_block, (const void*)k_scan_add, (const void*)k_pack_parts,
+                      (const void*)k_load_atoms, (const void*)k_zero3};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
   return 0;

@@ -1032,6 +1032,7 @@ int dlpgpu_dev_halo_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int cap
 }
 
 int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count) {
+  if (ctx) dlp_hostio_ints_stale(ctx);
   if (!ctx || count < 0 || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   HaloStage& st = ctx->stage[stage_of(mdir)];
@@ -1045,6 +1046,7 @@ int dlpgpu_dev_halo_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev,
 }
 
 int dlpgpu_dev_halo_end(dlpgpu_ctx* ctx) {
+  if (ctx) dlp_hostio_ints_stale(ctx);
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "halo_end: sites not set");
@@ -1265,6 +1267,7 @@ int dlpgpu_dev_relocate_pack(dlpgpu_ctx* ctx, int mdir, double* sendbuf_dev, int
 }
 
 int dlpgpu_dev_relocate_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_dev, int count) {
+  if (ctx) dlp_hostio_ints_stale(ctx);
   if (!ctx || count < 0 || stage_of(mdir) < 0) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (count == 0) return 0;
@@ -1276,6 +1279,7 @@ int dlpgpu_dev_relocate_unpack(dlpgpu_ctx* ctx, int mdir, const double* recvbuf_
 }
 
 int dlpgpu_dev_relocate_end(dlpgpu_ctx* ctx, int* natms_now) {
+  if (ctx) dlp_hostio_ints_stale(ctx);
   if (!ctx) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -1446,6 +1450,7 @@ int dlpgpu_dev_xchg_rebuild(dlpgpu_ctx* ctx, const int neigh[6], unsigned long l
   if (!ctx || !neigh) return DLPGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->xr_ready) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: exchange region not ready");
+  dlp_hostio_ints_stale(ctx);
   if (ctx->nsites < 1) return dlp_fail(ctx, DLPGPU_ERR_STATE, "xchg_rebuild: sites not set");
   cudaStream_t s = ctx->stream;
   const int nr = ctx->xr_nranks, cap_r = ctx->xr_cap_r, cap_h = ctx->xr_cap_h;

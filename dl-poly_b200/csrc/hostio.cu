@@ -1,0 +1,422 @@
+// hostio.cu -- how the drop-in entry points move the caller's corePart records (include/dlpgpu.h: dlpgpu_link_cell_pairs,
+// dlpgpu_two_body_forces, dlpgpu_vnl_check, dlpgpu_vnl_set_check, dlpgpu_spme_forces).
+//
+// The reference keeps positions, forces and the charge of an atom in one 64-byte record (particle.F90 corePart) and every
+// force provider ADDS into parts%f (drivers.F90:655-660).  Of those 64 bytes the device needs 32 per step (x, y, z, charge
+// of parts(1:nlast)) and hands back 24 (the force it computed for parts(1:natms)).  Two ways to move them:
+//
+// * whole records (dlpgpu_set_host_threads(ctx, 0), the default): parts(1:nlast) go up as they are from the caller's array,
+//   which is page-locked on first sight; the device adds its forces to the copy and parts(1:natms) come back in one copy.
+//   148 MB per 1 M-ion step, 2.7 ms at the 55 GB/s of the pool's boxes, no host work.  Strided DMA or zero-copy access to the
+//   useful bytes is slower still (scripts/pcie_test.cu).
+// * packed (dlpgpu_set_host_threads(ctx, n >= 1)): n host threads of the library (de)interleave the fields in chunks that
+//   overlap with the DMA engine:
+//     up:    workers copy {x, y, z, chge} of a chunk of records into a page-locked staging buffer laid out like the device's
+//            posq array (non-temporal stores); the calling thread queues the chunk's H2D copy, straight into posq, as soon
+//            as the chunk is packed;
+//     down:  the device interleaves its force arrays into {fx, fy, fz} triples, the calling thread queues one D2H copy and
+//            one event per chunk, workers add a chunk's triples into parts%f as soon as its event has completed -- the same
+//            one rounding per component as the reference's accumulation into parts%f.  The device never sees parts%f.
+//   64 MB per 1 M-ion step over PCIe, but 280 MB through the host's memory system: it pays when a rank has a dozen otherwise
+//   idle cores (measured on the pool's 16-vCPU boxes, 1 M ions: 15.4 / 9.5 / 6.8 / 5.2 / 4.2 ms per step with 1 / 2 / 4 / 8 /
+//   12 threads against 4.6 ms for whole records; profiles/r2_s48_*).
+// ltype / ltg / lfrzn of link_cell_pairs are compared with the page-locked copy of the previous call chunk by chunk in both
+// modes; only chunks that differ are copied again (in a serial run the local atoms never change their order).
+// Counters of the bytes that really crossed PCIe are kept for bench.py (dlpgpu_transfer_bytes).
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <sched.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXCH = 64;   // chunks per transfer (one event each on the way down)
+
+// A fixed set of workers that run fn(0), fn(1), ... fn(n-1), handing the chunks out in increasing order.
+class HostPool {
+ public:
+  explicit HostPool(int nthreads) : nthreads_(nthreads) {
+    for (int c = 0; c < MAXCH; ++c) done_[c].store(0, std::memory_order_relaxed);
+    for (int t = 0; t < nthreads_; ++t) th_.emplace_back([this] { work(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int threads() const { return nthreads_; }
+  void start(int n, std::function<void(int)> fn) {   // the previous job must have been waited for (wait_all)
+    if (nthreads_ == 0) {   // no workers: the calling thread does the chunks itself
+      for (int c = 0; c < n; ++c) { fn(c); done_[c].store(1, std::memory_order_relaxed); }
+      return;
+    }
+    for (int c = 0; c < n; ++c) done_[c].store(0, std::memory_order_relaxed);
+    next_.store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = std::move(fn); n_ = n; left_ = nthreads_; ++gen_;
+    }
+    cv_.notify_all();
+  }
+  void wait_chunk(int c) {
+    unsigned spins = 0;
+    while (!done_[c].load(std::memory_order_acquire)) pause(++spins);
+  }
+  void wait_all() {
+    if (nthreads_ == 0) return;
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [this] { return left_ == 0; });
+  }
+  static void pause(unsigned spins) {
+    if (spins & 0x3f) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    } else {
+      std::this_thread::yield();
+    }
+  }
+
+ private:
+  void work() {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::function<void(int)> fn;
+      int n;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_; fn = fn_; n = n_;
+      }
+      for (;;) {
+        const int c = next_.fetch_add(1, std::memory_order_relaxed);
+        if (c >= n) break;
+        fn(c);
+        done_[c].store(1, std::memory_order_release);
+      }
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--left_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  int nthreads_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, cv_done_;
+  std::function<void(int)> fn_;
+  int n_ = 0, left_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+  std::atomic<int> next_{0};
+  std::atomic<int> done_[MAXCH];
+};
+
+struct HostIO {
+  HostPool* pool = nullptr;
+  int threads = -1;             // -1: not chosen yet, 0: whole records by DMA, >= 1: packed fields through that many workers
+  double* up = nullptr;  size_t up_cap = 0;     // page-locked {x, y, z, chge} per record
+  double* dn = nullptr;  size_t dn_cap = 0;     // page-locked {fx, fy, fz} per local atom
+  int* ints = nullptr;   size_t ints_cap = 0;   // page-locked ltype | ltg | lfrzn of the previous link_cell_pairs call
+  int ints_n = -1;                              // records the device copies of the three arrays are valid for
+  bool frzn_given = false;
+  DBuf<double> f3;                              // device-side interleaved forces
+  DBuf<dlpgpu_corepart> parts_dev;              // whole-record mode: device copy of the caller's records
+  void* reg_ptr = nullptr; size_t reg_bytes = 0; bool reg_ours = false;   // the caller's array, page-locked by us
+  cudaEvent_t ev[MAXCH] = {};
+  std::atomic<int> avail[MAXCH];
+  unsigned long long h2d = 0, d2h = 0;
+};
+
+int default_threads() {   // whole records unless the user opts in: a library cannot know how many cores its rank may take
+  if (const char* e = getenv("DLPGPU_HOST_THREADS")) { const int v = atoi(e); if (v >= 0) return std::min(v, 64); }
+  return 0;
+}
+
+HostIO* io_of(dlpgpu_ctx* ctx) {
+  if (!ctx->hostio) {
+    HostIO* io = new HostIO();
+    for (int c = 0; c < MAXCH; ++c) io->avail[c].store(0, std::memory_order_relaxed);
+    ctx->hostio = io;
+  }
+  HostIO* io = static_cast<HostIO*>(ctx->hostio);
+  if (io->threads < 0) io->threads = default_threads();
+  if (!io->pool || io->pool->threads() != io->threads) {
+    delete io->pool;
+    io->pool = new HostPool(io->threads);
+  }
+  return io;
+}
+
+template <typename T>
+cudaError_t grow_pinned(T*& p, size_t& cap, size_t n) {
+  if (n <= cap) return cudaSuccess;
+  if (p) cudaFreeHost(p);
+  p = nullptr; cap = 0;
+  const size_t ncap = n + n / 8 + 1024;
+  cudaError_t e = cudaHostAlloc((void**)&p, ncap * sizeof(T), cudaHostAllocDefault);
+  if (e == cudaSuccess) cap = ncap;
+  return e;
+}
+
+// chunk length: a multiple of 4096 records, about 60 chunks for a large array (never more than MAXCH), at least 16 k records
+int chunk_len(int n) {
+  int len = ((n / 60 + 4095) / 4096) * 4096;
+  return std::max(len, 16384);
+}
+
+// the caller's corePart array (config%parts) lives at one address for the whole run: page-lock it on first sight so that the
+// whole-record copies run at full PCIe rate; memory that is already pinned (or cannot be pinned) is used as it is
+void pin_host_parts(HostIO* io, const void* p, size_t bytes) {
+  if (!p || bytes == 0) return;
+  if (io->reg_ptr == p && io->reg_bytes >= bytes) return;
+  if (io->reg_ptr && io->reg_ours) cudaHostUnregister(io->reg_ptr);
+  io->reg_ptr = const_cast<void*>(p); io->reg_bytes = bytes;
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+  io->reg_ours = (e == cudaSuccess);
+  if (e != cudaSuccess) cudaGetLastError();
+}
+
+__global__ void k_unpack_parts(const dlpgpu_corepart* __restrict__ parts, int n, double4* __restrict__ posq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dlpgpu_corepart p = parts[i];
+  posq[i] = make_double4(p.xxx, p.yyy, p.zzz, p.chge);
+}
+__global__ void k_add_forces(dlpgpu_corepart* __restrict__ parts, int n, const double* __restrict__ fx, const double* __restrict__ fy,
+                             const double* __restrict__ fz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  parts[i].fxx += fx[i]; parts[i].fyy += fy[i]; parts[i].fzz += fz[i];
+}
+
+__global__ void k_pack_f3(int n, const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz, double* __restrict__ f3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f3[3 * (size_t)i] = fx[i]; f3[3 * (size_t)i + 1] = fy[i]; f3[3 * (size_t)i + 2] = fz[i];
+}
+
+}  // namespace
+
+void dlp_hostio_release(dlpgpu_ctx* ctx) {
+  if (!ctx->hostio) return;
+  HostIO* io = static_cast<HostIO*>(ctx->hostio);
+  delete io->pool;
+  if (io->up) cudaFreeHost(io->up);
+  if (io->dn) cudaFreeHost(io->dn);
+  if (io->ints) cudaFreeHost(io->ints);
+  io->f3.release(ctx->stream); io->parts_dev.release(ctx->stream);
+  if (io->reg_ptr && io->reg_ours) cudaHostUnregister(io->reg_ptr);
+  for (int c = 0; c < MAXCH; ++c) if (io->ev[c]) cudaEventDestroy(io->ev[c]);
+  delete io;
+  ctx->hostio = nullptr;
+}
+
+// parts(1:n) -> posq(1:n) on the device (x, y, z, chge); queued on the context's stream, the staging buffer is free again
+// once the stream has passed the copies (every drop-in entry point synchronises before it returns)
+int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
+  if (n <= 0) return 0;
+  HostIO* io = io_of(ctx);
+  if (io->threads == 0) {   // whole records
+    pin_host_parts(io, parts, (size_t)n * sizeof(dlpgpu_corepart));
+    CK(io->parts_dev.ensure(n, ctx->stream));
+    CK(cudaMemcpyAsync(io->parts_dev.p, parts, (size_t)n * sizeof(dlpgpu_corepart), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_unpack_parts, cdiv(n, 256), 256, 0, io->parts_dev.p, n, ctx->posq.p);
+    io->h2d += (unsigned long long)n * sizeof(dlpgpu_corepart);
+    ctx->tol_fresh = false; ctx->pub_fresh = false;
+    ctx->parts_resident = 0; ctx->parts_current = false;
+    return 0;
+  }
+  if ((size_t)4 * n > io->up_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(grow_pinned(io->up, io->up_cap, (size_t)4 * n));
+  }
+  const int len = chunk_len(n), nch = cdiv(n, len);
+  double* up = io->up;
+  io->pool->start(nch, [=](int c) {
+    const int a = c * len, b = std::min(n, a + len);
+    for (int i = a; i < b; ++i) {
+      const dlpgpu_corepart& p = parts[i];
+      double* q = up + 4 * (size_t)i;
+#if defined(__x86_64__)
+      _mm_stream_pd(q, _mm_loadu_pd(&p.xxx));             // the staging buffer is only read by the DMA engine: keep it out of the caches
+      _mm_stream_pd(q + 2, _mm_set_pd(p.chge, p.zzz));
+#else
+      q[0] = p.xxx; q[1] = p.yyy; q[2] = p.zzz; q[3] = p.chge;
+#endif
+    }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+  });
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < nch; ++c) {
+    io->pool->wait_chunk(c);
+    const int a = c * len, b = std::min(n, a + len);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->posq.p + a, up + 4 * (size_t)a, (size_t)(b - a) * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  io->pool->wait_all();
+  CK(e);
+  io->h2d += (unsigned long long)n * 4 * sizeof(double);
+  ctx->tol_fresh = false; ctx->pub_fresh = false;
+  ctx->parts_resident = 0; ctx->parts_current = false;
+  return 0;
+}
+
+// ltype / ltg / lfrzn(1:n) of link_cell_pairs -> device arrays; chunks equal to what the device already holds are skipped
+int dlp_upload_ints(dlpgpu_ctx* ctx, int n, const int* ltype, const int* ltg, const int* lfrzn) {
+  if (n <= 0) return 0;
+  HostIO* io = io_of(ctx);
+  const bool fresh = n != io->ints_n || (lfrzn != nullptr) != io->frzn_given || (size_t)3 * n > io->ints_cap;
+  if ((size_t)3 * n > io->ints_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(grow_pinned(io->ints, io->ints_cap, (size_t)3 * n));
+  }
+  const int len = chunk_len(n), nch = cdiv(n, len);
+  int* sh = io->ints;
+  const int* src[3] = {ltype, ltg, lfrzn};
+  int* dst[3] = {ctx->ltype.p, ctx->ltg.p, ctx->lfrzn.p};
+  static_assert(MAXCH <= 64, "one bit per chunk");
+  std::atomic<unsigned long long> changed[3];
+  for (auto& w : changed) w.store(0);
+  std::atomic<unsigned long long>* ch = changed;
+  io->pool->start(nch, [=](int c) {
+    const int a = c * len, b = std::min(n, a + len);
+    const size_t bytes = (size_t)(b - a) * sizeof(int);
+    for (int k = 0; k < 3; ++k) {
+      if (!src[k]) continue;
+      int* s = sh + (size_t)k * n + a;
+      if (fresh || std::memcmp(s, src[k] + a, bytes) != 0) {
+        std::memcpy(s, src[k] + a, bytes);
+        ch[k].fetch_or(1ull << c, std::memory_order_relaxed);
+      }
+    }
+  });
+  cudaError_t e = cudaSuccess;
+  unsigned long long moved = 0;
+  for (int c = 0; c < nch; ++c) {
+    io->pool->wait_chunk(c);
+    const int a = c * len, b = std::min(n, a + len);
+    const size_t bytes = (size_t)(b - a) * sizeof(int);
+    for (int k = 0; k < 3; ++k)
+      if (src[k] && (changed[k].load(std::memory_order_relaxed) >> c & 1ull) && e == cudaSuccess) {
+        e = cudaMemcpyAsync(dst[k] + a, sh + (size_t)k * n + a, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        moved += bytes;
+      }
+  }
+  io->pool->wait_all();
+  CK(e);
+  if (!lfrzn && (fresh || io->frzn_given)) CK(cudaMemsetAsync(ctx->lfrzn.p, 0, (size_t)n * sizeof(int), ctx->stream));
+  io->ints_n = n; io->frzn_given = lfrzn != nullptr;
+  io->h2d += moved;
+  return 0;
+}
+
+// the device copies of ltype / ltg / lfrzn were overwritten by somebody else (native driver, SPME drop-in ...)
+void dlp_hostio_ints_stale(dlpgpu_ctx* ctx) {
+  if (ctx->hostio) static_cast<HostIO*>(ctx->hostio)->ints_n = -1;
+}
+
+// parts(1:natms)%f += the device's force arrays; returns when the caller's records are complete.  Everything the stream
+// holds in front of the copies (the force kernels) overlaps with nothing here, but copy and host-side addition pipeline.
+int dlp_download_add_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts) {
+  if (natms <= 0) return 0;
+  HostIO* io = io_of(ctx);
+  cudaStream_t s = ctx->stream;
+  if (io->threads == 0) {   // whole records: the device copy still holds the caller's forces, the sum is formed there
+    if (io->parts_dev.cap < (size_t)natms) return dlp_fail(ctx, DLPGPU_ERR_STATE, "drop-in forces: the records were never uploaded in whole-record mode");
+    LAUNCH(ctx, k_add_forces, cdiv(natms, 256), 256, 0, io->parts_dev.p, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p);
+    CK(cudaMemcpyAsync(parts, io->parts_dev.p, (size_t)natms * sizeof(dlpgpu_corepart), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    io->d2h += (unsigned long long)natms * sizeof(dlpgpu_corepart);
+    return 0;
+  }
+  if ((size_t)3 * natms > io->dn_cap) {
+    CK(cudaStreamSynchronize(s));
+    CK(grow_pinned(io->dn, io->dn_cap, (size_t)3 * natms));
+  }
+  CK(io->f3.ensure((size_t)3 * natms, s));
+  const int len = chunk_len(natms), nch = cdiv(natms, len);
+  for (int c = 0; c < nch; ++c) {
+    if (!io->ev[c]) CK(cudaEventCreateWithFlags(&io->ev[c], cudaEventDisableTiming));
+    io->avail[c].store(0, std::memory_order_relaxed);
+  }
+  LAUNCH(ctx, k_pack_f3, cdiv(natms, 256), 256, 0, natms, ctx->fx.p, ctx->fy.p, ctx->fz.p, io->f3.p);
+  for (int c = 0; c < nch; ++c) {
+    const int a = c * len, b = std::min(natms, a + len);
+    CK(cudaMemcpyAsync(io->dn + 3 * (size_t)a, io->f3.p + 3 * (size_t)a, (size_t)(b - a) * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(io->ev[c], s));
+  }
+  const double* dn = io->dn;
+  std::atomic<int>* avail = io->avail;
+  io->pool->start(nch, [=](int c) {
+    unsigned spins = 0;
+    int v;
+    while ((v = avail[c].load(std::memory_order_acquire)) == 0) HostPool::pause(++spins);
+    if (v < 0) return;   // the copy failed: leave the records alone
+    const int a = c * len, b = std::min(natms, a + len);
+    for (int i = a; i < b; ++i) {
+      dlpgpu_corepart& p = parts[i];
+      const double* f = dn + 3 * (size_t)i;
+      p.fxx += f[0]; p.fyy += f[1]; p.fzz += f[2];
+    }
+  });
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < nch; ++c) {
+    if (e == cudaSuccess) e = cudaEventSynchronize(io->ev[c]);
+    io->avail[c].store(e == cudaSuccess ? 1 : -1, std::memory_order_release);
+  }
+  io->pool->wait_all();
+  CK(e);
+  io->d2h += (unsigned long long)natms * 3 * sizeof(double);
+  return 0;
+}
+
+extern "C" {
+
+int dlpgpu_set_host_threads(dlpgpu_ctx* ctx, int nthreads) {
+  if (!ctx || nthreads < 0 || nthreads > 64) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->hostio) io_of(ctx);
+  HostIO* io = static_cast<HostIO*>(ctx->hostio);
+  if (io->threads != nthreads) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->parts_resident = 0; ctx->parts_current = false;   // the two modes keep the uploaded records in different places
+  }
+  io->threads = nthreads;
+  io_of(ctx);
+  return 0;
+}
+
+int dlpgpu_transfer_bytes(dlpgpu_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h, int reset) {
+  if (!ctx) return DLPGPU_ERR_ARG;
+  HostIO* io = ctx->hostio ? static_cast<HostIO*>(ctx->hostio) : nullptr;
+  if (h2d) *h2d = io ? io->h2d : 0;
+  if (d2h) *d2h = io ? io->d2h : 0;
+  if (io && reset) { io->h2d = 0; io->d2h = 0; }
+  return 0;
+}
+
+}  // extern "C"
+
+int dlp_preload_hostio() {
+  cudaFuncAttributes a;
+  const void* ks[] = {(const void*)k_pack_f3, (const void*)k_unpack_parts, (const void*)k_add_forces};
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
+  return 0;
+}

@@ -173,13 +173,24 @@ class ShortRange:
 
     def two_body_forces(self, natms, nlast, parts, unchanged_since_list=False):
         """Adds the pair forces into parts['fxx','fyy','fzz'][:natms]; returns the 16 partial sums of the C ABI.
-        unchanged_since_list: the caller asserts parts has not been written since link_cell_pairs (skips the upload)."""
+        unchanged_since_list: the caller asserts parts has not been written since link_cell_pairs (skips the upload; with
+        set_host_threads(n >= 1) only positions and charges matter, see include/dlpgpu.h)."""
         assert parts.dtype == COREPART and parts.flags.c_contiguous
         if unchanged_since_list:
             self._ck(self.L.dlpgpu_parts_unchanged_since_list(self.h))
         out = np.zeros(16)
         self._ck(self.L.dlpgpu_two_body_forces(self.h, int(natms), int(nlast), ptr(parts), ptr(out)))
         return out
+
+    def set_host_threads(self, n):
+        """0: whole corePart records by DMA (default); n >= 1: n host threads (de)interleave the useful fields (csrc/hostio.cu)."""
+        self._ck(self.L.dlpgpu_set_host_threads(self.h, int(n)))
+
+    def transfer_bytes(self, reset=False):
+        """(h2d, d2h) bytes the drop-in entry points have copied over PCIe since the last reset."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._ck(self.L.dlpgpu_transfer_bytes(self.h, C.byref(a), C.byref(b), int(bool(reset))))
+        return a.value, b.value
 
     def rdf_collect(self, ntypes, rdf_list, n_pairs, max_grid, rdf=None):
         """rdf_collect + rdf_excl_collect on the device list; rdf: (n_pairs, max_grid) float64 counts, incremented."""

@@ -34,6 +34,8 @@ SIGNATURES = {
     "dlpgpu_link_cell_pairs": (ci, [vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, pi_]),
     "dlpgpu_two_body_forces": (ci, [vp, ci, ci, vp, vp]),
     "dlpgpu_parts_unchanged_since_list": (ci, [vp]),
+    "dlpgpu_set_host_threads": (ci, [vp, ci]),
+    "dlpgpu_transfer_bytes": (ci, [vp, vp, vp, ci]),
     "dlpgpu_rdf_collect": (ci, [vp, ci, vp, ci, ci, vp]),
     "dlpgpu_vnl_check": (ci, [vp, ci, vp, pd_]),
     "dlpgpu_vnl_set_check": (ci, [vp, ci, vp]),

@@ -338,10 +338,11 @@ Contains
     Real(Kind=wp),            Intent(InOut)         :: engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex
     Logical, Optional,        Intent(In   )         :: list_just_built   !! link_cell_pairs_gpu ran in this calculate_forces
                                                                          !! AND nothing has written config%parts since --
-                                                                         !! forces included: pass neigh%update only when no
-                                                                         !! tersoff / three-body / four-body provider is
-                                                                         !! active (they add into parts%f between the two
-                                                                         !! calls, drivers.F90:675-700); otherwise .false.
+                                                                         !! forces included unless dlpgpu_set_host_threads
+                                                                         !! chose the packed mode: pass neigh%update only
+                                                                         !! when no tersoff / three-body / four-body
+                                                                         !! provider is active (they add into parts%f
+                                                                         !! between the two calls, drivers.F90:675-700).
 
     Real(c_double) :: out(16)
 

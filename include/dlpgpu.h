@@ -107,13 +107,23 @@ int dlpgpu_link_cell_pairs(dlpgpu_ctx* ctx, int natms, int nlast, const dlpgpu_c
  * of parts(1:natms) are incremented.  out[0..5] = engvdw, virvdw, engcpe_rl, vircpe_rl, engcpe_ex, vircpe_ex;
  * out[6..14] = this rank's contribution to stats%stress(1:9); out[15] = 0. */
 int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepart* parts, double out[16]);
-/* The caller asserts that NO FIELD of parts(1:nlast) -- positions, charges AND forces -- has been written since the last
- * dlpgpu_link_cell_pairs: the next dlpgpu_two_body_forces then works on the copy that call left on the device, skips its own
- * 64 nlast-byte upload, and returns parts(1:natms) = that copy + the pair forces.  calculate_forces runs tersoff_forces,
- * three_body_forces and four_body_forces between the two calls when the FIELD defines such terms (drivers.F90:675-700), and
- * they add into parts%f: with any of them active the assertion is FALSE and must not be made (their contributions would be
- * overwritten by the stale copy).  It holds for force fields whose only providers before two_body_forces are the pair terms
- * themselves (every BASELINE configuration).  One-shot: consumed by the next dlpgpu_two_body_forces. */
+/* How the drop-in entry points move corePart records (csrc/hostio.cu).  nthreads = 0 (default; or the environment variable
+ * DLPGPU_HOST_THREADS): whole records -- parts(1:nlast) go up as they are from the caller's array, which the library
+ * page-locks on first sight, the device adds its forces to that copy and parts(1:natms) come back: 64 nlast + 64 natms bytes
+ * per step, no host work.  nthreads >= 1 (at most 64): packed -- that many host threads of the library copy x, y, z, chge
+ * (32 of a record's 64 bytes) into page-locked staging buffers and ADD the returned forces (24 bytes per local atom) into
+ * parts(1:natms)%f, chunk by chunk under the DMA transfers; the caller's array is left pageable.  Half the PCIe traffic for
+ * about twice the traffic through the host's memory: worth it from about a dozen otherwise idle cores per rank.
+ * dlpgpu_transfer_bytes reports the bytes the entry points have copied over PCIe since the counters were last reset. */
+int dlpgpu_set_host_threads(dlpgpu_ctx* ctx, int nthreads);
+int dlpgpu_transfer_bytes(dlpgpu_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h, int reset);
+/* The caller asserts that positions and charges of parts(1:nlast) have not been written since the last
+ * dlpgpu_link_cell_pairs: the next dlpgpu_two_body_forces then works on what that call left on the device and skips its own
+ * upload.  In whole-record mode (the default, see dlpgpu_set_host_threads) the assertion COVERS parts%f TOO: the device adds
+ * its forces to the copy of the records it holds and returns parts(1:natms) = that copy + the pair forces, so contributions
+ * that tersoff_forces, three_body_forces or four_body_forces added in between (drivers.F90:675-700) would be overwritten --
+ * with any of them active do not make the assertion.  In packed mode the device never sees parts%f (the library's host side
+ * adds the returned forces), so only positions and charges matter.  One-shot: consumed by the next dlpgpu_two_body_forces. */
 int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
 /* SPME reciprocal-space Coulomb term, ewald_spme_forces_coul (ewald_spole.F90:244-477; SURVEY section 8f row 4, beyond the hot path
  * of the north star): B-spline charge spreading (ewald_general.F90:517-576), forward transform, the reference's influence
@@ -128,7 +138,7 @@ int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
 int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines);
 int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]);
 /* the same with the caller's corePart array (drop-in for the call at two_body.F90:298-302 when comm%mxnode == 1): parts(1:natms) are
- * uploaded, the reciprocal forces ADDED to parts(1:natms)%f, the records copied back.  It reuses the device atom arrays, so the
+ * uploaded, the reciprocal forces come back and are ADDED to parts(1:natms)%f.  It reuses the device atom arrays, so the
  * neighbour list held by the context is invalidated: call it BEFORE dlpgpu_link_cell_pairs of the step, or from a context of its own. */
 int dlpgpu_spme_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts, int megatm, double out[16]);
 /* stats%collect_pp (statistics.F90:227, set by the per-particle / heat-flux options): while on, two_body_forces (drop-in and

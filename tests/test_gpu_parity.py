@@ -788,3 +788,83 @@ def test_spme_dropin_adds_into_the_callers_records():
     for k in ("xxx", "yyy", "zzz", "chge"):
         assert np.array_equal(parts[k], before[k])
     sr.close()
+
+
+@pytest.mark.parametrize("threads", [0, 1, 3])
+def test_dropin_record_transfer_modes(threads):
+    """csrc/hostio.cu: whole records by DMA (0 host threads, the default) or packed fields -- x, y, z, chge up, this provider's
+    forces back, added into parts%f by the library's host threads.  Both give the same forces and sums; positions / charges of
+    the caller's records are never written; halo records keep their forces.  Packed mode only: whatever another provider
+    (tersoff, three-body ...: drivers.F90:675-700) put into parts%f between link_cell_pairs and two_body_forces stays.  The int
+    arrays of a second link_cell_pairs call are re-sent only where they changed."""
+    s = systems.nacl((6, 6, 6), rcut=8.0, padding=0.3, temperature=1200.0)
+    w = world_for(s, P=1)
+    w.two_body()
+    d = domain_inputs(w, 0)
+    kw = dict(lbook=s.lbook, megfrz=s.megfrz, list_excl=d["list_excl"], max_list=d["max_list"])
+    natms, nlast = d["natms"], d["nlast"]
+    up_rec, down_rec = (64, 64) if threads == 0 else (32, 24)
+    rng = np.random.default_rng(7)
+    sr = make_sr(s, d["dd"])
+    sr.set_host_threads(threads)
+    zero = d["parts"].copy()
+    for k in ("fxx", "fyy", "fzz"):
+        zero[k] = 0.0
+    sr.transfer_bytes(reset=True)
+    sr.link_cell_pairs(natms, nlast, zero, d["ltype"], d["ltg"], d["lfrzn"], want_list=False, **kw)
+    n_int = 2 + (d["lfrzn"] is not None)
+    assert sr.transfer_bytes()[0] == up_rec * nlast + 4 * n_int * nlast
+    sr.transfer_bytes(reset=True)
+    out0 = sr.two_body_forces(natms, nlast, zero, unchanged_since_list=True)
+    assert sr.transfer_bytes() == (0, down_rec * natms)             # coordinates reused, only the results came back
+    f0 = parts_forces(zero, natms)
+    fo = parts_forces(d["parts"], natms)
+    assert force_errors(f0, fo)[0] <= FORCE_TOL
+    other = d["parts"].copy()
+    for k in ("fxx", "fyy", "fzz"):
+        other[k] = rng.normal(size=nlast) * 1.0e3
+    before = other.copy()
+    sr.transfer_bytes(reset=True)
+    sr.link_cell_pairs(natms, nlast, other, d["ltype"], d["ltg"], d["lfrzn"], want_list=False, **kw)
+    assert sr.transfer_bytes()[0] == up_rec * nlast                  # same int arrays as before: none of them sent again
+    if threads > 0:
+        for k in ("fxx", "fyy", "fzz"):                              # "another provider" adds after the list build
+            other[k][:natms] += 17.0
+            before[k][:natms] += 17.0
+    out1 = sr.two_body_forces(natms, nlast, other, unchanged_since_list=True)
+    delta = np.stack([other[k][:natms] - before[k][:natms] for k in ("fxx", "fyy", "fzz")], 1)
+    assert np.abs(delta - f0).max() <= 1e-9 * np.abs(f0).max()       # f_before + f rounds once at |f_before| ~ 1e3
+    assert np.allclose(out1, out0, rtol=1e-12, atol=1e-12 * np.abs(out0).max())
+    for k in ("fxx", "fyy", "fzz"):
+        assert np.array_equal(other[k][natms:], before[k][natms:])   # halo records: forces untouched
+    for k in ("xxx", "yyy", "zzz", "chge"):
+        assert np.array_equal(other[k], before[k])
+    # plain call (own upload)
+    sr.transfer_bytes(reset=True)
+    again = zero.copy()
+    for k in ("fxx", "fyy", "fzz"):
+        again[k] = 0.0
+    sr.two_body_forces(natms, nlast, again)
+    assert sr.transfer_bytes() == (up_rec * nlast, down_rec * natms)
+    assert np.abs(parts_forces(again, natms) - f0).max() <= 1e-12 * np.abs(f0).max()
+    # one atom of another type: the chunk that holds it is sent again and the forces follow
+    lt = d["ltype"].copy()
+    lt[5] = lt[5] % 2 + 1
+    sr.transfer_bytes(reset=True)
+    sr.link_cell_pairs(natms, nlast, again, lt, d["ltg"], d["lfrzn"], want_list=False, **kw)
+    sent = sr.transfer_bytes()[0] - up_rec * nlast
+    assert 0 < sent <= 4 * nlast
+    for k in ("fxx", "fyy", "fzz"):
+        again[k] = 0.0
+    sr.two_body_forces(natms, nlast, again, unchanged_since_list=True)
+    assert np.abs(parts_forces(again, natms)[5] - f0[5]).max() > 1e-6 * np.abs(f0).max()
+    # switching the mode invalidates what the device holds of the caller's records
+    sr.set_host_threads(2 if threads == 0 else 0)
+    with pytest.raises(Exception):
+        sr.two_body_forces(natms, nlast, again, unchanged_since_list=True)
+    for k in ("fxx", "fyy", "fzz"):
+        zero[k] = 0.0
+    sr.link_cell_pairs(natms, nlast, zero, d["ltype"], d["ltg"], d["lfrzn"], want_list=False, **kw)
+    sr.two_body_forces(natms, nlast, zero, unchanged_since_list=True)
+    assert np.abs(parts_forces(zero, natms) - f0).max() <= 1e-12 * np.abs(f0).max()
+    sr.close()
