@@ -608,11 +608,14 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     if transport is not None:
         t = transport.allreduce_max(t)
     up, down = sr2.transfer_bytes()
+    tt = sr2.transfer_times()
     h2d = up / steps                                       # x, y, z, chge of parts(1:nlast) per step + the chunks of ltype / ltg / lfrzn that changed
     d2h = down / steps + 16 * 8                            # forces of parts(1:natms) + the 16 sums
     sr2.close()
     return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
             "steps": steps, "rebuild_every": interval, "ms_per_step": 1e3 * t / steps, "host_threads": host_threads,
+            "host_ms": {"upload_per_call": 1e3 * tt["upload_s"] / max(tt["uploads"], 1), "force_kernels_per_call": 1e3 * tt["wait_s"] / max(tt["downloads"], 1),
+                        "download_per_call": 1e3 * tt["download_s"] / max(tt["downloads"], 1)} if host_threads else None,
             "api": "dlpgpu_link_cell_pairs + dlpgpu_two_body_forces (include/dlpgpu.h) on host corePart arrays"}
 
 

@@ -124,6 +124,7 @@ struct dlpgpu_ctx {
   void* hostio = nullptr;             // hostio.cu: worker pool, page-locked staging buffers and byte counters of the drop-in entry points
   int* dc_pinned = nullptr;           // page-locked image of the exchange's device counts (dlpgpu_dev_xchg_init allocates it)
   std::vector<int> st_uploaded;       // the stencil arrays the device currently holds (dlp_build_lists uploads on change)
+  DBuf<int> row_perm;                 // rows of each window of DLP_ROW_WIN atoms ordered by length (longest first, -1 = no row): k_pair_v2 deals them to its warps
   DBuf<float> cell_box;               // {lo, hi} float4 per link cell: bounding boxes of the cells' atoms (k_cell_boxes)
   DBuf<unsigned> fnbr;                // frozen-frozen partners per row (kept for rdf_frzn_collect only), pitch fpitch
   DBuf<int> nfnbr;
@@ -258,6 +259,7 @@ int dlp_fail(dlpgpu_ctx* ctx, int code, const char* fmt, ...);
     int _rc = (expr);       \
     if (_rc != 0) return _rc; \
   } while (0)
+#define DLP_ROW_WIN 64   // rows per block pass of k_pair_v2 (512 threads / 8 lanes per row)
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                    \
   do {                                                               \
     kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \

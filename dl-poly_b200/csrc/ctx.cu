@@ -180,7 +180,7 @@ int dlpgpu_destroy(dlpgpu_ctx* ctx) {
   if (ctx->tab2_tex) { cudaDestroyTextureObject(ctx->tab2_tex); ctx->tab2_tex = 0; }
   if (ctx->tab2h_tex) { cudaDestroyTextureObject(ctx->tab2h_tex); ctx->tab2h_tex = 0; }
   dlp_spme_release(ctx);
-  ctx->fnbr.release(ctx->stream); ctx->nfnbr.release(ctx->stream); ctx->cell_box.release(ctx->stream); ctx->movers.release(ctx->stream);
+  ctx->fnbr.release(ctx->stream); ctx->nfnbr.release(ctx->stream); ctx->row_perm.release(ctx->stream); ctx->cell_box.release(ctx->stream); ctx->movers.release(ctx->stream);
   ctx->pp_pos.release(ctx->stream); ctx->pp_neg.release(ctx->stream); ctx->pp_energy.release(ctx->stream); ctx->pp_stress.release(ctx->stream);
   ctx->tab2h.release(ctx->stream); ctx->tab2s.release(ctx->stream); ctx->rdf_list.release(ctx->stream); ctx->rdf_hist.release(ctx->stream);
   ctx->tab4.release(ctx->stream); ctx->tab2.release(ctx->stream); ctx->cnt64.release(ctx->stream); ctx->info_s.release(ctx->stream); ctx->st_rows.release(ctx->stream);

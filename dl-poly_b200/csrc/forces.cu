@@ -720,7 +720,9 @@ template <int TPR, int VT, int EW, int SG, int TX = 0, int NT = 512, int XC = 0>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const double4* __restrict__ posq_s, const unsigned* __restrict__ nbr,
           const int* __restrict__ nnbr, const double2* __restrict__ tab, double* __restrict__ fpos, double* __restrict__ fneg,
-          double* __restrict__ partial, const unsigned* __restrict__ xnbr = nullptr, const int* __restrict__ nxnbr = nullptr) {
+          double* __restrict__ partial, const int* __restrict__ row_perm, const unsigned* __restrict__ xnbr = nullptr,
+          const int* __restrict__ nxnbr = nullptr) {
+  static_assert(NT / TPR == DLP_ROW_WIN, "row_perm is built for windows of one block pass");
   extern __shared__ __align__(16) double2 s_tab[];
   for (int k = threadIdx.x; k < ((TX & 8) ? 1 : 2) * P.ne; k += NT) s_tab[k] = tab[k];
   __syncthreads();
@@ -740,9 +742,14 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
   // rows are dealt to the blocks pass by pass (block b takes rows b RPB ... of every window of gridDim.x RPB rows), so the
   // SMs work on one compact slab of the box at a time and share its coordinates and j-side accumulators in L2: giving each
   // block one long run of consecutive rows instead costs 35 % (1.73 against 1.28 ms on 1 M NaCl ions, scripts/chunk_probe.py)
+  // within a pass the rows are taken in order of length (row_perm, longest first: the four rows of a warp are about equally
+  // long), and the length classes rotate over the warps from pass to pass so that every warp sees long and short rows alike
+  constexpr int GPW = 32 / TPR, NW = NT / 32;   // row groups per warp, warps
   for (int base = blockIdx.x * RPB; base < P.natms; base += gridDim.x * RPB) {
-    const int t = min(base + grp, P.natms - 1);             // surplus groups of the last pass redo the last row and drop it
-    const bool rowlive = base + grp < P.natms;
+    const int cls = ((grp / GPW) + base / (int)(gridDim.x * RPB)) % NW;   // + the number of the pass
+    const int tp = row_perm[base + cls * GPW + (grp % GPW)];
+    const bool rowlive = tp >= 0;                           // surplus slots of the last window redo row 0 and drop it
+    const int t = max(tp, 0);
     const double4 pi = posq_s[loc_slot[t]];
     const int npad = rowlive ? (nnbr[t] + 2 * TPR - 1) & ~(2 * TPR - 1) : 0;   // rows are sentinel-padded past npad + 2 TPR (dlp_pad_row)
     const double qi_s = pi.w * P.scaling;                                     // ewald_spole.F90:114
@@ -1144,7 +1151,7 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
   do {                                                                                                                         \
     CK(cudaFuncSetAttribute(k_pair_v2<8, V, E, S, TXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));              \
     LAUNCH(ctx, (k_pair_v2<8, V, E, S, TXV>), blocks, 512, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p, \
-           t2, fpos, fneg, ctx->partial.p);                                                                                    \
+           t2, fpos, fneg, ctx->partial.p, ctx->row_perm.p);                                                                                  \
   } while (0)
     const int v = P.vdw_on ? 1 : 0, e = P.ew_on ? 1 : 0, sg = (!v || !e || P.same_grid) ? 1 : 0;
     // measured on B200, 1 M NaCl ions: all six reads in LDS 1.438 ms, vdW h through the texture pipe 1.394 ms, combined fp32 h
@@ -1158,17 +1165,17 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
           const size_t smem8 = (size_t)ctx->tab2_ne * 16;
           CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 8, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
           LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 8, 512, 1>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p,
-                 ctx->nnbr.p, t2s, fpos, fneg, ctx->partial.p, ctx->xnbr.p, ctx->nxnbr.p);
+                 ctx->nnbr.p, t2s, fpos, fneg, ctx->partial.p, ctx->row_perm.p, ctx->xnbr.p, ctx->nxnbr.p);
         } else {
           CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 2, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
           LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 2, 512, 1>), blocks, 512, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p,
-                 ctx->nnbr.p, t2, fpos, fneg, ctx->partial.p, ctx->xnbr.p, ctx->nxnbr.p);
+                 ctx->nnbr.p, t2, fpos, fneg, ctx->partial.p, ctx->row_perm.p, ctx->xnbr.p, ctx->nxnbr.p);
         }
       } else if (sg && tx == 8) {
         const size_t smem8 = (size_t)ctx->tab2_ne * 16;
         CK(cudaFuncSetAttribute(k_pair_v2<8, 1, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
         LAUNCH(ctx, (k_pair_v2<8, 1, 1, 1, 8>), blocks, 512, smem8, Q, ctx->tab2h_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
-               t2s, fpos, fneg, ctx->partial.p);
+               t2s, fpos, fneg, ctx->partial.p, ctx->row_perm.p);
       } else if (sg) DLP_V2(1, 1, 1, 2);
       else DLP_V2(1, 1, 0, 2);
     } else if (v) {

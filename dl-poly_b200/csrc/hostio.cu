@@ -24,6 +24,7 @@
 // modes; only chunks that differ are copied again (in a serial run the local atoms never change their order).
 // Counters of the bytes that really crossed PCIe are kept for bench.py (dlpgpu_transfer_bytes).
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <functional>
@@ -140,7 +141,11 @@ struct HostIO {
   cudaEvent_t ev[MAXCH] = {};
   std::atomic<int> avail[MAXCH];
   unsigned long long h2d = 0, d2h = 0;
+  double t_up = 0.0, t_wait = 0.0, t_down = 0.0;   // seconds: uploads (call to last copy queued), download: call to first chunk on the host, first chunk to return
+  int n_up = 0, n_down = 0;
 };
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int default_threads() {   // whole records unless the user opts in: a library cannot know how many cores its rank may take
   if (const char* e = getenv("DLPGPU_HOST_THREADS")) { const int v = atoi(e); if (v >= 0) return std::min(v, 64); }
@@ -246,6 +251,7 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
     CK(grow_pinned(io->up, io->up_cap, (size_t)4 * n));
   }
   const int len = chunk_len(n), nch = cdiv(n, len);
+  const double t0 = now_s();
   double* up = io->up;
   io->pool->start(nch, [=](int c) {
     const int a = c * len, b = std::min(n, a + len);
@@ -272,6 +278,7 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   }
   io->pool->wait_all();
   CK(e);
+  io->t_up += now_s() - t0; io->n_up++;
   io->h2d += (unsigned long long)n * 4 * sizeof(double);
   ctx->tol_fresh = false; ctx->pub_fresh = false;
   ctx->parts_resident = 0; ctx->parts_current = false;
@@ -377,12 +384,16 @@ int dlp_download_add_forces(dlpgpu_ctx* ctx, int natms, dlpgpu_corepart* parts) 
     }
   });
   cudaError_t e = cudaSuccess;
+  const double t0 = now_s();
+  double t1 = t0;
   for (int c = 0; c < nch; ++c) {
     if (e == cudaSuccess) e = cudaEventSynchronize(io->ev[c]);
+    if (c == 0) t1 = now_s();
     io->avail[c].store(e == cudaSuccess ? 1 : -1, std::memory_order_release);
   }
   io->pool->wait_all();
   CK(e);
+  io->t_wait += t1 - t0; io->t_down += now_s() - t1; io->n_down++;
   io->d2h += (unsigned long long)natms * 3 * sizeof(double);
   return 0;
 }
@@ -408,7 +419,15 @@ int dlpgpu_transfer_bytes(dlpgpu_ctx* ctx, unsigned long long* h2d, unsigned lon
   HostIO* io = ctx->hostio ? static_cast<HostIO*>(ctx->hostio) : nullptr;
   if (h2d) *h2d = io ? io->h2d : 0;
   if (d2h) *d2h = io ? io->d2h : 0;
-  if (io && reset) { io->h2d = 0; io->d2h = 0; }
+  if (io && reset) { io->h2d = 0; io->d2h = 0; io->t_up = io->t_wait = io->t_down = 0.0; io->n_up = io->n_down = 0; }
+  return 0;
+}
+
+int dlpgpu_transfer_times(dlpgpu_ctx* ctx, double out[5]) {
+  if (!ctx || !out) return DLPGPU_ERR_ARG;
+  HostIO* io = ctx->hostio ? static_cast<HostIO*>(ctx->hostio) : nullptr;
+  out[0] = io ? io->t_up : 0.0; out[1] = io ? io->t_wait : 0.0; out[2] = io ? io->t_down : 0.0;
+  out[3] = io ? io->n_up : 0; out[4] = io ? io->n_down : 0;
   return 0;
 }
 

@@ -192,6 +192,12 @@ class ShortRange:
         self._ck(self.L.dlpgpu_transfer_bytes(self.h, C.byref(a), C.byref(b), int(bool(reset))))
         return a.value, b.value
 
+    def transfer_times(self):
+        """Packed mode: host seconds in uploads, waiting for the force kernels, in downloads; and the call counts."""
+        out = np.zeros(5)
+        self._ck(self.L.dlpgpu_transfer_times(self.h, ptr(out)))
+        return {"upload_s": out[0], "wait_s": out[1], "download_s": out[2], "uploads": int(out[3]), "downloads": int(out[4])}
+
     def rdf_collect(self, ntypes, rdf_list, n_pairs, max_grid, rdf=None):
         """rdf_collect + rdf_excl_collect on the device list; rdf: (n_pairs, max_grid) float64 counts, incremented."""
         lst = np.ascontiguousarray(rdf_list, dtype=np.int32)

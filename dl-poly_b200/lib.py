@@ -36,6 +36,7 @@ SIGNATURES = {
     "dlpgpu_parts_unchanged_since_list": (ci, [vp]),
     "dlpgpu_set_host_threads": (ci, [vp, ci]),
     "dlpgpu_transfer_bytes": (ci, [vp, vp, vp, ci]),
+    "dlpgpu_transfer_times": (ci, [vp, vp]),
     "dlpgpu_rdf_collect": (ci, [vp, ci, vp, ci, ci, vp]),
     "dlpgpu_vnl_check": (ci, [vp, ci, vp, pd_]),
     "dlpgpu_vnl_set_check": (ci, [vp, ci, vp]),

@@ -117,6 +117,10 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
  * dlpgpu_transfer_bytes reports the bytes the entry points have copied over PCIe since the counters were last reset. */
 int dlpgpu_set_host_threads(dlpgpu_ctx* ctx, int nthreads);
 int dlpgpu_transfer_bytes(dlpgpu_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h, int reset);
+/* packed mode, host clock since the last reset: out[0] = seconds inside the uploads (first record packed to last copy queued),
+ * out[1] = seconds a force download waited for its first chunk (the force kernels), out[2] = seconds from there to the last
+ * record updated, out[3], out[4] = number of uploads / downloads. */
+int dlpgpu_transfer_times(dlpgpu_ctx* ctx, double out[5]);
 /* The caller asserts that positions and charges of parts(1:nlast) have not been written since the last
  * dlpgpu_link_cell_pairs: the next dlpgpu_two_body_forces then works on what that call left on the device and skips its own
  * upload.  In whole-record mode (the default, see dlpgpu_set_host_threads) the assertion COVERS parts%f TOO: the device adds
