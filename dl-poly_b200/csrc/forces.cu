@@ -741,7 +741,8 @@ k_pair_v2(P2 P, cudaTextureObject_t tex, const int* __restrict__ loc_slot, const
 
   // rows are dealt to the blocks pass by pass (block b takes rows b RPB ... of every window of gridDim.x RPB rows), so the
   // SMs work on one compact slab of the box at a time and share its coordinates and j-side accumulators in L2: giving each
-  // block one long run of consecutive rows instead costs 35 % (1.73 against 1.28 ms on 1 M NaCl ions, scripts/chunk_probe.py)
+  // block one long run of consecutive rows instead costs 35 % (1.73 against 1.28 ms on 1 M NaCl ions, scripts/chunk_probe.py),
+  // and so does every step towards it: 2 / 4 / 8 / 32 consecutive windows per block 1.224 / 1.246 / 1.299 / 1.596 against 1.212 ms
   // within a pass the rows are taken in order of length (row_perm, longest first: the four rows of a warp are about equally
   // long), and the length classes rotate over the warps from pass to pass so that every warp sees long and short rows alike
   constexpr int GPW = 32 / TPR, NW = NT / 32;   // row groups per warp, warps
