@@ -559,7 +559,7 @@ def run_gpu(args):
 def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
     """The same metric through dlpgpu_link_cell_pairs / dlpgpu_two_body_forces with host (pinned) corePart buffers:
     every step sends parts(1:nlast) up and brings the forces of parts(1:natms) back -- whole 64-byte records by DMA, or, when
-    the rank has a dozen cores to itself, x, y, z, chge (32 B) up and the forces (24 B) down, (de)interleaved by the library's
+    the rank has a dozen cores to itself, x, y, z (24 B) up and the forces (24 B) down, (de)interleaved by the library's
     host threads (csrc/hostio.cu); every `interval`-th step (the rebuild frequency observed in the device-resident run) also
     rebuilds the list from host arrays.  The byte counts are the library's own counters."""
     from dl_poly_b200 import engine
@@ -609,7 +609,7 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
         t = transport.allreduce_max(t)
     up, down = sr2.transfer_bytes()
     tt = sr2.transfer_times()
-    h2d = up / steps                                       # x, y, z, chge of parts(1:nlast) per step + the chunks of ltype / ltg / lfrzn that changed
+    h2d = up / steps                                       # parts(1:nlast) per step (whole records, or x, y, z and the charges that changed) + the chunks of ltype / ltg / lfrzn that changed
     d2h = down / steps + 16 * 8                            # forces of parts(1:natms) + the 16 sums
     sr2.close()
     return {"value": natoms_total * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),

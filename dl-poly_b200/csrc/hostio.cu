@@ -11,13 +11,14 @@
 //   useful bytes is slower still (scripts/pcie_test.cu).
 // * packed (dlpgpu_set_host_threads(ctx, n >= 1)): n host threads of the library (de)interleave the fields in chunks that
 //   overlap with the DMA engine:
-//     up:    workers copy {x, y, z, chge} of a chunk of records into a page-locked staging buffer laid out like the device's
-//            posq array (non-temporal stores); the calling thread queues the chunk's H2D copy, straight into posq, as soon
-//            as the chunk is packed;
+//     up:    workers copy {x, y, z} of a chunk of records into a page-locked staging buffer (non-temporal stores) and compare
+//            the charge with the copy the device holds (charges only change place when the local order changes); the
+//            calling thread queues the chunk's H2D copy -- and the chunk's charges if any differed -- as soon as the chunk is
+//            packed; one small kernel merges coordinates and charges into the device's posq array;
 //     down:  the device interleaves its force arrays into {fx, fy, fz} triples, the calling thread queues one D2H copy and
 //            one event per chunk, workers add a chunk's triples into parts%f as soon as its event has completed -- the same
 //            one rounding per component as the reference's accumulation into parts%f.  The device never sees parts%f.
-//   64 MB per 1 M-ion step over PCIe, but 280 MB through the host's memory system: it pays when a rank has a dozen otherwise
+//   56 MB per 1 M-ion step over PCIe, but 280 MB through the host's memory system: it pays when a rank has a dozen otherwise
 //   idle cores (measured on the pool's 16-vCPU boxes, 1 M ions: 15.4 / 9.5 / 6.8 / 5.2 / 4.2 ms per step with 1 / 2 / 4 / 8 /
 //   12 threads against 4.6 ms for whole records; profiles/r2_s48_*).
 // ltype / ltg / lfrzn of link_cell_pairs are compared with the page-locked copy of the previous call chunk by chunk in both
@@ -130,7 +131,11 @@ class HostPool {
 struct HostIO {
   HostPool* pool = nullptr;
   int threads = -1;             // -1: not chosen yet, 0: whole records by DMA, >= 1: packed fields through that many workers
-  double* up = nullptr;  size_t up_cap = 0;     // page-locked {x, y, z, chge} per record
+  double* up = nullptr;  size_t up_cap = 0;     // page-locked {x, y, z} per record
+  double* chg = nullptr; size_t chg_cap = 0;    // page-locked copy of the charges the device holds (they change with the local order only)
+  int chg_n = -1;                               // records chg / chg_dev are valid for
+  const double* chg_dev_seen = nullptr;
+  DBuf<double> xyz3, chg_dev;                   // device side of the two
   double* dn = nullptr;  size_t dn_cap = 0;     // page-locked {fx, fy, fz} per local atom
   int* ints = nullptr;   size_t ints_cap = 0;   // page-locked ltype | ltg | lfrzn of the previous link_cell_pairs call
   int ints_n = -1;                              // records the device copies of the three arrays are valid for
@@ -196,6 +201,11 @@ void pin_host_parts(HostIO* io, const void* p, size_t bytes) {
   if (e != cudaSuccess) cudaGetLastError();
 }
 
+__global__ void k_merge_xyzq(int n, const double* __restrict__ xyz3, const double* __restrict__ chg, double4* __restrict__ posq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  posq[i] = make_double4(xyz3[3 * (size_t)i], xyz3[3 * (size_t)i + 1], xyz3[3 * (size_t)i + 2], chg[i]);
+}
 __global__ void k_unpack_parts(const dlpgpu_corepart* __restrict__ parts, int n, double4* __restrict__ posq) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -222,6 +232,8 @@ void dlp_hostio_release(dlpgpu_ctx* ctx) {
   HostIO* io = static_cast<HostIO*>(ctx->hostio);
   delete io->pool;
   if (io->up) cudaFreeHost(io->up);
+  if (io->chg) cudaFreeHost(io->chg);
+  io->xyz3.release(ctx->stream); io->chg_dev.release(ctx->stream);
   if (io->dn) cudaFreeHost(io->dn);
   if (io->ints) cudaFreeHost(io->ints);
   io->f3.release(ctx->stream); io->parts_dev.release(ctx->stream);
@@ -246,40 +258,67 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
     ctx->parts_resident = 0; ctx->parts_current = false;
     return 0;
   }
-  if ((size_t)4 * n > io->up_cap) {
+  if ((size_t)3 * n > io->up_cap || (size_t)n > io->chg_cap) {
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(grow_pinned(io->up, io->up_cap, (size_t)4 * n));
+    CK(grow_pinned(io->up, io->up_cap, (size_t)3 * n));
+    if ((size_t)n > io->chg_cap) { CK(grow_pinned(io->chg, io->chg_cap, (size_t)n)); io->chg_n = -1; }
   }
+  CK(io->xyz3.ensure((size_t)3 * n, ctx->stream)); CK(io->chg_dev.ensure((size_t)n, ctx->stream));
+  const bool fresh = io->chg_n != n || io->chg_dev_seen != io->chg_dev.p;
   const int len = chunk_len(n), nch = cdiv(n, len);
   const double t0 = now_s();
   double* up = io->up;
+  double* chg = io->chg;
+  std::atomic<unsigned long long> changed{0};
+  std::atomic<unsigned long long>* ch = &changed;
   io->pool->start(nch, [=](int c) {
     const int a = c * len, b = std::min(n, a + len);
-    for (int i = a; i < b; ++i) {
-      const dlpgpu_corepart& p = parts[i];
-      double* q = up + 4 * (size_t)i;
+    bool diff = fresh;
+    int i = a;
 #if defined(__x86_64__)
-      _mm_stream_pd(q, _mm_loadu_pd(&p.xxx));             // the staging buffer is only read by the DMA engine: keep it out of the caches
-      _mm_stream_pd(q + 2, _mm_set_pd(p.chge, p.zzz));
-#else
-      q[0] = p.xxx; q[1] = p.yyy; q[2] = p.zzz; q[3] = p.chge;
+    // the staging buffer is only read by the DMA engine: non-temporal stores keep it out of the caches and save the read for
+    // ownership; two records make three aligned 16-byte stores (chunks start at even records, 48 bytes per pair)
+    for (; i + 1 < b; i += 2) {
+      const dlpgpu_corepart& p0 = parts[i];
+      const dlpgpu_corepart& p1 = parts[i + 1];
+      double* q = up + 3 * (size_t)i;
+      _mm_stream_pd(q, _mm_loadu_pd(&p0.xxx));
+      _mm_stream_pd(q + 2, _mm_set_pd(p1.xxx, p0.zzz));
+      _mm_stream_pd(q + 4, _mm_loadu_pd(&p1.yyy));
+      if (std::memcmp(&chg[i], &p0.chge, sizeof(double)) != 0) { chg[i] = p0.chge; diff = true; }
+      if (std::memcmp(&chg[i + 1], &p1.chge, sizeof(double)) != 0) { chg[i + 1] = p1.chge; diff = true; }
+    }
 #endif
+    for (; i < b; ++i) {
+      const dlpgpu_corepart& p = parts[i];
+      double* q = up + 3 * (size_t)i;
+      q[0] = p.xxx; q[1] = p.yyy; q[2] = p.zzz;
+      if (std::memcmp(&chg[i], &p.chge, sizeof(double)) != 0) { chg[i] = p.chge; diff = true; }
     }
 #if defined(__x86_64__)
     _mm_sfence();
 #endif
+    if (diff) ch->fetch_or(1ull << c, std::memory_order_relaxed);
   });
   cudaError_t e = cudaSuccess;
+  unsigned long long moved = 0;
   for (int c = 0; c < nch; ++c) {
     io->pool->wait_chunk(c);
     const int a = c * len, b = std::min(n, a + len);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(ctx->posq.p + a, up + 4 * (size_t)a, (size_t)(b - a) * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+      e = cudaMemcpyAsync(io->xyz3.p + 3 * (size_t)a, up + 3 * (size_t)a, (size_t)(b - a) * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    moved += (unsigned long long)(b - a) * 3 * sizeof(double);
+    if ((changed.load(std::memory_order_relaxed) >> c & 1ull) && e == cudaSuccess) {
+      e = cudaMemcpyAsync(io->chg_dev.p + a, chg + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+      moved += (unsigned long long)(b - a) * sizeof(double);
+    }
   }
   io->pool->wait_all();
   CK(e);
+  LAUNCH(ctx, k_merge_xyzq, cdiv(n, 256), 256, 0, n, io->xyz3.p, io->chg_dev.p, ctx->posq.p);
+  io->chg_n = n; io->chg_dev_seen = io->chg_dev.p;
   io->t_up += now_s() - t0; io->n_up++;
-  io->h2d += (unsigned long long)n * 4 * sizeof(double);
+  io->h2d += moved;
   ctx->tol_fresh = false; ctx->pub_fresh = false;
   ctx->parts_resident = 0; ctx->parts_current = false;
   return 0;
@@ -435,7 +474,7 @@ int dlpgpu_transfer_times(dlpgpu_ctx* ctx, double out[5]) {
 
 int dlp_preload_hostio() {
   cudaFuncAttributes a;
-  const void* ks[] = {(const void*)k_pack_f3, (const void*)k_unpack_parts, (const void*)k_add_forces};
+  const void* ks[] = {(const void*)k_pack_f3, (const void*)k_unpack_parts, (const void*)k_add_forces, (const void*)k_merge_xyzq};
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
   return 0;
 }

@@ -110,8 +110,8 @@ int dlpgpu_two_body_forces(dlpgpu_ctx* ctx, int natms, int nlast, dlpgpu_corepar
 /* How the drop-in entry points move corePart records (csrc/hostio.cu).  nthreads = 0 (default; or the environment variable
  * DLPGPU_HOST_THREADS): whole records -- parts(1:nlast) go up as they are from the caller's array, which the library
  * page-locks on first sight, the device adds its forces to that copy and parts(1:natms) come back: 64 nlast + 64 natms bytes
- * per step, no host work.  nthreads >= 1 (at most 64): packed -- that many host threads of the library copy x, y, z, chge
- * (32 of a record's 64 bytes) into page-locked staging buffers and ADD the returned forces (24 bytes per local atom) into
+ * per step, no host work.  nthreads >= 1 (at most 64): packed -- that many host threads of the library copy x, y, z (24 of a
+ * record's 64 bytes; the charges only where they differ from what the device holds) into page-locked staging buffers and ADD the returned forces (24 bytes per local atom) into
  * parts(1:natms)%f, chunk by chunk under the DMA transfers; the caller's array is left pageable.  Half the PCIe traffic for
  * about twice the traffic through the host's memory: worth it from about a dozen otherwise idle cores per rank.
  * dlpgpu_transfer_bytes reports the bytes the entry points have copied over PCIe since the counters were last reset. */

@@ -803,7 +803,8 @@ def test_dropin_record_transfer_modes(threads):
     d = domain_inputs(w, 0)
     kw = dict(lbook=s.lbook, megfrz=s.megfrz, list_excl=d["list_excl"], max_list=d["max_list"])
     natms, nlast = d["natms"], d["nlast"]
-    up_rec, down_rec = (64, 64) if threads == 0 else (32, 24)
+    up_rec, down_rec = (64, 64) if threads == 0 else (24, 24)      # packed: x, y, z up (+ 8 for the charge where it changed)
+    up_first = 64 if threads == 0 else 32
     rng = np.random.default_rng(7)
     sr = make_sr(s, d["dd"])
     sr.set_host_threads(threads)
@@ -813,7 +814,7 @@ def test_dropin_record_transfer_modes(threads):
     sr.transfer_bytes(reset=True)
     sr.link_cell_pairs(natms, nlast, zero, d["ltype"], d["ltg"], d["lfrzn"], want_list=False, **kw)
     n_int = 2 + (d["lfrzn"] is not None)
-    assert sr.transfer_bytes()[0] == up_rec * nlast + 4 * n_int * nlast
+    assert sr.transfer_bytes()[0] == up_first * nlast + 4 * n_int * nlast
     sr.transfer_bytes(reset=True)
     out0 = sr.two_body_forces(natms, nlast, zero, unchanged_since_list=True)
     assert sr.transfer_bytes() == (0, down_rec * natms)             # coordinates reused, only the results came back
@@ -858,6 +859,17 @@ def test_dropin_record_transfer_modes(threads):
         again[k] = 0.0
     sr.two_body_forces(natms, nlast, again, unchanged_since_list=True)
     assert np.abs(parts_forces(again, natms)[5] - f0[5]).max() > 1e-6 * np.abs(f0).max()
+    # a changed charge travels with its chunk
+    if threads > 0:
+        q = again.copy()
+        q["chge"][7] *= 0.5
+        for k in ("fxx", "fyy", "fzz"):
+            q[k] = 0.0
+        sr.transfer_bytes(reset=True)
+        sr.two_body_forces(natms, nlast, q)
+        sent = sr.transfer_bytes()[0] - up_rec * nlast
+        assert 0 < sent <= 8 * nlast
+        assert np.abs(parts_forces(q, natms)[7]).max() > 0 and not np.allclose(parts_forces(q, natms)[7], parts_forces(again, natms)[7])
     # switching the mode invalidates what the device holds of the caller's records
     sr.set_host_threads(2 if threads == 0 else 0)
     with pytest.raises(Exception):
