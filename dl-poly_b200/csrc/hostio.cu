@@ -133,7 +133,7 @@ struct HostIO {
   int threads = -1;             // -1: not chosen yet, 0: whole records by DMA, >= 1: packed fields through that many workers
   double* up = nullptr;  size_t up_cap = 0;     // page-locked {x, y, z} per record
   double* chg = nullptr; size_t chg_cap = 0;    // page-locked copy of the charges the device holds (they change with the local order only)
-  int chg_n = -1;                               // records chg / chg_dev are valid for
+  int chg_n = 0;                                // leading records for which chg and chg_dev hold the same, valid charges
   const double* chg_dev_seen = nullptr;
   DBuf<double> xyz3, chg_dev;                   // device side of the two
   double* dn = nullptr;  size_t dn_cap = 0;     // page-locked {fx, fy, fz} per local atom
@@ -261,10 +261,11 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   if ((size_t)3 * n > io->up_cap || (size_t)n > io->chg_cap) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(grow_pinned(io->up, io->up_cap, (size_t)3 * n));
-    if ((size_t)n > io->chg_cap) { CK(grow_pinned(io->chg, io->chg_cap, (size_t)n)); io->chg_n = -1; }
+    if ((size_t)n > io->chg_cap) { CK(grow_pinned(io->chg, io->chg_cap, (size_t)n)); io->chg_n = 0; }
   }
   CK(io->xyz3.ensure((size_t)3 * n, ctx->stream)); CK(io->chg_dev.ensure((size_t)n, ctx->stream));
-  const bool fresh = io->chg_n != n || io->chg_dev_seen != io->chg_dev.p;
+  if (io->chg_dev_seen != io->chg_dev.p) io->chg_n = 0;   // the device array was re-allocated
+  const int known = io->chg_n;                             // vnl_check sends natms records, the force call nlast: a prefix stays valid
   const int len = chunk_len(n), nch = cdiv(n, len);
   const double t0 = now_s();
   double* up = io->up;
@@ -273,7 +274,7 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   std::atomic<unsigned long long>* ch = &changed;
   io->pool->start(nch, [=](int c) {
     const int a = c * len, b = std::min(n, a + len);
-    bool diff = fresh;
+    bool diff = b > known;
     int i = a;
 #if defined(__x86_64__)
     // the staging buffer is only read by the DMA engine: non-temporal stores keep it out of the caches and save the read for
@@ -316,7 +317,7 @@ int dlp_upload_parts(dlpgpu_ctx* ctx, int n, const dlpgpu_corepart* parts) {
   io->pool->wait_all();
   CK(e);
   LAUNCH(ctx, k_merge_xyzq, cdiv(n, 256), 256, 0, n, io->xyz3.p, io->chg_dev.p, ctx->posq.p);
-  io->chg_n = n; io->chg_dev_seen = io->chg_dev.p;
+  io->chg_n = std::max(known, n); io->chg_dev_seen = io->chg_dev.p;
   io->t_up += now_s() - t0; io->n_up++;
   io->h2d += moved;
   ctx->tol_fresh = false; ctx->pub_fresh = false;

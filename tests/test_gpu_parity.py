@@ -848,6 +848,15 @@ def test_dropin_record_transfer_modes(threads):
     sr.two_body_forces(natms, nlast, again)
     assert sr.transfer_bytes() == (up_rec * nlast, down_rec * natms)
     assert np.abs(parts_forces(again, natms) - f0).max() <= 1e-12 * np.abs(f0).max()
+    # vnl_check sends parts(1:natms), the force call parts(1:nlast): neither re-sends a charge
+    sr.transfer_bytes(reset=True)
+    assert sr.vnl_check(natms, again) == 0.0
+    assert sr.transfer_bytes()[0] == up_rec * natms
+    sr.transfer_bytes(reset=True)
+    sr.two_body_forces(natms, nlast, again)
+    assert sr.transfer_bytes()[0] == up_rec * nlast
+    for k in ("fxx", "fyy", "fzz"):
+        again[k] = 0.0
     # one atom of another type: the chunk that holds it is sent again and the forces follow
     lt = d["ltype"].copy()
     lt[5] = lt[5] % 2 + 1
