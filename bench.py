@@ -362,6 +362,38 @@ def sub_run(torch, dd, transport, local, world, workload, strong, dt, steps, war
             "flop_per_atom_step": roof["flop_per_atom_step"], "gpu_launches": res["launches"]}
 
 
+def spme_sub_run_domains(torch, dd, transport, local, world, workload, cells, calls=10, warmup=3):
+    """The same call over the N domains of the weak-scaling system (replicated grid: every rank spreads its own atoms, the charge
+    grids are summed over the ranks by one all-reduce, every rank transforms the whole grid and gathers its own forces,
+    dl-poly_b200/dd.py::Domain.spme_forces); CUDA events on the library's stream, max over the ranks."""
+    import _pkg
+    _pkg.load()
+    from dl_poly_b200 import tables
+    sysm = make_system(workload, DIMS[world], cells)
+    if not sysm.ff.ew_active:
+        return None
+    _, kdim = tables.spme_grid(1.0e-6, sysm.rcut, sysm.cell)
+    dom = dd.Domain(sysm, device=local, transport=transport)
+    dom.set_spme(kdim, 8)
+    for _ in range(warmup):
+        out = dom.spme_forces()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    transport.barrier()
+    torch.cuda.synchronize()
+    ev0.record(dom.stream)
+    for _ in range(calls):
+        out = dom.spme_forces()
+    ev1.record(dom.stream)
+    torch.cuda.synchronize()
+    ms = transport.allreduce_max(ev0.elapsed_time(ev1) / calls)
+    tot = dom.gsum(out)
+    dom.close()
+    return {"what": "ewald_spme_forces_coul over %d domains with a replicated grid (spread per rank, all-reduce of the charge grids, whole-grid "
+                    "cuFFT Z2Z + influence function per rank, gather per rank); not part of `value`" % world,
+            "atoms": sysm.megatm, "grid": list(kdim), "bspline_order": 8, "ms_per_call": ms, "calls": calls,
+            "engcpe_rc": float(tot[0]), "vircpe_rc": float(tot[1])}
+
+
 def spme_sub_run(torch, local, workload, cells, calls=10, warmup=3):
     """SURVEY section 8f row 4 (beyond the north star's path, first version): the SPME reciprocal-space call of the same melt on ONE
     domain, timed with CUDA events on the library's stream next to the short-range numbers.  Grid and alpha as control.F90:1707-1713
@@ -515,6 +547,13 @@ def run_gpu(args):
                 if spme is not None:
                     extra["spme"] = spme
             except Exception as e:          # cuFFT missing on the box: the short-range line stands on its own
+                extra["spme"] = {"unavailable": repr(e)[:200]}
+        else:
+            try:
+                spme = spme_sub_run_domains(torch, dd, transport, local, world, args.workload, args.cells_per_gpu)
+                if spme is not None:
+                    extra["spme"] = spme
+            except Exception as e:
                 extra["spme"] = {"unavailable": repr(e)[:200]}
 
     cpu = None

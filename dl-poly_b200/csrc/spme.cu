@@ -310,39 +310,33 @@ int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines) {
   return 0;
 }
 
-// out[0] = engcpe_rc (reciprocal energy + self interaction), out[1] = vircpe_rc, out[2..10] = the nine stress contributions
-// (stats%stress += ...), out[11] = the reciprocal energy alone, out[12] = the self interaction
-int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
-  if (!ctx || !out || megatm < 1) return DLPGPU_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  if (!ctx->spme_plan_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "spme_forces: call dlpgpu_set_spme first");
-  if (!ctx->ew_on) return dlp_fail(ctx, DLPGPU_ERR_STATE, "spme_forces: no Ewald parameters (dlpgpu_set_ewald)");
-  if (ctx->nx * ctx->ny * ctx->nz > 1)
-    return dlp_fail(ctx, DLPGPU_ERR_STATE, "spme_forces: this version holds the whole grid on one domain (mxnode = 1)");
-  cudaStream_t s = ctx->stream;
-  const int natms = ctx->natms;
-  SpmeP P{};
+}  // extern "C"
+
+// ---- the stages of ewald_spme_forces_coul.  One domain runs them back to back (dlpgpu_dev_spme_forces); several domains keep a
+// REPLICATED grid: every rank spreads its own atoms onto a grid of the whole cell, the host side sums the grids over the ranks
+// (one all-reduce over NVLink: 46 MB at 180^3), every rank transforms the whole grid itself (0.3 ms at 180^3 -- less than the
+// transposes of a distributed transform would cost on one NVSwitch node, and 180 GB of HBM hold the grid many times over) and
+// gathers the forces of its own atoms; what the reference exchanges through exchange_grid and its parallel DaFT transform
+// (ewald_spole.F90:336-420, parallel_fft.F90) shrinks to that one sum plus the three doubles of the net force.
+namespace {
+struct SpmeGeom { SpmeP P; double inv[9], det, scale, kmx, kmy, kmz, cut2, conv, test_fac; size_t ntot; int blocks_a, blocks_g; };
+
+int spme_geometry(dlpgpu_ctx* ctx, const char* who, SpmeGeom& G) {
+  if (!ctx->spme_plan_valid) return dlp_fail(ctx, DLPGPU_ERR_STATE, "%s: call dlpgpu_set_spme first", who);
+  if (!ctx->ew_on) return dlp_fail(ctx, DLPGPU_ERR_STATE, "%s: no Ewald parameters (dlpgpu_set_ewald)", who);
+  SpmeP& P = G.P;
   for (int d = 0; d < 3; ++d) P.K[d] = ctx->spme_k[d];
-  P.n = ctx->spme_n; P.natms = natms;
-  double inv[9], det = 0.0;
-  invert9(ctx->cell, inv, &det);
-  if (std::fabs(det) < 1.0e-6) return dlp_fail(ctx, 120, "spme_forces: singular cell");
-  for (int k = 0; k < 9; ++k) P.rc[k] = inv[k];
-  const size_t ntot = (size_t)P.K[0] * P.K[1] * P.K[2];
-  double2* grid = reinterpret_cast<double2*>(ctx->spme_grid.p);
-  double* rgrid = ctx->spme_rgrid.p;   // the charge grid, later the real potential grid
-  CK(cudaMemsetAsync(rgrid, 0, ntot * sizeof(double), s));
-  CK(cudaMemsetAsync(ctx->spme_tot.p, 0, 16 * sizeof(double), s));
-  CK(ctx->spme_fraw.ensure((size_t)3 * std::max(natms, 1), s));
-  const int blocks_a = std::max(1, std::min(cdiv(std::max(natms, 1), SPME_APB), ctx->sm_count * 8));
-  const int blocks_g = std::max(1, std::min(cdiv((long long)ntot, 256), ctx->sm_count * 16));
-  if (natms > 0) LAUNCH(ctx, k_spme_spread, blocks_a, SPME_GROUP * SPME_NG, 0, P, ctx->posq.p, rgrid, ctx->spme_tot.p);
-  LAUNCH(ctx, k_spme_real_to_complex, blocks_g, 256, 0, ntot, rgrid, grid);
-  if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_FWD) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme_forces: forward FFT failed");
+  P.n = ctx->spme_n; P.natms = ctx->natms;
+  invert9(ctx->cell, G.inv, &G.det);
+  if (std::fabs(G.det) < 1.0e-6) return dlp_fail(ctx, 120, "%s: singular cell", who);
+  for (int k = 0; k < 9; ++k) P.rc[k] = G.inv[k];
+  G.ntot = (size_t)P.K[0] * P.K[1] * P.K[2];
+  G.blocks_a = std::max(1, std::min(cdiv(std::max(ctx->natms, 1), SPME_APB), ctx->sm_count * 8));
+  G.blocks_g = std::max(1, std::min(cdiv((long long)G.ntot, 256), ctx->sm_count * 16));
   // the spherical cutoff of the reference: 0.525 min_d(K_d * width_d of the reciprocal cell), ewald_spole.F90:1287-1291
   double w[3];
   {
-    const double* a = inv; const double* b = inv + 3; const double* c = inv + 6;   // rows of rcell as lattice vectors (dcell)
+    const double* a = G.inv; const double* b = G.inv + 3; const double* c = G.inv + 6;   // rows of rcell as lattice vectors (dcell)
     auto cross = [](const double* u, const double* v, double* o) { o[0] = u[1] * v[2] - u[2] * v[1]; o[1] = u[2] * v[0] - u[0] * v[2]; o[2] = u[0] * v[1] - u[1] * v[0]; };
     auto nrm3 = [](const double* u) { return std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]); };
     double bc[3], ca[3], ab[3];
@@ -352,35 +346,112 @@ int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
   }
   const double cut = 0.5 * 1.05 * std::min(P.K[0] * w[0], std::min(P.K[1] * w[1], P.K[2] * w[2]));
   const double pi = 3.14159265358979323846264338327950288;
-  const double conv = pi / ctx->alpha, test_fac = (1.0e-6 / conv) * (1.0e-6 / conv);
-  LAUNCH(ctx, k_spme_influence, blocks_g, 256, 0, P, conv, test_fac, cut * cut, ctx->spme_norm2.p,
-         ctx->spme_kmax, grid, ctx->spme_tot.p);
-  if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_INV) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme_forces: backward FFT failed");
-  LAUNCH(ctx, k_spme_complex_to_real, blocks_g, 256, 0, ntot, grid, rgrid);
+  G.cut2 = cut * cut;
+  G.conv = pi / ctx->alpha; G.test_fac = (1.0e-6 / G.conv) * (1.0e-6 / G.conv);
   // recip_kmax = Matmul(Reshape(rcell, [3, 3]), k_vec_dim_real): component a = sum_b rcell(a + 3 (b - 1)) K_b  (ewald_general.F90:755-756)
-  const double kmx = inv[0] * P.K[0] + inv[3] * P.K[1] + inv[6] * P.K[2], kmy = inv[1] * P.K[0] + inv[4] * P.K[1] + inv[7] * P.K[2],
-               kmz = inv[2] * P.K[0] + inv[5] * P.K[1] + inv[8] * P.K[2];
-  const double volm = std::fabs(det);
-  const double scale = pi * SQRPI * (1.0 / (ctx->alpha * ctx->alpha)) * (0.5 / volm) * ctx->scaling;   // ewald_spole.F90:299, pot_order 1
-  if (natms > 0) {
-    LAUNCH(ctx, k_spme_gather, blocks_a, SPME_GROUP * SPME_NG, 0, P, kmx, kmy, kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
-    LAUNCH(ctx, k_spme_finish, cdiv(natms, 256), 256, 0, natms, 1.0 / (double)megatm, scale * 2.0, ctx->spme_fraw.p, ctx->spme_tot.p, ctx->fx.p,
-           ctx->fy.p, ctx->fz.p);
-  }
+  G.kmx = G.inv[0] * P.K[0] + G.inv[3] * P.K[1] + G.inv[6] * P.K[2]; G.kmy = G.inv[1] * P.K[0] + G.inv[4] * P.K[1] + G.inv[7] * P.K[2];
+  G.kmz = G.inv[2] * P.K[0] + G.inv[5] * P.K[1] + G.inv[8] * P.K[2];
+  G.scale = pi * SQRPI * (1.0 / (ctx->alpha * ctx->alpha)) * (0.5 / std::fabs(G.det)) * ctx->scaling;   // ewald_spole.F90:299, pot_order 1
+  return 0;
+}
+
+// spme_construct_charge_array of this rank's atoms onto rgrid (zeroed here); sum q^2 of the rank goes to the totals
+int spme_spread(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(rgrid, 0, G.ntot * sizeof(double), s));
+  CK(cudaMemsetAsync(ctx->spme_tot.p, 0, 16 * sizeof(double), s));
+  if (ctx->natms > 0) LAUNCH(ctx, k_spme_spread, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, ctx->posq.p, rgrid, ctx->spme_tot.p);
+  return 0;
+}
+// charge grid of the WHOLE system -> potential grid (in place); the stress kernel sums go to the totals
+int spme_solve(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
+  double2* grid = reinterpret_cast<double2*>(ctx->spme_grid.p);
+  LAUNCH(ctx, k_spme_real_to_complex, G.blocks_g, 256, 0, G.ntot, rgrid, grid);
+  if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_FWD) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: forward FFT failed");
+  LAUNCH(ctx, k_spme_influence, G.blocks_g, 256, 0, G.P, G.conv, G.test_fac, G.cut2, ctx->spme_norm2.p, ctx->spme_kmax, grid, ctx->spme_tot.p);
+  if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_INV) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: backward FFT failed");
+  LAUNCH(ctx, k_spme_complex_to_real, G.blocks_g, 256, 0, G.ntot, grid, rgrid);
+  return 0;
+}
+// spme_calc_force_energy for this rank's atoms: raw forces into spme_fraw, energy and raw force total of the rank into the totals
+int spme_gather(dlpgpu_ctx* ctx, const SpmeGeom& G, const double* rgrid) {
+  CK(ctx->spme_fraw.ensure((size_t)3 * std::max(ctx->natms, 1), ctx->stream));
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_spme_gather, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, G.kmx, G.kmy, G.kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
+  return 0;
+}
+// forces += (raw - net force of ALL atoms / megatm) * 2 scale; sums of this rank.  ftot: the net raw force over all ranks (nullptr: the
+// rank's own, i.e. one domain); stress_share: the k-space stress sums were formed from the whole grid on every rank, each reports 1 / nranks
+int spme_finish(dlpgpu_ctx* ctx, const SpmeGeom& G, int megatm, const double* ftot, double stress_share, double out[16]) {
+  cudaStream_t s = ctx->stream;
+  if (ftot) CK(cudaMemcpyAsync(ctx->spme_tot.p + 1, ftot, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (ctx->natms > 0)
+    LAUNCH(ctx, k_spme_finish, cdiv(ctx->natms, 256), 256, 0, ctx->natms, 1.0 / (double)megatm, G.scale * 2.0, ctx->spme_fraw.p, ctx->spme_tot.p,
+           ctx->fx.p, ctx->fy.p, ctx->fz.p);
   double t[16];
   CK(cudaMemcpyAsync(t, ctx->spme_tot.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   for (int k = 0; k < 16; ++k) out[k] = 0.0;
-  const double eng = t[0] * scale;
+  const double eng = t[0] * G.scale;
   const double self = -t[10] * ctx->scaling * ctx->alpha / SQRPI;            // spme.F90:220-224
   // stress_temp(beta, alpha) column-major, symmetric: [xx xy xz / xy yy yz / xz yz zz] * scale, diagonal += eng (:448-451)
   const double sx[9] = {t[4], t[5], t[6], t[5], t[7], t[8], t[6], t[8], t[9]};
-  for (int k = 0; k < 9; ++k) out[2 + k] = sx[k] * scale + ((k % 4 == 0) ? eng : 0.0);
+  for (int k = 0; k < 9; ++k) out[2 + k] = sx[k] * G.scale * stress_share + ((k % 4 == 0) ? eng : 0.0);
   out[0] = eng + self;
   out[1] = -(out[2] + out[6] + out[10]);
   out[11] = eng; out[12] = self;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// out[0] = engcpe_rc (reciprocal energy + self interaction), out[1] = vircpe_rc, out[2..10] = the nine stress contributions
+// (stats%stress += ...), out[11] = the reciprocal energy alone, out[12] = the self interaction
+int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]) {
+  if (!ctx || !out || megatm < 1) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->nx * ctx->ny * ctx->nz > 1)
+    return dlp_fail(ctx, DLPGPU_ERR_STATE, "spme_forces: one call serves one domain (mxnode = 1); several domains run the stages dlpgpu_dev_spme_spread / "
+                                           "_solve / _gather / _finish around a sum of the charge grids");
+  SpmeGeom G{};
+  CKRC(spme_geometry(ctx, "spme_forces", G));
+  double* rgrid = ctx->spme_rgrid.p;   // the charge grid, later the real potential grid
+  CKRC(spme_spread(ctx, G, rgrid));
+  CKRC(spme_solve(ctx, G, rgrid));
+  CKRC(spme_gather(ctx, G, rgrid));
+  return spme_finish(ctx, G, megatm, nullptr, 1.0, out);
+}
+
+// the stages for several domains (replicated grid, see above).  grid_dev: K1 K2 K3 doubles of DEVICE memory owned by the caller
+// (z fastest), so that the host side can sum it over the ranks with whatever collective it has (NCCL all-reduce, peer copies).
+int dlpgpu_dev_spme_spread(dlpgpu_ctx* ctx, double* grid_dev) {
+  if (!ctx || !grid_dev) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  SpmeGeom G{};
+  CKRC(spme_geometry(ctx, "spme_spread", G));
+  return spme_spread(ctx, G, grid_dev);
+}
+// grid_dev = the SUM of the ranks' charge grids; on return the potential grid, and ftot_local = the rank's raw net force
+int dlpgpu_dev_spme_solve_gather(dlpgpu_ctx* ctx, double* grid_dev, double ftot_local[3]) {
+  if (!ctx || !grid_dev || !ftot_local) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  SpmeGeom G{};
+  CKRC(spme_geometry(ctx, "spme_solve_gather", G));
+  CKRC(spme_solve(ctx, G, grid_dev));
+  CKRC(spme_gather(ctx, G, grid_dev));
+  CK(cudaMemcpyAsync(ftot_local, ctx->spme_tot.p + 1, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// ftot_global = sum of ftot_local over the ranks; out as for dlpgpu_dev_spme_forces, this rank's share (the ranks' outs add up)
+int dlpgpu_dev_spme_finish(dlpgpu_ctx* ctx, int megatm, const double ftot_global[3], int nranks, double out[16]) {
+  if (!ctx || !ftot_global || !out || megatm < 1 || nranks < 1) return DLPGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  SpmeGeom G{};
+  CKRC(spme_geometry(ctx, "spme_finish", G));
+  return spme_finish(ctx, G, megatm, ftot_global, 1.0 / (double)nranks, out);
 }
 
 }  // extern "C"

@@ -176,6 +176,14 @@ def assign_domains(xyz, cell, nx, ny, nz):
 
 
 # ---------------------------------------------------------------------------------------------- transports
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class SelfTransport:
     """mxnode == 1 in every direction: never called with a remote peer."""
     rank, world = 0, 1
@@ -191,6 +199,9 @@ class SelfTransport:
 
     def allgather_bytes(self, blob):
         return np.ascontiguousarray(blob, dtype=np.uint8).copy()
+
+    def allreduce_sum_device(self, t, stream=None):
+        return t
 
     def barrier(self):
         pass
@@ -238,6 +249,21 @@ class ThreadTransport:
 
     def barrier(self):
         self.g.bar.wait()
+
+    def allreduce_sum_device(self, t, stream=None):
+        """Sum of the ranks' device tensors, in place, in rank order on every rank (same bits everywhere)."""
+        import torch
+        (stream or torch.cuda.current_stream()).synchronize()          # my contribution is complete
+        posts = self._all(t)
+        with torch.cuda.stream(stream) if stream is not None else _nullcontext():
+            tot = posts[0].clone()
+            for p in posts[1:]:
+                tot += p
+        (stream or torch.cuda.current_stream()).synchronize()
+        self.g.bar.wait()                                               # everybody has read everybody's contribution
+        with torch.cuda.stream(stream) if stream is not None else _nullcontext():
+            t.copy_(tot)
+        return t
 
     def exchange_counts(self, n_send, dst, src):
         """deport_data.F90:1888-1893 between threads: every rank posts (dst, count); the receiver picks the one addressed to it."""
@@ -302,6 +328,15 @@ class TorchTransport:
         t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64), device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+    def allreduce_sum_device(self, t, stream=None):
+        """In-place all-reduce of a device tensor (NCCL over NVLink; gloo in the CPU tests), enqueued on ``stream``."""
+        if stream is not None:
+            with self.torch.cuda.stream(stream):
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
 
     def allgather_bytes(self, blob):
         t_blob = self.torch.from_numpy(np.ascontiguousarray(blob, dtype=np.uint8).copy()).to(self.device)
@@ -645,6 +680,26 @@ class Domain:
     def gsum(self, out):
         """two_body.F90:729 / drivers.F90:795."""
         return self.t.allreduce_sum(out)
+
+    # ---- SPME reciprocal space over the domains (ewald_spole.F90:244-477 with a replicated grid, csrc/spme.cu)
+    def set_spme(self, kdim, nsplines=8):
+        self.sr.set_spme(kdim, nsplines)
+        self._spme_grid = self.torch.empty(int(kdim[0]) * int(kdim[1]) * int(kdim[2]), dtype=self.torch.float64, device=self.device)
+
+    def spme_forces(self):
+        """ewald_spme_forces_coul for this rank's atoms: every rank spreads its charges onto a grid of the whole cell, the grids
+        are summed over the ranks (one all-reduce), every rank transforms the whole grid and gathers its own forces; the net
+        force is removed with the sum over all ranks.  Adds into the device force arrays; returns this rank's out[16] (the
+        ranks' energies, virials and stresses add up under gsum)."""
+        g = self._spme_grid
+        with self.torch.cuda.stream(self.stream):
+            self.sr.dev_spme_spread(g.data_ptr())
+        self.t.allreduce_sum_device(g, self.stream)
+        with self.torch.cuda.stream(self.stream):
+            ftot = self.sr.dev_spme_solve_gather(g.data_ptr())
+        ftot = self.t.allreduce_sum(ftot)
+        with self.torch.cuda.stream(self.stream):
+            return self.sr.dev_spme_finish(self.sys.megatm, ftot, self.world)
 
     def close(self):
         self.sr.close()

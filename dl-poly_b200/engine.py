@@ -125,6 +125,23 @@ class ShortRange:
         self._ck(self.L.dlpgpu_dev_spme_forces(self.h, int(megatm), ptr(out)))
         return out
 
+    def dev_spme_spread(self, grid_ptr):
+        """Stage 1 of the several-domain SPME: this rank's charges onto the caller's device grid (K1 K2 K3 doubles, zeroed here)."""
+        self._ck(self.L.dlpgpu_dev_spme_spread(self.h, C.c_void_p(int(grid_ptr))))
+
+    def dev_spme_solve_gather(self, grid_ptr):
+        """Stage 2: the summed charge grid -> potential grid, forces of this rank's atoms; returns the rank's raw net force."""
+        ft = np.zeros(3)
+        self._ck(self.L.dlpgpu_dev_spme_solve_gather(self.h, C.c_void_p(int(grid_ptr)), ptr(ft)))
+        return ft
+
+    def dev_spme_finish(self, megatm, ftot_global, nranks):
+        """Stage 3: net force of all ranks removed, forces added to the device arrays; this rank's share of out[16]."""
+        out = np.zeros(16)
+        ft = np.ascontiguousarray(ftot_global, dtype=np.float64)
+        self._ck(self.L.dlpgpu_dev_spme_finish(self.h, int(megatm), ptr(ft), int(nranks), ptr(out)))
+        return out
+
     def spme_forces(self, natms, parts, megatm):
         """Drop-in form: parts (host corePart array) up, reciprocal forces added to parts%f, records back; returns out[16]."""
         assert parts.dtype == COREPART and parts.flags.c_contiguous

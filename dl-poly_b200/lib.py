@@ -94,6 +94,9 @@ SIGNATURES = {
     "dlpgpu_set_spme": (ci, [vp, vp, ci]),
     "dlpgpu_dev_spme_forces": (ci, [vp, ci, vp]),
     "dlpgpu_spme_forces": (ci, [vp, ci, vp, ci, vp]),
+    "dlpgpu_dev_spme_spread": (ci, [vp, vp]),
+    "dlpgpu_dev_spme_solve_gather": (ci, [vp, vp, vp]),
+    "dlpgpu_dev_spme_finish": (ci, [vp, ci, vp, ci, vp]),
     "dlpgpu_set_collect_pp": (ci, [vp, ci]),
     "dlpgpu_get_pp": (ci, [vp, ci, vp, vp]),
     "dlpgpu_pair_kernel_used": (ci, [vp, pi_, pd_]),

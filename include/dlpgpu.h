@@ -132,8 +132,8 @@ int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
 /* SPME reciprocal-space Coulomb term, ewald_spme_forces_coul (ewald_spole.F90:244-477; SURVEY section 8f row 4, beyond the hot path
  * of the north star): B-spline charge spreading (ewald_general.F90:517-576), forward transform, the reference's influence
  * function inside its spherical k cutoff with the stress kernel (ewald_spole.F90:1257-1386), backward transform, force / energy
- * gather with the net force removed (ewald_general.F90:717-869), self interaction (spme.F90:159-231).  First version: the whole
- * grid lives on one domain (mxnode = 1; DLPGPU_ERR_STATE otherwise); the 3-D transforms are cuFFT's, loaded on first use.
+ * gather with the net force removed (ewald_general.F90:717-869), self interaction (spme.F90:159-231).  dlpgpu_dev_spme_forces serves
+ * one domain (mxnode = 1; DLPGPU_ERR_STATE otherwise; several domains: the staged calls below); the 3-D transforms are cuFFT's, loaded on first use.
  * set_spme: kdim = ewld%kspace%k_vec_dim (after adjust_kmax), nsplines = bspline%num_splines (3..12); alpha, the Coulomb
  * scaling and the cell come from dlpgpu_set_ewald / dlpgpu_set_cell.
  * dev_spme_forces works on the device-resident atoms (1:natms), ADDS the reciprocal forces to the device force arrays and
@@ -141,6 +141,17 @@ int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
  * stats%stress(1:9), out[11] = the reciprocal energy alone, out[12] = the self interaction.  megatm = atoms in the system. */
 int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines);
 int dlpgpu_dev_spme_forces(dlpgpu_ctx* ctx, int megatm, double out[16]);
+/* The same over several domains, with a REPLICATED grid instead of the reference's distributed one (exchange_grid + the parallel
+ * DaFT transform, ewald_spole.F90:336-420, parallel_fft.F90): every rank spreads its own atoms onto a grid of the whole cell
+ * (spread; grid_dev = K1 K2 K3 doubles of DEVICE memory owned by the caller, z fastest, zeroed by the call), the host side sums
+ * the ranks' grids with the collective it has (NCCL all-reduce over NVLink, dl-poly_b200/dd.py), every rank transforms the
+ * whole grid and gathers the forces of its own atoms (solve_gather; ftot_local = the rank's raw net force), and after the sum of
+ * those three doubles over the ranks the net force is removed and the forces are ADDED to the device force arrays (finish; out
+ * as for dlpgpu_dev_spme_forces, this rank's share: the ranks' outs add up under gsum -- the k-space stress, formed from the whole
+ * grid on every rank, is reported as 1 / nranks of itself). */
+int dlpgpu_dev_spme_spread(dlpgpu_ctx* ctx, double* grid_dev);
+int dlpgpu_dev_spme_solve_gather(dlpgpu_ctx* ctx, double* grid_dev, double ftot_local[3]);
+int dlpgpu_dev_spme_finish(dlpgpu_ctx* ctx, int megatm, const double ftot_global[3], int nranks, double out[16]);
 /* the same with the caller's corePart array (drop-in for the call at two_body.F90:298-302 when comm%mxnode == 1): parts(1:natms) are
  * uploaded, the reciprocal forces come back and are ADDED to parts(1:natms)%f.  It reuses the device atom arrays, so the
  * neighbour list held by the context is invalidated: call it BEFORE dlpgpu_link_cell_pairs of the step, or from a context of its own. */

@@ -20,6 +20,13 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 t = dd.TorchTransport(torch.device("cuda", local))
 which = sys.argv[1] if len(sys.argv) > 1 else "nacl"
 rep = dd_common.check_rank(t, local, which)
+spme = None
+if which == "nacl":     # the several-domain SPME (replicated grid, NCCL all-reduce of the charge grids) against the one-domain oracle
+    mine = dd_common.spme_rank(t, local, which)
+    reps = [None] * world
+    dist.all_gather_object(reps, mine)
+    if rank == 0:
+        spme = dd_common.spme_compare(reps, which)
 if rank == 0:
-    print("dd_check %s world=%d %s OK" % (which, world, rep))
+    print("dd_check %s world=%d %s spme=%s OK" % (which, world, rep, spme))
 dist.destroy_process_group()

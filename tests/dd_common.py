@@ -171,3 +171,52 @@ def check_rank(t, device, which="nacl", stream_ctx=None, lazy_steps=10, log=None
         log(rep)
     dom.close()
     return rep
+
+
+def spme_rank(t, device, which):
+    """One rank of the several-domain SPME: its own atoms, the replicated grid summed over the ranks (dd.Domain.spme_forces)."""
+    from oracle import spme_oracle as so
+    s = make_system(which)
+    dom = dd.Domain(s, device=device, transport=t)
+    _, kdim = so.spme_grid(1.0e-6, s.rcut, s.cell)
+    dom.set_spme(kdim, 8)
+    out = dom.spme_forces()
+    tot = dom.gsum(out)
+    natms, _ = dom.sr.dev_counts()
+    pg = dom.sr.dev_get_parts()
+    f = np.stack([pg["fxx"], pg["fyy"], pg["fzz"]], 1)[:natms]
+    ltg = dom.sr.dev_get_ints(natms)["ltg"][:natms]
+    # a second call ADDS the same forces again
+    dom.spme_forces()
+    pg2 = dom.sr.dev_get_parts()
+    f2 = np.stack([pg2["fxx"], pg2["fyy"], pg2["fzz"]], 1)[:natms]
+    assert np.abs(f2 - 2.0 * f).max() <= 1e-12 * max(np.abs(f).max(), 1.0)
+    t.barrier()
+    dom.close()
+    return {"tot": tot, "ltg": ltg, "f": f, "kdim": kdim}
+
+
+def spme_compare(reps, which):
+    """Per-atom forces by global id and the gsum-med sums of the ranks' reports against the one-domain numpy oracle."""
+    from oracle import spme_oracle as so
+    from util import per_atom_force_error
+    s = make_system(which)
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]
+    q = s.charge_site[s.lsite - 1]
+    ref = so.ewald_spme_forces_coul(s.cell, xyz, q, s.ff.alpha, reps[0]["kdim"], 8, s.ff.scaling)
+    f = np.zeros((s.megatm, 3))
+    seen = np.zeros(s.megatm, dtype=int)
+    for r in reps:
+        f[r["ltg"] - 1] = r["f"]
+        seen[r["ltg"] - 1] += 1
+    assert (seen == 1).all()
+    rep = per_atom_force_error(f, ref["forces"])
+    assert rep["max_normalised"] <= FORCE_TOL and rep["per_atom_significant"] <= FORCE_TOL, rep
+    tot = reps[0]["tot"]
+    for r in reps[1:]:
+        assert np.array_equal(r["tot"], tot)
+    assert abs(tot[11] - ref["eng_recip"]) <= ENERGY_TOL * abs(ref["eng_recip"])
+    assert abs(tot[0] - ref["engcpe_rc"]) <= ENERGY_TOL * abs(ref["engcpe_rc"])
+    assert abs(tot[1] - ref["vircpe_rc"]) <= ENERGY_TOL * abs(ref["vircpe_rc"])
+    assert np.abs(tot[2:11] - ref["stress"]).max() <= ENERGY_TOL * np.abs(ref["stress"]).max()
+    return rep

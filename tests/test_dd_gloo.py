@@ -82,6 +82,9 @@ for q, mdir in enumerate(dd.MDIRS):
     assert torch.all(v[:, 0] == src) and torch.all(v[:, 1] == mdir) and torch.all(v[:, 2] == torch.arange(n, dtype=torch.float64))
 assert t.allreduce_max(float(rank)) == world - 1
 assert np.allclose(t.allreduce_sum([1.0, rank]), [world, sum(range(world))])
+x = torch.full((5,), float(rank + 1), dtype=torch.float64)       # the charge-grid sum of the several-domain SPME
+t.allreduce_sum_device(x)
+assert torch.all(x == float(sum(range(1, world + 1))))
 t.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

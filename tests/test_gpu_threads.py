@@ -6,6 +6,7 @@ on the record of a 1-GPU box; tests/test_gpu_multi.py runs the same check with o
 import gc
 import threading
 
+import numpy as np
 import pytest
 
 from dl_poly_b200 import dd
@@ -14,7 +15,7 @@ import dd_common
 pytestmark = pytest.mark.gpu
 
 
-def run_threads(world, which):
+def run_threads(world, which, fn=None, need_ok=True):
     grp = dd.ThreadGroup(world)
     reps, errs = [None] * world, [None] * world
 
@@ -22,7 +23,7 @@ def run_threads(world, which):
         import torch
         try:
             torch.cuda.set_device(0)
-            reps[rank] = dd_common.check_rank(grp.transport(rank), 0, which)
+            reps[rank] = (fn or dd_common.check_rank)(grp.transport(rank), 0, which)
         except BaseException as e:          # a failing rank must not leave the others waiting at a barrier for ever
             errs[rank] = e
             grp.bar.abort()
@@ -45,6 +46,8 @@ def run_threads(world, which):
     if real:
         raise AssertionError("rank errors: " + " || ".join("rank %d: %r" % (r, e) for r, e in enumerate(errs) if e is not None)) from real[0]
     assert all(e is None for e in errs), errs
+    if not need_ok:
+        return reps
     assert all(r is not None and r["ok"] for r in reps)
     return reps[0]
 
@@ -69,3 +72,13 @@ def test_scanning_migration_stages_against_oracle(monkeypatch):
     assert rep["ranks"] == 4 and rep["migrated_atoms"] > 0
     rep = run_threads(8, "nacl_hot")
     assert rep["migrated_atoms"] > 50
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_spme_over_domains_against_oracle(world):
+    """f4 over several domains (replicated grid: spread per rank, sum of the grids over the ranks, whole-grid transform and gather
+    per rank, net force of all ranks removed) against the one-domain numpy oracle of the whole system: per-atom forces by global
+    id, energy / virial / stress after gsum."""
+    reps = run_threads(world, "nacl", fn=dd_common.spme_rank, need_ok=False)
+    rep = dd_common.spme_compare(reps, "nacl")
+    print("SPME over %d domains: %s" % (world, rep))
