@@ -41,7 +41,7 @@ Module dlp_gpu_binding
   Type(c_ptr), Save :: ctx = c_null_ptr
 
   Public :: dlp_gpu_init, dlp_gpu_finalise, dlp_gpu_set_forcefield, link_cell_pairs_gpu, two_body_pairs_gpu, rdf_collect_gpu, &
-            dlp_gpu_vnl_tolerance
+            dlp_gpu_vnl_tolerance, dlp_gpu_set_host_threads
 
   Interface
     Function dlpgpu_create(ctx, device) Bind(C, name='dlpgpu_create') Result(rc)
@@ -146,6 +146,33 @@ Module dlp_gpu_binding
       Real(c_double), Intent(Out) :: out(16)
       Integer(c_int)              :: rc
     End Function
+    Function dlpgpu_set_host_threads(ctx, nthreads) Bind(C, name='dlpgpu_set_host_threads') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value    :: ctx
+      Integer(c_int), Value :: nthreads
+      Integer(c_int)        :: rc
+    End Function
+    Function dlpgpu_dev_spme_spread(ctx, grid_dev) Bind(C, name='dlpgpu_dev_spme_spread') Result(rc)
+      Import :: c_ptr, c_int
+      Type(c_ptr), Value :: ctx
+      Type(c_ptr), Value :: grid_dev
+      Integer(c_int)     :: rc
+    End Function
+    Function dlpgpu_dev_spme_solve_gather(ctx, grid_dev, ftot_local) Bind(C, name='dlpgpu_dev_spme_solve_gather') Result(rc)
+      Import :: c_ptr, c_int, c_double
+      Type(c_ptr), Value          :: ctx
+      Type(c_ptr), Value          :: grid_dev
+      Real(c_double), Intent(Out) :: ftot_local(3)
+      Integer(c_int)              :: rc
+    End Function
+    Function dlpgpu_dev_spme_finish(ctx, megatm, ftot_global, nranks, out) Bind(C, name='dlpgpu_dev_spme_finish') Result(rc)
+      Import :: c_ptr, c_int, c_double
+      Type(c_ptr), Value          :: ctx
+      Integer(c_int), Value       :: megatm, nranks
+      Real(c_double), Intent(In)  :: ftot_global(3)
+      Real(c_double), Intent(Out) :: out(16)
+      Integer(c_int)              :: rc
+    End Function
     Function dlpgpu_set_collect_pp(ctx, on) Bind(C, name='dlpgpu_set_collect_pp') Result(rc)
       Import :: c_ptr, c_int
       Type(c_ptr), Value    :: ctx
@@ -223,6 +250,15 @@ Contains
     Call check(dlpgpu_set_cell(ctx, config%cell, Int(config%imcon, c_int)), 'set_cell')
     Call check(dlpgpu_set_cutoffs(ctx, neigh%cutoff, neigh%padding, neigh%pdplnc), 'set_cutoffs')
   End Subroutine dlp_gpu_init
+
+  Subroutine dlp_gpu_set_host_threads(nthreads)
+    !! how config%parts travels (include/dlpgpu.h): 0 = whole corePart records by DMA (default); n >= 1 = n host threads of the
+    !! library copy x, y, z up and ADD the returned forces into parts%f -- use the cores the rank's OpenMP team would have had
+    !! (a dozen or more pay off); in that mode the list_just_built assertion of two_body_pairs_gpu no longer covers parts%f
+    Integer, Intent(In) :: nthreads
+
+    Call check(dlpgpu_set_host_threads(ctx, Int(nthreads, c_int)), 'set_host_threads')
+  End Subroutine dlp_gpu_set_host_threads
 
   Subroutine dlp_gpu_set_forcefield(ntpatm, vdws, electro, ewld, rcut, eps)
     !! once after vdw_generate / vdw_table_read / erfcgen (two_body.F90:188 computes the same scaling)
