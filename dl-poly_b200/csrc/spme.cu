@@ -46,18 +46,29 @@ struct AtomSpl {
   int idx[3];
   double q;
   double v[3][SPME_MAXN], d[3][SPME_MAXN];
+  // periodic wrap of the footprint, resolved once per atom and dimension instead of once per grid point (an integer modulo per
+  // point made both kernels issue-bound: 1125 warp instructions per atom in the gather): element offsets of plane ix, row iy, iz
+  long long ox[SPME_MAXN];
+  int oy[SPME_MAXN], oz[SPME_MAXN];
 };
 
 // threads 0..2 of an atom's group fill its three spline sets
+__device__ __forceinline__ int wrapk(int i, int K) { i %= K; return i < 0 ? i + K : i; }
+
 __device__ __forceinline__ void atom_splines(const SpmeP& P, const double4& p, int dim, AtomSpl& s) {
   const double u = (double)P.K[dim] * (P.rc[dim] * p.x + P.rc[dim + 3] * p.y + P.rc[dim + 6] * p.z + 0.5);   // ewald_spole.F90:311-318
   const double t = trunc(u);
   s.idx[dim] = (int)t;
   bspline_fill(u - t, P.n, s.v[dim], s.d[dim]);
+  int w = wrapk((int)t, P.K[dim]);
+  for (int j = 0; j < P.n; ++j) {   // grid index Int(u) - j, wrapped: one step down at a time
+    if (dim == 0) s.ox[j] = (long long)w * P.K[1] * P.K[2];
+    else if (dim == 1) s.oy[j] = w * P.K[2];
+    else s.oz[j] = w;
+    w = w == 0 ? P.K[dim] - 1 : w - 1;
+  }
   if (dim == 0) s.q = p.w;
 }
-
-__device__ __forceinline__ int wrapk(int i, int K) { i %= K; return i < 0 ? i + K : i; }
 
 constexpr int SPME_GROUP = 64;      // threads per atom: an n x n face of its footprint (n <= 8), looped for larger orders
 constexpr int SPME_NG = 4;          // groups per block
@@ -65,8 +76,10 @@ constexpr int SPME_AGP = 8;         // atoms a group takes per block pass: the s
 constexpr int SPME_APB = SPME_NG * SPME_AGP;   // ... filled together (one thread per atom and dimension), then each group walks its atoms
 
 // spme_construct_charge_array: Q(j,k,l) += q vx vy vz over the n^3 footprint (real grid, z fastest); also sum q^2 (self interaction)
+template <int NF>   // NF: the spline order when it is known at compile time (8, the default of the reference), 0: P.n
 __global__ void __launch_bounds__(SPME_GROUP * SPME_NG)
 k_spme_spread(SpmeP P, const double4* __restrict__ posq, double* __restrict__ rgrid, double* __restrict__ totals) {
+  const int n = NF ? NF : P.n;
   __shared__ AtomSpl s_a[SPME_APB];
   const int g = threadIdx.x / SPME_GROUP, t = threadIdx.x % SPME_GROUP;
   double q2 = 0.0;
@@ -83,14 +96,12 @@ k_spme_spread(SpmeP P, const double4* __restrict__ posq, double* __restrict__ rg
       const AtomSpl& s = s_a[sl];
       if (t == 0) q2 += s.q * s.q;
       if (!(fabs(s.q) > ZERO_PLUS)) continue;                                  // ewald_general.F90:536
-      for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
-        const int py = f / P.n, pz = f % P.n;
-        const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
+      for (int f = t; f < n * n; f += SPME_GROUP) {
+        const int py = f / n, pz = f % n;
+        double* const col = rgrid + (s.oy[py] + s.oz[pz]);
         const double fyz = s.q * s.v[2][pz] * s.v[1][py];
-        for (int px = 0; px < P.n; ++px) {
-          const int ix = wrapk(s.idx[0] - px, P.K[0]);
-          atomicAdd(&rgrid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz], fyz * s.v[0][px]);
-        }
+#pragma unroll
+        for (int px = 0; px < n; ++px) atomicAdd(col + s.ox[px], fyz * s.v[0][px]);
       }
     }
   }
@@ -150,9 +161,11 @@ __global__ void k_spme_influence(SpmeP P, double conv, double test_fac, double c
 }
 
 // spme_calc_force_energy: per atom, energy and the three force sums over its footprint of the (real) potential grid
+template <int NF>
 __global__ void __launch_bounds__(SPME_GROUP * SPME_NG)
 k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __restrict__ posq, const double* __restrict__ rgrid,
               double* __restrict__ fraw, double* __restrict__ totals) {
+  const int n = NF ? NF : P.n;
   __shared__ AtomSpl s_a[SPME_APB];
   __shared__ double s_red[SPME_NG][SPME_GROUP / 32][4];
   const int g = threadIdx.x / SPME_GROUP, t = threadIdx.x % SPME_GROUP;
@@ -170,14 +183,14 @@ k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __rest
       const bool live = a < P.natms && fabs(s.q) > ZERO_PLUS;                  // ewald_general.F90:779
       double e = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
       if (live) {
-        for (int f = t; f < P.n * P.n; f += SPME_GROUP) {
-          const int py = f / P.n, pz = f % P.n;
-          const int iy = wrapk(s.idx[1] - py, P.K[1]), iz = wrapk(s.idx[2] - pz, P.K[2]);
+        for (int f = t; f < n * n; f += SPME_GROUP) {
+          const int py = f / n, pz = f % n;
+          const double* const col = rgrid + (s.oy[py] + s.oz[pz]);
           const double y0 = s.v[1][py], z0 = s.v[2][pz], y1 = s.d[1][py], z1 = s.d[2][pz];
           double sx0 = 0.0, sx1 = 0.0;                                         // sum over x of phi vx, phi vx'
-          for (int px = 0; px < P.n; ++px) {
-            const int ix = wrapk(s.idx[0] - px, P.K[0]);
-            const double phi = rgrid[((size_t)ix * P.K[1] + iy) * P.K[2] + iz];
+#pragma unroll
+          for (int px = 0; px < n; ++px) {
+            const double phi = col[s.ox[px]];
             sx0 += phi * s.v[0][px]; sx1 += phi * s.d[0][px];
           }
           e += y0 * z0 * sx0;
@@ -360,7 +373,10 @@ int spme_spread(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(rgrid, 0, G.ntot * sizeof(double), s));
   CK(cudaMemsetAsync(ctx->spme_tot.p, 0, 16 * sizeof(double), s));
-  if (ctx->natms > 0) LAUNCH(ctx, k_spme_spread, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, ctx->posq.p, rgrid, ctx->spme_tot.p);
+  if (ctx->natms > 0) {
+    if (G.P.n == 8) LAUNCH(ctx, k_spme_spread<8>, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, ctx->posq.p, rgrid, ctx->spme_tot.p);
+    else LAUNCH(ctx, k_spme_spread<0>, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, ctx->posq.p, rgrid, ctx->spme_tot.p);
+  }
   return 0;
 }
 // charge grid of the WHOLE system -> potential grid (in place); the stress kernel sums go to the totals
@@ -376,8 +392,12 @@ int spme_solve(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
 // spme_calc_force_energy for this rank's atoms: raw forces into spme_fraw, energy and raw force total of the rank into the totals
 int spme_gather(dlpgpu_ctx* ctx, const SpmeGeom& G, const double* rgrid) {
   CK(ctx->spme_fraw.ensure((size_t)3 * std::max(ctx->natms, 1), ctx->stream));
-  if (ctx->natms > 0)
-    LAUNCH(ctx, k_spme_gather, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, G.kmx, G.kmy, G.kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
+  if (ctx->natms > 0) {
+    if (G.P.n == 8)
+      LAUNCH(ctx, k_spme_gather<8>, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, G.kmx, G.kmy, G.kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
+    else
+      LAUNCH(ctx, k_spme_gather<0>, G.blocks_a, SPME_GROUP * SPME_NG, 0, G.P, G.kmx, G.kmy, G.kmz, ctx->posq.p, rgrid, ctx->spme_fraw.p, ctx->spme_tot.p);
+  }
   return 0;
 }
 // forces += (raw - net force of ALL atoms / megatm) * 2 scale; sums of this rank.  ftot: the net raw force over all ranks (nullptr: the
@@ -457,7 +477,7 @@ int dlpgpu_dev_spme_finish(dlpgpu_ctx* ctx, int megatm, const double ftot_global
 }  // extern "C"
 
 int dlp_preload_spme() {
-  const void* ks[] = {(const void*)k_spme_spread, (const void*)k_spme_influence, (const void*)k_spme_gather, (const void*)k_spme_finish, (const void*)k_spme_real_to_complex,
+  const void* ks[] = {(const void*)k_spme_spread<8>, (const void*)k_spme_spread<0>, (const void*)k_spme_influence, (const void*)k_spme_gather<8>, (const void*)k_spme_gather<0>, (const void*)k_spme_finish, (const void*)k_spme_real_to_complex,
                       (const void*)k_spme_complex_to_real};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();
