@@ -161,6 +161,7 @@ __global__ void k_spme_influence(SpmeP P, double conv, double test_fac, double c
 }
 
 // spme_calc_force_energy: per atom, energy and the three force sums over its footprint of the (real) potential grid
+// (one warp per atom, two columns per lane and no cross-warp stage, measured slower: 2.89 against 2.56 ms per call)
 template <int NF>
 __global__ void __launch_bounds__(SPME_GROUP * SPME_NG)
 k_spme_gather(SpmeP P, double kmx, double kmy, double kmz, const double4* __restrict__ posq, const double* __restrict__ rgrid,
