@@ -1180,7 +1180,8 @@ int dlp_two_body(dlpgpu_ctx* ctx, int zero_forces, double out[16]) {
       else DLP_V2(1, 1, 0, 2);
     } else if (v && mean < 48.0) {
       // short rows (argon at rc 8.5 A: 28 partners): 4 lanes per row, 8 rows per warp, two blocks of 256 threads per SM
-      // (1 M argon atoms: 0.372 against 0.398 ms with 8 lanes per row)
+      // (1 M argon atoms: 0.372 against 0.398 ms with 8 lanes per row; the long rows of the NaCl melt lose with 4 lanes per row
+      // and windows of 128 rows: 1.344 against 1.22 ms)
       const int blocks4 = std::max(1, std::min(cdiv(natms, 64), ctx->sm_count * 2));
       CK(cudaFuncSetAttribute(k_pair_v2<4, 1, 0, 1, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       LAUNCH(ctx, (k_pair_v2<4, 1, 0, 1, 2, 256>), blocks4, 256, smem2, Q, ctx->tab2_tex, ctx->loc_slot.p, ctx->posq_s.p, ctx->nbr.p, ctx->nnbr.p,
