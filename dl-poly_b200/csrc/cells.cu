@@ -596,16 +596,22 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
   }
   __syncthreads();
   const int ncell_dom = g.nlx * g.nly * g.nlz;
-  const int cd = blockIdx.x * LC_WARPS + wid;
-  if (cd >= ncell_dom) return;
   const int nlp = g.nlp;
+  long long written = 0;
+  int ovf = 0;   // longest row that did not fit (error 106), reported once per warp
+  // the warps draw their link cells from a queue (cells hold 0 ... 15 atoms: dealt statically, eight to a block, the block waits
+  // for its fullest cell); cells are handed out in order, so neighbouring warps still work on neighbouring cells
+  for (;;) {
+  int cd = 0;
+  if (lane == 0) cd = (int)atomicAdd(&cnt64[2], 1ull);
+  cd = __shfl_sync(DLP_FULL, cd, 0);
+  if (cd >= ncell_dom) break;
   const int cx = cd % g.nlx + nlp, cy = (cd / g.nlx) % g.nly + nlp, cz = cd / (g.nlx * g.nly) + nlp;
   const int ic = 1 + cx + g.sx * (cy + g.sy * cz);
   const int s_own0 = lct_start[ic], s_own1 = lct_start[ic + 1];
-  if (s_own1 == s_own0) return;
+  if (s_own1 == s_own0) continue;
+  __syncwarp();
   const int total = lc_run_table(g, nrows, rows, lct_start, cx, cy, cz, s_run0[wid], s_pre[wid], lane, box, rc2_trim);
-  long long written = 0;
-  int ovf = 0;   // longest row that did not fit (error 106), reported once per warp
   for (int a0 = s_own0; a0 < s_own1; a0 += 32) {   // atoms of the cell, 32 at a time (one pass unless the cell is crowded)
     const int na = min(32, s_own1 - a0);
     int cnt = 0, xcnt = 0, fcnt = 0;
@@ -840,6 +846,7 @@ k_list_cell(LCGeom g, int natms, int pitch, int xpitch, int megfrz, int lbook, i
     for (int a = 0; a < na; ++a)   // sentinel padding the pair kernel relies on
       dlp_pad_row(nbr + (size_t)(t0 + a) * pitch, min(__shfl_sync(DLP_FULL, cnt, a), pitch - DLP_ROW_PAD), sentinel, lane, 32);
   }
+  }   // cell queue
   if (ovf > 0) { atomicOr(&status[0], 1); atomicMax(&status[1], ovf); }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) written += __shfl_xor_sync(DLP_FULL, written, d);
@@ -989,16 +996,17 @@ int dlp_build_lists(dlpgpu_ctx* ctx, int want_ref_list, int* ibig) {
           CK(ctx->cell_box.ensure((size_t)8 * (g.ncells + 2), s));
           LAUNCH(ctx, k_cell_boxes, cdiv(g.ncells + 1, 128), 128, 0, g.ncells, ctx->lct_start.p, ctx->posq_s.p, reinterpret_cast<float4*>(ctx->cell_box.p));
         }
+const int lc_grid = std::max(1, std::min(cdiv(ncd, LC_WARPS), ctx->sm_count * 8));   // resident blocks; the warps draw cells from a queue
 #define DLP_LC_ARGS g, natms, ctx->pitch, std::max(ctx->xpitch, 1), ctx->megfrz, ctx->lbook, ctx->max_exclude, ctx->excl_by_gid, \
                (int)hrows.size(), reinterpret_cast<const LCRow*>(ctx->st_rows.p), ctx->at_list.p, ctx->lct_start.p, ctx->cell_s.p, \
                ctx->scan_out.p, ctx->posq_s.p, ctx->info_s.p, ctx->vdw_on ? ctx->pair_k.p : nullptr, ctx->ntypes, ctx->excl.p, ctx->nbr.p, \
                ctx->nnbr.p, ctx->xnbr.p, ctx->nxnbr.p, ctx->status.p, ctx->cnt64.p, sentinel, 1, \
                ctx->fnbr.p, ctx->nfnbr.p, ctx->fpitch, trim ? reinterpret_cast<const float4*>(ctx->cell_box.p) : nullptr, rc2_trim
-        if (simple && lk == 2) LAUNCH(ctx, (k_list_cell<1, 1>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else if (simple) LAUNCH(ctx, (k_list_cell<1, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else if (lean && lk == 2) LAUNCH(ctx, (k_list_cell<2, 1>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else if (lean) LAUNCH(ctx, (k_list_cell<2, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS);
-        else { LAUNCH(ctx, (k_list_cell<0, 0>), cdiv(ncd, LC_WARPS), LC_WARPS * 32, 0, DLP_LC_ARGS); ctx->frz_rows_valid = ctx->fpitch > 0; }
+        if (simple && lk == 2) LAUNCH(ctx, (k_list_cell<1, 1>), lc_grid, LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (simple) LAUNCH(ctx, (k_list_cell<1, 0>), lc_grid, LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (lean && lk == 2) LAUNCH(ctx, (k_list_cell<2, 1>), lc_grid, LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else if (lean) LAUNCH(ctx, (k_list_cell<2, 0>), lc_grid, LC_WARPS * 32, 0, DLP_LC_ARGS);
+        else { LAUNCH(ctx, (k_list_cell<0, 0>), lc_grid, LC_WARPS * 32, 0, DLP_LC_ARGS); ctx->frz_rows_valid = ctx->fpitch > 0; }
 #undef DLP_LC_ARGS
       } else {   // very fine sub-celling (nlp >= 4): the per-atom kernel has no run-table limit
         LAUNCH(ctx, k_list_dev<true>, cdiv(natms, wpb), wpb * 32, 0, g, natms, ctx->pitch, ctx->xpitch, ctx->megfrz, ctx->lbook,
