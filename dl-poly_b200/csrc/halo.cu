@@ -101,6 +101,22 @@ __device__ __forceinline__ double vnl_displacement(int imcon, const Mat9& cell, 
     return sqrt(x * x + y * y + z * z);                            // :166
   }
 }
+// maximum of r >= 0 over the block into *tol_bits (the bits of a non-negative double are order-preserving): one atomic per block --
+// one per warp put 31 k atomics of a 1 M-atom pass on a single L2 address, which serialises them
+__device__ __forceinline__ void block_max_to(double r, unsigned long long* tol_bits) {
+  __shared__ double s_max[32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) s_max[w] = r;
+  __syncthreads();
+  if (w == 0) {
+    r = lane < nw ? s_max[lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
+    if (lane == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));
+  }
+}
 __global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const double4* __restrict__ posq, const double* __restrict__ xbg,
                           const double* __restrict__ ybg, const double* __restrict__ zbg, unsigned long long* __restrict__ tol_bits) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,9 +125,7 @@ __global__ void k_vnl_tol(int natms, int imcon, Mat9 cell, Mat9 rcell, const dou
     double4 p = posq[i];
     r = vnl_displacement(imcon, cell, rcell, p.x - xbg[i], p.y - ybg[i], p.z - zbg[i]);   // neighbours.F90:157-161
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
-  if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));   // r >= 0: bits are order-preserving
+  block_max_to(r, tol_bits);
 }
 // velocity-Verlet stage 1 (nve.F90:163-173, same contraction as forces.cu::k_vv) fused with what always follows it in the
 // native driver: the displacement test of vnl_check on the new positions and the copy into the peer-visible buffer of the
@@ -135,11 +149,7 @@ __global__ void k_vv1_fused(int natms, double dt, int imcon, Mat9 cell, Mat9 rce
     if (pub) pub[i] = p;
     if (tol_bits) r = vnl_displacement(imcon, cell, rcell, p.x - xbg[i], p.y - ybg[i], p.z - zbg[i]);
   }
-  if (tol_bits) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) r = fmax(r, __shfl_xor_sync(DLP_FULL, r, d));
-    if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(tol_bits, (unsigned long long)__double_as_longlong(r));
-  }
+  if (tol_bits) block_max_to(r, tol_bits);
 }
 
 // ---------------------------------------------------------------- halo build
