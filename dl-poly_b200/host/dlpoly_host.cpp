@@ -617,6 +617,8 @@ void gpu_short_range::vnl_check(bool l_str, double& width, neighbours_type& neig
   if (neigh.padding != padding_before) ck(dlpgpu_set_cutoffs(ctx_, neigh.cutoff, neigh.padding, neigh.pdplnc));
 }
 
+void gpu_short_range::set_host_threads(int nthreads) { ck(dlpgpu_set_host_threads(ctx_, nthreads)); }
+
 void gpu_short_range::vnl_set_check(neighbours_type& neigh, const configuration_type& config) {
   if (!neigh.unconditional_update) return;
   neigh.newjob = false;

@@ -177,6 +177,9 @@ class gpu_short_range {
   // once, after set_bounds / read_field / vdw_generate / erfcgen (dlp_gpu_init + dlp_gpu_set_forcefield)
   void init(const domains_type& domain, const configuration_type& config, const neighbours_type& neigh);
   void set_forcefield(const vdw_type& vdws, const electrostatic_type& electro, const ewald_type& ewld, double rcut);
+  // how config.parts travels (include/dlpgpu.h: dlpgpu_set_host_threads): 0 = whole corePart records by DMA (default), n >= 1 =
+  // n host threads of the library copy x, y, z up and ADD the returned forces into parts%f (worth it from ~12 spare cores)
+  void set_host_threads(int nthreads);
 
   // neighbours.F90:123-296
   void vnl_check(bool l_str, double& width, neighbours_type& neigh, stats_type& stat, const domains_type& domain,
