@@ -133,6 +133,8 @@ struct dlpgpu_ctx {
   // SPME reciprocal space (spme.cu)
   int spme_k[3] = {0, 0, 0}, spme_n = 0, spme_kmax = 0, spme_plan = 0;
   bool spme_plan_valid = false;
+  int spme_plan_d2z = 0, spme_plan_z2d = 0;   // real-to-complex pair of plans (orthogonal cells), created on first use
+  bool spme_r2c_valid = false;
   DBuf<double> spme_grid, spme_rgrid, spme_norm2, spme_fraw, spme_tot;
   bool collect_pp = false;            // dlpgpu_set_collect_pp: stats%collect_pp
   int pp_natms = -1;

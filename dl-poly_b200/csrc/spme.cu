@@ -121,12 +121,17 @@ __global__ void k_spme_complex_to_real(size_t n, const double2* __restrict__ c, 
 
 // spme_construct_potential_grid_coul between the two transforms: potential_component = B(m) S(m) exp(-x^2) / (sqrt(pi) x^2) inside
 // the spherical cutoff, x = pi |m| / alpha, and the stress kernel sum m_a m_b Re[comp (-2 (1 + x^2) / m^2) conj(S)]
+// HALF: the grid is the non-redundant half of the transform of a real array (l = 0 .. K3 / 2, the layout of cufftExecD2Z): an element
+// with 0 < l < K3 / 2 (or l = (K3 - 1) / 2 ... for odd K3) stands for itself and its conjugate partner, whose kernel value and stress
+// term are the same in an orthogonal cell, so its stress term counts twice
+template <bool HALF>
 __global__ void k_spme_influence(SpmeP P, double conv, double test_fac, double cut2, const double* __restrict__ norm2, int kmax,
                                  double2* __restrict__ grid, double* __restrict__ totals) {
-  const size_t ntot = (size_t)P.K[0] * P.K[1] * P.K[2];
+  const int K2l = HALF ? P.K[2] / 2 + 1 : P.K[2];   // stored extent of the fastest dimension
+  const size_t ntot = (size_t)P.K[0] * P.K[1] * K2l;
   double st[6] = {0, 0, 0, 0, 0, 0};
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < ntot; e += (size_t)gridDim.x * blockDim.x) {
-    const int l = (int)(e % P.K[2]), k = (int)((e / P.K[2]) % P.K[1]), j = (int)(e / ((size_t)P.K[2] * P.K[1]));
+    const int l = (int)(e % K2l), k = (int)((e / K2l) % P.K[1]), j = (int)(e / ((size_t)K2l * P.K[1]));
     const int jj = 2 * j > P.K[0] ? j - P.K[0] : j, kk = 2 * k > P.K[1] ? k - P.K[1] : k, ll = 2 * l > P.K[2] ? l - P.K[2] : l;
     // recip_pos = jj rcell(1:9:3) + kk rcell(2:9:3) + ll rcell(3:9:3)
     const double m0 = jj * P.rc[0] + kk * P.rc[1] + ll * P.rc[2], m1 = jj * P.rc[3] + kk * P.rc[4] + ll * P.rc[5],
@@ -140,6 +145,14 @@ __global__ void k_spme_influence(SpmeP P, double conv, double test_fac, double c
       c = make_double2(fac * S.x, fac * S.y);
       const double pv = (c.x * S.x + c.y * S.y) * (-2.0 * ((1.0 + x2) / k2));
       st[0] += m0 * m0 * pv; st[1] += m0 * m1 * pv; st[2] += m0 * m2 * pv; st[3] += m1 * m1 * pv; st[4] += m1 * m2 * pv; st[5] += m2 * m2 * pv;
+      if (HALF && l != 0 && 2 * l != P.K[2]) {
+        // the conjugate partner (K1 - j, K2 - k, K3 - l) that the half spectrum leaves out: same kernel value, its own m vector -- a
+        // Nyquist index keeps + K / 2 (the reference's 2 j > K test), every other component changes sign
+        const int jp = 2 * j == P.K[0] ? jj : -jj, kp = 2 * k == P.K[1] ? kk : -kk, lp = -ll;
+        const double p0 = jp * P.rc[0] + kp * P.rc[1] + lp * P.rc[2], p1 = jp * P.rc[3] + kp * P.rc[4] + lp * P.rc[5],
+                     p2 = jp * P.rc[6] + kp * P.rc[7] + lp * P.rc[8];
+        st[0] += p0 * p0 * pv; st[1] += p0 * p1 * pv; st[2] += p0 * p2 * pv; st[3] += p1 * p1 * pv; st[4] += p1 * p2 * pv; st[5] += p2 * p2 * pv;
+      }
     }
     grid[e] = c;
   }
@@ -253,10 +266,12 @@ void invert9(const double* a0, double* b0, double* det) {
 typedef int (*fn_plan3d)(int*, int, int, int, int);
 typedef int (*fn_setstream)(int, cudaStream_t);
 typedef int (*fn_execz2z)(int, void*, void*, int);
+typedef int (*fn_execr)(int, void*, void*);
 typedef int (*fn_destroy)(int);
-struct CufftApi { void* lib = nullptr; fn_plan3d plan3d = nullptr; fn_setstream set_stream = nullptr; fn_execz2z exec = nullptr; fn_destroy destroy = nullptr; };
+struct CufftApi { void* lib = nullptr; fn_plan3d plan3d = nullptr; fn_setstream set_stream = nullptr; fn_execz2z exec = nullptr; fn_destroy destroy = nullptr;
+                  fn_execr exec_d2z = nullptr, exec_z2d = nullptr; };
 CufftApi g_fft;
-constexpr int CUFFT_Z2Z_TYPE = 0x69, CUFFT_FWD = -1, CUFFT_INV = 1;
+constexpr int CUFFT_Z2Z_TYPE = 0x69, CUFFT_D2Z_TYPE = 0x6a, CUFFT_Z2D_TYPE = 0x6c, CUFFT_FWD = -1, CUFFT_INV = 1;
 
 bool load_cufft() {
   if (g_fft.lib) return true;
@@ -267,6 +282,8 @@ bool load_cufft() {
   g_fft.set_stream = (fn_setstream)dlsym(g_fft.lib, "cufftSetStream");
   g_fft.exec = (fn_execz2z)dlsym(g_fft.lib, "cufftExecZ2Z");
   g_fft.destroy = (fn_destroy)dlsym(g_fft.lib, "cufftDestroy");
+  g_fft.exec_d2z = (fn_execr)dlsym(g_fft.lib, "cufftExecD2Z");
+  g_fft.exec_z2d = (fn_execr)dlsym(g_fft.lib, "cufftExecZ2D");
   return g_fft.plan3d && g_fft.set_stream && g_fft.exec && g_fft.destroy;
 }
 
@@ -275,6 +292,8 @@ bool load_cufft() {
 void dlp_spme_release(dlpgpu_ctx* ctx) {
   if (ctx->spme_plan_valid && g_fft.destroy) g_fft.destroy(ctx->spme_plan);
   ctx->spme_plan_valid = false;
+  if (ctx->spme_r2c_valid && g_fft.destroy) { g_fft.destroy(ctx->spme_plan_d2z); g_fft.destroy(ctx->spme_plan_z2d); }
+  ctx->spme_r2c_valid = false;
   ctx->spme_grid.release(ctx->stream); ctx->spme_rgrid.release(ctx->stream); ctx->spme_norm2.release(ctx->stream); ctx->spme_fraw.release(ctx->stream); ctx->spme_tot.release(ctx->stream);
 }
 
@@ -288,6 +307,7 @@ int dlpgpu_set_spme(dlpgpu_ctx* ctx, const int kdim[3], int nsplines) {
     if (kdim[d] < nsplines || kdim[d] > 2048) return dlp_fail(ctx, DLPGPU_ERR_ARG, "set_spme: grid dimension %d not supported", kdim[d]);
   if (!load_cufft()) return dlp_fail(ctx, DLPGPU_ERR_STATE, "set_spme: cuFFT (libcufft.so) could not be loaded");
   if (ctx->spme_plan_valid) { g_fft.destroy(ctx->spme_plan); ctx->spme_plan_valid = false; }
+  if (ctx->spme_r2c_valid) { g_fft.destroy(ctx->spme_plan_d2z); g_fft.destroy(ctx->spme_plan_z2d); ctx->spme_r2c_valid = false; }
   for (int d = 0; d < 3; ++d) ctx->spme_k[d] = kdim[d];
   ctx->spme_n = nsplines;
   const int n = nsplines, kmax = std::max(kdim[0], std::max(kdim[1], kdim[2]));
@@ -380,12 +400,31 @@ int spme_spread(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
   }
   return 0;
 }
-// charge grid of the WHOLE system -> potential grid (in place); the stress kernel sums go to the totals
+// charge grid of the WHOLE system -> potential grid (in place); the stress kernel sums go to the totals.  Orthogonal cells take the
+// real-to-complex transforms (half the spectrum: the kernel is even in m there, Nyquist planes included -- a triclinic cell breaks
+// that on the Nyquist planes, where the reference takes + K / 2 for both members of a conjugate pair, so it keeps the complex path)
 int spme_solve(dlpgpu_ctx* ctx, const SpmeGeom& G, double* rgrid) {
   double2* grid = reinterpret_cast<double2*>(ctx->spme_grid.p);
+  const double* c = ctx->cell;
+  const bool ortho = c[1] == 0.0 && c[2] == 0.0 && c[3] == 0.0 && c[5] == 0.0 && c[6] == 0.0 && c[7] == 0.0;
+  if (ortho && g_fft.exec_d2z && g_fft.exec_z2d) {
+    if (!ctx->spme_r2c_valid) {
+      int p1 = 0, p2 = 0;
+      if (g_fft.plan3d(&p1, G.P.K[0], G.P.K[1], G.P.K[2], CUFFT_D2Z_TYPE) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: cufftPlan3d (D2Z) failed");
+      if (g_fft.plan3d(&p2, G.P.K[0], G.P.K[1], G.P.K[2], CUFFT_Z2D_TYPE) != 0) { g_fft.destroy(p1); return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: cufftPlan3d (Z2D) failed"); }
+      if (g_fft.set_stream(p1, ctx->stream) != 0 || g_fft.set_stream(p2, ctx->stream) != 0) { g_fft.destroy(p1); g_fft.destroy(p2); return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: cufftSetStream failed"); }
+      ctx->spme_plan_d2z = p1; ctx->spme_plan_z2d = p2; ctx->spme_r2c_valid = true;
+    }
+    const size_t nhalf = (size_t)G.P.K[0] * G.P.K[1] * (G.P.K[2] / 2 + 1);
+    const int blocks_h = std::max(1, std::min(cdiv((long long)nhalf, 256), ctx->sm_count * 16));
+    if (g_fft.exec_d2z(ctx->spme_plan_d2z, rgrid, grid) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: forward FFT (D2Z) failed");
+    LAUNCH(ctx, k_spme_influence<true>, blocks_h, 256, 0, G.P, G.conv, G.test_fac, G.cut2, ctx->spme_norm2.p, ctx->spme_kmax, grid, ctx->spme_tot.p);
+    if (g_fft.exec_z2d(ctx->spme_plan_z2d, grid, rgrid) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: backward FFT (Z2D) failed");
+    return 0;
+  }
   LAUNCH(ctx, k_spme_real_to_complex, G.blocks_g, 256, 0, G.ntot, rgrid, grid);
   if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_FWD) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: forward FFT failed");
-  LAUNCH(ctx, k_spme_influence, G.blocks_g, 256, 0, G.P, G.conv, G.test_fac, G.cut2, ctx->spme_norm2.p, ctx->spme_kmax, grid, ctx->spme_tot.p);
+  LAUNCH(ctx, k_spme_influence<false>, G.blocks_g, 256, 0, G.P, G.conv, G.test_fac, G.cut2, ctx->spme_norm2.p, ctx->spme_kmax, grid, ctx->spme_tot.p);
   if (g_fft.exec(ctx->spme_plan, grid, grid, CUFFT_INV) != 0) return dlp_fail(ctx, DLPGPU_ERR_CUDA, "spme: backward FFT failed");
   LAUNCH(ctx, k_spme_complex_to_real, G.blocks_g, 256, 0, G.ntot, grid, rgrid);
   return 0;
@@ -478,7 +517,7 @@ int dlpgpu_dev_spme_finish(dlpgpu_ctx* ctx, int megatm, const double ftot_global
 }  // extern "C"
 
 int dlp_preload_spme() {
-  const void* ks[] = {(const void*)k_spme_spread<8>, (const void*)k_spme_spread<0>, (const void*)k_spme_influence, (const void*)k_spme_gather<8>, (const void*)k_spme_gather<0>, (const void*)k_spme_finish, (const void*)k_spme_real_to_complex,
+  const void* ks[] = {(const void*)k_spme_spread<8>, (const void*)k_spme_spread<0>, (const void*)k_spme_influence<true>, (const void*)k_spme_influence<false>, (const void*)k_spme_gather<8>, (const void*)k_spme_gather<0>, (const void*)k_spme_finish, (const void*)k_spme_real_to_complex,
                       (const void*)k_spme_complex_to_real};
   cudaFuncAttributes a;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();

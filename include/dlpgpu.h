@@ -133,7 +133,9 @@ int dlpgpu_parts_unchanged_since_list(dlpgpu_ctx* ctx);
  * of the north star): B-spline charge spreading (ewald_general.F90:517-576), forward transform, the reference's influence
  * function inside its spherical k cutoff with the stress kernel (ewald_spole.F90:1257-1386), backward transform, force / energy
  * gather with the net force removed (ewald_general.F90:717-869), self interaction (spme.F90:159-231).  dlpgpu_dev_spme_forces serves
- * one domain (mxnode = 1; DLPGPU_ERR_STATE otherwise; several domains: the staged calls below); the 3-D transforms are cuFFT's, loaded on first use.
+ * one domain (mxnode = 1; DLPGPU_ERR_STATE otherwise; several domains: the staged calls below); the 3-D transforms are cuFFT's, loaded on first use
+ * (real-to-complex on half the spectrum in orthogonal cells, complex in parallelepiped cells: the reference's + K / 2 convention on
+ * the Nyquist planes is not even in m there).
  * set_spme: kdim = ewld%kspace%k_vec_dim (after adjust_kmax), nsplines = bspline%num_splines (3..12); alpha, the Coulomb
  * scaling and the cell come from dlpgpu_set_ewald / dlpgpu_set_cell.
  * dev_spme_forces works on the device-resident atoms (1:natms), ADDS the reciprocal forces to the device force arrays and

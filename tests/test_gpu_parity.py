@@ -764,6 +764,31 @@ def test_spme_reciprocal_space_against_oracle(name, nspl):
     sr.close()
 
 
+def test_spme_triclinic_cell_keeps_the_complex_transforms():
+    """Orthogonal cells take real-to-complex transforms (half the spectrum); in a parallelepiped cell the reference's influence function
+    is not even in m on the Nyquist planes (it takes + K / 2 for both members of a conjugate pair, ewald_spole.F90:1305-1320), so the
+    library keeps the complex transforms there.  A sheared NaCl cell against the numpy oracle."""
+    from oracle import spme_oracle as so
+    base = systems.nacl(4, rcut=8.0, padding=0.2)
+    M = np.array([[1.0, 0.20, 0.10], [0.0, 1.0, 0.15], [0.0, 0.0, 1.0]])
+    s = systems.System("nacl-sheared", (base.cell.reshape(3, 3) @ M).reshape(9), base.xyz @ M, base.lsite, base.type_site, base.charge_site,
+                       base.weight_site, base.ff, base.rcut, base.padding)
+    assert s.imcon == 3
+    xyz = dd.read_config_fold(s.xyz, s.cell)[0]
+    q = s.charge_site[s.lsite - 1]
+    _, kdim = so.spme_grid(1.0e-6, s.rcut, s.cell)
+    ref = so.ewald_spme_forces_coul(s.cell, xyz, q, s.ff.alpha, kdim, 8, s.ff.scaling)
+    sr = native_serial(s)
+    sr.set_spme(kdim, 8)
+    out = sr.dev_spme_forces(s.megatm)
+    f = parts_forces(sr.dev_get_parts(), s.megatm)
+    assert abs(out[0] - ref["engcpe_rc"]) <= 1e-10 * abs(ref["engcpe_rc"]) and abs(out[1] - ref["vircpe_rc"]) <= 1e-10 * abs(ref["vircpe_rc"])
+    assert np.abs(out[2:11] - ref["stress"]).max() <= 1e-10 * np.abs(ref["stress"]).max()
+    rep = per_atom_force_error(f, ref["forces"])
+    assert rep["max_normalised"] <= FORCE_TOL and rep["per_atom_significant"] <= FORCE_TOL, rep
+    sr.close()
+
+
 def test_spme_dropin_adds_into_the_callers_records():
     """dlpgpu_spme_forces (host corePart array): the reciprocal forces are ADDED to what parts%f holds, positions and charges
     come back untouched, the sums equal the device-resident call's."""
