@@ -618,7 +618,9 @@ def run_e2e(args, torch, dom, transport, world, natoms_total, interval):
         sr2.set_force_mode(args.force_mode)
     # packed transfers pay from about a dozen otherwise idle cores per rank (csrc/hostio.cu); below that whole records by DMA
     cpus_per_rank = len(os.sched_getaffinity(0)) // max(1, world)
-    host_threads = min(cpus_per_rank - 1, 32) if cpus_per_rank >= 12 else 0
+    # ... and while the ranks of the box do not saturate the host's memory system between them: packed mode moves ~330 MB per rank
+    # and step through host memory (148 MB by DMA), measured to pay at 1 rank (3.5 against 4.4 ms) and to break even at 2
+    host_threads = min(cpus_per_rank - 1, 32) if (cpus_per_rank >= 12 and world <= 2) else 0
     if os.environ.get("DLPGPU_HOST_THREADS"):
         host_threads = int(os.environ["DLPGPU_HOST_THREADS"])
     sr2.set_host_threads(host_threads)
